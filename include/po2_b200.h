@@ -1,0 +1,110 @@
+/*
+ * po2_b200.h -- C ABI of libpo2b200.so: the B200 (sm_100a) implementation of the
+ * mschoenb97/po2_quantization hot path (PO2 / PO2+ quantizers + quantized-conv forward).
+ *
+ * The reference has no native interface for this path: it is ~13 ATen calls per tensor in
+ * utils/quantizers.py and one F.conv2d in models/quantized_conv.py.  Each entry point below
+ * names the reference lines whose *body* it replaces; INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions (all entry points)
+ *   - every pointer is a DEVICE pointer owned by the caller; the library allocates nothing and
+ *     keeps no reference after the call returns;
+ *   - work is enqueued on `stream` (a CUstream / cudaStream_t passed as void*), never
+ *     synchronised, and is CUDA-graph capturable;
+ *   - return value: 0 = success, > 0 = a cudaError_t from the launch, < 0 = PO2_E_* argument
+ *     error.  Nothing throws or exits;
+ *   - re-entrant; the only process-global state is lazily cached device attributes;
+ *   - element counts are 64-bit (the quantizer sweep reaches 2^32 elements).
+ */
+#ifndef PO2_B200_H_
+#define PO2_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* storage dtypes of x / y (the arithmetic is integer exponent/mantissa work on these bits) */
+enum { PO2_F32 = 0, PO2_BF16 = 1, PO2_F16 = 2 };
+
+/* quantizer: utils/quantizers.py:19-36 (PowerOfTwoQuantizer), :39-56 (PowerOfTwoPlusQuantizer) */
+enum { PO2_MODE_PO2 = 0, PO2_MODE_PO2_PLUS = 1 };
+
+/* which float log2 the rounding boundaries reproduce (tools/scan_boundaries.py):
+ *   IEEE       = correctly rounded log2 == torch's CPU kernels (the reference on a CPU);
+ *   TORCH_CUDA = torch's CUDA log2f / scalar-division kernels (the reference on a GPU).     */
+enum { PO2_FLAVOR_IEEE = 0, PO2_FLAVOR_TORCH_CUDA = 1 };
+
+/* weight formats accepted by po2_conv2d_fwd */
+enum {
+  PO2_W_F32_PO2 = 0,  /* fp32 values already on the grid +-scale*2^q (what quantize writes)   */
+  PO2_W_CODES = 1     /* packed sign+exponent codes (po2_quantize's `codes`) + scale           */
+};
+
+enum {
+  PO2_E_DTYPE = -1, PO2_E_BITS = -2, PO2_E_NULL = -3, PO2_E_SIZE = -4, PO2_E_ALIGN = -5,
+  PO2_E_SHAPE = -6, PO2_E_FLAVOR = -7, PO2_E_WORKSPACE = -8, PO2_E_MODE = -9,
+  PO2_E_UNSUPPORTED = -10
+};
+
+int po2_abi_version(void);
+/* static string for any return code of this library (also maps cudaError_t values) */
+const char* po2_error_string(int code);
+/* 1 if the torch_cuda boundary table was scanned on hardware and compiled in */
+int po2_have_torch_cuda_table(void);
+
+/* Bytes of zero-initialised device scratch that po2_absmax / po2_quantize_fused need.  The
+ * kernels leave it zeroed again, so one cudaMemset at allocation time is enough; it must not be
+ * shared by calls that can run concurrently (one per stream). */
+size_t po2_workspace_bytes(void);
+
+/* scale = max(abs(x))        -- utils/quantizers.py:23, :43 (torch.max(torch.abs(input))).
+ * NaN propagates (any NaN -> scale NaN), as torch.max does.  n == 0 -> PO2_E_SIZE (torch raises). */
+int po2_absmax(const void* x, int64_t n, int dtype, float* scale_out, void* workspace,
+               void* stream);
+
+/* y = 2^clamp(round(log2|x/scale|), fsr-2^(bits-1), fsr-1) * sign(x) * scale
+ *                            -- utils/quantizers.py:22-32 (mode 0) / :42-52 (mode 1), bit-exact.
+ * codes (optional): packed sign+exponent codes, bits<=4 two per byte (element 2i in the low
+ *   nibble), else one per byte; code = signbit<<(bits-1) | ((fsr-1)-q).
+ * zero_count (optional, caller-zeroed u32): number of inputs equal to +-0; those produce y = +0
+ *   (the reference's sign() is 0) but have no code of their own and are emitted as (+, min level).
+ * sse (optional, caller-zeroed double): accumulates sum((y-x)^2) -- models/quantized_conv.py:43,
+ *   utils/quantizers.py:149.
+ * bits in [2, 8].  x, y 16-byte aligned for the vector path (any alignment is accepted). */
+int po2_quantize(const void* x, void* y, void* codes, unsigned int* zero_count, double* sse,
+                 const float* scale, int64_t n, int dtype, int bits, int fsr, int mode,
+                 int flavor, void* stream);
+
+/* absmax + quantize in one call (what Quantizer.forward does): one register-resident
+ * cooperative launch when the tensor fits on chip, otherwise two streaming passes. */
+int po2_quantize_fused(const void* x, void* y, void* codes, unsigned int* zero_count,
+                       double* sse, float* scale_out, int64_t n, int dtype, int bits, int fsr,
+                       int mode, int flavor, void* workspace, void* stream);
+
+/* y = +-2^q * scale from packed codes (inverse of the `codes` output above) */
+int po2_dequantize(const void* codes, const float* scale, void* y, int64_t n, int dtype,
+                   int bits, int fsr, void* stream);
+
+/* Straight-through estimator -- utils/quantizers.py:34-36, :54-56: grad_input = grad_output.
+ * accumulate = 0: gx = g;  accumulate = 1: gx += g (fused .grad accumulation). */
+int po2_ste_backward(const void* g, void* gx, int64_t n, int dtype, int accumulate,
+                     void* stream);
+
+/* out = conv2d(x, W)  -- models/quantized_conv.py:36,38 (nn.Conv2d._conv_forward, bias=None,
+ * dilation=1, zero padding).  x: fp32 NCHW (B,C,H,W); out: fp32 NCHW (B,K,P,Q); W: (K,C/groups,R,S)
+ * in `w_format`.  compute = 0: bf16 tensor cores where the shape allows, 1: fp32 CUDA cores. */
+size_t po2_conv2d_workspace(int B, int C, int H, int W, int K, int R, int S, int stride, int pad,
+                            int groups, int compute);
+int po2_conv2d_fwd(const void* x, const void* w, const float* scale, void* out, int B, int C,
+                   int H, int W, int K, int R, int S, int stride, int pad, int groups,
+                   int w_format, int bits, int fsr, int compute, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PO2_B200_H_ */

@@ -1,0 +1,13 @@
+"""po2_quantization_b200 -- B200 (sm_100a) implementation of the po2_quantization hot path.
+
+Public surface mirrors the reference (utils/quantizers.py, models/quantized_conv.py):
+``PowerOfTwoQuantizer``, ``PowerOfTwoPlusQuantizer``, ``LinearPowerOfTwoQuantizer``,
+``LinearPowerOfTwoPlusQuantizer``, ``quantize_model``, ``quantizer_dict``, ``QuantizedConv2d``.
+"""
+from . import _lib, ops  # noqa: F401
+from .ops import get_log2_flavor, set_log2_flavor  # noqa: F401
+from .quantized_conv import QuantizedConv2d  # noqa: F401
+from .quantizers import (LinearPowerOfTwoPlusQuantizer, LinearPowerOfTwoQuantizer,  # noqa: F401
+                         PowerOfTwoPlusQuantizer, PowerOfTwoQuantizer, quantize_model, quantizer_dict)
+
+__version__ = "0.1.0"

@@ -1,0 +1,71 @@
+"""ctypes binding of libpo2b200.so (the C ABI declared in include/po2_b200.h).
+
+There is no fallback: if the library is missing and cannot be built, or a call fails, this
+raises.  torch is used by callers only for device memory and streams.
+"""
+import ctypes
+import os
+import threading
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libpo2b200.so")
+
+F32, BF16, F16 = 0, 1, 2
+MODE_PO2, MODE_PO2_PLUS = 0, 1
+FLAVOR_IEEE, FLAVOR_TORCH_CUDA = 0, 1
+W_F32_PO2, W_CODES = 0, 1
+
+_c = ctypes
+_vp, _i, _i64, _sz = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/po2_b200.h declares
+SIGNATURES = {
+    "po2_abi_version": (_i, []),
+    "po2_error_string": (_c.c_char_p, [_i]),
+    "po2_have_torch_cuda_table": (_i, []),
+    "po2_workspace_bytes": (_sz, []),
+    "po2_absmax": (_i, [_vp, _i64, _i, _vp, _vp, _vp]),
+    "po2_quantize": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "po2_quantize_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp, _vp]),
+    "po2_dequantize": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _vp]),
+    "po2_ste_backward": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
+    "po2_conv2d_workspace": (_sz, [_i] * 11),
+    "po2_conv2d_fwd": (_i, [_vp, _vp, _vp, _vp] + [_i] * 14 + [_vp, _sz, _vp]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+class Po2Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load (building first if the .so is absent) and type the library.  Raises on failure."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            from . import build as _build
+            _build.build()
+        try:
+            lib = ctypes.CDLL(LIB_PATH)
+        except OSError as e:  # pragma: no cover
+            raise Po2Error(f"cannot load {LIB_PATH}: {e}. Run `python -m po2_quantization_b200.build`; "
+                           "there is no CPU or PyTorch fallback for this path.") from e
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)     # AttributeError if the ABI and the header disagree
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(code: int, what: str):
+    if code != 0:
+        msg = load().po2_error_string(code).decode()
+        raise Po2Error(f"{what} failed ({code}): {msg}")

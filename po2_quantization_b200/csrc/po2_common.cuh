@@ -1,0 +1,81 @@
+// Shared device helpers for the PO2 kernels (sm_100a).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/po2_b200.h"
+
+#define PO2_NEVER 0xFFFFFFFFu
+
+namespace po2 {
+
+// ---- storage-dtype traits: the kernels work on raw bit patterns of the storage type ----------
+template <int DT> struct Tr;
+
+template <> struct Tr<PO2_F32> {
+  static constexpr int EB = 4;      // bytes per element
+  static constexpr int MB = 23;     // mantissa bits (binade index = magnitude >> MB)
+  static constexpr int EPV = 4;     // elements per 16-byte vector
+  static constexpr int NBIN = 256;  // number of binades
+  static constexpr uint32_t MAG = 0x7FFFFFFFu, SGN = 0x80000000u, QNAN = 0x7FC00000u, INF = 0x7F800000u;
+  static __device__ __forceinline__ float val(uint32_t p) { return __uint_as_float(p); }
+  static __device__ __forceinline__ uint32_t pat(float f) { return __float_as_uint(f); }
+};
+template <> struct Tr<PO2_BF16> {
+  static constexpr int EB = 2, MB = 7, EPV = 8, NBIN = 256;
+  static constexpr uint32_t MAG = 0x7FFFu, SGN = 0x8000u, QNAN = 0x7FC0u, INF = 0x7F80u;
+  static __device__ __forceinline__ float val(uint32_t p) { return __uint_as_float(p << 16); }
+  static __device__ __forceinline__ uint32_t pat(float f) {
+    return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f));
+  }
+};
+template <> struct Tr<PO2_F16> {
+  static constexpr int EB = 2, MB = 10, EPV = 8, NBIN = 32;
+  static constexpr uint32_t MAG = 0x7FFFu, SGN = 0x8000u, QNAN = 0x7E00u, INF = 0x7C00u;
+  static __device__ __forceinline__ float val(uint32_t p) {
+    return __half2float(__ushort_as_half((unsigned short)p));
+  }
+  static __device__ __forceinline__ uint32_t pat(float f) {
+    return (uint32_t)__half_as_ushort(__float2half_rn(f));
+  }
+};
+
+// round an fp32 intermediate to the storage grid (torch rounds half types after every op)
+template <int DT> __device__ __forceinline__ float round_storage(float f) {
+  if (DT == PO2_F32) return f;
+  return Tr<DT>::val(Tr<DT>::pat(f));
+}
+
+// exact 2^k as fp32 for any integer k (0 below 2^-149, +inf above 2^127) == torch's 2**q
+__device__ __forceinline__ float exp2_int(int k) {
+  if (k > 127) return __uint_as_float(0x7F800000u);
+  if (k >= -126) return __uint_as_float((uint32_t)(k + 127) << 23);
+  if (k >= -149) return __uint_as_float(1u << (k + 149));
+  return 0.0f;
+}
+
+// ---- streaming 128-bit global access ----------------------------------------------------------
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint4 ldg_keep(const uint4* p) {   // normal policy: leave it in L2
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream(uint4* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) {
+  return __reduce_max_sync(0xFFFFFFFFu, v);
+}
+
+}  // namespace po2

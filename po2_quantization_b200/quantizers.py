@@ -1,0 +1,134 @@
+"""Host-side mirror of the reference's ``utils/quantizers.py`` public surface.
+
+Same names, signatures and call protocols (``Q.apply(t, bits)``, ``Q.forward(None, t, bits=b)``,
+``quantize_model``, ``quantizer_dict``) -- SURVEY.md section 8b -- but PO2 / PO2+ run as
+hand-written sm_100a kernels through the C ABI (``po2::quantize``).  CUDA tensors only: there is
+no CPU fallback on this path.
+"""
+from typing import Callable, Optional
+
+import torch
+
+from . import ops
+from .quantized_conv import QuantizedConv2d
+
+
+class _Po2Base(torch.autograd.Function):
+    """Shared shell of the two quantizer classes; ``_PLUS`` selects the rounding rule."""
+    _PLUS = False
+
+    @classmethod
+    def _run(cls, input: torch.Tensor, bits: int, fsr: int) -> torch.Tensor:
+        ops._require_cuda(input, cls.__name__)
+        return ops.quantize(input, int(bits), int(fsr), cls._PLUS)
+
+
+class PowerOfTwoQuantizer(_Po2Base):
+    """2^round(log2|x/s|), s = max|x|, clamped to ``bits`` -- reference utils/quantizers.py:19-36."""
+    _PLUS = False
+
+    @staticmethod
+    def forward(ctx, input: torch.Tensor, bits: int = 4, fsr: int = 1):
+        return PowerOfTwoQuantizer._run(input, bits, fsr)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        # straight-through estimator, utils/quantizers.py:34-36: the same tensor object
+        return grad_output, None, None
+
+
+class PowerOfTwoPlusQuantizer(_Po2Base):
+    """2^round(log2(|x/s|/1.5)+0.5) -- reference utils/quantizers.py:39-56."""
+    _PLUS = True
+
+    @staticmethod
+    def forward(ctx, input: torch.Tensor, bits: int = 4, fsr: int = 1):
+        return PowerOfTwoPlusQuantizer._run(input, bits, fsr)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return grad_output, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# lin / lin+ (SURVEY.md section 8f "next" #1): per-input-channel uniform quantizer whose step is
+# constrained to a power of two.  Not on the accelerated path yet -- expressed with ATen ops in
+# the reference's op order (utils/quantizers.py:8-16, 59-136) so quantizer_dict stays complete.
+# ------------------------------------------------------------------------------------------------
+def _uniform_per_in_channel(w: torch.Tensor, step: torch.Tensor, bits: int) -> torch.Tensor:
+    s = step.view(-1, 1, 1)
+    lim = float(2 ** (bits - 1) - 1)
+    return s * torch.clamp(torch.round(w / s), min=-lim, max=lim)
+
+
+def _lin_forward(w: torch.Tensor, bits: int, num_iters: int, plus: bool) -> torch.Tensor:
+    hi = torch.amax(w, dim=(0, 2, 3))
+    lo = torch.amin(w, dim=(0, 2, 3))
+    step = (hi - lo) / (2 ** bits - 1)
+    q = _uniform_per_in_channel(w, step, bits) / step.view(-1, 1, 1)
+    for _ in range(num_iters):
+        step = torch.sum(q * w, dim=[0, 2, 3]) / torch.sum(q * q, dim=[0, 2, 3])
+        if plus:
+            step = torch.sqrt(torch.tensor(8.0 / 9.0)) * step
+        step = 2 ** torch.round(torch.log2(step))
+        q = _uniform_per_in_channel(w, step, bits) / step.view(-1, 1, 1)
+    return q * step.view(-1, 1, 1)
+
+
+class LinearPowerOfTwoQuantizer(torch.autograd.Function):
+    """reference utils/quantizers.py:59-96"""
+
+    @staticmethod
+    def forward(ctx, input: torch.Tensor, bits: int = 4, num_iters: int = 10):
+        return _lin_forward(input, bits, num_iters, plus=False)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return grad_output, None, None
+
+
+class LinearPowerOfTwoPlusQuantizer(torch.autograd.Function):
+    """reference utils/quantizers.py:99-136"""
+
+    @staticmethod
+    def forward(ctx, input: torch.Tensor, bits: int = 4, num_iters: int = 10):
+        return _lin_forward(input, bits, num_iters, plus=True)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return grad_output, None, None
+
+
+def quantize_model(model: torch.nn.Module, quantizer: Optional[Callable[..., None]], bits: int) -> float:
+    """Post-training quantization in place -- reference utils/quantizers.py:139-153.
+
+    Every parameter of every ``QuantizedConv2d`` is overwritten with its quantized value; returns
+    the mean squared quantization error as a Python float.  For the PO2 quantizers the squared
+    error comes out of the same kernel pass that quantizes (no extra reads of the weights)."""
+    total = None
+    numel = 0
+    with torch.no_grad():
+        for _, module in model.named_modules():
+            if not isinstance(module, QuantizedConv2d):
+                continue
+            for _, param in module.named_parameters():
+                if isinstance(quantizer, type) and issubclass(quantizer, _Po2Base) and param.is_cuda:
+                    qp, _codes, _scale, _zc, sse = ops.quantize_full(param, int(bits), 1, quantizer._PLUS)
+                    err = sse
+                else:
+                    qp = quantizer.forward(None, param, bits=bits)
+                    err = torch.sum((qp - param) ** 2).double()
+                total = err if total is None else total + err
+                numel += param.numel()
+                param.copy_(qp)
+    if total is None:
+        raise ZeroDivisionError("quantize_model: the model has no QuantizedConv2d parameters")
+    return float((total / numel).item())
+
+
+quantizer_dict = {
+    "lin": LinearPowerOfTwoQuantizer,
+    "lin+": LinearPowerOfTwoPlusQuantizer,
+    "po2": PowerOfTwoQuantizer,
+    "po2+": PowerOfTwoPlusQuantizer,
+}

@@ -1,0 +1,231 @@
+"""Parity of the sm_100a quantizer kernels (through the C ABI / torch ops) against the oracle and
+the committed reference vectors.  Bit-exact: integer comparison of the storage bit patterns."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import po2_oracle as O
+from tests import golden_util as G
+
+pytestmark = pytest.mark.gpu
+
+TD = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}
+
+
+def _to_dev(bits_arr, dt):
+    if dt == "f32":
+        return torch.from_numpy(bits_arr.view(np.int32).copy()).view(torch.float32).cuda()
+    return torch.from_numpy(bits_arr.view(np.int16).copy()).view(TD[dt]).cuda()
+
+
+def _bits(t):
+    t = t.detach().contiguous().cpu()
+    if t.dtype == torch.float32:
+        return t.view(torch.int32).numpy().view(np.uint32)
+    return t.view(torch.int16).numpy().view(np.uint16)
+
+
+def _assert_same(got_bits, ref_bits, dt, what):
+    ref_nan = G.nan_mask(ref_bits, dt)
+    got_nan = G.nan_mask(got_bits, dt)
+    assert np.array_equal(ref_nan, got_nan), f"{what}: NaN pattern differs"
+    bad = np.flatnonzero((got_bits != ref_bits) & ~ref_nan)
+    assert bad.size == 0, (what, bad[:8], got_bits[bad[:8]], ref_bits[bad[:8]])
+
+
+CASES = list(G.quantizer_cases())
+
+
+@pytest.fixture(scope="module")
+def P():
+    import po2_quantization_b200 as P
+    P.set_log2_flavor("ieee")
+    return P
+
+
+@pytest.mark.parametrize("key", [c[0] for c in CASES])
+def test_golden_vectors_bit_exact(P, key):
+    """CUDA kernels == unmodified reference (CPU) on every committed vector."""
+    _, name, dt, qn, bits, xb, yb = next(c for c in CASES if c[0] == key)
+    fsr = int(name[3:]) if name.startswith("fsr") else 1
+    x = _to_dev(xb, dt).reshape(-1)
+    Q = P.PowerOfTwoPlusQuantizer if qn == "po2+" else P.PowerOfTwoQuantizer
+    y = Q.forward(None, x, bits=bits, fsr=fsr)
+    assert y.dtype == x.dtype and y.shape == x.shape and y.data_ptr() != x.data_ptr()
+    _assert_same(_bits(y), yb, dt, key)
+
+
+@pytest.mark.parametrize("dt", ["f32", "bf16", "f16"])
+@pytest.mark.parametrize("plus", [False, True])
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 8, 9, 1023, 4099, 36864, 65536 + 5, (1 << 20) + 3])
+def test_vs_oracle_sizes(P, dt, plus, n):
+    rng = np.random.default_rng(n * 7 + plus)
+    x32 = (rng.standard_normal(n) * rng.choice([1e-3, 0.05, 1.0, 37.0])).astype(np.float32)
+    if n > 16:
+        x32[5] = 0.0
+        x32[11] = -0.0
+    x32 = O._round_storage(x32, dt)
+    xd = torch.from_numpy(x32).cuda().to(TD[dt])
+    for bits in (2, 3, 4, 5, 8):
+        y_ref, q, sign, scale = O.quantize(x32, bits, 1, plus, dt, return_parts=True)
+        y, codes, s, zc, sse = torch.ops.po2.quantize_full(xd, bits, 1, plus)
+        _assert_same(_bits(y), G.f32_to_bits(y_ref, dt), dt, f"y n={n} bits={bits}")
+        assert s.item() == float(scale)
+        ref_codes = O.pack_codes(O.exponent_codes(q, sign, bits), bits)
+        assert np.array_equal(codes.cpu().numpy(), ref_codes), f"codes n={n} bits={bits}"
+        assert zc.item() == int(np.sum(x32 == 0))
+        ref_sse = float(np.sum((y_ref.astype(np.float64) - x32.astype(np.float64)) ** 2))
+        assert abs(sse.item() - ref_sse) <= 1e-4 * max(ref_sse, 1e-30) + 1e-30
+        # codes -> values round trip reproduces y (zeros have no code: mask them)
+        back = torch.ops.po2.dequantize(codes, s, n, bits, 1, TD[dt])
+        nz = torch.from_numpy(x32 != 0).cuda()
+        assert torch.equal(back[nz].view(torch.int16 if dt != "f32" else torch.int32),
+                           y[nz].view(torch.int16 if dt != "f32" else torch.int32))
+
+
+@pytest.mark.parametrize("dt", ["f32", "bf16"])
+def test_unaligned_views_and_noncontiguous(P, dt):
+    rng = np.random.default_rng(3)
+    base = O._round_storage(rng.standard_normal(5000).astype(np.float32), dt)
+    bd = torch.from_numpy(base).cuda().to(TD[dt])
+    for off in (1, 2, 3, 5):
+        xv = bd[off:off + 4001]
+        y = P.PowerOfTwoQuantizer.forward(None, xv, bits=4)
+        ref = O.po2(base[off:off + 4001], 4, 1, dt)
+        _assert_same(_bits(y), G.f32_to_bits(ref, dt), dt, f"offset {off}")
+    # raw C-ABI call on a misaligned pointer takes the scalar kernel
+    from po2_quantization_b200 import ops
+    xv = bd[1:4002]
+    y = torch.empty(4008, dtype=TD[dt], device="cuda")[1:4002]
+    s = torch.empty((), dtype=torch.float32, device="cuda")
+    codes = torch.zeros(2001, dtype=torch.uint8, device="cuda")
+    ops.absmax_out(xv, s)
+    ops.quantize_out(xv, y, s, 4, 1, True, codes=codes)
+    yr, q, sg, sc = O.quantize(base[1:4002], 4, 1, True, dt, return_parts=True)
+    _assert_same(_bits(y), G.f32_to_bits(yr, dt), dt, "scalar path")
+    assert np.array_equal(codes.cpu().numpy(), O.pack_codes(O.exponent_codes(q, sg, 4), 4))
+    x2 = bd[:4096].reshape(64, 64).t()          # non-contiguous input
+    y2 = P.PowerOfTwoPlusQuantizer.forward(None, x2, bits=3)
+    ref2 = O.po2_plus(base[:4096].reshape(64, 64).T.copy().ravel(), 3, 1, dt).reshape(64, 64)
+    _assert_same(_bits(y2).ravel(), G.f32_to_bits(ref2.ravel(), dt), dt, "non-contiguous")
+
+
+@pytest.mark.parametrize("dt", ["f32", "bf16"])
+def test_two_pass_equals_fused_large(P, dt):
+    """Streaming two-pass path (absmax + quantize, forward and reversed walk) == fused path == oracle."""
+    from po2_quantization_b200 import ops
+    n = (1 << 24) + 11
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x = torch.randn(n, generator=g, device="cuda").to(TD[dt])
+    s = torch.empty((), dtype=torch.float32, device="cuda")
+    ops.absmax_out(x, s)
+    assert s.item() == x.abs().max().item()
+    outs = []
+    for plus in (False, True):
+        y1 = torch.empty_like(x)
+        ops.quantize_out(x, y1, s, 4, 1, plus)
+        y2 = torch.empty_like(x)
+        s2 = torch.empty_like(s)
+        ops.quantize_fused_out(x, y2, s2, 4, 1, plus)
+        assert torch.equal(y1.view(torch.int16 if dt != "f32" else torch.int32),
+                           y2.view(torch.int16 if dt != "f32" else torch.int32))
+        assert s2.item() == s.item()
+        outs.append(y1)
+    # oracle on a slice that contains the max (so the scale agrees)
+    imax = int(torch.argmax(x.abs()).item())
+    lo = max(0, min(imax - 1000, n - 200000))
+    xs = torch.cat([x[lo:lo + 200000], x[imax:imax + 1]]).float().cpu().numpy()
+    for plus, y in zip((False, True), outs):
+        ref = O.quantize(xs, 4, 1, plus, dt)
+        got = torch.cat([y[lo:lo + 200000], y[imax:imax + 1]])
+        _assert_same(_bits(got), G.f32_to_bits(ref, dt), dt, "large slice")
+
+
+def test_full_size_properties(P):
+    """BASELINE-size properties (2^28 fp32): idempotence, level set, sign, scale."""
+    n = 1 << 28
+    x = torch.randn(n, device="cuda")
+    for Q, bits in ((P.PowerOfTwoQuantizer, 4), (P.PowerOfTwoPlusQuantizer, 4), (P.PowerOfTwoPlusQuantizer, 8)):
+        y = Q.forward(None, x, bits=bits)
+        s = x.abs().max()
+        assert y.abs().max().item() == s.item()
+        y2 = Q.forward(None, y, bits=bits)
+        assert torch.equal(y2.view(torch.int32), y.view(torch.int32)), "not idempotent"
+        assert torch.equal(torch.signbit(y), torch.signbit(x))
+        r = (y.abs() / s)
+        e = torch.log2(r)
+        assert torch.equal(e, torch.round(e)), "levels are not powers of two times the scale"
+        assert e.min().item() >= 1 - 2 ** (bits - 1) and e.max().item() == 0
+        del y, y2, r, e
+
+
+def test_autograd_ste(P):
+    w = torch.randn(64, 16, 3, 3, device="cuda", requires_grad=True)
+    g = torch.randn_like(w)
+    for Q in (P.PowerOfTwoQuantizer, P.PowerOfTwoPlusQuantizer):
+        w.grad = None
+        y = Q.apply(w, 4)
+        y.backward(g)
+        assert torch.equal(w.grad, g)              # straight-through: utils/quantizers.py:34-36
+    assert Q.backward(None, g)[0] is g
+    gi = torch.zeros_like(g)
+    torch.ops.po2.ste_backward(g, gi, False)
+    assert torch.equal(gi, g)
+    torch.ops.po2.ste_backward(g, gi, True)
+    assert torch.equal(gi, g + g)
+    gb = g.bfloat16()[:1001 * 3].contiguous()
+    gi = torch.ones_like(gb)
+    torch.ops.po2.ste_backward(gb, gi, True)
+    assert torch.equal(gi, gb + 1)
+
+
+def test_errors_are_loud(P):
+    from po2_quantization_b200 import _lib
+    with pytest.raises(Exception):
+        P.PowerOfTwoQuantizer.forward(None, torch.randn(4), bits=4)       # CPU tensor: no fallback
+    with pytest.raises(Exception):
+        P.PowerOfTwoQuantizer.forward(None, torch.randn(4, device="cuda").double(), bits=4)
+    with pytest.raises(_lib.Po2Error):
+        P.PowerOfTwoQuantizer.forward(None, torch.randn(4, device="cuda"), bits=9)
+    with pytest.raises(RuntimeError):
+        P.PowerOfTwoQuantizer.forward(None, torch.empty(0, device="cuda"), bits=4)
+
+
+def test_cuda_graph_capture(P):
+    x = torch.randn(36864, device="cuda")
+    y_eager = P.PowerOfTwoPlusQuantizer.forward(None, x, bits=4)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        P.PowerOfTwoPlusQuantizer.forward(None, x, bits=4)            # warm-up on the side stream
+        torch.cuda.current_stream().synchronize()
+        with torch.cuda.graph(g, stream=s):
+            y = P.PowerOfTwoPlusQuantizer.forward(None, x, bits=4)
+    x.copy_(torch.randn_like(x))
+    g.replay()
+    torch.cuda.synchronize()
+    ref = O.po2_plus(x.cpu().numpy(), 4)
+    assert np.array_equal(_bits(y), ref.view(np.uint32))
+    assert y_eager.shape == y.shape
+
+
+def test_stock_torch_cuda_disagreements(P, tmp_path):
+    """Enumerate (not assert) where stock torch CUDA ops -- the reference run on this GPU -- differ
+    from the reference run on a CPU (== oracle == our default 'ieee' flavor)."""
+    import json
+    import os
+    from tests.torch_ref import quantize_ref
+    rep = {}
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(1 << 26, generator=g, device="cuda")
+    for plus in (False, True):
+        for bits in (4, 8):
+            Q = P.PowerOfTwoPlusQuantizer if plus else P.PowerOfTwoQuantizer
+            ours = Q.forward(None, x, bits=bits)
+            stock = quantize_ref(x, bits, 1, plus)
+            rep[f"{'po2+' if plus else 'po2'}|{bits}|ieee_vs_stock_cuda_mismatch_of_2^26"] = int((ours != stock).sum().item())
+    out = os.path.join(os.environ.get("GRAFT_REPO_ROOT", "."), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    json.dump(rep, open(os.path.join(out, "stock_cuda_disagreements.json"), "w"), indent=1)
+    print(rep)
