@@ -210,6 +210,44 @@ def test_cuda_graph_capture(P):
     assert y_eager.shape == y.shape
 
 
+def _boundary_inputs(plus, scale, device):
+    """fp32 values straddling every rounding boundary (same construction as make_golden.py)."""
+    centre = 0x400000 if plus else 0x3504F3
+    out = []
+    for e in range(-126, 0):
+        m = np.arange(centre - 40, centre + 41, dtype=np.int64)
+        out.append((((e + 127) << 23) | m).astype(np.uint32))
+    v = torch.from_numpy(np.concatenate(out).view(np.int32).copy()).view(torch.float32)
+    s = torch.tensor(scale, dtype=torch.float32)
+    x = v * s
+    xb = x.view(torch.int32)
+    x = torch.cat([torch.clamp(xb + d, min=0).view(torch.float32) for d in (-2, -1, 0, 1, 2)])
+    x = x[x <= s]
+    return torch.cat([x, s.reshape(1)]).to(device)
+
+
+@pytest.mark.parametrize("plus", [False, True])
+def test_torch_cuda_flavor_matches_stock_cuda_ops(P, plus):
+    """With the torch_cuda boundary table the kernels reproduce the reference *run on this GPU*
+    (stock ATen CUDA ops) bit for bit, including at every rounding boundary."""
+    from tests.torch_ref import quantize_ref
+    Q = P.PowerOfTwoPlusQuantizer if plus else P.PowerOfTwoQuantizer
+    P.set_log2_flavor("torch_cuda")
+    try:
+        g = torch.Generator(device="cuda").manual_seed(11)
+        xs = [torch.randn(1 << 24, generator=g, device="cuda"),
+              torch.randn(1 << 22, generator=g, device="cuda") ** 3 * 1e-3]
+        xs += [_boundary_inputs(plus, sc, "cuda") for sc in (1.0, 1.337, 0.0517, 1.4142135, 1.3333334, 7.7e30)]
+        for x in xs:
+            for bits in (3, 4, 8):
+                ours = Q.forward(None, x, bits=bits)
+                stock = quantize_ref(x, bits, 1, plus)
+                neq = (ours.view(torch.int32) != stock.view(torch.int32))
+                assert int(neq.sum().item()) == 0, (bits, x[neq][:5], ours[neq][:5], stock[neq][:5])
+    finally:
+        P.set_log2_flavor("ieee")
+
+
 def test_stock_torch_cuda_disagreements(P, tmp_path):
     """Enumerate (not assert) where stock torch CUDA ops -- the reference run on this GPU -- differ
     from the reference run on a CPU (== oracle == our default 'ieee' flavor)."""
