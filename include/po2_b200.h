@@ -85,6 +85,9 @@ int po2_quantize_fused(const void* x, void* y, void* codes, unsigned int* zero_c
                        double* sse, float* scale_out, int64_t n, int dtype, int bits, int fsr,
                        int mode, int flavor, void* workspace, void* stream);
 
+/* how many kernels po2_quantize_fused launches for an aligned tensor of n elements (1 or 2) */
+int po2_quantize_fused_launches(int64_t n, int dtype);
+
 /* y = +-2^q * scale from packed codes (inverse of the `codes` output above) */
 int po2_dequantize(const void* codes, const float* scale, void* y, int64_t n, int dtype,
                    int bits, int fsr, void* stream);

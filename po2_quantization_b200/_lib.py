@@ -27,6 +27,7 @@ SIGNATURES = {
     "po2_absmax": (_i, [_vp, _i64, _i, _vp, _vp, _vp]),
     "po2_quantize": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "po2_quantize_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp, _vp]),
+    "po2_quantize_fused_launches": (_i, [_i64, _i]),
     "po2_dequantize": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _vp]),
     "po2_ste_backward": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     "po2_conv2d_workspace": (_sz, [_i] * 11),

@@ -26,13 +26,17 @@ struct Workspace {            // zero-initialised by the caller once; kernels le
 };
 
 struct LevelTab {
-  uint2 bt[256];              // per binade of |x|: .x = first threshold above the base level,
-                              //                    .y = base level | (irregular << 8)
+  uint2 bt[256];              // per binade of |x| (fast path): .x = first threshold above the
+                              //   binade's base level, .y = output pattern of the base level,
+                              //   bit 31 = "irregular binade, take the exact slow path"
+  uint8_t cb[256];            // per binade: base level (number of thresholds below the binade)
   uint32_t X[132];            // X[j]: smallest magnitude pattern with level >= j; X[nlev] = never
   uint32_t Y[128];            // Y[j]: output magnitude pattern of level j
   int special;                // 0: finite scale > 0; 1: scale NaN or 0 (all NaN); 2: scale +Inf
   uint32_t yinf;              // special == 2: pattern of 2^qmin * Inf in the storage dtype
 };
+
+#define PO2_IRR 0x80000000u
 
 // Smallest magnitude pattern x (storage grid) with round_storage(x / s) >= b.  The predicate is
 // monotone in x; start from fl(b*s) and walk (<= 2 steps in practice), bisect if that fails.
@@ -99,7 +103,15 @@ __device__ void build_levels(LevelTab& T, float s, int bits, int fsr, int mode, 
       cnt += (X < lo);
       inside += (X >= lo && X < hi);
     }
-    T.bt[ex] = make_uint2(T.X[cnt + 1], (uint32_t)cnt | (inside > 1 ? 0x100u : 0u));
+    // Fast path in this binade: y = Y[cnt] + ((a >= X[cnt+1]) << MB).  That is exact when there is
+    // at most one threshold inside and stepping one level up doubles the output pattern exactly.
+    // Binade 0 (zeros and subnormal inputs) always takes the slow path, which also owns the
+    // sign(0) == 0 rule, so the fast path never tests for zero.
+    const uint32_t ylo = T.Y[cnt];
+    bool regular = (ex != 0) && inside <= 1;
+    if (inside == 1) regular = regular && (cnt + 1 < nlev) && (T.Y[cnt + 1] == ylo + (1u << Tr<DT>::MB));
+    T.bt[ex] = make_uint2(T.X[cnt + 1], ylo | (regular ? 0u : PO2_IRR));
+    T.cb[ex] = (uint8_t)cnt;
   }
   __syncthreads();
 }
@@ -109,18 +121,15 @@ struct Acc {                  // per-thread side outputs
   float sse;
 };
 
-// One element: storage pattern in, storage pattern out; `code` gets sign<<(bits-1) | magnitude.
+// One element, exact general path: storage pattern in, storage pattern out; `code` gets
+// sign<<(bits-1) | magnitude.
 template <int DT>
 __device__ __forceinline__ uint32_t quant_one(uint32_t u, const LevelTab& T, int nlev_m1,
-                                              int sign_shift, uint32_t& code, Acc& acc,
-                                              bool want_sse) {
+                                           int sign_shift, uint32_t& code, Acc& acc,
+                                           bool want_sse) {
   const uint32_t a = u & Tr<DT>::MAG;
-  const uint2 e = T.bt[a >> Tr<DT>::MB];
-  uint32_t j = (e.y & 0xFFu) + (a >= e.x ? 1u : 0u);
-  if (e.y & 0x100u) {                                    // >1 threshold in this binade (rare)
-    j = e.y & 0xFFu;
-    while (a >= T.X[j + 1]) ++j;
-  }
+  uint32_t j = T.cb[a >> Tr<DT>::MB];
+  while (a >= T.X[j + 1]) ++j;
   const uint32_t yb = T.Y[j];
   const bool nz = (a != 0);
   const uint32_t sg = nz ? (u & Tr<DT>::SGN) : 0u;      // torch.sign(+-0) == 0 -> y = +0
@@ -132,6 +141,21 @@ __device__ __forceinline__ uint32_t quant_one(uint32_t u, const LevelTab& T, int
     acc.sse = fmaf(d, d, acc.sse);
   }
   return out;
+}
+
+// One element, fast path (regular binades): mask, shift, one 64-bit shared load, compare, add,
+// sign merge.  `irr` collects the irregular flag; the caller redoes the vector if it is set.
+template <int DT, bool CODES>
+__device__ __forceinline__ uint32_t quant_fast(uint32_t u, const LevelTab& T, uint32_t& irr,
+                                               int nlev_m1, int sign_shift, uint32_t& code) {
+  const uint32_t a = u & Tr<DT>::MAG;
+  const uint32_t ex = a >> Tr<DT>::MB;
+  const uint2 e = T.bt[ex];
+  const uint32_t up = (a >= e.x) ? 1u : 0u;
+  const uint32_t t = e.y + (up << Tr<DT>::MB);
+  irr |= e.y;
+  if (CODES) code = (uint32_t)(nlev_m1 - (int)T.cb[ex] - (int)up) | (((u & Tr<DT>::SGN) ? 1u : 0u) << sign_shift);
+  return (t & Tr<DT>::MAG) | (u & Tr<DT>::SGN);
 }
 
 // Non-finite / zero scale: the reference's float pipeline evaluated literally.
@@ -181,47 +205,100 @@ __device__ void quant_pair(const void* x, void* y, uint8_t* codes, int64_t ip, i
   }
 }
 
-// One 16-byte vector (EPV elements) in registers -> quantized vector + packed codes.
+// codes travel as one byte per element in a register pair (element i in byte i)
 template <int DT>
-__device__ __forceinline__ uint4 quant_vec(const uint4& v, const LevelTab& T, int nlev_m1,
-                                           int sshift, bool codes4, uint8_t* codes, int64_t iv,
-                                           Acc& acc, bool want_sse) {
-  uint4 o;
-  if (DT == PO2_F32) {
-    uint32_t c0, c1, c2, c3;
-    o.x = quant_one<DT>(v.x, T, nlev_m1, sshift, c0, acc, want_sse);
-    o.y = quant_one<DT>(v.y, T, nlev_m1, sshift, c1, acc, want_sse);
-    o.z = quant_one<DT>(v.z, T, nlev_m1, sshift, c2, acc, want_sse);
-    o.w = quant_one<DT>(v.w, T, nlev_m1, sshift, c3, acc, want_sse);
-    if (codes) {
-      if (codes4) reinterpret_cast<unsigned short*>(codes)[iv] =
-          (unsigned short)(c0 | (c1 << 4) | (c2 << 8) | (c3 << 12));
-      else reinterpret_cast<uint32_t*>(codes)[iv] = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
-    }
+__device__ __forceinline__ void store_codes(uint8_t* codes, int64_t iv, bool codes4, uint2 cb) {
+  if (codes4) {                                          // squeeze bytes to nibbles
+    uint32_t a = cb.x | (cb.x >> 4);                     // bytes 0,2 now hold nibble pairs (0,1),(2,3)
+    a = (a & 0xFFu) | ((a >> 8) & 0xFF00u);
+    if (DT == PO2_F32) { reinterpret_cast<unsigned short*>(codes)[iv] = (unsigned short)a; return; }
+    uint32_t b = cb.y | (cb.y >> 4);
+    b = (b & 0xFFu) | ((b >> 8) & 0xFF00u);
+    reinterpret_cast<uint32_t*>(codes)[iv] = a | (b << 16);
+  } else if (DT == PO2_F32) {
+    reinterpret_cast<uint32_t*>(codes)[iv] = cb.x;
   } else {
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t ow[4], c[8];
+    reinterpret_cast<uint2*>(codes)[iv] = cb;
+  }
+}
+
+struct SlowOut { uint4 o; uint2 cb; uint32_t zeros; float sse; };
+
+// exact general path for a whole vector (rare: zeros, subnormals, irregular binades); everything
+// is passed and returned by value so the hot loop keeps its vectors in registers
+template <int DT>
+__device__ __noinline__ SlowOut quant_vec_slow(uint4 v, const LevelTab* Tp, int nlev_m1, int sshift,
+                                               bool want_sse) {
+  const LevelTab& T = *Tp;
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint32_t ow[4], c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  Acc acc{0u, 0.0f};
+  if (DT == PO2_F32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ow[i] = quant_one<DT>(w[i], T, nlev_m1, sshift, c[i], acc, want_sse);
+  } else {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const uint32_t lo = quant_one<DT>(w[i] & 0xFFFFu, T, nlev_m1, sshift, c[2 * i], acc, want_sse);
       const uint32_t hi = quant_one<DT>(w[i] >> 16, T, nlev_m1, sshift, c[2 * i + 1], acc, want_sse);
       ow[i] = lo | (hi << 16);
     }
-    o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-    if (codes) {
-      if (codes4) {
-        uint32_t p = 0;
+  }
+  SlowOut r;
+  r.o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  r.cb = make_uint2(c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24), c[4] | (c[5] << 8) | (c[6] << 16) | (c[7] << 24));
+  r.zeros = acc.zeros;
+  r.sse = acc.sse;
+  return r;
+}
+
+// One 16-byte vector (EPV elements) in registers -> quantized vector (+ packed codes, + SSE).
+template <int DT, bool CODES, bool SSE>
+__device__ __forceinline__ uint4 quant_vec_t(const uint4& v, const LevelTab& T, int nlev_m1, int sshift,
+                                             bool codes4, uint8_t* codes, int64_t iv, Acc& acc) {
+  constexpr bool want_sse = SSE;
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint32_t ow[4], irr = 0;
+  uint2 cb = make_uint2(0u, 0u);
+  if (DT == PO2_F32) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) p |= c[i] << (4 * i);
-        reinterpret_cast<uint32_t*>(codes)[iv] = p;
-      } else {
-        uint2 p;
-        p.x = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
-        p.y = c[4] | (c[5] << 8) | (c[6] << 16) | (c[7] << 24);
-        reinterpret_cast<uint2*>(codes)[iv] = p;
+    for (int i = 0; i < 4; ++i) {
+      uint32_t c = 0;
+      ow[i] = quant_fast<DT, CODES>(w[i], T, irr, nlev_m1, sshift, c);
+      if (CODES) cb.x |= c << (8 * i);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t c0 = 0, c1 = 0;
+      const uint32_t lo = quant_fast<DT, CODES>(w[i] & 0xFFFFu, T, irr, nlev_m1, sshift, c0);
+      const uint32_t hi = quant_fast<DT, CODES>(w[i] >> 16, T, irr, nlev_m1, sshift, c1);
+      ow[i] = lo | (hi << 16);
+      if (CODES) {
+        const uint32_t cc = (c0 | (c1 << 8)) << (16 * (i & 1));
+        if (i < 2) cb.x |= cc; else cb.y |= cc;
       }
     }
   }
+  uint4 o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  if (irr & PO2_IRR) {
+    const SlowOut r = quant_vec_slow<DT>(v, &T, nlev_m1, sshift, want_sse);
+    o = r.o; cb = r.cb;
+    acc.zeros += r.zeros; acc.sse += r.sse;
+  } else if (want_sse) {
+    if (DT == PO2_F32) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const float d = __uint_as_float(ow[i]) - __uint_as_float(w[i]); acc.sse = fmaf(d, d, acc.sse); }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float d0 = Tr<DT>::val(ow[i] & 0xFFFFu) - Tr<DT>::val(w[i] & 0xFFFFu);
+        const float d1 = Tr<DT>::val(ow[i] >> 16) - Tr<DT>::val(w[i] >> 16);
+        acc.sse = fmaf(d0, d0, acc.sse); acc.sse = fmaf(d1, d1, acc.sse);
+      }
+    }
+  }
+  if (CODES) store_codes<DT>(codes, iv, codes4, cb);
   return o;
 }
 
@@ -323,7 +400,7 @@ __global__ void __launch_bounds__(256) absmax_kernel(const void* __restrict__ x,
 // ------------------------------------------------------------------------------------------------
 // pass 2: quantize / dequantize / code emit
 // ------------------------------------------------------------------------------------------------
-template <int DT>
+template <int DT, bool CODES, bool SSE>
 __global__ void __launch_bounds__(256) quantize_kernel(const uint4* __restrict__ x,
                                                        uint4* __restrict__ y, uint8_t* codes,
                                                        unsigned int* zero_count, double* sse,
@@ -335,11 +412,13 @@ __global__ void __launch_bounds__(256) quantize_kernel(const uint4* __restrict__
   constexpr int EPV = Tr<DT>::EPV;
   build_levels<DT>(T, *scale, bits, fsr, mode, flavor);
   const int nlev_m1 = (1 << (bits - 1)) - 1, sshift = bits - 1;
-  const bool codes4 = bits <= 4, want_sse = (sse != nullptr);
+  const bool codes4 = bits <= 4;
+  constexpr bool want_sse = SSE;
   const int64_t n_vec = n / EPV;
   Acc acc{0u, 0.0f};
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+#define QV(v, iv) quant_vec_t<DT, CODES, SSE>(v, T, nlev_m1, sshift, codes4, codes, iv, acc)
   if (!T.special) {
     // the absmax pass left the END of x in L2 last; walking backwards re-reads it from there
     const int64_t last = n_vec - 1;
@@ -348,14 +427,14 @@ __global__ void __launch_bounds__(256) quantize_kernel(const uint4* __restrict__
       if (reverse) { i0 = last - i0; i1 = last - i1; i2 = last - i2; i3 = last - i3; }
       const uint4 a = ldg_stream(x + i0), b = ldg_stream(x + i1);
       const uint4 c = ldg_stream(x + i2), d = ldg_stream(x + i3);
-      stg_stream(y + i0, quant_vec<DT>(a, T, nlev_m1, sshift, codes4, codes, i0, acc, want_sse));
-      stg_stream(y + i1, quant_vec<DT>(b, T, nlev_m1, sshift, codes4, codes, i1, acc, want_sse));
-      stg_stream(y + i2, quant_vec<DT>(c, T, nlev_m1, sshift, codes4, codes, i2, acc, want_sse));
-      stg_stream(y + i3, quant_vec<DT>(d, T, nlev_m1, sshift, codes4, codes, i3, acc, want_sse));
+      stg_stream(y + i0, QV(a, i0));
+      stg_stream(y + i1, QV(b, i1));
+      stg_stream(y + i2, QV(c, i2));
+      stg_stream(y + i3, QV(d, i3));
     }
     for (; i < n_vec; i += stride) {
       const int64_t i0 = reverse ? last - i : i;
-      stg_stream(y + i0, quant_vec<DT>(ldg_stream(x + i0), T, nlev_m1, sshift, codes4, codes, i0, acc, want_sse));
+      stg_stream(y + i0, QV(ldg_stream(x + i0), i0));
     }
     if (blockIdx.x == 0 && threadIdx.x < EPV / 2) {
       const int64_t ip = n_vec * (EPV / 2) + threadIdx.x;
@@ -365,6 +444,7 @@ __global__ void __launch_bounds__(256) quantize_kernel(const uint4* __restrict__
     const int64_t n_pair = (n + 1) / 2;
     for (; i < n_pair; i += stride) quant_pair<DT>(x, y, codes, i, n, T, bits, acc, false);
   }
+#undef QV
   flush_acc(acc, zero_count, sse, smf);
 }
 
@@ -394,7 +474,7 @@ __global__ void __launch_bounds__(256) quantize_scalar_kernel(const void* __rest
 constexpr int FUSED_THREADS = 512;
 constexpr int FUSED_R = 8;    // 16-byte vectors held per thread
 
-template <int DT>
+template <int DT, bool CODES, bool SSE>
 __global__ void __launch_bounds__(FUSED_THREADS) fused_kernel(const uint4* __restrict__ x,
                                                               uint4* __restrict__ y, uint8_t* codes,
                                                               unsigned int* zero_count, double* sse,
@@ -442,13 +522,14 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_kernel(const uint4* __res
   if (gtid == 0) *scale_out = s;
   build_levels<DT>(T, s, bits, fsr, mode, flavor);
   const int nlev_m1 = (1 << (bits - 1)) - 1, sshift = bits - 1;
-  const bool codes4 = bits <= 4, want_sse = (sse != nullptr);
+  const bool codes4 = bits <= 4;
+  constexpr bool want_sse = SSE;
   Acc acc{0u, 0.0f};
   if (!T.special) {
 #pragma unroll
     for (int r = 0; r < FUSED_R; ++r) {
       const int64_t i = gtid + r * total;
-      if (i < n_vec) stg_stream(y + i, quant_vec<DT>(v[r], T, nlev_m1, sshift, codes4, codes, i, acc, want_sse));
+      if (i < n_vec) stg_stream(y + i, quant_vec_t<DT, CODES, SSE>(v[r], T, nlev_m1, sshift, codes4, codes, i, acc));
     }
     if (blockIdx.x == 0 && threadIdx.x < EPV / 2) {
       const int64_t ip = n_vec * (EPV / 2) + threadIdx.x;
@@ -542,7 +623,10 @@ static DevInfo g_dev[64];
 
 template <int DT> static int fused_occupancy() {
   int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fused_kernel<DT>, FUSED_THREADS, 0);
+  int a = 0, b = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, fused_kernel<DT, false, false>, FUSED_THREADS, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fused_kernel<DT, true, true>, FUSED_THREADS, 0);
+  nb = a < b ? a : b;
   return nb;
 }
 
@@ -585,6 +669,13 @@ static int grid_for(int64_t work_items, int threads, int per_thread, int max_blo
   return (int)b;
 }
 
+// compile-time (CODES, SSE) variants selected from the optional pointers
+#define PO2_VARIANT(codes, sse, ...)                                                   \
+  if (codes) { if (sse) { constexpr bool CODES = true, SSE = true; __VA_ARGS__; }      \
+               else { constexpr bool CODES = true, SSE = false; __VA_ARGS__; } }       \
+  else { if (sse) { constexpr bool CODES = false, SSE = true; __VA_ARGS__; }           \
+         else { constexpr bool CODES = false, SSE = false; __VA_ARGS__; } }
+
 #define PO2_DISPATCH(dtype, ...)                                        \
   switch (dtype) {                                                      \
     case PO2_F32: { constexpr int DT = PO2_F32; __VA_ARGS__; } break;   \
@@ -611,8 +702,8 @@ static int launch_quantize(const void* x, void* y, void* codes, unsigned int* zc
   const bool codes_ok = !codes || aligned16(codes);
   if (aligned16(x) && aligned16(y) && codes_ok) {
     const int blocks = grid_for(n / epv + 1, 256, 4, I->sms * 8);
-    PO2_DISPATCH(dtype, quantize_kernel<DT><<<blocks, 256, 0, st>>>(
-        (const uint4*)x, (uint4*)y, (uint8_t*)codes, zc, sse, scale, n, bits, fsr, mode, flavor, reverse));
+    PO2_DISPATCH(dtype, PO2_VARIANT(codes, sse, quantize_kernel<DT, CODES, SSE><<<blocks, 256, 0, st>>>(
+        (const uint4*)x, (uint4*)y, (uint8_t*)codes, zc, sse, scale, n, bits, fsr, mode, flavor, reverse)));
   } else {
     const int blocks = grid_for((n + 1) / 2, 256, 4, I->sms * 8);
     PO2_DISPATCH(dtype, quantize_scalar_kernel<DT><<<blocks, 256, 0, st>>>(
@@ -667,6 +758,16 @@ int po2_quantize(const void* x, void* y, void* codes, unsigned int* zero_count, 
                          (cudaStream_t)stream);
 }
 
+// 1 if a tensor of n elements takes the single register-resident launch, 2 for the two passes
+int po2_quantize_fused_launches(int64_t n, int dtype) {
+  if (check_common(n, dtype)) return 0;
+  const DevInfo* I = dev_info();
+  if (!I) return 0;
+  const int64_t n_vec = n / (16 / elem_bytes(dtype));
+  const int64_t max_blocks = (int64_t)I->sms * I->fused_blocks_per_sm[dtype];
+  return (max_blocks > 0 && n_vec <= max_blocks * (int64_t)FUSED_THREADS * FUSED_R) ? 1 : 2;
+}
+
 int po2_quantize_fused(const void* x, void* y, void* codes, unsigned int* zero_count, double* sse,
                        float* scale_out, int64_t n, int dtype, int bits, int fsr, int mode,
                        int flavor, void* workspace, void* stream) {
@@ -693,12 +794,12 @@ int po2_quantize_fused(const void* x, void* y, void* codes, unsigned int* zero_c
     void* args[] = {&xv, &yv, &cp, &zero_count, &sse, &scale_out, &n, &bits, &fsr, &mode, &flavor, &ws};
     cudaError_t err;
     if (blocks == 1) {
-      PO2_DISPATCH(dtype, fused_kernel<DT><<<1, FUSED_THREADS, 0, st>>>(
-          xv, yv, cp, zero_count, sse, scale_out, n, bits, fsr, mode, flavor, ws));
+      PO2_DISPATCH(dtype, PO2_VARIANT(codes, sse, fused_kernel<DT, CODES, SSE><<<1, FUSED_THREADS, 0, st>>>(
+          xv, yv, cp, zero_count, sse, scale_out, n, bits, fsr, mode, flavor, ws)));
       err = cudaGetLastError();
     } else {
-      PO2_DISPATCH(dtype, err = cudaLaunchCooperativeKernel((const void*)fused_kernel<DT>, dim3((unsigned)blocks),
-                                                         dim3(FUSED_THREADS), args, 0, st));
+      PO2_DISPATCH(dtype, PO2_VARIANT(codes, sse, err = cudaLaunchCooperativeKernel(
+          (const void*)fused_kernel<DT, CODES, SSE>, dim3((unsigned)blocks), dim3(FUSED_THREADS), args, 0, st)));
     }
     return (int)err;
   }

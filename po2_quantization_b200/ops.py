@@ -41,6 +41,14 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
 
 _workspaces = {}
 
+# number of kernels of libpo2b200.so launched through this module (bench.py's `gpu_launches`)
+LAUNCHES = 0
+
+
+def conv_backend_name() -> str:
+    """Which kernel QuantizedConv2d's convolution runs on (reported by bench.py)."""
+    return "cudnn (torch F.conv2d on the po2-quantized weight)"
+
 
 def _workspace(device: torch.device) -> torch.Tensor:
     """Zero-initialised scratch, one per (device, stream); the kernels leave it zeroed."""
@@ -65,13 +73,17 @@ def _code_bytes(n: int, bits: int) -> int:
 # raw launchers (no autograd, no dispatcher) -- also what bench.py times
 # ------------------------------------------------------------------------------------------------
 def absmax_out(x: torch.Tensor, scale: torch.Tensor) -> None:
+    global LAUNCHES
     lib = _lib.load()
+    LAUNCHES += 1
     _lib.check(lib.po2_absmax(x.data_ptr(), x.numel(), _DT[x.dtype], scale.data_ptr(),
                               _workspace(x.device).data_ptr(), _stream_ptr(x.device)), "po2_absmax")
 
 
 def quantize_out(x, y, scale, bits, fsr, plus, codes=None, zero_count=None, sse=None, flavor=None):
+    global LAUNCHES
     lib = _lib.load()
+    LAUNCHES += 1
     _lib.check(lib.po2_quantize(
         x.data_ptr(), y.data_ptr(), codes.data_ptr() if codes is not None else None,
         zero_count.data_ptr() if zero_count is not None else None,
@@ -80,7 +92,10 @@ def quantize_out(x, y, scale, bits, fsr, plus, codes=None, zero_count=None, sse=
 
 
 def quantize_fused_out(x, y, scale, bits, fsr, plus, codes=None, zero_count=None, sse=None, flavor=None):
+    global LAUNCHES
     lib = _lib.load()
+    aligned = (x.data_ptr() | y.data_ptr()) % 16 == 0
+    LAUNCHES += lib.po2_quantize_fused_launches(x.numel(), _DT[x.dtype]) if aligned else 2
     _lib.check(lib.po2_quantize_fused(
         x.data_ptr(), y.data_ptr(), codes.data_ptr() if codes is not None else None,
         zero_count.data_ptr() if zero_count is not None else None,

@@ -65,3 +65,25 @@ def test_levels_are_powers_of_two():
         lv = np.unique(np.abs(y) / s)
         assert lv.size <= 2 ** (bits - 1)
         assert np.all(np.log2(lv) == np.rint(np.log2(lv)))
+
+
+TD = None
+
+
+@pytest.mark.parametrize("key", [c[0] for c in CASES])
+def test_torch_restatement_matches_reference_bits(key):
+    """oracle/po2_oracle_torch.py (the CPU-baseline arm) == unmodified reference, bit for bit."""
+    import torch
+    from oracle.po2_oracle_torch import quantize_ref
+    td = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}
+    _, name, dt, qn, bits, xb, yb = next(c for c in CASES if c[0] == key)
+    fsr = int(name[3:]) if name.startswith("fsr") else 1
+    if dt == "f32":
+        x = torch.from_numpy(xb.view(np.int32).copy()).view(torch.float32)
+    else:
+        x = torch.from_numpy(xb.view(np.int16).copy()).view(td[dt])
+    y = quantize_ref(x, bits, fsr, qn == "po2+")
+    got = y.view(torch.int32 if dt == "f32" else torch.int16).numpy().view(np.uint32 if dt == "f32" else np.uint16)
+    ref_nan = G.nan_mask(yb, dt)
+    assert np.array_equal(ref_nan, G.nan_mask(got, dt))
+    assert np.all((got.ravel() == np.asarray(yb).ravel()) | ref_nan.ravel()), key
