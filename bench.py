@@ -56,7 +56,7 @@ class ClockSampler:
                     self.rows.append(f)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.05)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -124,6 +124,19 @@ def run_ours(a):
         loss.backward()
         opt.step()
         loss_buf.copy_(loss.detach())
+
+    if a.profile_step:
+        # one eager step between cudaProfilerStart/Stop: `ncu --profile-from-start off` lists exactly
+        # the kernels of a step (profiles/ launch list)
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        step()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        print(json.dumps({"profile_step": True, "launches_of_libpo2b200": ops.LAUNCHES}))
+        return
 
     # ---- CUDA graph of the whole step (single GPU; DDP/SyncBN collectives stay eager at N>1)
     graph = None
@@ -360,6 +373,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep-log2", type=int, default=28)
+    ap.add_argument("--profile-step", action="store_true", help="run one eager step inside cudaProfilerStart/Stop and exit")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)
