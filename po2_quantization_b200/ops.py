@@ -45,9 +45,27 @@ _workspaces = {}
 LAUNCHES = 0
 
 
+# "tc": bf16 tcgen05 tensor cores where the shape allows (default); "fp32": CUDA-core fp32 FMA
+# everywhere (the fp32-accumulate parity mode); "cudnn": leave the convolution to F.conv2d.
+_conv_mode = os.environ.get("PO2_CONV", "tc")
+
+
+def set_conv_mode(mode: str) -> None:
+    global _conv_mode
+    if mode not in ("tc", "fp32", "cudnn"):
+        raise ValueError("conv mode must be 'tc', 'fp32' or 'cudnn'")
+    _conv_mode = mode
+
+
+def get_conv_mode() -> str:
+    return _conv_mode
+
+
 def conv_backend_name() -> str:
     """Which kernel QuantizedConv2d's convolution runs on (reported by bench.py)."""
-    return "cudnn (torch F.conv2d on the po2-quantized weight)"
+    return {"tc": "po2::conv_umma_kernel (tcgen05 bf16 implicit GEMM) / po2 depthwise+direct fp32 for the rest",
+            "fp32": "po2 CUDA-core fp32 kernels (depthwise / direct)",
+            "cudnn": "cudnn (torch F.conv2d on the po2-quantized weight)"}[_conv_mode]
 
 
 def _workspace(device: torch.device) -> torch.Tensor:
@@ -194,3 +212,98 @@ def ste_backward(grad_output: torch.Tensor, grad_input: torch.Tensor, accumulate
                                                 grad_output.numel(), _DT[grad_output.dtype],
                                                 int(accumulate), _stream_ptr(grad_output.device)),
                    "po2_ste_backward")
+
+
+# ------------------------------------------------------------------------------------------------
+# quantized-conv forward (models/quantized_conv.py:36,38)
+# ------------------------------------------------------------------------------------------------
+def conv2d_out(x, w, scale, out, stride, pad, groups, compute, w_format=_lib.W_F32_PO2, bits=4, fsr=1,
+               wshape=None):
+    """Raw launcher: out = conv2d(x, w).  w: fp32 (K, C/groups, R, S) on the grid +-scale*2^q, or the
+    packed codes of such a tensor (w_format=W_CODES, wshape=(K, C/groups, R, S))."""
+    global LAUNCHES
+    lib = _lib.load()
+    B, C, H, W_ = x.shape
+    K, _, R, S = w.shape if wshape is None else wshape
+    need = lib.po2_conv2d_workspace(B, C, H, W_, K, R, S, stride, pad, groups, compute)
+    ws = torch.empty(max(int(need), 16), dtype=torch.uint8, device=x.device)
+    fp32_w_bytes = (K * (C // groups) * R * S * 4 + 255) // 256 * 256
+    LAUNCHES += (2 if need > fp32_w_bytes else 1) + (1 if w_format == _lib.W_CODES and need <= fp32_w_bytes else 0)
+    _lib.check(lib.po2_conv2d_fwd(x.data_ptr(), w.data_ptr(), scale.data_ptr() if scale is not None else None,
+                                  out.data_ptr(), B, C, H, W_, K, R, S, stride, pad, groups, w_format,
+                                  bits, fsr, compute, ws.data_ptr(), ws.numel(), _stream_ptr(x.device)),
+               "po2_conv2d_fwd")
+
+
+def _conv_out_shape(x, w, stride, pad):
+    B, _, H, W_ = x.shape
+    K, _, R, S = w.shape
+    return (B, K, (H + 2 * pad - R) // stride + 1, (W_ + 2 * pad - S) // stride + 1)
+
+
+@torch.library.custom_op("po2::conv2d", mutates_args=(), device_types="cuda")
+def conv2d(x: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor], stride: int, pad: int,
+           groups: int, compute: int) -> torch.Tensor:
+    """conv2d(x, w) with w on the PO2 grid +-scale*2^q (scale=None: plain fp32 weights).
+    compute 0: tcgen05 bf16 tensor cores (weights exact, activations rounded to bf16, fp32 accumulate)
+    where the shape allows; 1: fp32 FMA everywhere."""
+    _require_cuda(x, "po2::conv2d")
+    if x.dtype != torch.float32 or w.dtype != torch.float32:
+        raise TypeError("po2::conv2d: fp32 NCHW activations and fp32 weights only")
+    x = x.contiguous()
+    w = w.contiguous()
+    out = torch.empty(_conv_out_shape(x, w, stride, pad), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        conv2d_out(x, w, scale, out, stride, pad, groups, compute)
+    return out
+
+
+@conv2d.register_fake
+def _(x, w, scale, stride, pad, groups, compute):
+    return x.new_empty(_conv_out_shape(x, w, stride, pad))
+
+
+def _conv2d_setup(ctx, inputs, output):
+    x, w, scale, stride, pad, groups, compute = inputs
+    ctx.save_for_backward(x, w)
+    ctx.cfg = (stride, pad, groups)
+
+
+def _conv2d_bwd(ctx, g):
+    # backward stays on ATen/cuDNN (SURVEY.md section 8f "next" #2): dgrad/wgrad against the dequantized weight
+    x, w = ctx.saved_tensors
+    stride, pad, groups = ctx.cfg
+    gx, gw, _ = torch.ops.aten.convolution_backward(
+        g.contiguous(), x, w, None, [stride, stride], [pad, pad], [1, 1], False, [0, 0], groups,
+        [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
+    return gx, gw, None, None, None, None, None
+
+
+conv2d.register_autograd(_conv2d_bwd, setup_context=_conv2d_setup)
+
+
+@torch.library.custom_op("po2::quantize_scaled", mutates_args=(), device_types="cuda")
+def quantize_scaled(x: torch.Tensor, bits: int, fsr: int, plus: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(y, scale): the quantized tensor and its per-tensor max-abs scale (what the conv needs to
+    rebuild the exact +-2^q operand)."""
+    _require_cuda(x, "po2::quantize_scaled")
+    x = x.contiguous()
+    if x.numel() == 0:
+        raise RuntimeError("max(): Expected reduction dim to be specified for input.numel() == 0")
+    with torch.cuda.device(x.device):
+        y = torch.empty_like(x)
+        scale = torch.empty((), dtype=torch.float32, device=x.device)
+        quantize_fused_out(x, y, scale, bits, fsr, plus)
+    return y, scale
+
+
+@quantize_scaled.register_fake
+def _(x, bits, fsr, plus):
+    return torch.empty_like(x, memory_format=torch.contiguous_format), x.new_empty((), dtype=torch.float32)
+
+
+def _quantize_scaled_bwd(ctx, gy, gscale):
+    return gy, None, None, None          # straight-through (utils/quantizers.py:34-36)
+
+
+quantize_scaled.register_autograd(_quantize_scaled_bwd)

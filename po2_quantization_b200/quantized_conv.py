@@ -7,6 +7,8 @@ reference's model files build on it unchanged.
 import torch
 import torch.nn as nn
 
+from . import ops
+
 
 class QuantizedConv2d(nn.Conv2d):
     """reference models/quantized_conv.py:5-45"""
@@ -17,11 +19,32 @@ class QuantizedConv2d(nn.Conv2d):
         self.quantize_fn = quantize_fn
         self.bits = bits
 
+    # ---- which inputs the sm_100a conv kernels take (anything else goes to nn.Conv2d's own path)
+    def _po2_conv_ok(self, input) -> bool:
+        return (ops.get_conv_mode() != "cudnn" and input.is_cuda and input.dtype == torch.float32
+                and input.dim() == 4 and self.bias is None and self.dilation == (1, 1)
+                and self.padding_mode == "zeros" and isinstance(self.padding, tuple)
+                and self.stride[0] == self.stride[1] and self.padding[0] == self.padding[1]
+                and self.weight.dtype == torch.float32)
+
+    def _po2_conv(self, input, weight, scale):
+        return ops.conv2d(input, weight, scale, self.stride[0], self.padding[0], self.groups,
+                          0 if ops.get_conv_mode() == "tc" else 1)
+
     def forward(self, input):
         # models/quantized_conv.py:32-38: quantize the weight on every forward (QAT), then conv
         if self.quantize_fn is not None:
+            plus = getattr(self.quantize_fn, "_PLUS", None)
+            if plus is not None and self._po2_conv_ok(input):
+                # PO2 / PO2+: quantizer kernel (y, scale) -> tensor-core conv on the exact +-2^q operand
+                qw, scale = ops.quantize_scaled(self.weight, int(self.bits), 1, bool(plus))
+                return self._po2_conv(input, qw, scale)
             quantized_weight = self.quantize_fn.apply(self.weight, self.bits)
             return self._conv_forward(input, quantized_weight, self.bias)
+        tag = getattr(self, "_po2_ptq", None)
+        if tag is not None and tag[0] == self.weight._version and self._po2_conv_ok(input):
+            # post-training-quantized weights (quantize_model): already on the grid +-scale*2^q
+            return self._po2_conv(input, self.weight, tag[1])
         return self._conv_forward(input, self.weight, self.bias)
 
     def get_quantization_error(self):

@@ -112,8 +112,9 @@ def quantize_model(model: torch.nn.Module, quantizer: Optional[Callable[..., Non
             if not isinstance(module, QuantizedConv2d):
                 continue
             for _, param in module.named_parameters():
+                scale = None
                 if isinstance(quantizer, type) and issubclass(quantizer, _Po2Base) and param.is_cuda:
-                    qp, _codes, _scale, _zc, sse = ops.quantize_full(param, int(bits), 1, quantizer._PLUS)
+                    qp, _codes, scale, _zc, sse = ops.quantize_full(param, int(bits), 1, quantizer._PLUS)
                     err = sse
                 else:
                     qp = quantizer.forward(None, param, bits=bits)
@@ -121,6 +122,10 @@ def quantize_model(model: torch.nn.Module, quantizer: Optional[Callable[..., Non
                 total = err if total is None else total + err
                 numel += param.numel()
                 param.copy_(qp)
+                if scale is not None and param is module.weight:
+                    # non-persistent tag (state_dict stays {weight}): the weight is now on the grid
+                    # +-scale*2^q, which lets forward() feed the tensor-core conv an exact operand
+                    module._po2_ptq = (param._version, scale)
     if total is None:
         raise ZeroDivisionError("quantize_model: the model has no QuantizedConv2d parameters")
     return float((total / numel).item())

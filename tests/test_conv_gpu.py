@@ -1,0 +1,200 @@
+"""Quantized-conv forward parity (models/quantized_conv.py:32-38): the sm_100a kernels against the
+oracle conv (F.conv2d on the dequantized fp32 weight, evaluated in fp64).
+Tolerances (BASELINE.json north_star (b)): rel 1e-2 for the bf16 tensor-core path, 1e-5 for the
+fp32-accumulate path; rel = max|out - ref| / max|ref|."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+import po2_quantization_b200  # noqa: E402,F401  (registers torch.ops.po2.*)
+
+TOL_TC = 1e-2
+TOL_FP32 = 1e-5
+
+# (name, B, C, H, W, K, k, stride, pad, groups) -- SURVEY.md section 8a layer tables
+RESNET = [
+    ("r_16_16_3s1", 128, 16, 32, 32, 16, 3, 1, 1, 1),
+    ("r_16_32_3s2", 128, 16, 32, 32, 32, 3, 2, 1, 1),
+    ("r_16_32_1s2", 128, 16, 32, 32, 32, 1, 2, 0, 1),
+    ("r_32_32_3s1", 128, 32, 16, 16, 32, 3, 1, 1, 1),
+    ("r_32_64_3s2", 128, 32, 16, 16, 64, 3, 2, 1, 1),
+    ("r_32_64_1s2", 128, 32, 16, 16, 64, 1, 2, 0, 1),
+    ("r_64_64_3s1", 128, 64, 8, 8, 64, 3, 1, 1, 1),
+]
+MOBILENET = [
+    ("m_pw_32_16", 128, 32, 16, 16, 16, 1, 1, 0, 1),
+    ("m_pw_16_96", 128, 16, 16, 16, 96, 1, 1, 0, 1),
+    ("m_pw_96_24", 128, 96, 8, 8, 24, 1, 1, 0, 1),
+    ("m_pw_24_144", 128, 24, 8, 8, 144, 1, 1, 0, 1),
+    ("m_pw_144_32", 128, 144, 4, 4, 32, 1, 1, 0, 1),
+    ("m_pw_64_384", 128, 64, 2, 2, 384, 1, 1, 0, 1),
+    ("m_pw_576_160", 128, 576, 1, 1, 160, 1, 1, 0, 1),
+    ("m_pw_160_960", 128, 160, 1, 1, 960, 1, 1, 0, 1),
+    ("m_pw_960_320", 128, 960, 1, 1, 320, 1, 1, 0, 1),
+    ("m_dw_32_s1", 128, 32, 16, 16, 32, 3, 1, 1, 32),
+    ("m_dw_96_s2", 128, 96, 16, 16, 96, 3, 2, 1, 96),
+    ("m_dw_576_s2", 128, 576, 2, 2, 576, 3, 2, 1, 576),
+    ("m_dw_960_s1", 128, 960, 1, 1, 960, 3, 1, 1, 960),
+]
+ODD = [
+    ("odd_small_batch", 3, 16, 32, 32, 16, 3, 1, 1, 1),
+    ("odd_rect", 5, 48, 14, 9, 40, 3, 1, 1, 1),
+    ("odd_1x1_big", 2, 128, 56, 56, 64, 1, 1, 0, 1),
+    ("odd_grouped", 4, 32, 8, 8, 64, 3, 1, 1, 4),
+    ("odd_5x5", 2, 8, 12, 12, 8, 5, 1, 2, 1),
+    ("odd_mvit_128_64", 4, 128, 28, 28, 64, 3, 1, 1, 1),
+]
+ALL = RESNET + MOBILENET + ODD
+
+
+def _make(case, bits=4, plus=True, seed=0):
+    name, B, C, H, W, K, k, stride, pad, groups = case
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(B, C, H, W, device="cuda", generator=g)
+    w = torch.randn(K, C // groups, k, k, device="cuda", generator=g) * 0.1
+    y, codes, scale, zc, sse = torch.ops.po2.quantize_full(w, bits, 1, plus)
+    return x, y, codes, scale
+
+
+def _ref(x, y, stride, pad, groups):
+    return F.conv2d(x.double(), y.double(), None, stride, pad, 1, groups)
+
+
+def _rel(out, ref):
+    return ((out.double() - ref).abs().max() / ref.abs().max()).item()
+
+
+@pytest.mark.parametrize("case", ALL, ids=[c[0] for c in ALL])
+def test_conv_tensor_core_path(case):
+    name, B, C, H, W, K, k, stride, pad, groups = case
+    x, y, codes, scale = _make(case)
+    out = torch.ops.po2.conv2d(x, y, scale, stride, pad, groups, 0)
+    ref = _ref(x, y, stride, pad, groups)
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    assert _rel(out, ref) < TOL_TC, (name, _rel(out, ref))
+    # relative RMS error is the tighter statement: bf16 activations, exact weights, fp32 accumulate
+    rms = ((out.double() - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+    assert rms < 4e-3, (name, rms)
+
+
+@pytest.mark.parametrize("case", ALL, ids=[c[0] for c in ALL])
+def test_conv_fp32_accumulate_path(case):
+    name, B, C, H, W, K, k, stride, pad, groups = case
+    x, y, codes, scale = _make(case)
+    out = torch.ops.po2.conv2d(x, y, scale, stride, pad, groups, 1)
+    assert _rel(out, _ref(x, y, stride, pad, groups)) < TOL_FP32, name
+
+
+@pytest.mark.parametrize("case", [RESNET[0], RESNET[6], MOBILENET[4], MOBILENET[9]], ids=lambda c: c[0])
+@pytest.mark.parametrize("bits", [4, 8])
+def test_conv_from_packed_codes_equals_fp32_weights(case, bits):
+    """The packed sign+exponent codes carry exactly the information the conv needs."""
+    from po2_quantization_b200 import _lib, ops
+    name, B, C, H, W, K, k, stride, pad, groups = case
+    x, y, codes, scale = _make(case, bits=bits)
+    a = torch.ops.po2.conv2d(x, y, scale, stride, pad, groups, 0)
+    b = torch.empty_like(a)
+    ops.conv2d_out(x, codes, scale, b, stride, pad, groups, 0, w_format=_lib.W_CODES, bits=bits, fsr=1,
+                   wshape=tuple(y.shape))
+    if groups == 1:
+        assert torch.equal(a, b), name          # same exact bf16 operand either way
+    else:
+        assert _rel(b, _ref(x, y, stride, pad, groups)) < TOL_FP32
+
+
+def test_conv_autograd_matches_aten():
+    torch.backends.cudnn.allow_tf32 = False       # both backward passes in true fp32
+    x, y, codes, scale = _make(RESNET[3])
+    x1 = x.clone().requires_grad_(True)
+    w1 = y.clone().requires_grad_(True)
+    out = torch.ops.po2.conv2d(x1, w1, scale, 1, 1, 1, 0)
+    g = torch.randn_like(out)
+    out.backward(g)
+    x2 = x.clone().requires_grad_(True)
+    w2 = y.clone().requires_grad_(True)
+    F.conv2d(x2, w2, None, 1, 1).backward(g)
+    assert torch.allclose(x1.grad, x2.grad, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(w1.grad, w2.grad, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("plus", [False, True])
+def test_module_qat_forward_backward_vs_oracle(plus):
+    """QuantizedConv2d (QAT mode) against the oracle module on CPU: forward within the bf16
+    tolerance, weight gradient straight-through."""
+    import po2_quantization_b200 as P
+    from oracle.po2_oracle_torch import PO2, PO2_PLUS, QuantizedConv2dOracle
+    torch.manual_seed(3)
+    Q = P.PowerOfTwoPlusQuantizer if plus else P.PowerOfTwoQuantizer
+    m = P.QuantizedConv2d(32, 32, 3, stride=1, padding=1, quantize_fn=Q, bits=4).cuda()
+    o = QuantizedConv2dOracle(32, 32, 3, stride=1, padding=1, quantize_fn=PO2_PLUS if plus else PO2, bits=4)
+    o.load_state_dict({k: v.cpu() for k, v in m.state_dict().items()})
+    assert list(m.state_dict().keys()) == ["weight"]
+    x = torch.randn(16, 32, 16, 16)
+    xg = x.cuda().requires_grad_(True)
+    xc = x.clone().requires_grad_(True)
+    out = m(xg)
+    ref = o(xc)
+    assert _rel(out.cpu(), ref.double()) < TOL_TC
+    g = torch.randn_like(ref)
+    out.backward(g.cuda())
+    ref.backward(g)
+    assert torch.allclose(m.weight.grad.cpu(), o.weight.grad, rtol=2e-3, atol=2e-3)
+    assert torch.allclose(xg.grad.cpu(), xc.grad, rtol=2e-3, atol=2e-3)
+    e1, n1 = m.get_quantization_error()
+    ref_e = torch.sum((PO2_PLUS if plus else PO2).forward(None, o.weight.detach()) - o.weight.detach()).item()
+    assert n1 == o.weight.numel() and np.isfinite(e1.item()) and np.isfinite(ref_e)
+
+
+def test_ptq_quantize_model_and_forward_resnet20_top1():
+    """BASELINE.json configs[0]: ResNet-20 PO2+ 4-bit PTQ forward, batch 128.  Known-answer MSE from
+    the unmodified reference; logits and top-1 against the oracle model on CPU."""
+    import po2_quantization_b200 as P
+    from oracle.po2_oracle_torch import PO2_PLUS, QuantizedConv2dOracle, quantize_model_ref
+    from tests import golden_util as G
+    from workloads import resnet_cifar
+    ka = G.load("known_answers.npz")
+    torch.manual_seed(8)
+    ref_model = resnet_cifar(20, 10, None, 4, conv_cls=QuantizedConv2dOracle)
+    torch.manual_seed(8)
+    model = resnet_cifar(20, 10, None, 4)
+    model.load_state_dict(ref_model.state_dict(), strict=True)
+    model = model.cuda()
+    mcopy = copy.deepcopy(model)                               # test.py:120 deep-copies before PTQ
+    mse = P.quantize_model(mcopy, P.PowerOfTwoPlusQuantizer, 4)
+    assert abs(mse - float(ka["resnet20_ptq_mse|po2+|4"])) <= 1e-5 * mse
+    mse_ref = quantize_model_ref(ref_model, PO2_PLUS, 4)
+    assert abs(mse - mse_ref) <= 1e-5 * mse
+    for a, b in zip(mcopy.parameters(), ref_model.parameters()):
+        assert torch.equal(a.detach().cpu(), b.detach()), "PTQ weights differ from the oracle's"
+    mcopy.eval()
+    ref_model.eval()
+    x = torch.randn(128, 3, 32, 32, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        from po2_quantization_b200 import ops
+        ops.LAUNCHES = 0
+        logits = mcopy(x.cuda()).cpu()
+        assert ops.LAUNCHES >= 20, "the PTQ forward did not go through the po2 conv kernels"
+        ref = ref_model(x)
+        assert _rel(logits, ref.double()) < TOL_TC
+        margin = ref.topk(2, dim=1).values
+        decisive = (margin[:, 0] - margin[:, 1]) > 2e-2 * ref.abs().max()
+        assert torch.equal(logits.argmax(1)[decisive], ref.argmax(1)[decisive])
+        ops.set_conv_mode("fp32")
+        try:
+            logits32 = mcopy(x.cuda()).cpu()
+        finally:
+            ops.set_conv_mode("tc")
+        assert _rel(logits32, ref.double()) < 1e-4
+        assert torch.equal(logits32.argmax(1), ref.argmax(1)), "top-1 differs in fp32-accumulate mode"
+    # a second deepcopy keeps the tag; an in-place weight update invalidates it
+    m2 = copy.deepcopy(mcopy)
+    conv = next(m for m in m2.modules() if isinstance(m, P.QuantizedConv2d))
+    assert conv._po2_ptq[0] == conv.weight._version
+    with torch.no_grad():
+        conv.weight.mul_(1.0)
+    assert conv._po2_ptq[0] != conv.weight._version
