@@ -4,6 +4,8 @@
 attributes (``quantize_fn``, ``bits``), ``state_dict`` (``{weight}``) and methods, so the
 reference's model files build on it unchanged.
 """
+import copy
+
 import torch
 import torch.nn as nn
 
@@ -18,6 +20,17 @@ class QuantizedConv2d(nn.Conv2d):
         super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias)
         self.quantize_fn = quantize_fn
         self.bits = bits
+
+    def __deepcopy__(self, memo):
+        # test.py:120 deep-copies models; a copied Parameter restarts its version counter, so the
+        # (non-persistent) PTQ tag is re-keyed to the copy instead of silently going stale
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        new.__dict__ = {k: copy.deepcopy(v, memo) for k, v in self.__dict__.items()}
+        tag = self.__dict__.get("_po2_ptq")
+        if tag is not None and tag[0] == self.weight._version:
+            new.__dict__["_po2_ptq"] = (new.weight._version, new.__dict__["_po2_ptq"][1])
+        return new
 
     # ---- which inputs the sm_100a conv kernels take (anything else goes to nn.Conv2d's own path)
     def _po2_conv_ok(self, input) -> bool:

@@ -1,0 +1,91 @@
+"""Per-layer quantized-conv forward timings: po2 tensor-core path vs po2 fp32 path vs cuDNN (TF32, the
+reference's default on a GPU) for the layer shapes of SURVEY.md section 8a.
+
+    python tools/bench_conv.py [--batch 128] [--out gpurun_out/conv_layers.json]
+
+CUDA events, median of --iters after warm-up; the 320 MB flush buffer is rewritten between
+iterations so every layer starts with a cold L2.
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import po2_quantization_b200  # noqa: E402,F401
+from po2_quantization_b200 import ops  # noqa: E402
+
+SHAPES = [  # name, C, H, W, K, k, stride, pad, groups, count in ResNet-56 (0 = other model)
+    ("r56 16->16 3x3 s1 @32", 16, 32, 32, 16, 3, 1, 1, 1, 18),
+    ("r56 16->32 3x3 s2 @32", 16, 32, 32, 32, 3, 2, 1, 1, 1),
+    ("r56 16->32 1x1 s2 @32", 16, 32, 32, 32, 1, 2, 0, 1, 1),
+    ("r56 32->32 3x3 s1 @16", 32, 16, 16, 32, 3, 1, 1, 1, 17),
+    ("r56 32->64 3x3 s2 @16", 32, 16, 16, 64, 3, 2, 1, 1, 1),
+    ("r56 32->64 1x1 s2 @16", 32, 16, 16, 64, 1, 2, 0, 1, 1),
+    ("r56 64->64 3x3 s1 @8", 64, 8, 8, 64, 3, 1, 1, 1, 17),
+    ("mbv2 pw 16->96 @16", 16, 16, 16, 96, 1, 1, 0, 1, 0),
+    ("mbv2 pw 144->32 @4", 144, 4, 4, 32, 1, 1, 0, 1, 0),
+    ("mbv2 pw 960->320 @1", 960, 1, 1, 320, 1, 1, 0, 1, 0),
+    ("mbv2 dw 96 s2 @16", 96, 16, 16, 96, 3, 2, 1, 96, 0),
+    ("mbv2 dw 384 s1 @2", 384, 2, 2, 384, 3, 1, 1, 384, 0),
+    ("mvit 128->64 3x3 @28", 128, 28, 28, 64, 3, 1, 1, 1, 0),
+    ("mvit 32->128 1x1 @112", 32, 112, 112, 128, 1, 1, 0, 1, 0),
+]
+
+
+def timeit(fn, iters, flush):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.add_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--iters", type=int, default=15)
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+    flush = torch.zeros(320 * 1024 * 1024 // 4, dtype=torch.int32, device="cuda")
+    rows = []
+    for name, C, H, W, K, k, stride, pad, groups, cnt in SHAPES:
+        B = a.batch if H * W * C * a.batch * 4 < (2 << 30) else 32
+        x = torch.randn(B, C, H, W, device="cuda")
+        w = torch.randn(K, C // groups, k, k, device="cuda") * 0.1
+        y, codes, scale, _, _ = torch.ops.po2.quantize_full(w, 4, 1, True)
+        P, Q = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        out = torch.empty(B, K, P, Q, device="cuda")
+        flops = 2.0 * B * K * P * Q * (C // groups) * k * k
+        bytes_io = 4.0 * (x.numel() + out.numel())
+        r = {"layer": name, "batch": B, "gflop": flops / 1e9, "io_mb": bytes_io / 1e6, "count_r56": cnt}
+        r["us_po2_tc"] = timeit(lambda: ops.conv2d_out(x, y, scale, out, stride, pad, groups, 0), a.iters, flush)
+        r["us_po2_fp32"] = timeit(lambda: ops.conv2d_out(x, y, scale, out, stride, pad, groups, 1), a.iters, flush)
+        torch.backends.cudnn.allow_tf32 = True
+        r["us_cudnn_tf32"] = timeit(lambda: F.conv2d(x, y, None, stride, pad, 1, groups), a.iters, flush)
+        torch.backends.cudnn.allow_tf32 = False
+        r["us_cudnn_fp32"] = timeit(lambda: F.conv2d(x, y, None, stride, pad, 1, groups), a.iters, flush)
+        r["tflops_po2_tc"] = flops / r["us_po2_tc"] / 1e6
+        r["io_GBs_po2_tc"] = bytes_io / r["us_po2_tc"] / 1e3
+        rows.append(r)
+        print(json.dumps(r), flush=True)
+    tot = lambda key: sum(r[key] * r["count_r56"] for r in rows)
+    print(json.dumps({"resnet56_forward_qconv_us": {k: tot(k) for k in ("us_po2_tc", "us_po2_fp32", "us_cudnn_tf32", "us_cudnn_fp32")}}))
+    if a.out:
+        json.dump(rows, open(a.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
