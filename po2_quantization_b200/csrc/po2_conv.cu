@@ -90,39 +90,57 @@ __device__ __forceinline__ uint32_t make_idesc(uint32_t n) {
 // ------------------------------------------------------------------------------------------------
 // geometry shared by host and device
 // ------------------------------------------------------------------------------------------------
+struct FastDiv {            // n / d for 0 <= n < 2^31 via one mul-hi (d >= 1)
+  uint32_t mul, shr, d;
+};
+__host__ __device__ __forceinline__ int fdiv(int n, const FastDiv& f) {
+  if (f.d <= 1) return n;
+#ifdef __CUDA_ARCH__
+  return (int)(__umulhi((uint32_t)n, f.mul) >> f.shr);
+#else
+  return (int)(((uint64_t)(uint32_t)n * f.mul) >> 32 >> f.shr);
+#endif
+}
+
 struct ConvGeom {
   int B, C, H, W, K, R, S, stride, pad, groups;
-  int P, Q;            // output height / width
-  // K3 flat layout (stride 1): one zero column per row and one zero row per image are shared pads
-  int pitch;           // W + (S == 3)
-  int rows_img;        // H + (R == 3)
-  int halo;            // (R==3)*pitch + (S==3)   flat positions of context before / after a tile
-  int Ltot;            // flat positions that can hold an output
-  int Cpad, CC, nchunk;  // channels padded to 16, channels per K chunk, chunks
-  int NT, ntiles_n;    // padded out-channel tile (mult of 16, <= 256), number of N tiles
-  int MT;              // 128-row M tiles per CTA
-  int strip;           // smem positions per CTA = MT*128 + 2*halo
+  int P, Q;              // output height / width
+  // ---- K3 "flat padded" output-position space: position L = row * pitch + col, rows of all images
+  // stacked; one zero column per row / one zero row per image are shared by neighbouring windows
+  int pitch, rows_img, top;   // Q + (S==3), P + (R==3), number of pad rows before image 0
+  int Ltot;              // number of flat positions
+  int halo_before;       // flat positions of context in front of a 128-position tile
+  int strip;             // positions per A stage = 128 + halo_before + halo_after
+  int nphase;            // 1, or 4 input parity phases for 3x3 stride 2
+  int ntaps;
+  int tap_phase[9];      // which phase plane set a tap reads
+  int tap_off[9];        // strip index of the tap's row for tile row 0 (>= 0)
+  int Cpad, CC, nchunk;  // channels padded to 16; channels per pipeline stage; stages per item
+  int NT, ntiles_n;      // out-channel tile (multiple of 16, <= 256) and their count
+  int nitems_m, m_step;  // 128-position items; items advance by m_step per CTA iteration
+  int nst;               // A pipeline stages
+  uint32_t a_stage_bytes, b_slab_bytes;
+  FastDiv div_pitch, div_rows, div_strip;
 };
 
 // ------------------------------------------------------------------------------------------------
 // weight pack: fp32 PO2-grid weights (or codes) -> exact bf16 +-2^q in the B-operand layout
-//   Bp[nt][chunk][tap][cg][n][8]   (cg: group of 8 channels inside the chunk, n: channel in N tile)
+//   Bp[nt][tap][cg][n][8]   (cg: group of 8 input channels, n: out channel inside the N tile)
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_weights_kernel(const float* __restrict__ w, const uint8_t* __restrict__ codes,
                                     const float* __restrict__ scale, __nv_bfloat16* __restrict__ Bp,
                                     ConvGeom g, int bits, int fsr) {
-  const int taps = g.R * g.S;
-  const int64_t total = (int64_t)g.ntiles_n * g.nchunk * taps * (g.CC / 8) * g.NT * 8;
+  const int taps = g.ntaps, ncg = g.Cpad / 8;
+  const int64_t total = (int64_t)g.ntiles_n * taps * ncg * g.NT * 8;
   const float s = scale ? *scale : 1.0f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t t = i;
     const int j = (int)(t % 8); t /= 8;
     const int n = (int)(t % g.NT); t /= g.NT;
-    const int cg = (int)(t % (g.CC / 8)); t /= (g.CC / 8);
+    const int cg = (int)(t % ncg); t /= ncg;
     const int tap = (int)(t % taps); t /= taps;
-    const int chunk = (int)(t % g.nchunk); t /= g.nchunk;
     const int nt = (int)t;
-    const int c = chunk * g.CC + cg * 8 + j;
+    const int c = cg * 8 + j;
     const int k = nt * g.NT + n;
     float v = 0.0f;
     if (c < g.C && k < g.K) {
@@ -143,130 +161,243 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const uint8_t* 
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3: tcgen05 implicit-GEMM conv (stride 1; 3x3 pad 1 or 1x1 pad 0; groups == 1)
+// K3: persistent, warp-specialised tcgen05 implicit-GEMM conv (groups == 1; 3x3 pad 1 or 1x1 pad 0;
+// stride 1 or 2).  Per CTA: warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 = TMEM
+// allocator + weight-slab bulk copy + the single MMA-issuing thread, warps 5-12 activation producers.
+//   producers --full[s]--> MMA --tcgen05.commit: empty[s]--> producers      (A stages, ring of nst)
+//   MMA --tcgen05.commit: tmem_full[a]--> epilogue --tmem_empty[a]--> MMA   (2 accumulator stages)
 // ------------------------------------------------------------------------------------------------
-constexpr int K3_THREADS = 256;
+constexpr int K3_EPI_WARPS = 4;
+constexpr int K3_PROD_WARPS = 8;
+constexpr int K3_PROD_GROUPS = 4;
+constexpr int K3_THREADS = 32 * (K3_EPI_WARPS + 1 + K3_PROD_WARPS);
+constexpr int K3_MAX_STAGES = 6;
+constexpr uint32_t K3_SMEM_BUDGET = 220 * 1024;
+constexpr uint32_t K3_B_BUDGET = 112 * 1024;
 
-__device__ __forceinline__ bool decode_pos(const ConvGeom& g, int L, int& img, int& h, int& w) {
-  // flat position -> (image, row, col); false for the shared zero pads and out-of-range positions
-  if (L < 0 || L >= g.Ltot) return false;
-  const int row = L / g.pitch;
-  w = L - row * g.pitch;
-  const int r0 = row - (g.R == 3 ? 1 : 0);        // first flat row is the top pad of image 0
-  if (r0 < 0) return false;
-  img = r0 / g.rows_img;
-  h = r0 - img * g.rows_img;
-  return (w < g.W) && (h < g.H) && (img < g.B);
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(K3_THREADS) conv_umma_kernel(const float* __restrict__ x,
-                                                               const __nv_bfloat16* __restrict__ Bp,
-                                                               const float* __restrict__ scale,
-                                                               float* __restrict__ out, ConvGeom g) {
+// flat position -> (image, out row, out col); false for the shared zero pads / out of range
+__device__ __forceinline__ bool decode_pos(const ConvGeom& g, int L, int& img, int& a, int& b) {
+  if (L < 0 || L >= g.Ltot) return false;
+  const int row = fdiv(L, g.div_pitch);
+  b = L - row * g.pitch;
+  const int r0 = row - g.top;
+  if (r0 < 0) return false;
+  img = fdiv(r0, g.div_rows);
+  a = r0 - img * g.rows_img;
+  return (b < g.Q) && (a < g.P) && (img < g.B);
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+template <int NTAPS>
+__global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* __restrict__ x,
+                                                                  const __nv_bfloat16* __restrict__ Bp,
+                                                                  const float* __restrict__ scale,
+                                                                  float* __restrict__ out, ConvGeom g) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int taps = g.R * g.S;
-  const uint32_t a_bytes = (uint32_t)(g.CC / 8) * g.strip * 16;
-  const uint32_t b_bytes = (uint32_t)taps * (g.CC / 8) * g.NT * 16;
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + a_bytes;
-  uint64_t* bar_b = reinterpret_cast<uint64_t*>(smem + a_bytes + b_bytes);
-  uint64_t* bar_mma = bar_b + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_b + 2);
+  uint8_t* sB = smem;
+  uint8_t* sA = smem + g.b_slab_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)g.nst * g.a_stage_bytes);
+  uint64_t* full = bars;                        // [nst]   producers -> MMA
+  uint64_t* empty = bars + K3_MAX_STAGES;       // [nst]   MMA (commit) -> producers
+  uint64_t* tfull = bars + 2 * K3_MAX_STAGES;   // [2]     MMA (commit) -> epilogue
+  uint64_t* tempty = tfull + 2;                 // [2]     epilogue -> MMA
+  uint64_t* bfull = tempty + 2;                 // weight slab landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nt = blockIdx.y;
-  const int L0 = blockIdx.x * g.MT * 128;                 // first output position of this CTA
+  const int nt = blockIdx.x % g.ntiles_n;
+  const int m_first = blockIdx.x / g.ntiles_n;
   uint32_t ncols = 32;
-  while ((int)ncols < g.MT * g.NT) ncols <<= 1;
+  while ((int)ncols < 2 * g.NT) ncols <<= 1;
 
-  if (warp == 0) tmem_alloc(tmem_slot, ncols);
-  if (tid == 32) {
-    mbar_init(bar_b, 1);
-    mbar_init(bar_mma, 1);
-    fence_mbar_init();
+  if (warp == K3_EPI_WARPS) {
+    tmem_alloc(tmem_slot, ncols);
+    if (lane == 0) {
+      for (int i = 0; i < g.nst; ++i) { mbar_init(full + i, K3_PROD_WARPS / K3_PROD_GROUPS); mbar_init(empty + i, 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, K3_EPI_WARPS); }
+      mbar_init(bfull, 1);
+      fence_mbar_init();
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t idesc = make_idesc((uint32_t)g.NT);
-  const int HW = g.H * g.W;
+  const int HW = g.H * g.W, PQ = g.P * g.Q;
+  const int ngrpCC = g.CC / 8;
 
-  for (int chunk = 0; chunk < g.nchunk; ++chunk) {
-    if (chunk > 0) mbar_wait(bar_mma, (chunk - 1) & 1);   // previous chunk's MMAs have consumed smem
-    if (tid == 0) {
-      mbar_expect_tx(bar_b, b_bytes);
-      bulk_g2s(sB, Bp + ((int64_t)(nt * g.nchunk + chunk) * b_bytes) / 2, b_bytes, bar_b);
+  if (warp == K3_EPI_WARPS) {
+    // =========================== MMA issuer ===========================
+    // The whole warp runs this loop with warp-uniform values (so descriptors stay on the uniform
+    // datapath); one elected lane issues tcgen05.mma / tcgen05.commit.
+    const bool leader = elect_one();
+    if (leader) {
+      mbar_expect_tx(bfull, g.b_slab_bytes);
+      bulk_g2s(sB, reinterpret_cast<const uint8_t*>(Bp) + (size_t)nt * g.b_slab_bytes, g.b_slab_bytes, bfull);
     }
-    // ---- A: fp32 NCHW -> bf16 [channel group][flat position][8 channels], zero pads materialised
-    const int ngrp = g.CC / 8;
-    const int items = ngrp * g.strip;
-    for (int it = tid; it < items; it += K3_THREADS) {
-      const int grp = it / g.strip;
-      const int lloc = it - grp * g.strip;
-      int img, h, w;
-      uint4 packed = make_uint4(0u, 0u, 0u, 0u);
-      if (decode_pos(g, L0 - g.halo + lloc, img, h, w)) {
-        const int c0 = chunk * g.CC + grp * 8;
-        const float* px = x + ((int64_t)img * g.C + c0) * HW + h * g.W + w;
-        float v[8];
+    mbar_wait(bfull, 0);
+    const uint32_t idesc = make_idesc((uint32_t)g.NT);
+    const uint32_t a_plane16 = (uint32_t)g.strip, b_plane16 = (uint32_t)g.NT;     // plane strides in 16-byte units
+    // descriptor words: lo = start>>4 | LBO>>4 << 16 ; hi = SBO>>4 (=8) | version 1 << 14
+    const uint32_t desc_hi = 8u | (1u << 14);
+    const uint32_t a_lo_fixed = a_plane16 << 16, b_lo_fixed = b_plane16 << 16;
+    const uint32_t b0_16 = smem_u32(sB) >> 4, a0_16 = smem_u32(sA) >> 4;
+    const uint32_t a_stage16 = g.a_stage_bytes >> 4;
+    const int ncg = g.Cpad / 8, nchunk = g.nchunk, nst = g.nst, CC = g.CC, Cpad = g.Cpad, NT = g.NT;
+    uint32_t a_tap16[NTAPS], b_tap16[NTAPS];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (c0 + j < g.C) ? __ldg(px + (int64_t)j * HW) : 0.0f;
-        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
-        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
-        packed = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
-                            *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
-      }
-      *reinterpret_cast<uint4*>(sA + ((size_t)grp * g.strip + lloc) * 16) = packed;
+    for (int tap = 0; tap < NTAPS; ++tap) {
+      a_tap16[tap] = (uint32_t)(g.tap_phase[tap] * ngrpCC) * a_plane16 + (uint32_t)g.tap_off[tap];
+      b_tap16[tap] = (uint32_t)(tap * ncg) * b_plane16;
     }
-    fence_proxy_async();                                    // generic-proxy smem writes -> tensor core
-    __syncthreads();
-    if (tid == 0) {
-      mbar_wait(bar_b, chunk & 1);
+    uint32_t it = 0, item = 0;
+    for (int m = m_first; m < g.nitems_m; m += g.m_step, ++item) {
+      const uint32_t acc = item & 1;
+      mbar_wait(tempty + acc, ((item >> 1) & 1) ^ 1);            // epilogue has drained this accumulator
       tc_fence_after();
-      const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-      const uint32_t a_plane = (uint32_t)g.strip * 16, b_plane = (uint32_t)g.NT * 16;
-      for (int mt = 0; mt < g.MT; ++mt) {
-        const uint32_t d = tmem_base + (uint32_t)(mt * g.NT);
-        for (int tap = 0; tap < taps; ++tap) {
-          const int r = tap / g.S, s = tap - r * g.S;
-          const uint32_t a_tap = a0 + (uint32_t)(mt * 128 + r * g.pitch + s) * 16;
-          const uint32_t b_tap = b0 + (uint32_t)tap * ngrp * b_plane;
-          for (int ks = 0; ks < g.CC / 16; ++ks) {
-            const uint64_t ad = make_desc(a_tap + (uint32_t)ks * 2 * a_plane, a_plane, 128);
-            const uint64_t bd = make_desc(b_tap + (uint32_t)ks * 2 * b_plane, b_plane, 128);
-            umma_bf16(d, ad, bd, idesc, (chunk | tap | ks) != 0);
+      const uint32_t d = tmem_base + acc * (uint32_t)NT;
+      for (int chunk = 0; chunk < nchunk; ++chunk, ++it) {
+        const uint32_t s = it % (uint32_t)nst;
+        mbar_wait(full + s, (it / (uint32_t)nst) & 1);
+        tc_fence_after();
+        const uint32_t a_s16 = a0_16 + s * a_stage16;
+        const uint32_t b_c16 = b0_16 + (uint32_t)(chunk * ngrpCC) * b_plane16;
+        const int ksteps = min(CC, Cpad - chunk * CC) / 16;
+        if (leader) {
+#pragma unroll
+          for (int tap = 0; tap < NTAPS; ++tap) {
+            uint32_t alo = (a_s16 + a_tap16[tap]) | a_lo_fixed;
+            uint32_t blo = (b_c16 + b_tap16[tap]) | b_lo_fixed;
+            for (int ks = 0; ks < ksteps; ++ks) {
+              umma_bf16(d, ((uint64_t)desc_hi << 32) | alo, ((uint64_t)desc_hi << 32) | blo, idesc,
+                        (uint32_t)((chunk | tap | ks) != 0));
+              alo += 2 * a_plane16;                              // next 16 channels: two planes on
+              blo += 2 * b_plane16;
+            }
+          }
+          umma_commit(empty + s);                                // stage reusable once these MMAs retire
+          if (chunk == nchunk - 1) umma_commit(tfull + acc);     // accumulator complete
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < K3_EPI_WARPS) {
+    // =========================== epilogue: TMEM -> scale -> NCHW fp32 ===========================
+    const float sc = scale ? *scale : 1.0f;
+    const int K = g.K, NT = g.NT, m_step = g.m_step, nitems = g.nitems_m;
+    const int kbase = nt * NT;
+    uint32_t item = 0;
+    for (int m = m_first; m < nitems; m += m_step, ++item) {
+      const uint32_t acc = item & 1;
+      int img = 0, a = 0, b = 0;
+      const bool valid = decode_pos(g, m * 128 + warp * 32 + lane, img, a, b);
+      const int obase = (img * K + kbase) * PQ + a * g.Q + b;          // < 2^31 (checked on the host)
+      mbar_wait(tfull + acc, (item >> 1) & 1);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * (uint32_t)NT;
+      for (int cb = 0; cb < NT / 16; ++cb) {
+        uint32_t r[16];
+        tmem_ld16(trow + (uint32_t)cb * 16, r);
+        if (valid) {
+          float* po = out + obase + cb * 16 * PQ;
+          const int kleft = K - (kbase + cb * 16);
+          if (kleft >= 16) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) po[j * PQ] = __uint_as_float(r[j]) * sc;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < kleft) po[j * PQ] = __uint_as_float(r[j]) * sc;
           }
         }
       }
-      umma_commit(bar_mma);                                 // implies tcgen05.fence::before_thread_sync
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + acc);
     }
-  }
-  // ---- epilogue: TMEM -> registers -> scale -> NCHW fp32 (coalesced along w per out channel)
-  mbar_wait(bar_mma, (g.nchunk - 1) & 1);
-  tc_fence_after();
-  const float sc = scale ? *scale : 1.0f;
-  const int q4 = warp & 3, half = warp >> 2;                // lane quarter, column half
-  const int nchunks16 = g.NT / 16;
-  for (int mt = 0; mt < g.MT; ++mt) {
-    const int L = L0 + mt * 128 + q4 * 32 + lane;
-    int img = 0, h = 0, w = 0;
-    const bool valid = decode_pos(g, L, img, h, w);
-    for (int cb = half; cb < nchunks16; cb += 2) {
-      uint32_t r[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(mt * g.NT + cb * 16), r);
-      if (valid) {
-        const int k0 = nt * g.NT + cb * 16;
-        float* po = out + ((int64_t)img * g.K + k0) * HW + h * g.W + w;
+  } else {
+    // =========================== producers: fp32 NCHW -> bf16 flat K-major strips ===========================
+    // The producer warps form K3_PROD_GROUPS independent groups; group q fills every stage `it` with
+    // it % groups == q on its own, so that many stages are in flight against global-memory latency
+    // at once (a thread cannot start its next stage before the loads of the current one return).
+    constexpr int WPG = K3_PROD_WARPS / K3_PROD_GROUPS;   // warps per group
+    constexpr int NPG = 32 * WPG;                         // threads per group
+    const int pw = warp - (K3_EPI_WARPS + 1);
+    const int grp_id = pw / WPG;
+    const int gt = tid - 32 * (K3_EPI_WARPS + 1) - grp_id * NPG;
+    const int strip = g.strip, C = g.C, H = g.H, W = g.W, stride = g.stride, CC = g.CC, Cpad = g.Cpad;
+    const int nphase = g.nphase, nchunk = g.nchunk, nst = g.nst, m_step = g.m_step, nitems = g.nitems_m;
+    const int halo = g.halo_before;
+    const uint32_t a_stage_bytes = g.a_stage_bytes;
+    uint32_t it = 0;
+    for (int m = m_first; m < nitems; m += m_step) {
+      const int Ls = m * 128 - halo;
+      for (int chunk = 0; chunk < nchunk; ++chunk, ++it) {
+        if ((int)(it % K3_PROD_GROUPS) != grp_id) continue;
+        const uint32_t s = it % (uint32_t)nst;
+        mbar_wait(empty + s, ((it / (uint32_t)nst) & 1) ^ 1);
+        uint8_t* stage = sA + (size_t)s * a_stage_bytes;
+        const int cbase = chunk * CC;
+        const int ngrp = min(CC, Cpad - cbase) / 8;
+        const int nitem = ngrp * strip;                    // (channel group, position) items per phase
+        for (int ph = 0; ph < nphase; ++ph) {
+          const int pr = ph >> 1, pc = ph & 1;
+          const int poff = pr * W + pc;
+          uint8_t* sph = stage + (size_t)ph * ngrpCC * strip * 16;
+          for (int i0 = gt; i0 < nitem; i0 += 2 * NPG) {
+            float v[2][8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (k0 + j < g.K) po[(int64_t)j * HW] = __uint_as_float(r[j]) * sc;
+            for (int u = 0; u < 2; ++u) {                  // 16 independent loads in flight per thread
+              const int i = i0 + u * NPG;
+              int cvalid = 0, idx = 0;
+              if (i < nitem) {
+                const int grp = fdiv(i, g.div_strip);
+                const int lloc = i - grp * strip;
+                int img, a, b;
+                if (decode_pos(g, Ls + lloc, img, a, b)) {
+                  const int ih = a * stride + pr, iw = b * stride + pc;
+                  if (ih < H && iw < W) {
+                    const int c0 = cbase + grp * 8;
+                    cvalid = C - c0;
+                    idx = ((img * C + c0) * H + ih) * W + iw;
+                  }
+                }
+              }
+              const float* px = x + idx;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[u][j] = (j < cvalid) ? __ldg(px + j * HW) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int i = i0 + u * NPG;
+              if (i < nitem) {
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[u][0], v[u][1]), p1 = __floats2bfloat162_rn(v[u][2], v[u][3]);
+                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[u][4], v[u][5]), p3 = __floats2bfloat162_rn(v[u][6], v[u][7]);
+                *reinterpret_cast<uint4*>(sph + (size_t)i * 16) =           // i == grp*strip + lloc
+                    make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                               *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+              }
+            }
+          }
+        }
+        fence_proxy_async();                          // generic-proxy smem writes -> tensor-core reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full + s);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, ncols);
+  if (warp == K3_EPI_WARPS) tmem_dealloc(tmem_base, ncols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -371,6 +502,18 @@ static int sm_count() {
   return g_sms > 0 ? g_sms : 148;
 }
 
+static FastDiv make_fastdiv(uint32_t d) {
+  // s = ceil(log2 d), mul = ceil(2^(31+s) / d) in [2^31, 2^32): floor(n/d) == umulhi(n, mul) >> (s-1)
+  // for every 0 <= n < 2^31 (error term e = mul*d - 2^(31+s) < d <= 2^s, so n*e < 2^(31+s)).
+  FastDiv f; f.d = d; f.mul = 0; f.shr = 0;
+  if (d <= 1) return f;
+  uint32_t sh = 0;
+  while ((1u << sh) < d) ++sh;
+  f.mul = (uint32_t)(((1ull << (31 + sh)) + d - 1) / d);
+  f.shr = sh - 1;
+  return f;
+}
+
 static bool fill_geom(ConvGeom& g, int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups) {
   if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0 || R <= 0 || S <= 0 || stride <= 0 || pad < 0 || groups <= 0) return false;
   if (C % groups || K % groups) return false;
@@ -381,41 +524,74 @@ static bool fill_geom(ConvGeom& g, int B, int C, int H, int W, int K, int R, int
   return g.P > 0 && g.Q > 0;
 }
 
-// K3 takes: dense, stride 1, square 3x3 pad 1 or 1x1 pad 0
+// K3 takes: dense, square 3x3 pad 1 or 1x1 pad 0, stride 1 or 2
 static bool umma_eligible(const ConvGeom& g) {
-  if (g.groups != 1 || g.stride != 1) return false;
+  if (g.groups != 1 || (g.stride != 1 && g.stride != 2)) return false;
   if (!((g.R == 3 && g.S == 3 && g.pad == 1) || (g.R == 1 && g.S == 1 && g.pad == 0))) return false;
   return true;
 }
 
 static size_t umma_smem_bytes(const ConvGeom& g) {
-  return (size_t)(g.CC / 8) * g.strip * 16 + (size_t)g.R * g.S * (g.CC / 8) * g.NT * 16 + 64;
+  return (size_t)g.b_slab_bytes + (size_t)g.nst * g.a_stage_bytes + (3 * K3_MAX_STAGES + 8) * 8 + 16;
 }
 
-static void plan_umma(ConvGeom& g) {
+// returns false if the shape does not fit the kernel's shared-memory plan
+static bool plan_umma(ConvGeom& g) {
   const bool k3 = (g.R == 3);
-  g.pitch = g.W + (k3 ? 1 : 0);
-  g.rows_img = g.H + (k3 ? 1 : 0);
-  g.halo = k3 ? g.pitch + 1 : 0;
-  g.Ltot = (g.B * g.rows_img + (k3 ? 1 : 0)) * g.pitch;
+  g.ntaps = g.R * g.S;
+  g.pitch = g.Q + (k3 ? 1 : 0);
+  g.rows_img = g.P + (k3 ? 1 : 0);
+  g.top = k3 ? 1 : 0;
+  g.Ltot = (g.B * g.rows_img + g.top) * g.pitch;
+  int halo_after = 0;
+  if (!k3) {
+    g.nphase = 1; g.halo_before = 0;
+    g.tap_phase[0] = 0; g.tap_off[0] = 0;
+  } else if (g.stride == 1) {
+    g.nphase = 1; g.halo_before = g.pitch + 1; halo_after = g.pitch + 1;
+    for (int r = 0; r < 3; ++r) for (int s = 0; s < 3; ++s) {
+      g.tap_phase[r * 3 + s] = 0;
+      g.tap_off[r * 3 + s] = g.halo_before + (r - 1) * g.pitch + (s - 1);
+    }
+  } else {
+    // stride 2: input row 2p+r-1 is parity phase (r != 1) at half-res row p - (r == 0); same for columns
+    g.nphase = 4; g.halo_before = g.pitch + 1;
+    for (int r = 0; r < 3; ++r) for (int s = 0; s < 3; ++s) {
+      g.tap_phase[r * 3 + s] = ((r != 1) ? 2 : 0) | ((s != 1) ? 1 : 0);
+      g.tap_off[r * 3 + s] = g.halo_before - (r == 0 ? g.pitch : 0) - (s == 0 ? 1 : 0);
+    }
+  }
+  g.strip = 128 + g.halo_before + halo_after;
   g.Cpad = (g.C + 15) / 16 * 16;
-  g.CC = g.Cpad < 64 ? g.Cpad : 64;
-  g.nchunk = (g.Cpad + g.CC - 1) / g.CC;
+  // N tile: the whole-K weight slab of one tile must fit its smem budget
   const int Kp = (g.K + 15) / 16 * 16;
-  g.ntiles_n = (Kp + 255) / 256;
+  int NT = Kp < 256 ? Kp : 256;
+  while (NT > 16 && (size_t)g.ntaps * g.Cpad * NT * 2 > K3_B_BUDGET) NT -= 16;
+  if ((size_t)g.ntaps * g.Cpad * NT * 2 > K3_B_BUDGET) return false;
+  g.ntiles_n = (Kp + NT - 1) / NT;
   g.NT = ((Kp + g.ntiles_n - 1) / g.ntiles_n + 15) / 16 * 16;
-  // M tiles per CTA: as many as TMEM (512 cols) and smem allow while still giving every SM >= 2 CTAs
-  const int mtiles = (g.Ltot + 127) / 128;
-  int MT = 4;
-  while (MT > 1 && (MT * g.NT > 512 || (mtiles + MT - 1) / MT * g.ntiles_n < 2 * sm_count())) MT >>= 1;
-  g.MT = MT;
-  g.strip = g.MT * 128 + 2 * g.halo;
-  while (g.MT > 1 && umma_smem_bytes(g) > 200 * 1024) { g.MT >>= 1; g.strip = g.MT * 128 + 2 * g.halo; }
+  g.b_slab_bytes = (uint32_t)g.ntaps * g.Cpad * g.NT * 2;
+  // channels per A stage: keep a stage <= ~24 KB so that >= 3 stages fit beside the slab
+  int CC = g.Cpad;
+  while (CC > 16 && (size_t)g.nphase * CC * g.strip * 2 > 24 * 1024) CC -= 16;
+  g.CC = CC;
+  g.nchunk = (g.Cpad + CC - 1) / CC;
+  g.a_stage_bytes = (uint32_t)g.nphase * CC * g.strip * 2;
+  int nst = (int)((K3_SMEM_BUDGET - g.b_slab_bytes - 512) / g.a_stage_bytes);
+  if (nst > K3_MAX_STAGES) nst = K3_MAX_STAGES;
+  if (nst < 2) return false;
+  g.nst = nst;
+  g.nitems_m = (g.Ltot + 127) / 128;
+  int per_n = sm_count() / g.ntiles_n;
+  if (per_n < 1) per_n = 1;
+  g.m_step = g.nitems_m < per_n ? g.nitems_m : per_n;
+  g.div_pitch = make_fastdiv((uint32_t)g.pitch);
+  g.div_rows = make_fastdiv((uint32_t)g.rows_img);
+  g.div_strip = make_fastdiv((uint32_t)g.strip);
+  return true;
 }
 
-static size_t umma_pack_bytes(const ConvGeom& g) {
-  return (size_t)g.ntiles_n * g.nchunk * g.R * g.S * (g.CC / 8) * g.NT * 16;
-}
+static size_t umma_pack_bytes(const ConvGeom& g) { return (size_t)g.ntiles_n * g.b_slab_bytes; }
 
 }  // namespace po2
 
@@ -428,10 +604,7 @@ size_t po2_conv2d_workspace(int B, int C, int H, int W, int K, int R, int S, int
   ConvGeom g;
   if (!fill_geom(g, B, C, H, W, K, R, S, stride, pad, groups)) return 0;
   size_t bytes = (size_t)K * (C / groups) * R * S * sizeof(float);       // decoded fp32 weights (codes input)
-  if (compute == 0 && umma_eligible(g)) {
-    plan_umma(g);
-    if (umma_smem_bytes(g) <= 200 * 1024) bytes += umma_pack_bytes(g) + 256;
-  }
+  if (compute == 0 && umma_eligible(g) && plan_umma(g)) bytes += umma_pack_bytes(g) + 256;
   return (bytes + 255) / 256 * 256;
 }
 
@@ -450,30 +623,30 @@ int po2_conv2d_fwd(const void* x, const void* w, const float* scale, void* out, 
   const int64_t wn = (int64_t)K * (C / groups) * R * S;
   const size_t wbytes = ((size_t)wn * sizeof(float) + 255) / 256 * 256;
 
-  if (compute == 0 && umma_eligible(g)) {
-    plan_umma(g);
-    const size_t smem = umma_smem_bytes(g);
-    if (smem <= 200 * 1024) {
-      if (!workspace || workspace_bytes < need) return PO2_E_WORKSPACE;
-      __nv_bfloat16* Bp = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(workspace) + wbytes);
-      const int64_t total = (int64_t)umma_pack_bytes(g) / 2;
-      const int pblocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-      pack_weights_kernel<<<pblocks, 256, 0, st>>>(
-          w_format == PO2_W_CODES ? nullptr : (const float*)w, w_format == PO2_W_CODES ? (const uint8_t*)w : nullptr,
-          w_format == PO2_W_CODES ? nullptr : scale, Bp, g, bits, fsr);
-      cudaError_t e = cudaGetLastError();
+  if (compute == 0 && umma_eligible(g) && plan_umma(g)) {
+    if (!workspace || workspace_bytes < need) return PO2_E_WORKSPACE;
+    __nv_bfloat16* Bp = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(workspace) + wbytes);
+    const int64_t total = (int64_t)umma_pack_bytes(g) / 2;
+    const int pblocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+    pack_weights_kernel<<<pblocks, 256, 0, st>>>(
+        w_format == PO2_W_CODES ? nullptr : (const float*)w, w_format == PO2_W_CODES ? (const uint8_t*)w : nullptr,
+        w_format == PO2_W_CODES ? nullptr : scale, Bp, g, bits, fsr);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    static bool attr_set = false;
+    if (!attr_set) {
+      e = cudaFuncSetAttribute(conv_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_SMEM_BUDGET + 1024);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(conv_umma_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_SMEM_BUDGET + 1024);
       if (e != cudaSuccess) return (int)e;
-      static bool attr_set = false;
-      if (!attr_set) {
-        e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 64);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-      }
-      const int mtiles = (g.Ltot + 127) / 128;
-      dim3 grid((mtiles + g.MT - 1) / g.MT, g.ntiles_n);
-      conv_umma_kernel<<<grid, K3_THREADS, smem, st>>>((const float*)x, Bp, scale, (float*)out, g);
-      return (int)cudaGetLastError();
+      attr_set = true;
     }
+    const int grid = g.ntiles_n * g.m_step;
+    if (g.ntaps == 1)
+      conv_umma_kernel<1><<<grid, K3_THREADS, umma_smem_bytes(g), st>>>((const float*)x, Bp, scale, (float*)out, g);
+    else
+      conv_umma_kernel<9><<<grid, K3_THREADS, umma_smem_bytes(g), st>>>((const float*)x, Bp, scale, (float*)out, g);
+    return (int)cudaGetLastError();
   }
   // CUDA-core paths work on fp32 weights
   const float* wf = (const float*)w;

@@ -1,10 +1,12 @@
-"""Per-layer quantized-conv forward timings: po2 tensor-core path vs po2 fp32 path vs cuDNN (TF32, the
-reference's default on a GPU) for the layer shapes of SURVEY.md section 8a.
+"""Per-layer quantized-conv forward timings: po2 tensor-core path vs cuDNN (TF32 = the reference's
+default on a GPU; fp32) for the layer shapes of SURVEY.md section 8a.
 
     python tools/bench_conv.py [--batch 128] [--out gpurun_out/conv_layers.json]
 
-CUDA events, median of --iters after warm-up; the 320 MB flush buffer is rewritten between
-iterations so every layer starts with a cold L2.
+Each candidate is captured in a CUDA graph (so Python/launch overhead is not what is measured);
+"cold" = graph of [rewrite a 320 MB buffer; conv] minus graph of [rewrite the buffer], i.e. the conv
+starts with its operands out of L2; "warm" = 20 back-to-back convs, operands L2-resident where they
+fit.  po2 timings include the weight-pack kernel that runs before every conv in QAT mode.
 """
 import argparse
 import json
@@ -36,19 +38,29 @@ SHAPES = [  # name, C, H, W, K, k, stride, pad, groups, count in ResNet-56 (0 = 
 ]
 
 
-def timeit(fn, iters, flush):
-    for _ in range(3):
-        fn()
+def graph_time(body, reps, iters=5):
+    """median ms of one replay of a graph that runs `body` `reps` times"""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        body()
+        torch.cuda.current_stream().synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(reps):
+                body()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g.replay()
     torch.cuda.synchronize()
     ts = []
     for _ in range(iters):
-        flush.add_(1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        fn()
+        g.replay()
         b.record()
         torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b) * 1e3)
+        ts.append(a.elapsed_time(b))
     ts.sort()
     return ts[len(ts) // 2]
 
@@ -56,13 +68,14 @@ def timeit(fn, iters, flush):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=128)
-    ap.add_argument("--iters", type=int, default=15)
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     flush = torch.zeros(320 * 1024 * 1024 // 4, dtype=torch.int32, device="cuda")
+    REPS = 10
+    t_flush = graph_time(lambda: flush.add_(1), REPS)
     rows = []
     for name, C, H, W, K, k, stride, pad, groups, cnt in SHAPES:
-        B = a.batch if H * W * C * a.batch * 4 < (2 << 30) else 32
+        B = a.batch
         x = torch.randn(B, C, H, W, device="cuda")
         w = torch.randn(K, C // groups, k, k, device="cuda") * 0.1
         y, codes, scale, _, _ = torch.ops.po2.quantize_full(w, 4, 1, True)
@@ -71,20 +84,27 @@ def main():
         flops = 2.0 * B * K * P * Q * (C // groups) * k * k
         bytes_io = 4.0 * (x.numel() + out.numel())
         r = {"layer": name, "batch": B, "gflop": flops / 1e9, "io_mb": bytes_io / 1e6, "count_r56": cnt}
-        r["us_po2_tc"] = timeit(lambda: ops.conv2d_out(x, y, scale, out, stride, pad, groups, 0), a.iters, flush)
-        r["us_po2_fp32"] = timeit(lambda: ops.conv2d_out(x, y, scale, out, stride, pad, groups, 1), a.iters, flush)
+        cands = {"po2_tc": lambda: ops.conv2d_out(x, y, scale, out, stride, pad, groups, 0)}
         torch.backends.cudnn.allow_tf32 = True
-        r["us_cudnn_tf32"] = timeit(lambda: F.conv2d(x, y, None, stride, pad, 1, groups), a.iters, flush)
-        torch.backends.cudnn.allow_tf32 = False
-        r["us_cudnn_fp32"] = timeit(lambda: F.conv2d(x, y, None, stride, pad, 1, groups), a.iters, flush)
-        r["tflops_po2_tc"] = flops / r["us_po2_tc"] / 1e6
-        r["io_GBs_po2_tc"] = bytes_io / r["us_po2_tc"] / 1e3
+        F.conv2d(x, y, None, stride, pad, 1, groups)
+        cands["cudnn_tf32"] = lambda: F.conv2d(x, y, None, stride, pad, 1, groups)
+        for key, fn in cands.items():
+            def cold():
+                flush.add_(1)
+                fn()
+            r[f"us_{key}_cold"] = (graph_time(cold, REPS) - t_flush) / REPS * 1e3
+            r[f"us_{key}_warm"] = graph_time(fn, 20) / 20 * 1e3
+        r["tflops_po2_tc_cold"] = flops / r["us_po2_tc_cold"] / 1e6
+        r["io_GBs_po2_tc_cold"] = bytes_io / r["us_po2_tc_cold"] / 1e3
+        r["io_GBs_cudnn_cold"] = bytes_io / r["us_cudnn_tf32_cold"] / 1e3
         rows.append(r)
-        print(json.dumps(r), flush=True)
+        print(json.dumps({k_: (round(v, 2) if isinstance(v, float) else v) for k_, v in r.items()}), flush=True)
     tot = lambda key: sum(r[key] * r["count_r56"] for r in rows)
-    print(json.dumps({"resnet56_forward_qconv_us": {k: tot(k) for k in ("us_po2_tc", "us_po2_fp32", "us_cudnn_tf32", "us_cudnn_fp32")}}))
+    summ = {"resnet56_forward_qconv_us": {k_: round(tot(k_), 1) for k_ in
+            ("us_po2_tc_cold", "us_po2_tc_warm", "us_cudnn_tf32_cold", "us_cudnn_tf32_warm")}}
+    print(json.dumps(summ))
     if a.out:
-        json.dump(rows, open(a.out, "w"), indent=1)
+        json.dump({"rows": rows, **summ}, open(a.out, "w"), indent=1)
 
 
 if __name__ == "__main__":
