@@ -1,0 +1,95 @@
+"""CPU tests of the host-side mirror: API surface, lin/lin+ parity with reference vectors, and the
+quantize_model / QuantizedConv2d control flow driven through a fake backend (the oracle) so that no
+GPU is needed.  The kernels themselves are covered by the -m gpu suite."""
+import copy
+import inspect
+
+import numpy as np
+import pytest
+import torch
+
+import po2_quantization_b200 as P
+from po2_quantization_b200 import ops
+from tests import golden_util as G
+
+
+def test_public_surface_matches_reference_names():
+    assert list(P.quantizer_dict) == ["lin", "lin+", "po2", "po2+"]          # utils/quantizers.py:156-161
+    for cls in P.quantizer_dict.values():
+        assert issubclass(cls, torch.autograd.Function)
+        assert list(inspect.signature(cls.forward).parameters)[:3] == ["ctx", "input", "bits"]
+    sig = inspect.signature(P.QuantizedConv2d.__init__)
+    assert [p for p in sig.parameters][1:] == ["in_channels", "out_channels", "kernel_size", "stride", "padding",
+                                               "dilation", "groups", "bias", "quantize_fn", "bits"]
+    assert sig.parameters["padding"].default == 1 and sig.parameters["bias"].default is False   # :11-17
+    m = P.QuantizedConv2d(16, 32, 3, 2, quantize_fn=P.PowerOfTwoQuantizer, bits=3)
+    assert isinstance(m, torch.nn.Conv2d) and list(m.state_dict()) == ["weight"]
+    assert m.quantize_fn is P.PowerOfTwoQuantizer and m.bits == 3
+    g = torch.ones(3)
+    assert P.PowerOfTwoQuantizer.backward(None, g)[0] is g and P.PowerOfTwoPlusQuantizer.backward(None, g)[1:] == (None, None)
+    from drop_in.utils.quantizers import quantizer_dict as qd2
+    from drop_in.models.quantized_conv import QuantizedConv2d as qc2
+    assert qd2 is P.quantizer_dict and qc2 is P.QuantizedConv2d
+
+
+def test_lin_quantizers_match_reference_vectors():
+    z = G.load("lin_golden.npz")
+    w = torch.from_numpy(z["w"])
+    for name, cls in (("lin", P.LinearPowerOfTwoQuantizer), ("lin+", P.LinearPowerOfTwoPlusQuantizer)):
+        for bits in (3, 4):
+            got = cls.forward(None, w, bits=bits).numpy()
+            assert np.array_equal(got.view(np.uint32), z[f"{name}|{bits}"].view(np.uint32)), (name, bits)
+
+
+@pytest.fixture
+def oracle_backend(monkeypatch):
+    """Route the two quantizer ops through the oracle (TEST fake backend, never shipped)."""
+    from oracle.po2_oracle_torch import quantize_ref
+
+    def fake_quantize(x, bits, fsr, plus):
+        return quantize_ref(x.detach(), bits, fsr, plus)
+
+    def fake_full(x, bits, fsr, plus):
+        y = quantize_ref(x.detach(), bits, fsr, plus)
+        return (y, torch.zeros(1, dtype=torch.uint8), x.detach().abs().max().float(),
+                torch.zeros((), dtype=torch.int32), ((y - x.detach()).double() ** 2).sum())
+    monkeypatch.setattr(ops, "quantize", fake_quantize)
+    monkeypatch.setattr(ops, "quantize_full", fake_full)
+    monkeypatch.setattr(ops, "_require_cuda", lambda t, what: None)
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True), raising=False)
+    yield
+    
+
+def test_quantize_model_control_flow_and_known_answers(oracle_backend):
+    """utils/quantizers.py:139-153 on the seeded ResNet-20: the reference's own MSE values."""
+    from workloads import resnet_cifar
+    ka = G.load("known_answers.npz")
+    for qn, Q in (("po2", P.PowerOfTwoQuantizer), ("po2+", P.PowerOfTwoPlusQuantizer)):
+        for bits in (3, 4):
+            torch.manual_seed(8)
+            model = resnet_cifar(20, 10, None, bits)
+            before = copy.deepcopy(model.state_dict())
+            mse = P.quantize_model(model, Q, bits)
+            assert abs(mse - float(ka[f"resnet20_ptq_mse|{qn}|{bits}"])) <= 2e-6 * mse
+            after = model.state_dict()
+            changed = [k for k in before if not torch.equal(before[k], after[k])]
+            qconv = [n + ".weight" for n, m in model.named_modules() if isinstance(m, P.QuantizedConv2d)]
+            assert sorted(changed) == sorted(qconv) and len(qconv) == 20       # stem conv / fc untouched
+            assert "conv1.weight" not in changed
+            assert all(hasattr(m, "_po2_ptq") for m in model.modules() if isinstance(m, P.QuantizedConv2d))
+
+
+def test_quantize_model_without_quantized_layers_raises():
+    with pytest.raises(ZeroDivisionError):
+        P.quantize_model(torch.nn.Sequential(torch.nn.Conv2d(3, 3, 1)), P.PowerOfTwoQuantizer, 4)
+
+
+def test_flavor_and_mode_switches():
+    assert P.get_log2_flavor() in ("ieee", "torch_cuda")
+    with pytest.raises(ValueError):
+        P.set_log2_flavor("glibc")
+    with pytest.raises(ValueError):
+        ops.set_conv_mode("magic")
+    P.set_log2_flavor("torch_cuda")
+    assert P.get_log2_flavor() == "torch_cuda"
+    P.set_log2_flavor("ieee")
