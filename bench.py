@@ -109,6 +109,23 @@ def run_ours(a):
         dist.init_process_group("nccl", device_id=device)
     from po2_quantization_b200 import ops
 
+    # Everything (model/DDP construction, warm-up, capture, replay, timing events) runs on ONE side
+    # stream: CUDA-graph capture is illegal on the legacy default stream, and DDP's AccumulateGrad
+    # hooks must be created on the stream the captured step later runs on.
+    side = torch.cuda.Stream(device)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        _run_ours_on_stream(a, ops, world, rank, local_rank, device)
+    if world > 1:
+        # A captured graph keeps NCCL work objects alive and destroy_process_group() can then wait
+        # forever at interpreter exit; every rank is past its last collective here, so leave hard.
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
+def _run_ours_on_stream(a, ops, world, rank, local_rank, device):
     B = a.batch
     model, opt, crit = build_training(device, world, local_rank, B)
     g = torch.Generator().manual_seed(1000 + rank)
@@ -138,26 +155,26 @@ def run_ours(a):
         print(json.dumps({"profile_step": True, "launches_of_libpo2b200": ops.LAUNCHES}))
         return
 
-    # ---- CUDA graph of the whole step (single GPU; DDP/SyncBN collectives stay eager at N>1)
+    # ---- CUDA graph of the whole step.  With DDP (N>1) the NCCL all-reduce and the SyncBatchNorm
+    # collectives are captured too (ProcessGroupNCCL supports capture); DDP needs its bucket rebuild
+    # (iteration 2) to have happened, hence 11 eager warm-up steps on the capture stream first.
     graph = None
     launches_per_step = None
     for _ in range(3):
         step()
     torch.cuda.synchronize()
-    if not a.no_graph and world == 1:
+    if not a.no_graph:
         try:
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                for _ in range(3):
-                    step()
-                torch.cuda.current_stream().synchronize()
-                graph = torch.cuda.CUDAGraph()
-                ops.LAUNCHES = 0
-                with torch.cuda.graph(graph, stream=s):
-                    step()
-                launches_per_step = ops.LAUNCHES
-            torch.cuda.current_stream().wait_stream(s)
+            for _ in range(11 if world > 1 else 3):
+                step()
+            torch.cuda.current_stream().synchronize()
+            if world > 1:
+                torch.distributed.barrier()
+            graph = torch.cuda.CUDAGraph()
+            ops.LAUNCHES = 0
+            with torch.cuda.graph(graph, stream=torch.cuda.current_stream()):
+                step()
+            launches_per_step = ops.LAUNCHES
             torch.cuda.synchronize()
         except Exception as e:  # pragma: no cover
             print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
@@ -213,8 +230,6 @@ def run_ours(a):
         torch.distributed.barrier()
 
     if rank != 0:
-        if world > 1:
-            torch.distributed.destroy_process_group()
         return
     ms_step = ms_total / a.steps
     out = {
@@ -239,8 +254,6 @@ def run_ours(a):
     if world == 1 and not a.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(B, steps=2)
     print(json.dumps(out), flush=True)
-    if world > 1:
-        torch.distributed.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------
