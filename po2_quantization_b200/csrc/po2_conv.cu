@@ -13,6 +13,8 @@
 //   K4  conv_depthwise_kernel groups == C == K, 3x3: CUDA-core, HBM/L2-bound.
 //   --  conv_direct_kernel    any dense/grouped shape in fp32 FMA (the "fp32-accumulate" parity path and
 //                            the fallback for shapes K3 does not take).
+#include <limits.h>
+
 #include "po2_common.cuh"
 
 namespace po2 {
@@ -62,6 +64,13 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.eq.b32 p, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -120,7 +129,9 @@ struct ConvGeom {
   int nitems_m, m_step;  // 128-position items; items advance by m_step per CTA iteration
   int nst;               // A pipeline stages
   uint32_t a_stage_bytes, b_slab_bytes;
-  FastDiv div_pitch, div_rows, div_strip;
+  FastDiv div_pitch, div_rows, div_strip, div_ipr;
+  int vec4, items_per_row;   // producer fast path: float4 loads along W
+  int prod_groups;           // independent producer groups (stages in flight per CTA)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -167,10 +178,25 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const uint8_t* 
 //   producers --full[s]--> MMA --tcgen05.commit: empty[s]--> producers      (A stages, ring of nst)
 //   MMA --tcgen05.commit: tmem_full[a]--> epilogue --tmem_empty[a]--> MMA   (2 accumulator stages)
 // ------------------------------------------------------------------------------------------------
+#ifdef PO2_K3_TRACE
+// debug-only event trace (tools/trace_conv.py builds a separate library with -DPO2_K3_TRACE):
+// SM-clock timestamps into shared memory (cheap), dumped to global memory at kernel end
+__device__ long long* g_k3_trace = nullptr;              // [cta < 4][role 0..7][event 0..63] = clock64
+__shared__ long long k3_trace_smem[8 * 64];
+__device__ __forceinline__ void k3_trace(int role, int ev) {
+  if (ev < 64) k3_trace_smem[role * 64 + ev] = clock64();
+}
+#define K3_TRACE(role, ev) k3_trace(role, ev)
+#else
+#define K3_TRACE(role, ev)
+#endif
+
 constexpr int K3_EPI_WARPS = 4;
 constexpr int K3_PROD_WARPS = 8;
-constexpr int K3_PROD_GROUPS = 4;
-constexpr int K3_THREADS = 32 * (K3_EPI_WARPS + 1 + K3_PROD_WARPS);
+constexpr int K3_MAX_PROD_GROUPS = 4;
+constexpr int PU = 4;               // producer items in flight per thread (x8 loads each)
+constexpr int K3_MMA_WARPS = 2;         // two issuing warps alternate tiles so one's barrier/fence latency hides behind the other's MMAs
+constexpr int K3_THREADS = 32 * (K3_EPI_WARPS + K3_MMA_WARPS + K3_PROD_WARPS);
 constexpr int K3_MAX_STAGES = 6;
 constexpr uint32_t K3_SMEM_BUDGET = 220 * 1024;
 constexpr uint32_t K3_B_BUDGET = 112 * 1024;
@@ -214,6 +240,11 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef PO2_K3_TRACE
+  for (int i = tid; i < 8 * 64; i += K3_THREADS) k3_trace_smem[i] = 0;
+  __syncthreads();
+#endif
+  if (tid == 0) K3_TRACE(6, 0);
   const int nt = blockIdx.x % g.ntiles_n;
   const int m_first = blockIdx.x / g.ntiles_n;
   uint32_t ncols = 32;
@@ -222,7 +253,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
   if (warp == K3_EPI_WARPS) {
     tmem_alloc(tmem_slot, ncols);
     if (lane == 0) {
-      for (int i = 0; i < g.nst; ++i) { mbar_init(full + i, K3_PROD_WARPS / K3_PROD_GROUPS); mbar_init(empty + i, 1); }
+      for (int i = 0; i < g.nst; ++i) { mbar_init(full + i, K3_PROD_WARPS / g.prod_groups); mbar_init(empty + i, 1); }
       for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, K3_EPI_WARPS); }
       mbar_init(bfull, 1);
       fence_mbar_init();
@@ -232,15 +263,18 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) K3_TRACE(6, 1);
   const int HW = g.H * g.W, PQ = g.P * g.Q;
   const int ngrpCC = g.CC / 8;
 
-  if (warp == K3_EPI_WARPS) {
-    // =========================== MMA issuer ===========================
+  if (warp >= K3_EPI_WARPS && warp < K3_EPI_WARPS + K3_MMA_WARPS) {
+    // =========================== MMA issuers ===========================
+    // Issuer q takes the tiles whose index has parity q and always accumulates into TMEM stage q.
     // The whole warp runs this loop with warp-uniform values (so descriptors stay on the uniform
     // datapath); one elected lane issues tcgen05.mma / tcgen05.commit.
     const bool leader = elect_one();
-    if (leader) {
+    const uint32_t me = (uint32_t)(warp - K3_EPI_WARPS);
+    if (leader && me == 0) {
       mbar_expect_tx(bfull, g.b_slab_bytes);
       bulk_g2s(sB, reinterpret_cast<const uint8_t*>(Bp) + (size_t)nt * g.b_slab_bytes, g.b_slab_bytes, bfull);
     }
@@ -259,54 +293,76 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
       a_tap16[tap] = (uint32_t)(g.tap_phase[tap] * ngrpCC) * a_plane16 + (uint32_t)g.tap_off[tap];
       b_tap16[tap] = (uint32_t)(tap * ncg) * b_plane16;
     }
-    uint32_t it = 0, item = 0;
-    for (int m = m_first; m < g.nitems_m; m += g.m_step, ++item) {
-      const uint32_t acc = item & 1;
-      mbar_wait(tempty + acc, ((item >> 1) & 1) ^ 1);            // epilogue has drained this accumulator
-      tc_fence_after();
-      const uint32_t d = tmem_base + acc * (uint32_t)NT;
-      for (int chunk = 0; chunk < nchunk; ++chunk, ++it) {
-        const uint32_t s = it % (uint32_t)nst;
-        mbar_wait(full + s, (it / (uint32_t)nst) & 1);
-        tc_fence_after();
+    const int nitems = g.nitems_m, m_step = g.m_step;
+    uint32_t s = 0, sphase = 0, aphase = 0;                        // A-stage ring position / my accumulator's phase
+    const uint32_t acc = me;
+    const uint32_t d = tmem_base + acc * (uint32_t)NT;
+    uint32_t tile = 0;
+    for (int m = m_first; m < nitems; m += m_step, ++tile) {
+      if ((tile & 1u) != me) {                                   // the other issuer's tile: just advance the ring
+        for (int chunk = 0; chunk < nchunk; ++chunk)
+          if (++s == (uint32_t)nst) { s = 0; sphase ^= 1; }
+        continue;
+      }
+      mbar_wait(tempty + acc, aphase ^ 1);                       // epilogue has drained this accumulator
+      for (int chunk = 0; chunk < nchunk; ++chunk) {
+        mbar_wait(full + s, sphase);
+        tc_fence_after();                                        // orders the MMAs after both waits above
+        if (leader) K3_TRACE((int)me * 7, 2 * (int)((tile >> 1) * nchunk + chunk));
         const uint32_t a_s16 = a0_16 + s * a_stage16;
         const uint32_t b_c16 = b0_16 + (uint32_t)(chunk * ngrpCC) * b_plane16;
         const int ksteps = min(CC, Cpad - chunk * CC) / 16;
         if (leader) {
+          // k-step outer (1-4 iterations), taps inner and fully unrolled: straight-line MMA issue with
+          // per-tap descriptor words that only need the stage / k-step offset added
+          uint32_t a_off = a_s16 | a_lo_fixed, b_off = b_c16 | b_lo_fixed;
+          for (int ks = 0; ks < ksteps; ++ks) {
 #pragma unroll
-          for (int tap = 0; tap < NTAPS; ++tap) {
-            uint32_t alo = (a_s16 + a_tap16[tap]) | a_lo_fixed;
-            uint32_t blo = (b_c16 + b_tap16[tap]) | b_lo_fixed;
-            for (int ks = 0; ks < ksteps; ++ks) {
-              umma_bf16(d, ((uint64_t)desc_hi << 32) | alo, ((uint64_t)desc_hi << 32) | blo, idesc,
-                        (uint32_t)((chunk | tap | ks) != 0));
-              alo += 2 * a_plane16;                              // next 16 channels: two planes on
-              blo += 2 * b_plane16;
+            for (int tap = 0; tap < NTAPS; ++tap) {
+#ifdef PO2_K3_ONE_TAP
+              if (tap > 0) break;                                // timing experiment only (wrong results)
+#endif
+              const uint64_t ad = ((uint64_t)desc_hi << 32) | (a_off + a_tap16[tap]);
+              const uint64_t bd = ((uint64_t)desc_hi << 32) | (b_off + b_tap16[tap]);
+              if (tap == 0) umma_bf16(d, ad, bd, idesc, (uint32_t)((chunk | ks) != 0));
+              else umma_bf16_acc(d, ad, bd, idesc);
             }
+            a_off += 2 * a_plane16;                              // next 16 channels: two planes on
+            b_off += 2 * b_plane16;
           }
           umma_commit(empty + s);                                // stage reusable once these MMAs retire
           if (chunk == nchunk - 1) umma_commit(tfull + acc);     // accumulator complete
+          K3_TRACE((int)me * 7, 2 * (int)((tile >> 1) * nchunk + chunk) + 1);
         }
         __syncwarp();
+        if (++s == (uint32_t)nst) { s = 0; sphase ^= 1; }
       }
+      aphase ^= 1;
     }
   } else if (warp < K3_EPI_WARPS) {
     // =========================== epilogue: TMEM -> scale -> NCHW fp32 ===========================
     const float sc = scale ? *scale : 1.0f;
     const int K = g.K, NT = g.NT, m_step = g.m_step, nitems = g.nitems_m;
     const int kbase = nt * NT;
-    uint32_t item = 0;
+    uint32_t item = 0, acc = 0, aphase = 0;
     for (int m = m_first; m < nitems; m += m_step, ++item) {
-      const uint32_t acc = item & 1;
       int img = 0, a = 0, b = 0;
       const bool valid = decode_pos(g, m * 128 + warp * 32 + lane, img, a, b);
       const int obase = (img * K + kbase) * PQ + a * g.Q + b;          // < 2^31 (checked on the host)
-      mbar_wait(tfull + acc, (item >> 1) & 1);
+      mbar_wait(tfull + acc, aphase);
       tc_fence_after();
+      if (warp == 0 && lane == 0) K3_TRACE(1, 2 * (int)item);
       const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * (uint32_t)NT;
       for (int cb = 0; cb < NT / 16; ++cb) {
+#ifdef PO2_K3_NO_EPI
+        break;                                                     // timing experiment only (no output)
+#endif
         uint32_t r[16];
         tmem_ld16(trow + (uint32_t)cb * 16, r);
+#ifdef PO2_K3_NO_STORE
+        if (r[0] == 0x12345678u) out[0] = 1.0f;                    // timing experiment: TMEM load only
+        continue;
+#endif
         if (valid) {
           float* po = out + obase + cb * 16 * PQ;
           const int kleft = K - (kbase + cb * 16);
@@ -323,40 +379,112 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + acc);
+      if (warp == 0 && lane == 0) K3_TRACE(1, 2 * (int)item + 1);
+      acc ^= 1;
+      aphase ^= (acc == 0);
     }
   } else {
     // =========================== producers: fp32 NCHW -> bf16 flat K-major strips ===========================
     // The producer warps form K3_PROD_GROUPS independent groups; group q fills every stage `it` with
     // it % groups == q on its own, so that many stages are in flight against global-memory latency
     // at once (a thread cannot start its next stage before the loads of the current one return).
-    constexpr int WPG = K3_PROD_WARPS / K3_PROD_GROUPS;   // warps per group
-    constexpr int NPG = 32 * WPG;                         // threads per group
-    const int pw = warp - (K3_EPI_WARPS + 1);
+    const int ngroups = g.prod_groups;                    // 1, 2 or 4 (few tiles per CTA -> fewer, wider groups)
+    const int WPG = K3_PROD_WARPS / ngroups;              // warps per group
+    const int NPG = 32 * WPG;                             // threads per group
+    const int pw = warp - (K3_EPI_WARPS + K3_MMA_WARPS);
     const int grp_id = pw / WPG;
-    const int gt = tid - 32 * (K3_EPI_WARPS + 1) - grp_id * NPG;
+    const int gt = tid - 32 * (K3_EPI_WARPS + K3_MMA_WARPS) - grp_id * NPG;
     const int strip = g.strip, C = g.C, H = g.H, W = g.W, stride = g.stride, CC = g.CC, Cpad = g.Cpad;
     const int nphase = g.nphase, nchunk = g.nchunk, nst = g.nst, m_step = g.m_step, nitems = g.nitems_m;
     const int halo = g.halo_before;
     const uint32_t a_stage_bytes = g.a_stage_bytes;
-    uint32_t it = 0;
+    uint32_t it = 0, s = 0, sphase = 0;
+    int turn = 0;                                         // which group owns stage `it`
     for (int m = m_first; m < nitems; m += m_step) {
       const int Ls = m * 128 - halo;
       for (int chunk = 0; chunk < nchunk; ++chunk, ++it) {
-        if ((int)(it % K3_PROD_GROUPS) != grp_id) continue;
-        const uint32_t s = it % (uint32_t)nst;
-        mbar_wait(empty + s, ((it / (uint32_t)nst) & 1) ^ 1);
-        uint8_t* stage = sA + (size_t)s * a_stage_bytes;
+        const uint32_t s_cur = s, ph_cur = sphase;
+        const bool mine = (turn == grp_id);
+        if (++s == (uint32_t)nst) { s = 0; sphase ^= 1; }
+        if (++turn == ngroups) turn = 0;
+        if (!mine) continue;
+        mbar_wait(empty + s_cur, ph_cur ^ 1);
+        if (gt == 0) K3_TRACE(2 + grp_id, 2 * (int)(it / ngroups));
+        uint8_t* stage = sA + (size_t)s_cur * a_stage_bytes;
         const int cbase = chunk * CC;
         const int ngrp = min(CC, Cpad - cbase) / 8;
         const int nitem = ngrp * strip;                    // (channel group, position) items per phase
+        if (g.vec4) {
+          // ---- fast path (stride 1, W % 4 == 0): one item = 4 consecutive pixels of one image row x
+          // 8 channels = 8 x LDG.128 -> 4 x STS.128; the shared zero column is one extra item per row
+          const int pitch = g.pitch, W4 = W >> 2, ipr = g.items_per_row;     // W4 (+1 with a pad column)
+          const int rowA = Ls >= 0 ? fdiv(Ls, g.div_pitch) : -((-Ls + pitch - 1) / pitch);
+          const int rowB = fdiv(Ls + strip - 1, g.div_pitch);
+          const int nrow_items = (rowB - rowA + 1) * ipr;
+          const int nall = ngrp * nrow_items;                 // (channel group, row item) pairs of this stage
+          const float inv_items = 1.0f / (float)nrow_items;
+          for (int i0 = gt; i0 < nall; i0 += 2 * NPG) {
+            float4 v[2][8];
+            int lbase[2], npos[2], gsel[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {                // 16 x 128-bit loads in flight per thread
+              const int i = i0 + u * NPG;
+              lbase[u] = 0; npos[u] = 0; gsel[u] = 0;
+              bool ok = false;
+              int idx = 0, cvalid = 0;
+              if (i < nall) {
+                int grp = (int)(((float)i + 0.5f) * inv_items);         // i / nrow_items (exact for these sizes)
+                int j = i - grp * nrow_items;
+                if (j < 0) { --grp; j += nrow_items; } else if (j >= nrow_items) { ++grp; j -= nrow_items; }
+                const int rr = fdiv(j, g.div_ipr);
+                const int q4 = j - rr * ipr;
+                const int row = rowA + rr;
+                const int c0 = cbase + grp * 8;
+                gsel[u] = grp;
+                cvalid = C - c0;
+                lbase[u] = row * pitch + q4 * 4 - Ls;                       // strip index of pixel 0 of the item
+                npos[u] = q4 < W4 ? 4 : pitch - W;                          // the pad item covers only the pad column
+                const int r0 = row - g.top;
+                if (q4 < W4 && r0 >= 0) {
+                  const int img = fdiv(r0, g.div_rows);
+                  const int a = r0 - img * g.rows_img;
+                  if (a < H && img < g.B) { ok = true; idx = ((img * C + c0) * H + a) * W + q4 * 4; }
+                }
+              }
+              const float4* px = reinterpret_cast<const float4*>(x + idx);
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                v[u][c] = (ok && c < cvalid) ? __ldg(px + (size_t)c * (HW >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              uint8_t* sgrp = stage + (size_t)gsel[u] * strip * 16;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int lloc = lbase[u] + e;
+                if (e < npos[u] && lloc >= 0 && lloc < strip) {
+#define PO2_C4(q, e_) ((e_) == 0 ? (q).x : (e_) == 1 ? (q).y : (e_) == 2 ? (q).z : (q).w)
+                  __nv_bfloat162 p0 = __floats2bfloat162_rn(PO2_C4(v[u][0], e), PO2_C4(v[u][1], e));
+                  __nv_bfloat162 p1 = __floats2bfloat162_rn(PO2_C4(v[u][2], e), PO2_C4(v[u][3], e));
+                  __nv_bfloat162 p2 = __floats2bfloat162_rn(PO2_C4(v[u][4], e), PO2_C4(v[u][5], e));
+                  __nv_bfloat162 p3 = __floats2bfloat162_rn(PO2_C4(v[u][6], e), PO2_C4(v[u][7], e));
+#undef PO2_C4
+                  *reinterpret_cast<uint4*>(sgrp + (size_t)lloc * 16) =
+                      make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                                 *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+                }
+              }
+            }
+          }
+        } else
         for (int ph = 0; ph < nphase; ++ph) {
           const int pr = ph >> 1, pc = ph & 1;
-          const int poff = pr * W + pc;
           uint8_t* sph = stage + (size_t)ph * ngrpCC * strip * 16;
-          for (int i0 = gt; i0 < nitem; i0 += 2 * NPG) {
-            float v[2][8];
+          for (int i0 = gt; i0 < nitem; i0 += PU * NPG) {
+            // PU items (PU*8 independent loads) in flight per thread before the first conversion
+            float v[PU][8];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {                  // 16 independent loads in flight per thread
+            for (int u = 0; u < PU; ++u) {
               const int i = i0 + u * NPG;
               int cvalid = 0, idx = 0;
               if (i < nitem) {
@@ -377,7 +505,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
               for (int j = 0; j < 8; ++j) v[u][j] = (j < cvalid) ? __ldg(px + j * HW) : 0.0f;
             }
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < PU; ++u) {
               const int i = i0 + u * NPG;
               if (i < nitem) {
                 __nv_bfloat162 p0 = __floats2bfloat162_rn(v[u][0], v[u][1]), p1 = __floats2bfloat162_rn(v[u][2], v[u][3]);
@@ -391,12 +519,19 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
         }
         fence_proxy_async();                          // generic-proxy smem writes -> tensor-core reads
         __syncwarp();
-        if (lane == 0) mbar_arrive(full + s);
+        if (lane == 0) mbar_arrive(full + s_cur);
+        if (gt == 0) K3_TRACE(2 + grp_id, 2 * (int)(it / ngroups) + 1);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) K3_TRACE(6, 2);
+#ifdef PO2_K3_TRACE
+  __syncthreads();
+  if (g_k3_trace && blockIdx.x < 4)
+    for (int i = tid; i < 8 * 64; i += K3_THREADS) g_k3_trace[blockIdx.x * 8 * 64 + i] = k3_trace_smem[i];
+#endif
   if (warp == K3_EPI_WARPS) tmem_dealloc(tmem_base, ncols);
 }
 
@@ -569,6 +704,11 @@ static bool plan_umma(ConvGeom& g) {
   while (NT > 16 && (size_t)g.ntaps * g.Cpad * NT * 2 > K3_B_BUDGET) NT -= 16;
   if ((size_t)g.ntaps * g.Cpad * NT * 2 > K3_B_BUDGET) return false;
   g.ntiles_n = (Kp + NT - 1) / NT;
+  g.nitems_m = (g.Ltot + 127) / 128;
+  // too few (M item, N tile) pairs to occupy the SMs: split N further (each CTA then moves a smaller
+  // weight slab; the activation strip is produced redundantly by CTAs that would otherwise idle)
+  while (g.nitems_m * g.ntiles_n * 2 <= sm_count() && (Kp / (g.ntiles_n * 2)) >= 16 && Kp % (g.ntiles_n * 2 * 16) == 0)
+    g.ntiles_n *= 2;
   g.NT = ((Kp + g.ntiles_n - 1) / g.ntiles_n + 15) / 16 * 16;
   g.b_slab_bytes = (uint32_t)g.ntaps * g.Cpad * g.NT * 2;
   // channels per A stage: keep a stage <= ~24 KB so that >= 3 stages fit beside the slab
@@ -581,13 +721,17 @@ static bool plan_umma(ConvGeom& g) {
   if (nst > K3_MAX_STAGES) nst = K3_MAX_STAGES;
   if (nst < 2) return false;
   g.nst = nst;
-  g.nitems_m = (g.Ltot + 127) / 128;
   int per_n = sm_count() / g.ntiles_n;
   if (per_n < 1) per_n = 1;
   g.m_step = g.nitems_m < per_n ? g.nitems_m : per_n;
+  const int stages_per_cta = ((g.nitems_m + g.m_step - 1) / g.m_step) * g.nchunk;
+  g.prod_groups = stages_per_cta >= 4 ? 4 : (stages_per_cta >= 2 ? 2 : 1);
   g.div_pitch = make_fastdiv((uint32_t)g.pitch);
   g.div_rows = make_fastdiv((uint32_t)g.rows_img);
   g.div_strip = make_fastdiv((uint32_t)g.strip);
+  g.vec4 = (g.stride == 1 && g.W % 4 == 0) ? 1 : 0;
+  g.items_per_row = g.W / 4 + (g.pitch > g.W ? 1 : 0);
+  g.div_ipr = make_fastdiv((uint32_t)(g.items_per_row > 0 ? g.items_per_row : 1));
   return true;
 }
 
@@ -598,6 +742,13 @@ static size_t umma_pack_bytes(const ConvGeom& g) { return (size_t)g.ntiles_n * g
 using namespace po2;
 
 extern "C" {
+
+#ifdef PO2_K3_TRACE
+int po2_debug_set_trace(void* buf) {
+  long long* p = (long long*)buf;
+  return (int)cudaMemcpyToSymbol(g_k3_trace, &p, sizeof(p));
+}
+#endif
 
 size_t po2_conv2d_workspace(int B, int C, int H, int W, int K, int R, int S, int stride, int pad,
                             int groups, int compute) {
