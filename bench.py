@@ -225,6 +225,7 @@ def _run_ours_on_stream(a, ops, world, rank, local_rank, device):
         barrier()
         ms_e2e = max_over_ranks(f0.elapsed_time(f1))
         roof, extra = (quantizer_roofline(device, a) if rank == 0 else (None, None))
+        conv_roof = conv_forward_roofline(device, B) if rank == 0 else None
     clocks = clk.summary()
     if world > 1:
         torch.distributed.barrier()
@@ -249,7 +250,7 @@ def _run_ours_on_stream(a, ops, world, rank, local_rank, device):
         "gpu_launches": launches_per_step * a.steps,
         "gpu_launches_per_step": launches_per_step,
         "clocks": clocks,
-        "roofline": roof, "roofline_extra": extra,
+        "roofline": roof, "roofline_extra": extra, "roofline_conv_forward": conv_roof,
     }
     if world == 1 and not a.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(B, steps=2)
@@ -300,6 +301,65 @@ def quantizer_roofline(device, a):
         r["frac_both_passes"] = r["both_passes_GBs"] / pk["hbm_gbs"]
         r["frac_absmax_pass"] = r["absmax_GBs"] / pk["hbm_gbs"]
     return roof, res
+
+
+def conv_forward_roofline(device, batch):
+    """Quantized-conv FORWARD of the ResNet-56 layer classes, timed live in CUDA graphs (the pack +
+    conv kernels of one QuantizedConv2d.forward), with a cold L2 (a 320 MB buffer is rewritten before
+    every conv).  These layers have 36-144 flop/B at the fp32 NCHW module boundary, so the binding
+    roof is HBM: algorithmic bytes = 4*(B*C*H*W + B*K*P*Q)."""
+    import torch.nn.functional as F
+    from po2_quantization_b200 import ops
+    pk = peaks()
+    flush = torch.zeros(320 * 1024 * 1024 // 4, dtype=torch.int32, device=device)
+
+    def graph_ms(body, reps=10, iters=5):
+        body()
+        torch.cuda.current_stream().synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=torch.cuda.current_stream()):
+            for _ in range(reps):
+                body()
+        torch.cuda.synchronize()
+        g.replay()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); g.replay(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return sorted(ts)[len(ts) // 2] / reps
+
+    t_flush = graph_ms(lambda: flush.add_(1))
+    layers = [("16->16 3x3 @32x32", 16, 32, 16, 18), ("32->32 3x3 @16x16", 32, 16, 32, 17), ("64->64 3x3 @8x8", 64, 8, 64, 17)]
+    rows, tot_us, tot_cudnn, tot_flop, tot_bytes = [], 0.0, 0.0, 0.0, 0.0
+    for name, C, HW, K, count in layers:
+        x = torch.randn(batch, C, HW, HW, device=device)
+        w = torch.randn(K, C, 3, 3, device=device) * 0.1
+        y, _, scale, _, _ = torch.ops.po2.quantize_full(w, 4, 1, False)
+        out = torch.empty(batch, K, HW, HW, device=device)
+
+        def ours():
+            flush.add_(1)
+            ops.conv2d_out(x, y, scale, out, 1, 1, 1, 0)
+
+        def cudnn():
+            flush.add_(1)
+            F.conv2d(x, y, None, 1, 1)
+        us = (graph_ms(ours) - t_flush) * 1e3
+        us_c = (graph_ms(cudnn) - t_flush) * 1e3
+        flop = 2.0 * batch * K * HW * HW * C * 9
+        byts = 4.0 * (x.numel() + out.numel())
+        rows.append({"layer": name, "count_in_resnet56": count, "us": us, "us_cudnn_tf32": us_c,
+                     "TFLOPs": flop / us / 1e6, "io_GBs": byts / us / 1e3, "frac_hbm": byts / us / 1e3 / pk["hbm_gbs"]})
+        tot_us += us * count; tot_cudnn += us_c * count; tot_flop += flop * count; tot_bytes += byts * count
+    return {"bound": "hbm", "kernel": "po2::conv_umma_kernel<9> (+pack_weights_kernel)", "unit": "GB/s",
+            "achieved": tot_bytes / tot_us / 1e3, "peak": pk["hbm_gbs"], "frac": tot_bytes / tot_us / 1e3 / pk["hbm_gbs"],
+            "traffic": None, "TFLOPs": tot_flop / tot_us / 1e6, "frac_of_bf16_peak": tot_flop / tot_us / 1e6 / pk["bf16_tflops"],
+            "resnet56_3x3_forward_us": tot_us, "resnet56_3x3_forward_us_cudnn_tf32": tot_cudnn,
+            "images_per_s_forward_qconv_only": batch / (tot_us * 1e-6), "layers": rows,
+            "note": "52 stride-1 3x3 quantized convs of ResNet-56 at batch %d, cold L2, CUDA-graph timed" % batch}
 
 
 # ------------------------------------------------------------------------------------------------

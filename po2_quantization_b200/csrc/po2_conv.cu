@@ -141,6 +141,10 @@ struct ConvGeom {
 __global__ void pack_weights_kernel(const float* __restrict__ w, const uint8_t* __restrict__ codes,
                                     const float* __restrict__ scale, __nv_bfloat16* __restrict__ Bp,
                                     ConvGeom g, int bits, int fsr) {
+  // programmatic dependent launch: the conv kernel behind us may start now; its MMA warp executes
+  // griddepcontrol.wait before it touches Bp, everything else (TMEM alloc, barrier init, the
+  // activation producers) overlaps with this kernel
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int taps = g.ntaps, ncg = g.Cpad / 8;
   const int64_t total = (int64_t)g.ntiles_n * taps * ncg * g.NT * 8;
   const float s = scale ? *scale : 1.0f;
@@ -275,6 +279,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
     const bool leader = elect_one();
     const uint32_t me = (uint32_t)(warp - K3_EPI_WARPS);
     if (leader && me == 0) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");       // the weight-pack kernel has completed and flushed
       mbar_expect_tx(bfull, g.b_slab_bytes);
       bulk_g2s(sB, reinterpret_cast<const uint8_t*>(Bp) + (size_t)nt * g.b_slab_bytes, g.b_slab_bytes, bfull);
     }
@@ -398,6 +403,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
     const int nphase = g.nphase, nchunk = g.nchunk, nst = g.nst, m_step = g.m_step, nitems = g.nitems_m;
     const int halo = g.halo_before;
     const uint32_t a_stage_bytes = g.a_stage_bytes;
+    const bool hw1 = (HW == 1) && (C % 4 == 0);
     uint32_t it = 0, s = 0, sphase = 0;
     int turn = 0;                                         // which group owns stage `it`
     for (int m = m_first; m < nitems; m += m_step) {
@@ -420,7 +426,10 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
           const int pitch = g.pitch, W4 = W >> 2, ipr = g.items_per_row;     // W4 (+1 with a pad column)
           const int rowA = Ls >= 0 ? fdiv(Ls, g.div_pitch) : -((-Ls + pitch - 1) / pitch);
           const int rowB = fdiv(Ls + strip - 1, g.div_pitch);
-          const int nrow_items = (rowB - rowA + 1) * ipr;
+          // only the row items that overlap the strip: [jA, jB] in the linearised (row, item) space
+          const int jA = min((Ls - rowA * pitch) >> 2, ipr - 1);
+          const int jB = (rowB - rowA) * ipr + min((Ls + strip - 1 - rowB * pitch) >> 2, ipr - 1);
+          const int nrow_items = jB - jA + 1;
           const int nall = ngrp * nrow_items;                 // (channel group, row item) pairs of this stage
           const float inv_items = 1.0f / (float)nrow_items;
           for (int i0 = gt; i0 < nall; i0 += 2 * NPG) {
@@ -436,6 +445,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
                 int grp = (int)(((float)i + 0.5f) * inv_items);         // i / nrow_items (exact for these sizes)
                 int j = i - grp * nrow_items;
                 if (j < 0) { --grp; j += nrow_items; } else if (j >= nrow_items) { ++grp; j -= nrow_items; }
+                j += jA;
                 const int rr = fdiv(j, g.div_ipr);
                 const int q4 = j - rr * ipr;
                 const int row = rowA + rr;
@@ -501,8 +511,15 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
                 }
               }
               const float* px = x + idx;
+              if (hw1) {                                   // 1x1 feature map: the 8 channels are 32 contiguous bytes
+                const float4 lo = cvalid > 0 ? __ldg(reinterpret_cast<const float4*>(px)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 hi = cvalid > 4 ? __ldg(reinterpret_cast<const float4*>(px) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[u][0] = lo.x; v[u][1] = lo.y; v[u][2] = lo.z; v[u][3] = lo.w;
+                v[u][4] = hi.x; v[u][5] = hi.y; v[u][6] = hi.z; v[u][7] = hi.w;
+              } else {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[u][j] = (j < cvalid) ? __ldg(px + j * HW) : 0.0f;
+                for (int j = 0; j < 8; ++j) v[u][j] = (j < cvalid) ? __ldg(px + j * HW) : 0.0f;
+              }
             }
 #pragma unroll
             for (int u = 0; u < PU; ++u) {
@@ -673,6 +690,11 @@ static size_t umma_smem_bytes(const ConvGeom& g) {
 // returns false if the shape does not fit the kernel's shared-memory plan
 static bool plan_umma(ConvGeom& g) {
   const bool k3 = (g.R == 3);
+  if (!k3 && g.stride == 1) {
+    // a 1x1 stride-1 conv has no spatial structure: view each image as ONE row of H*W pixels, which
+    // makes 2x2 / 4x4 feature maps eligible for the 128-bit producer path (W % 4 == 0)
+    g.W = g.H * g.W; g.H = 1; g.Q = g.P * g.Q; g.P = 1;
+  }
   g.ntaps = g.R * g.S;
   g.pitch = g.Q + (k3 ? 1 : 0);
   g.rows_img = g.P + (k3 ? 1 : 0);
@@ -705,15 +727,15 @@ static bool plan_umma(ConvGeom& g) {
   if ((size_t)g.ntaps * g.Cpad * NT * 2 > K3_B_BUDGET) return false;
   g.ntiles_n = (Kp + NT - 1) / NT;
   g.nitems_m = (g.Ltot + 127) / 128;
-  // too few (M item, N tile) pairs to occupy the SMs: split N further (each CTA then moves a smaller
-  // weight slab; the activation strip is produced redundantly by CTAs that would otherwise idle)
-  while (g.nitems_m * g.ntiles_n * 2 <= sm_count() && (Kp / (g.ntiles_n * 2)) >= 16 && Kp % (g.ntiles_n * 2 * 16) == 0)
-    g.ntiles_n *= 2;
+  // too few (M item, N tile) pairs to occupy the SMs: narrow the N tile (each CTA then moves a
+  // smaller weight slab; the activation strip is produced redundantly by CTAs that would otherwise idle)
+  while (NT > 16 && g.nitems_m * ((Kp + (NT - 16) - 1) / (NT - 16)) <= sm_count()) NT -= 16;
+  g.ntiles_n = (Kp + NT - 1) / NT;
   g.NT = ((Kp + g.ntiles_n - 1) / g.ntiles_n + 15) / 16 * 16;
   g.b_slab_bytes = (uint32_t)g.ntaps * g.Cpad * g.NT * 2;
-  // channels per A stage: keep a stage <= ~24 KB so that >= 3 stages fit beside the slab
+  // channels per A stage: keep a stage <= 32 KB so that >= 3 stages fit beside the slab
   int CC = g.Cpad;
-  while (CC > 16 && (size_t)g.nphase * CC * g.strip * 2 > 24 * 1024) CC -= 16;
+  while (CC > 16 && (size_t)g.nphase * CC * g.strip * 2 > 32 * 1024) CC -= 16;
   g.CC = CC;
   g.nchunk = (g.Cpad + CC - 1) / CC;
   g.a_stage_bytes = (uint32_t)g.nphase * CC * g.strip * 2;
@@ -792,12 +814,22 @@ int po2_conv2d_fwd(const void* x, const void* w, const float* scale, void* out, 
       if (e != cudaSuccess) return (int)e;
       attr_set = true;
     }
-    const int grid = g.ntiles_n * g.m_step;
-    if (g.ntaps == 1)
-      conv_umma_kernel<1><<<grid, K3_THREADS, umma_smem_bytes(g), st>>>((const float*)x, Bp, scale, (float*)out, g);
-    else
-      conv_umma_kernel<9><<<grid, K3_THREADS, umma_smem_bytes(g), st>>>((const float*)x, Bp, scale, (float*)out, g);
-    return (int)cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(g.ntiles_n * g.m_step));
+    cfg.blockDim = dim3(K3_THREADS);
+    cfg.dynamicSmemBytes = umma_smem_bytes(g);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // overlap our prologue with the pack kernel
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const float* xf = (const float*)x;
+    const __nv_bfloat16* bpc = Bp;
+    float* of = (float*)out;
+    if (g.ntaps == 1) e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<1>, xf, bpc, scale, of, g);
+    else e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<9>, xf, bpc, scale, of, g);
+    return (int)e;
   }
   // CUDA-core paths work on fp32 weights
   const float* wf = (const float*)w;

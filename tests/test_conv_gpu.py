@@ -198,3 +198,33 @@ def test_ptq_quantize_model_and_forward_resnet20_top1():
     with torch.no_grad():
         conv.weight.mul_(1.0)
     assert conv._po2_ptq[0] != conv.weight._version
+
+
+def test_ptq_forward_mobilenetv2_matches_oracle():
+    """BASELINE.json configs[2]: MobileNetV2 PO2+ 4-bit (17 depthwise + 33 pointwise quantized convs)."""
+    import po2_quantization_b200 as P
+    from oracle.po2_oracle_torch import PO2_PLUS, QuantizedConv2dOracle, quantize_model_ref
+    from po2_quantization_b200 import ops
+    from workloads import mobilenet_v2_cifar
+    torch.manual_seed(8)
+    ref_model = mobilenet_v2_cifar(10, None, 4, conv_cls=QuantizedConv2dOracle)
+    model = mobilenet_v2_cifar(10, None, 4)
+    model.load_state_dict(ref_model.state_dict(), strict=True)
+    model = model.cuda()
+    mse = P.quantize_model(model, P.PowerOfTwoPlusQuantizer, 4)
+    mse_ref = quantize_model_ref(ref_model, PO2_PLUS, 4)
+    assert abs(mse - mse_ref) <= 1e-5 * mse_ref
+    model.eval(); ref_model.eval()
+    x = torch.randn(32, 3, 32, 32, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        ops.LAUNCHES = 0
+        logits = model(x.cuda()).cpu()
+        assert ops.LAUNCHES >= 50
+        ref = ref_model(x)
+        assert _rel(logits, ref.double()) < TOL_TC
+        ops.set_conv_mode("fp32")
+        try:
+            logits32 = model(x.cuda()).cpu()
+        finally:
+            ops.set_conv_mode("tc")
+        assert _rel(logits32, ref.double()) < 1e-4
