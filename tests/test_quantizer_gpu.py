@@ -271,3 +271,60 @@ def test_stock_torch_cuda_disagreements(P, tmp_path):
     os.makedirs(out, exist_ok=True)
     json.dump(rep, open(os.path.join(out, "stock_cuda_disagreements.json"), "w"), indent=1)
     print(rep)
+
+
+@pytest.mark.parametrize("plus", [False, True])
+@pytest.mark.parametrize("scale", [1.0, 1.337])
+def test_exhaustive_fp32_patterns_vs_stock_cuda(P, plus, scale):
+    """Every fp32 bit pattern with 0 <= |x| <= scale (about 1.07e9 of them, both quantizers, bits 4
+    and 8) against the reference run on this GPU (stock ATen CUDA ops), bitwise, under the
+    torch_cuda boundary table.  The max is planted so that the tensor's scale is exactly `scale`."""
+    from oracle.po2_oracle_torch import quantize_ref
+    Q = P.PowerOfTwoPlusQuantizer if plus else P.PowerOfTwoQuantizer
+    top = int(torch.tensor(scale, dtype=torch.float32).view(torch.int32).item())
+    chunk = 1 << 27
+    P.set_log2_flavor("torch_cuda")
+    try:
+        for start in range(0, top + 1, chunk):
+            n = min(chunk, top + 1 - start)
+            bits_ = torch.arange(start, start + n, device="cuda", dtype=torch.int64).to(torch.int32)
+            x = bits_.view(torch.float32)
+            # alternate signs, plant the maximum at the end
+            x = torch.where((bits_ & 1).bool(), -x, x)
+            x = torch.cat([x, torch.tensor([scale], device="cuda")])
+            for nbits in (4, 8):
+                ours = Q.forward(None, x, bits=nbits)
+                stock = quantize_ref(x, nbits, 1, plus)
+                bad = ours.view(torch.int32) != stock.view(torch.int32)
+                # NaN == NaN (only the all-zero chunk head: 0/scale is fine, so no NaNs expected)
+                bad &= ~(torch.isnan(ours) & torch.isnan(stock))
+                nbad = int(bad.sum().item())
+                assert nbad == 0, (start, nbits, x[bad][:4], ours[bad][:4], stock[bad][:4])
+            del x, bits_
+    finally:
+        P.set_log2_flavor("ieee")
+
+
+def test_ieee_vs_torch_cuda_flavor_difference_is_the_enumerated_boundaries(P):
+    """The two flavors may differ ONLY at the boundaries DESIGN.md enumerates: for po2 (4-bit range)
+    not at all; for po2+ exactly at the three 1-ulp-shifted boundaries k = -6, -5, -4 (the k = -7
+    boundary lies below the 4-bit clamp: both of its sides map to the minimum level)."""
+    top = 0x3F800000
+    chunk = 1 << 27
+    diffs = {False: [], True: []}
+    for plus in (False, True):
+        Q = P.PowerOfTwoPlusQuantizer if plus else P.PowerOfTwoQuantizer
+        for start in range(0, top + 1, chunk):
+            n = min(chunk, top + 1 - start)
+            bits_ = torch.arange(start, start + n, device="cuda", dtype=torch.int64).to(torch.int32)
+            x = torch.cat([bits_.view(torch.float32), torch.ones(1, device="cuda")])
+            P.set_log2_flavor("ieee")
+            a = Q.forward(None, x, bits=4)
+            P.set_log2_flavor("torch_cuda")
+            b = Q.forward(None, x, bits=4)
+            P.set_log2_flavor("ieee")
+            d = (a.view(torch.int32) != b.view(torch.int32)).nonzero().flatten()
+            diffs[plus] += [int(v) for v in x[d].view(torch.int32).cpu()]
+    assert diffs[False] == []
+    # cuda boundaries are 1 ulp below the cpu ones at k=-6..-4: exactly those three patterns flip
+    assert sorted(diffs[True]) == [0x3C3FFFFE, 0x3CC00002, 0x3D3FFFFE], [hex(v) for v in diffs[True]]
