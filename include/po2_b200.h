@@ -107,6 +107,15 @@ int po2_conv2d_fwd(const void* x, const void* w, const float* scale, void* out, 
                    int w_format, int bits, int fsr, int compute, void* workspace,
                    size_t workspace_bytes, void* stream);
 
+/* Data gradient of the same conv (SURVEY.md section 8f "next" #2, first half): gx = dL/dx given g = dL/dout,
+ * for the stride-1 dense shapes (3x3 pad 1, 1x1 pad 0), on the tensor-core kernel with the
+ * channel-transposed, 180-degree-rotated PO2 weights (exact in bf16; g is rounded to bf16).
+ * Returns PO2_E_UNSUPPORTED for other shapes (the caller keeps aten.convolution_backward). */
+size_t po2_conv2d_dgrad_workspace(int B, int C, int H, int W, int K, int R, int S, int pad);
+int po2_conv2d_dgrad(const void* g, const void* w, const float* scale, void* gx, int B, int C, int H,
+                     int W, int K, int R, int S, int stride, int pad, int groups, int w_format,
+                     int bits, int fsr, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

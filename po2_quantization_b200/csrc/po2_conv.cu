@@ -140,7 +140,7 @@ struct ConvGeom {
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_weights_kernel(const float* __restrict__ w, const uint8_t* __restrict__ codes,
                                     const float* __restrict__ scale, __nv_bfloat16* __restrict__ Bp,
-                                    ConvGeom g, int bits, int fsr) {
+                                    ConvGeom g, int bits, int fsr, int transpose) {
   // programmatic dependent launch: the conv kernel behind us may start now; its MMA warp executes
   // griddepcontrol.wait before it touches Bp, everything else (TMEM alloc, barrier init, the
   // activation producers) overlaps with this kernel
@@ -159,7 +159,10 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const uint8_t* 
     const int k = nt * g.NT + n;
     float v = 0.0f;
     if (c < g.C && k < g.K) {
-      const int64_t wi = ((int64_t)k * g.C + c) * taps + tap;
+      // transpose (data-gradient conv): this conv's (k, c, tap) reads W_src[c][k][taps-1-tap], i.e. the
+      // forward weight with in/out channels swapped and the 3x3 window rotated by 180 degrees
+      const int64_t wi = transpose ? ((int64_t)c * g.K + k) * taps + (taps - 1 - tap)
+                                   : ((int64_t)k * g.C + c) * taps + tap;
       if (codes) {
         const uint32_t code = (bits <= 4) ? ((codes[wi >> 1] >> ((wi & 1) * 4)) & 0xFu) : codes[wi];
         const int mag = code & ((1u << (bits - 1)) - 1u);
@@ -759,6 +762,44 @@ static bool plan_umma(ConvGeom& g) {
 
 static size_t umma_pack_bytes(const ConvGeom& g) { return (size_t)g.ntiles_n * g.b_slab_bytes; }
 
+static int launch_umma(const void* x, const void* w, const float* scale, void* out, ConvGeom& g, int w_format,
+                       int bits, int fsr, int transpose, void* pack_buf, cudaStream_t st) {
+  {
+    __nv_bfloat16* Bp = reinterpret_cast<__nv_bfloat16*>(pack_buf);
+    const int64_t total = (int64_t)umma_pack_bytes(g) / 2;
+    const int pblocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+    pack_weights_kernel<<<pblocks, 256, 0, st>>>(
+        w_format == PO2_W_CODES ? nullptr : (const float*)w, w_format == PO2_W_CODES ? (const uint8_t*)w : nullptr,
+        w_format == PO2_W_CODES ? nullptr : scale, Bp, g, bits, fsr, transpose);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    static bool attr_set = false;
+    if (!attr_set) {
+      e = cudaFuncSetAttribute(conv_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_SMEM_BUDGET + 1024);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(conv_umma_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_SMEM_BUDGET + 1024);
+      if (e != cudaSuccess) return (int)e;
+      attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(g.ntiles_n * g.m_step));
+    cfg.blockDim = dim3(K3_THREADS);
+    cfg.dynamicSmemBytes = umma_smem_bytes(g);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // overlap our prologue with the pack kernel
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const float* xf = (const float*)x;
+    const __nv_bfloat16* bpc = Bp;
+    float* of = (float*)out;
+    if (g.ntaps == 1) e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<1>, xf, bpc, scale, of, g);
+    else e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<9>, xf, bpc, scale, of, g);
+    return (int)e;
+  }
+}
+
 }  // namespace po2
 
 using namespace po2;
@@ -798,38 +839,7 @@ int po2_conv2d_fwd(const void* x, const void* w, const float* scale, void* out, 
 
   if (compute == 0 && umma_eligible(g) && plan_umma(g)) {
     if (!workspace || workspace_bytes < need) return PO2_E_WORKSPACE;
-    __nv_bfloat16* Bp = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(workspace) + wbytes);
-    const int64_t total = (int64_t)umma_pack_bytes(g) / 2;
-    const int pblocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-    pack_weights_kernel<<<pblocks, 256, 0, st>>>(
-        w_format == PO2_W_CODES ? nullptr : (const float*)w, w_format == PO2_W_CODES ? (const uint8_t*)w : nullptr,
-        w_format == PO2_W_CODES ? nullptr : scale, Bp, g, bits, fsr);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return (int)e;
-    static bool attr_set = false;
-    if (!attr_set) {
-      e = cudaFuncSetAttribute(conv_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_SMEM_BUDGET + 1024);
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(conv_umma_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_SMEM_BUDGET + 1024);
-      if (e != cudaSuccess) return (int)e;
-      attr_set = true;
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(g.ntiles_n * g.m_step));
-    cfg.blockDim = dim3(K3_THREADS);
-    cfg.dynamicSmemBytes = umma_smem_bytes(g);
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // overlap our prologue with the pack kernel
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    const float* xf = (const float*)x;
-    const __nv_bfloat16* bpc = Bp;
-    float* of = (float*)out;
-    if (g.ntaps == 1) e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<1>, xf, bpc, scale, of, g);
-    else e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<9>, xf, bpc, scale, of, g);
-    return (int)e;
+    return launch_umma(x, w, scale, out, g, w_format, bits, fsr, 0, reinterpret_cast<char*>(workspace) + wbytes, st);
   }
   // CUDA-core paths work on fp32 weights
   const float* wf = (const float*)w;
@@ -863,6 +873,31 @@ int po2_conv2d_fwd(const void* x, const void* w, const float* scale, void* out, 
   if (bx > cap) bx = cap;
   conv_direct_kernel<<<dim3(bx, kblocks), 128, smem, st>>>((const float*)x, wf, (float*)out, g);
   return (int)cudaGetLastError();
+}
+
+// Data gradient of the quantized conv: gx = conv_transpose(g, W), computed as a forward conv of g with
+// the channel-transposed, 180-degree-rotated weights on the same tensor-core kernel (stride 1 only).
+// g: (B, K, P, Q) fp32, gx: (B, C, H, W) fp32, w: the FORWARD weight (K, C, R, S).
+int po2_conv2d_dgrad(const void* g_out, const void* w, const float* scale, void* gx, int B, int C, int H,
+                     int W, int K, int R, int S, int stride, int pad, int groups, int w_format, int bits,
+                     int fsr, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!g_out || !w || !gx) return PO2_E_NULL;
+  if (stride != 1 || groups != 1) return PO2_E_UNSUPPORTED;
+  if (!((R == 3 && S == 3 && pad == 1) || (R == 1 && S == 1 && pad == 0))) return PO2_E_UNSUPPORTED;
+  if (w_format != PO2_W_F32_PO2 && w_format != PO2_W_CODES) return PO2_E_UNSUPPORTED;
+  ConvGeom g;
+  if (!fill_geom(g, B, K, H, W, C, R, S, 1, pad, 1)) return PO2_E_SHAPE;      // in = K channels, out = C channels
+  if ((int64_t)B * C * H * W >= (1ll << 31) || (int64_t)B * K * H * W >= (1ll << 31)) return PO2_E_SIZE;
+  if (!plan_umma(g)) return PO2_E_UNSUPPORTED;
+  const size_t need = umma_pack_bytes(g) + 256;
+  if (!workspace || workspace_bytes < need) return PO2_E_WORKSPACE;
+  return launch_umma(g_out, w, scale, gx, g, w_format, bits, fsr, 1, workspace, (cudaStream_t)stream);
+}
+
+size_t po2_conv2d_dgrad_workspace(int B, int C, int H, int W, int K, int R, int S, int pad) {
+  ConvGeom g;
+  if (!fill_geom(g, B, K, H, W, C, R, S, 1, pad, 1) || !plan_umma(g)) return 0;
+  return (umma_pack_bytes(g) + 256 + 255) / 256 * 256;
 }
 
 }  // extern "C"

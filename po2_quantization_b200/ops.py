@@ -263,20 +263,65 @@ def _(x, w, scale, stride, pad, groups, compute):
     return x.new_empty(_conv_out_shape(x, w, stride, pad))
 
 
+# "tc": data gradient of stride-1 dense convs on the tensor-core kernel (grad rounded to bf16, weights
+# exact); "aten": everything through aten.convolution_backward (cuDNN)
+_dgrad_mode = os.environ.get("PO2_CONV_DGRAD", "tc")
+
+
+def set_dgrad_mode(mode: str) -> None:
+    global _dgrad_mode
+    if mode not in ("tc", "aten"):
+        raise ValueError("dgrad mode must be 'tc' or 'aten'")
+    _dgrad_mode = mode
+
+
+def conv2d_dgrad_out(g, w, scale, gx, pad) -> bool:
+    """gx = dL/dx of conv2d(x, w) (stride 1, dense) from g = dL/dout.  False if the shape is not taken."""
+    global LAUNCHES
+    lib = _lib.load()
+    B, C, H, W_ = gx.shape
+    K, _, R, S = w.shape
+    need = lib.po2_conv2d_dgrad_workspace(B, C, H, W_, K, R, S, pad)
+    if need == 0:
+        return False
+    ws = torch.empty(int(need), dtype=torch.uint8, device=g.device)
+    rc = lib.po2_conv2d_dgrad(g.data_ptr(), w.data_ptr(), scale.data_ptr() if scale is not None else None,
+                              gx.data_ptr(), B, C, H, W_, K, R, S, 1, pad, 1, _lib.W_F32_PO2, 4, 1,
+                              ws.data_ptr(), ws.numel(), _stream_ptr(g.device))
+    if rc == -10:                      # PO2_E_UNSUPPORTED
+        return False
+    _lib.check(rc, "po2_conv2d_dgrad")
+    LAUNCHES += 2
+    return True
+
+
 def _conv2d_setup(ctx, inputs, output):
     x, w, scale, stride, pad, groups, compute = inputs
-    ctx.save_for_backward(x, w)
-    ctx.cfg = (stride, pad, groups)
+    ctx.save_for_backward(x, w, scale) if scale is not None else ctx.save_for_backward(x, w)
+    ctx.has_scale = scale is not None
+    ctx.cfg = (stride, pad, groups, compute)
 
 
 def _conv2d_bwd(ctx, g):
-    # backward stays on ATen/cuDNN (SURVEY.md section 8f "next" #2): dgrad/wgrad against the dequantized weight
-    x, w = ctx.saved_tensors
-    stride, pad, groups = ctx.cfg
-    gx, gw, _ = torch.ops.aten.convolution_backward(
-        g.contiguous(), x, w, None, [stride, stride], [pad, pad], [1, 1], False, [0, 0], groups,
-        [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
-    return gx, gw, None, None, None, None, None
+    # weight gradient stays on ATen/cuDNN (SURVEY.md section 8f "next" #2); the data gradient of the
+    # stride-1 dense layers runs on the same tcgen05 kernel as the forward, with transposed weights
+    saved = ctx.saved_tensors
+    x, w = saved[0], saved[1]
+    scale = saved[2] if ctx.has_scale else None
+    stride, pad, groups, compute = ctx.cfg
+    need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+    g = g.contiguous()
+    gx = None
+    if (need_x and _dgrad_mode == "tc" and compute == 0 and stride == 1 and groups == 1 and scale is not None
+            and g.dtype == torch.float32):
+        cand = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            if conv2d_dgrad_out(g, w, scale, cand, pad):
+                gx = cand
+    gx2, gw, _ = torch.ops.aten.convolution_backward(
+        g, x, w, None, [stride, stride], [pad, pad], [1, 1], False, [0, 0], groups,
+        [need_x and gx is None, need_w, False])
+    return (gx if gx is not None else gx2), gw, None, None, None, None, None
 
 
 conv2d.register_autograd(_conv2d_bwd, setup_context=_conv2d_setup)
