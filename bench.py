@@ -292,7 +292,10 @@ def quantizer_roofline(device, a):
         del x, y
     r0 = res[0]
     roof = {"bound": "hbm", "kernel": r0["kernel"], "achieved": r0["achieved"], "peak": pk["hbm_gbs"],
-            "unit": "GB/s", "frac": r0["achieved"] / pk["hbm_gbs"], "traffic": None,
+            "unit": "GB/s", "frac": r0["achieved"] / pk["hbm_gbs"],
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size from the committed
+            # `ncu --set full` capture (profiles/r01_ncu_quantize_kernel_f32_2p28.csv): 1.074 GB + 1.028 GB
+            "traffic": 2.102e9 if a.sweep_log2 == 28 else None, "algorithmic_bytes": 8.0 * (1 << a.sweep_log2),
             "peak_source": pk["source"],
             "note": "algorithmic bytes = 8 B/element (4 read + 4 written) x 2^%d fp32 elements per launch; "
                     "inputs (%.1f GB) larger than L2" % (a.sweep_log2, 4 * (1 << a.sweep_log2) / 1e9)}

@@ -400,8 +400,18 @@ __global__ void __launch_bounds__(256) absmax_kernel(const void* __restrict__ x,
 // ------------------------------------------------------------------------------------------------
 // pass 2: quantize / dequantize / code emit
 // ------------------------------------------------------------------------------------------------
+#ifndef PO2_Q_UNROLL
+#define PO2_Q_UNROLL 4
+#endif
+#ifndef PO2_Q_MINBLOCKS
+#define PO2_Q_MINBLOCKS 1
+#endif
+#ifndef PO2_Q_CTAS_PER_SM
+#define PO2_Q_CTAS_PER_SM 16
+#endif
+
 template <int DT, bool CODES, bool SSE>
-__global__ void __launch_bounds__(256) quantize_kernel(const uint4* __restrict__ x,
+__global__ void __launch_bounds__(256, PO2_Q_MINBLOCKS) quantize_kernel(const uint4* __restrict__ x,
                                                        uint4* __restrict__ y, uint8_t* codes,
                                                        unsigned int* zero_count, double* sse,
                                                        const float* __restrict__ scale, int64_t n,
@@ -422,15 +432,17 @@ __global__ void __launch_bounds__(256) quantize_kernel(const uint4* __restrict__
   if (!T.special) {
     // the absmax pass left the END of x in L2 last; walking backwards re-reads it from there
     const int64_t last = n_vec - 1;
-    for (; i + 3 * stride < n_vec; i += 4 * stride) {
-      int64_t i0 = i, i1 = i + stride, i2 = i + 2 * stride, i3 = i + 3 * stride;
-      if (reverse) { i0 = last - i0; i1 = last - i1; i2 = last - i2; i3 = last - i3; }
-      const uint4 a = ldg_stream(x + i0), b = ldg_stream(x + i1);
-      const uint4 c = ldg_stream(x + i2), d = ldg_stream(x + i3);
-      stg_stream(y + i0, QV(a, i0));
-      stg_stream(y + i1, QV(b, i1));
-      stg_stream(y + i2, QV(c, i2));
-      stg_stream(y + i3, QV(d, i3));
+    constexpr int U = PO2_Q_UNROLL;                       // independent 128-bit loads in flight per thread
+    for (; i + (U - 1) * stride < n_vec; i += U * stride) {
+      uint4 v[U];
+      int64_t idx[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        idx[u] = reverse ? last - (i + u * stride) : i + u * stride;
+        v[u] = ldg_stream(x + idx[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) stg_stream(y + idx[u], QV(v[u], idx[u]));
     }
     for (; i < n_vec; i += stride) {
       const int64_t i0 = reverse ? last - i : i;
@@ -701,7 +713,7 @@ static int launch_quantize(const void* x, void* y, void* codes, unsigned int* zc
   const int epv = 16 / elem_bytes(dtype);
   const bool codes_ok = !codes || aligned16(codes);
   if (aligned16(x) && aligned16(y) && codes_ok) {
-    const int blocks = grid_for(n / epv + 1, 256, 4, I->sms * 8);
+    const int blocks = grid_for(n / epv + 1, 256, PO2_Q_UNROLL, I->sms * PO2_Q_CTAS_PER_SM);
     PO2_DISPATCH(dtype, PO2_VARIANT(codes, sse, quantize_kernel<DT, CODES, SSE><<<blocks, 256, 0, st>>>(
         (const uint4*)x, (uint4*)y, (uint8_t*)codes, zc, sse, scale, n, bits, fsr, mode, flavor, reverse)));
   } else {
