@@ -143,7 +143,9 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const uint8_t* 
                                     ConvGeom g, int bits, int fsr, int transpose) {
   // programmatic dependent launch: the conv kernel behind us may start now; its MMA warp executes
   // griddepcontrol.wait before it touches Bp, everything else (TMEM alloc, barrier init, the
-  // activation producers) overlaps with this kernel
+  // activation producers) overlaps with this kernel.  THIS kernel is launched with a normal
+  // (full) dependency on its predecessor, so everything earlier in the stream -- in particular the
+  // kernel that produced the conv's input x -- has completed and is visible before either starts.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int taps = g.ntaps, ncg = g.Cpad / 8;
   const int64_t total = (int64_t)g.ntiles_n * taps * ncg * g.NT * 8;
