@@ -253,3 +253,31 @@ def test_ptq_forward_mobilenetv2_matches_oracle():
         finally:
             ops.set_conv_mode("tc")
         assert _rel(logits32, ref.double()) < 1e-4
+
+
+@pytest.mark.parametrize("img,patch,batch", [((32, 32), (1, 1), 16), ((224, 224), (1, 1), 2), ((64, 64), (2, 2), 4)])
+def test_ptq_forward_mobilevit_8bit_matches_oracle(img, patch, batch):
+    """BASELINE.json configs[3]: MobileViT-xs PO2+ 8-bit PTQ inference (33 quantized convs; 8-bit
+    levels reach 2^-127).  224x224 is built directly with patch_size (1,1) as SURVEY.md section 8d says."""
+    import po2_quantization_b200 as P
+    from oracle.po2_oracle_torch import PO2_PLUS, QuantizedConv2dOracle, quantize_model_ref
+    from po2_quantization_b200 import ops
+    from workloads import mobilevit_xs
+    torch.manual_seed(8)
+    ref_model = mobilevit_xs(img, 1000, patch, None, 8, conv_cls=QuantizedConv2dOracle)
+    model = mobilevit_xs(img, 1000, patch, None, 8)
+    model.load_state_dict(ref_model.state_dict(), strict=True)
+    model = model.cuda()
+    mse = P.quantize_model(model, P.PowerOfTwoPlusQuantizer, 8)
+    mse_ref = quantize_model_ref(ref_model, PO2_PLUS, 8)
+    assert abs(mse - mse_ref) <= 1e-5 * mse_ref
+    for a, b in zip(model.parameters(), ref_model.parameters()):
+        assert torch.equal(a.detach().cpu(), b.detach()), "PTQ weights differ from the oracle's"
+    model.eval(); ref_model.eval()
+    x = torch.randn(batch, 3, *img, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        ops.LAUNCHES = 0
+        logits = model(x.cuda()).cpu()
+        assert ops.LAUNCHES >= 33
+        ref = ref_model(x)
+    assert _rel(logits, ref.double()) < TOL_TC

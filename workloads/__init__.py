@@ -4,3 +4,4 @@ around the hot path, not part of it: BN / ReLU / Linear are stock torch modules,
 names follow the reference's models so its checkpoints load."""
 from .resnet_cifar import resnet_cifar  # noqa: F401
 from .mobilenet_cifar import mobilenet_v2_cifar  # noqa: F401
+from .mobilevit import mobilevit_xs  # noqa: F401
