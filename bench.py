@@ -294,11 +294,13 @@ def quantizer_roofline(device, a):
     roof = {"bound": "hbm", "kernel": r0["kernel"], "achieved": r0["achieved"], "peak": pk["hbm_gbs"],
             "unit": "GB/s", "frac": r0["achieved"] / pk["hbm_gbs"],
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size from the committed
-            # `ncu --set full` capture (profiles/r01_ncu_quantize_kernel_f32_2p28.csv): 1.074 GB + 1.028 GB
-            "traffic": 2.102e9 if a.sweep_log2 == 28 else None, "algorithmic_bytes": 8.0 * (1 << a.sweep_log2),
+            # `ncu --set full` captures (profiles/r01_ncu_quantize_kernel_f32_2p28.csv: 1.074 + 1.028 GB;
+            # profiles/r01_ncu_quantize_kernel_f32_2p30.csv: 4.295 + 4.248 GB)
+            "traffic": {28: 2.102e9, 30: 8.543e9}.get(a.sweep_log2), "algorithmic_bytes": 8.0 * (1 << a.sweep_log2),
             "peak_source": pk["source"],
             "note": "algorithmic bytes = 8 B/element (4 read + 4 written) x 2^%d fp32 elements per launch; "
-                    "inputs (%.1f GB) larger than L2" % (a.sweep_log2, 4 * (1 << a.sweep_log2) / 1e9)}
+                    "inputs (%.1f GB) larger than L2; BASELINE's sweep tops out at 2^32 elements, see "
+                    "profiles/r01_quantizer_sweep_2p30_2p32.json" % (a.sweep_log2, 4 * (1 << a.sweep_log2) / 1e9)}
     for r in res:
         r["frac_quantize_pass"] = r["achieved"] / pk["hbm_gbs"]
         r["frac_both_passes"] = r["both_passes_GBs"] / pk["hbm_gbs"]
@@ -448,7 +450,7 @@ def main():
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sweep-log2", type=int, default=28)
+    ap.add_argument("--sweep-log2", type=int, default=30)
     ap.add_argument("--profile-step", action="store_true", help="run one eager step inside cudaProfilerStart/Stop and exit")
     a = ap.parse_args()
     if a.impl == "reference":
