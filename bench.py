@@ -136,7 +136,7 @@ def _run_ours_on_stream(a, ops, world, rank, local_rank, device):
     loss_buf = torch.zeros((), device=device)
 
     def step():
-        opt.zero_grad(set_to_none=False)
+        opt.zero_grad()  # reference train.py:81 (set_to_none=True: no fill / accumulate kernels)
         loss = crit(model(x_dev), y_dev)
         loss.backward()
         opt.step()
@@ -383,7 +383,7 @@ def cpu_training_step_fn(batch):
     y = torch.randint(0, 10, (batch,), generator=g)
 
     def step():
-        opt.zero_grad(set_to_none=False)
+        opt.zero_grad()  # reference train.py:81 (set_to_none=True: no fill / accumulate kernels)
         loss = crit(model(x), y)
         loss.backward()
         opt.step()

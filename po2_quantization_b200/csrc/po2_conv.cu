@@ -202,7 +202,6 @@ __device__ __forceinline__ void k3_trace(int role, int ev) {
 
 constexpr int K3_EPI_WARPS = 4;
 constexpr int K3_PROD_WARPS = 8;
-constexpr int K3_MAX_PROD_GROUPS = 4;
 constexpr int PU = 4;               // producer items in flight per thread (x8 loads each)
 constexpr int K3_MMA_WARPS = 2;         // two issuing warps alternate tiles so one's barrier/fence latency hides behind the other's MMAs
 constexpr int K3_THREADS = 32 * (K3_EPI_WARPS + K3_MMA_WARPS + K3_PROD_WARPS);
@@ -329,9 +328,6 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
           for (int ks = 0; ks < ksteps; ++ks) {
 #pragma unroll
             for (int tap = 0; tap < NTAPS; ++tap) {
-#ifdef PO2_K3_ONE_TAP
-              if (tap > 0) break;                                // timing experiment only (wrong results)
-#endif
               const uint64_t ad = ((uint64_t)desc_hi << 32) | (a_off + a_tap16[tap]);
               const uint64_t bd = ((uint64_t)desc_hi << 32) | (b_off + b_tap16[tap]);
               if (tap == 0) umma_bf16(d, ad, bd, idesc, (uint32_t)((chunk | ks) != 0));
@@ -364,15 +360,8 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
       if (warp == 0 && lane == 0) K3_TRACE(1, 2 * (int)item);
       const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * (uint32_t)NT;
       for (int cb = 0; cb < NT / 16; ++cb) {
-#ifdef PO2_K3_NO_EPI
-        break;                                                     // timing experiment only (no output)
-#endif
         uint32_t r[16];
         tmem_ld16(trow + (uint32_t)cb * 16, r);
-#ifdef PO2_K3_NO_STORE
-        if (r[0] == 0x12345678u) out[0] = 1.0f;                    // timing experiment: TMEM load only
-        continue;
-#endif
         if (valid) {
           float* po = out + obase + cb * 16 * PQ;
           const int kleft = K - (kbase + cb * 16);
