@@ -129,7 +129,7 @@ struct ConvGeom {
   int nitems_m, m_step;  // 128-position items; items advance by m_step per CTA iteration
   int nst;               // A pipeline stages
   uint32_t a_stage_bytes, b_slab_bytes;
-  FastDiv div_pitch, div_rows, div_strip, div_ipr;
+  FastDiv div_pitch, div_rows, div_strip, div_ipr, div_NT, div_ncg, div_taps;
   int vec4, items_per_row;   // producer fast path: float4 loads along W
   int prod_groups;           // independent producer groups (stages in flight per CTA)
 };
@@ -148,15 +148,15 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const uint8_t* 
   // kernel that produced the conv's input x -- has completed and is visible before either starts.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int taps = g.ntaps, ncg = g.Cpad / 8;
-  const int64_t total = (int64_t)g.ntiles_n * taps * ncg * g.NT * 8;
+  const int total = g.ntiles_n * taps * ncg * g.NT * 8;           // < 2^31 (weights)
   const float s = scale ? *scale : 1.0f;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t t = i;
-    const int j = (int)(t % 8); t /= 8;
-    const int n = (int)(t % g.NT); t /= g.NT;
-    const int cg = (int)(t % ncg); t /= ncg;
-    const int tap = (int)(t % taps); t /= taps;
-    const int nt = (int)t;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    // i = (((nt * taps + tap) * ncg + cg) * NT + n) * 8 + j, decoded with mul-hi divisions
+    const int j = i & 7;
+    int t = i >> 3;
+    int q = fdiv(t, g.div_NT);  const int n = t - q * g.NT;  t = q;
+    q = fdiv(t, g.div_ncg);     const int cg = t - q * ncg;   t = q;
+    q = fdiv(t, g.div_taps);    const int tap = t - q * taps; const int nt = q;
     const int c = cg * 8 + j;
     const int k = nt * g.NT + n;
     float v = 0.0f;
@@ -745,6 +745,9 @@ static bool plan_umma(ConvGeom& g) {
   g.div_pitch = make_fastdiv((uint32_t)g.pitch);
   g.div_rows = make_fastdiv((uint32_t)g.rows_img);
   g.div_strip = make_fastdiv((uint32_t)g.strip);
+  g.div_NT = make_fastdiv((uint32_t)g.NT);
+  g.div_ncg = make_fastdiv((uint32_t)(g.Cpad / 8));
+  g.div_taps = make_fastdiv((uint32_t)g.ntaps);
   g.vec4 = (g.stride == 1 && g.W % 4 == 0) ? 1 : 0;
   g.items_per_row = g.W / 4 + (g.pitch > g.W ? 1 : 0);
   g.div_ipr = make_fastdiv((uint32_t)(g.items_per_row > 0 ? g.items_per_row : 1));

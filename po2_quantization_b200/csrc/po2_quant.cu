@@ -63,8 +63,18 @@ __device__ uint32_t search_threshold(float b, float s, uint32_t s_pat) {
 }
 
 // Builds the level table for scale s in shared memory.  All threads of the CTA must call it.
+// The boundary of level `threadIdx.x` can be fetched before the scale is known (it does not depend on
+// it); kernels whose critical path runs through the scale pass it in to take the table's global load
+// off that path.
+__device__ __forceinline__ uint32_t prefetch_bound(int dt, int bits, int fsr, int mode, int flavor) {
+  const int k = fsr - (1 << (bits - 1)) + (int)threadIdx.x;
+  if ((int)threadIdx.x >= (1 << (bits - 1)) || k < PO2_KMIN || k > PO2_KMAX) return PO2_NEVER;
+  return PO2_BOUNDS[flavor][dt][mode][k - PO2_KMIN];
+}
+
 template <int DT>
-__device__ void build_levels(LevelTab& T, float s, int bits, int fsr, int mode, int flavor) {
+__device__ void build_levels(LevelTab& T, float s, int bits, int fsr, int mode, int flavor,
+                             bool have_pre = false, uint32_t pre_b = PO2_NEVER) {
   const int nlev = 1 << (bits - 1);
   const int qmin = fsr - nlev;
   const int tid = threadIdx.x, nthr = blockDim.x;
@@ -85,7 +95,7 @@ __device__ void build_levels(LevelTab& T, float s, int bits, int fsr, int mode, 
     if (j == 0 || special || k < PO2_KMIN) X = 0;
     else if (k > PO2_KMAX) X = PO2_NEVER;
     else {
-      const uint32_t b = PO2_BOUNDS[flavor][DT][mode][k - PO2_KMIN];
+      const uint32_t b = (have_pre && j == tid) ? pre_b : PO2_BOUNDS[flavor][DT][mode][k - PO2_KMIN];
       X = (b == PO2_NEVER) ? PO2_NEVER : search_threshold<DT>(__uint_as_float(b), s, s_pat);
     }
     T.X[j] = X;
@@ -492,14 +502,16 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_kernel(const uint4* __res
                                                               unsigned int* zero_count, double* sse,
                                                               float* __restrict__ scale_out,
                                                               int64_t n, int bits, int fsr, int mode,
-                                                              int flavor, Workspace* ws) {
+                                                              int flavor, Workspace* ws, int cluster) {
   __shared__ LevelTab T;
   __shared__ uint32_t sm[32];
   __shared__ float smf[32];
+  __shared__ uint32_t cl_max;                            // this CTA's max, read by its cluster peers
   constexpr int EPV = Tr<DT>::EPV;
   const int64_t n_vec = n / EPV;
   const int64_t total = (int64_t)gridDim.x * blockDim.x;
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t pre_b = prefetch_bound(DT, bits, fsr, mode, flavor);   // in flight together with the data
   uint4 v[FUSED_R];
   uint32_t m = 0;
 #pragma unroll
@@ -514,7 +526,22 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_kernel(const uint4* __res
     for (int64_t k = n_vec * EPV + threadIdx.x; k < n; k += blockDim.x)
       m = max(m, load_pat<DT>(x, k) & Tr<DT>::MAG);
   m = block_max_u32(m, sm);
-  if (gridDim.x > 1) {
+  if (gridDim.x > 1 && cluster) {
+    // the whole grid is one thread-block cluster: exchange the per-CTA maxima through distributed
+    // shared memory (two cluster barriers) instead of global atomics and a spin
+    if (threadIdx.x == 0) cl_max = m;
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    uint32_t mm = 0;
+    const uint32_t laddr = (uint32_t)__cvta_generic_to_shared(&cl_max);
+    for (uint32_t r = 0; r < gridDim.x; ++r) {
+      uint32_t raddr, val;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(r));
+      asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(val) : "r"(raddr) : "memory");
+      mm = max(mm, val);
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    m = mm;
+  } else if (gridDim.x > 1) {
     if (threadIdx.x == 0) {
       atomicMax(&ws->absmax, m);
       __threadfence();
@@ -532,7 +559,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_kernel(const uint4* __res
   }
   const float s = Tr<DT>::val(m);
   if (gtid == 0) *scale_out = s;
-  build_levels<DT>(T, s, bits, fsr, mode, flavor);
+  build_levels<DT>(T, s, bits, fsr, mode, flavor, true, pre_b);
   const int nlev_m1 = (1 << (bits - 1)) - 1, sshift = bits - 1;
   const bool codes4 = bits <= 4;
   constexpr bool want_sse = SSE;
@@ -796,19 +823,34 @@ int po2_quantize_fused(const void* x, void* y, void* codes, unsigned int* zero_c
   const int64_t per_block = (int64_t)FUSED_THREADS * FUSED_R;
   const bool vec_ok = aligned16(x) && aligned16(y) && (!codes || aligned16(codes));
   if (vec_ok && max_blocks > 0 && n_vec <= max_blocks * per_block) {
-    // one launch, x read from HBM once.  Spread over as many CTAs as have >= 1 vector per thread
+    // one launch, x read from HBM once.  Up to 8 CTAs form one thread-block cluster (max exchanged
+    // through DSMEM); larger tensors use a cooperative grid with a global-memory barrier.
     int64_t blocks = (n_vec + FUSED_THREADS - 1) / FUSED_THREADS;
     if (blocks < 1) blocks = 1;
-    if (blocks > max_blocks) blocks = max_blocks;
-    if (n_vec <= per_block) blocks = 1;                  // fits one CTA: no grid barrier at all
+    int cluster = 0;
+    if (n_vec <= per_block) blocks = 1;                  // fits one CTA: no exchange at all
+    else if (n_vec <= 8 * per_block) { if (blocks > 8) blocks = 8; cluster = 1; }
+    else if (blocks > max_blocks) blocks = max_blocks;
     Workspace* ws = (Workspace*)workspace;
     const uint4* xv = (const uint4*)x; uint4* yv = (uint4*)y; uint8_t* cp = (uint8_t*)codes;
-    void* args[] = {&xv, &yv, &cp, &zero_count, &sse, &scale_out, &n, &bits, &fsr, &mode, &flavor, &ws};
+    void* args[] = {&xv, &yv, &cp, &zero_count, &sse, &scale_out, &n, &bits, &fsr, &mode, &flavor, &ws, &cluster};
     cudaError_t err;
     if (blocks == 1) {
       PO2_DISPATCH(dtype, PO2_VARIANT(codes, sse, fused_kernel<DT, CODES, SSE><<<1, FUSED_THREADS, 0, st>>>(
-          xv, yv, cp, zero_count, sse, scale_out, n, bits, fsr, mode, flavor, ws)));
+          xv, yv, cp, zero_count, sse, scale_out, n, bits, fsr, mode, flavor, ws, 0)));
       err = cudaGetLastError();
+    } else if (cluster) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)blocks);
+      cfg.blockDim = dim3(FUSED_THREADS);
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)blocks; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      PO2_DISPATCH(dtype, PO2_VARIANT(codes, sse, err = cudaLaunchKernelEx(
+          &cfg, fused_kernel<DT, CODES, SSE>, xv, yv, cp, zero_count, sse, scale_out, n, bits, fsr, mode, flavor, ws, 1)));
     } else {
       PO2_DISPATCH(dtype, PO2_VARIANT(codes, sse, err = cudaLaunchCooperativeKernel(
           (const void*)fused_kernel<DT, CODES, SSE>, dim3((unsigned)blocks), dim3(FUSED_THREADS), args, 0, st)));
