@@ -107,6 +107,16 @@ int po2_conv2d_fwd(const void* x, const void* w, const float* scale, void* out, 
                    int w_format, int bits, int fsr, int compute, void* workspace,
                    size_t workspace_bytes, void* stream);
 
+/* QuantizedConv2d.forward in QAT mode as one call -- models/quantized_conv.py:34-36: quantize the fp32
+ * master weight w (K, C/groups, R, S) with PO2 (mode 0) / PO2+ (mode 1), then convolve.  qw_out receives
+ * the quantized weight (what quantize_fn.apply returns), scale_out its scale.  Where the shape allows,
+ * the quantizer kernel writes the conv's packed tensor-core operand itself (two launches in total).
+ * workspace: po2_conv2d_workspace(...) bytes; quant_workspace: po2_workspace_bytes() zeroed bytes. */
+int po2_qconv2d_fwd(const void* x, const void* w, void* qw_out, float* scale_out, void* out, int B, int C,
+                    int H, int W, int K, int R, int S, int stride, int pad, int groups, int bits, int fsr,
+                    int mode, int flavor, int compute, void* workspace, size_t workspace_bytes,
+                    void* quant_workspace, void* stream);
+
 /* Data gradient of the same conv (SURVEY.md section 8f "next" #2, first half): gx = dL/dx given g = dL/dout,
  * for the stride-1 dense shapes (3x3 pad 1, 1x1 pad 0), on the tensor-core kernel with the
  * channel-transposed, 180-degree-rotated PO2 weights (exact in bf16; g is rounded to bf16).

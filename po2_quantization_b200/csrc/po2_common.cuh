@@ -78,4 +78,41 @@ __device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) {
   return __reduce_max_sync(0xFFFFFFFFu, v);
 }
 
+// ---- n / d for 0 <= n < 2^31 via one mul-hi (d >= 1) -----------------------------------------------
+struct FastDiv {
+  uint32_t mul, shr, d;
+};
+__host__ __device__ __forceinline__ int fdiv(int n, const FastDiv& f) {
+  if (f.d <= 1) return n;
+#ifdef __CUDA_ARCH__
+  return (int)(__umulhi((uint32_t)n, f.mul) >> f.shr);
+#else
+  return (int)(((uint64_t)(uint32_t)n * f.mul) >> 32 >> f.shr);
+#endif
+}
+inline FastDiv make_fastdiv(uint32_t d) {
+  // s = ceil(log2 d), mul = ceil(2^(31+s) / d) in [2^31, 2^32): floor(n/d) == umulhi(n, mul) >> (s-1)
+  // for every 0 <= n < 2^31 (error term e = mul*d - 2^(31+s) < d <= 2^s, so n*e < 2^(31+s)).
+  FastDiv f; f.d = d; f.mul = 0; f.shr = 0;
+  if (d <= 1) return f;
+  uint32_t sh = 0;
+  while ((1u << sh) < d) ++sh;
+  f.mul = (uint32_t)(((1ull << (31 + sh)) + d - 1) / d);
+  f.shr = sh - 1;
+  return f;
+}
+
+// Optional epilogue of the fused quantizer: besides y it emits the conv's tensor-core B operand
+// Bp[nt][tap][c/8][n][8] = bf16(y / scale) = exact +-2^q (layout: csrc/po2_conv.cu).  Only for
+// weights whose C and K need no padding, so that every Bp entry is written.
+struct PackArgs {
+  __nv_bfloat16* Bp;         // nullptr: off
+  int C, K, taps, NT, ncg;   // ncg = C / 8
+  FastDiv div_ct, div_t, div_nt;   // by C*taps, taps, NT
+};
+
+// quantize w (fp32, n = K*C*taps elements) into y + scale AND the packed operand, one launch
+int fused_quantize_pack(const void* w, void* y, float* scale_out, int64_t n, int bits, int fsr, int mode,
+                        int flavor, void* workspace, const PackArgs& pk, cudaStream_t st);
+
 }  // namespace po2

@@ -99,18 +99,6 @@ __device__ __forceinline__ uint32_t make_idesc(uint32_t n) {
 // ------------------------------------------------------------------------------------------------
 // geometry shared by host and device
 // ------------------------------------------------------------------------------------------------
-struct FastDiv {            // n / d for 0 <= n < 2^31 via one mul-hi (d >= 1)
-  uint32_t mul, shr, d;
-};
-__host__ __device__ __forceinline__ int fdiv(int n, const FastDiv& f) {
-  if (f.d <= 1) return n;
-#ifdef __CUDA_ARCH__
-  return (int)(__umulhi((uint32_t)n, f.mul) >> f.shr);
-#else
-  return (int)(((uint64_t)(uint32_t)n * f.mul) >> 32 >> f.shr);
-#endif
-}
-
 struct ConvGeom {
   int B, C, H, W, K, R, S, stride, pad, groups;
   int P, Q;              // output height / width
@@ -648,18 +636,6 @@ static int sm_count() {
   return g_sms > 0 ? g_sms : 148;
 }
 
-static FastDiv make_fastdiv(uint32_t d) {
-  // s = ceil(log2 d), mul = ceil(2^(31+s) / d) in [2^31, 2^32): floor(n/d) == umulhi(n, mul) >> (s-1)
-  // for every 0 <= n < 2^31 (error term e = mul*d - 2^(31+s) < d <= 2^s, so n*e < 2^(31+s)).
-  FastDiv f; f.d = d; f.mul = 0; f.shr = 0;
-  if (d <= 1) return f;
-  uint32_t sh = 0;
-  while ((1u << sh) < d) ++sh;
-  f.mul = (uint32_t)(((1ull << (31 + sh)) + d - 1) / d);
-  f.shr = sh - 1;
-  return f;
-}
-
 static bool fill_geom(ConvGeom& g, int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups) {
   if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0 || R <= 0 || S <= 0 || stride <= 0 || pad < 0 || groups <= 0) return false;
   if (C % groups || K % groups) return false;
@@ -760,13 +736,16 @@ static int launch_umma(const void* x, const void* w, const float* scale, void* o
                        int bits, int fsr, int transpose, void* pack_buf, cudaStream_t st) {
   {
     __nv_bfloat16* Bp = reinterpret_cast<__nv_bfloat16*>(pack_buf);
-    const int64_t total = (int64_t)umma_pack_bytes(g) / 2;
-    const int pblocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-    pack_weights_kernel<<<pblocks, 256, 0, st>>>(
-        w_format == PO2_W_CODES ? nullptr : (const float*)w, w_format == PO2_W_CODES ? (const uint8_t*)w : nullptr,
-        w_format == PO2_W_CODES ? nullptr : scale, Bp, g, bits, fsr, transpose);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return (int)e;
+    cudaError_t e = cudaSuccess;
+    if (transpose >= 0) {                                  // transpose < 0: the operand is already packed
+      const int64_t total = (int64_t)umma_pack_bytes(g) / 2;
+      const int pblocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+      pack_weights_kernel<<<pblocks, 256, 0, st>>>(
+          w_format == PO2_W_CODES ? nullptr : (const float*)w, w_format == PO2_W_CODES ? (const uint8_t*)w : nullptr,
+          w_format == PO2_W_CODES ? nullptr : scale, Bp, g, bits, fsr, transpose);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return (int)e;
+    }
     static bool attr_set = false;
     if (!attr_set) {
       e = cudaFuncSetAttribute(conv_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_SMEM_BUDGET + 1024);
@@ -886,6 +865,42 @@ int po2_conv2d_dgrad(const void* g_out, const void* w, const float* scale, void*
   const size_t need = umma_pack_bytes(g) + 256;
   if (!workspace || workspace_bytes < need) return PO2_E_WORKSPACE;
   return launch_umma(g_out, w, scale, gx, g, w_format, bits, fsr, 1, workspace, (cudaStream_t)stream);
+}
+
+// QuantizedConv2d.forward in QAT mode as ONE call (models/quantized_conv.py:34-36): quantize the fp32
+// master weight (utils/quantizers.py:21-32 / 41-52) and convolve.  When the shape runs on the
+// tensor-core kernel and needs no channel padding, the quantizer kernel itself emits the packed
+// bf16 operand (no separate pack launch) and the conv kernel starts behind it with programmatic
+// dependent launch.  qw_out / scale_out receive the quantized weight and its scale (backward needs them).
+int po2_qconv2d_fwd(const void* x, const void* w_master, void* qw_out, float* scale_out, void* out, int B,
+                    int C, int H, int W, int K, int R, int S, int stride, int pad, int groups, int bits,
+                    int fsr, int mode, int flavor, int compute, void* workspace, size_t workspace_bytes,
+                    void* quant_workspace, void* stream) {
+  if (!x || !w_master || !qw_out || !scale_out || !out) return PO2_E_NULL;
+  if (!quant_workspace) return PO2_E_WORKSPACE;
+  ConvGeom g;
+  if (!fill_geom(g, B, C, H, W, K, R, S, stride, pad, groups)) return PO2_E_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t wn = (int64_t)K * (C / groups) * R * S;
+  if (compute == 0 && umma_eligible(g) && plan_umma(g) && g.Cpad == C && g.ntiles_n * g.NT == K) {
+    const size_t need = po2_conv2d_workspace(B, C, H, W, K, R, S, stride, pad, groups, compute);
+    const size_t wbytes = ((size_t)wn * sizeof(float) + 255) / 256 * 256;
+    if (!workspace || workspace_bytes < need) return PO2_E_WORKSPACE;
+    if ((int64_t)B * C * H * W >= (1ll << 31) || (int64_t)B * K * g.P * g.Q >= (1ll << 31)) return PO2_E_SIZE;
+    PackArgs pk;
+    pk.Bp = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(workspace) + wbytes);
+    pk.C = C; pk.K = K; pk.taps = g.ntaps; pk.NT = g.NT; pk.ncg = C / 8;
+    pk.div_ct = make_fastdiv((uint32_t)(C * g.ntaps));
+    pk.div_t = make_fastdiv((uint32_t)g.ntaps);
+    pk.div_nt = make_fastdiv((uint32_t)g.NT);
+    const int rc = fused_quantize_pack(w_master, qw_out, scale_out, wn, bits, fsr, mode, flavor, quant_workspace, pk, st);
+    if (rc == 0) return launch_umma(x, qw_out, scale_out, out, g, PO2_W_F32_PO2, bits, fsr, -1, pk.Bp, st);
+    if (rc != PO2_E_UNSUPPORTED) return rc;
+  }
+  if (int e = po2_quantize_fused(w_master, qw_out, nullptr, nullptr, nullptr, scale_out, wn, PO2_F32, bits, fsr,
+                                 mode, flavor, quant_workspace, stream)) return e;
+  return po2_conv2d_fwd(x, qw_out, scale_out, out, B, C, H, W, K, R, S, stride, pad, groups, PO2_W_F32_PO2, bits,
+                        fsr, compute, workspace, workspace_bytes, stream);
 }
 
 size_t po2_conv2d_dgrad_workspace(int B, int C, int H, int W, int K, int R, int S, int pad) {

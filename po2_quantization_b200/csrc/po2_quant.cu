@@ -493,6 +493,25 @@ __global__ void __launch_bounds__(256) quantize_scalar_kernel(const void* __rest
 // fused: absmax + quantize with x held in registers across the (grid-wide) max reduction.
 // Launched cooperatively when gridDim.x > 1 (all CTAs co-resident), plainly when it is 1.
 // ------------------------------------------------------------------------------------------------
+// Emit 4 consecutive quantized fp32 weights (element indices e0..e0+3 of a (K, C, R, S) tensor) into
+// the conv's B-operand layout as exact bf16 +-2^q (= y / scale).
+__device__ __forceinline__ void pack_vec(const PackArgs& pk, const uint4& o, int e0, float s) {
+  const uint32_t ob[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int e = e0 + j;
+    const int k = fdiv(e, pk.div_ct);
+    const int rem = e - k * pk.C * pk.taps;
+    const int c = fdiv(rem, pk.div_t);
+    const int tap = rem - c * pk.taps;
+    const int nt = fdiv(k, pk.div_nt);
+    const int n = k - nt * pk.NT;
+    const float yv = __uint_as_float(ob[j]);
+    const float r = (s == 1.0f) ? yv : __fdiv_rn(yv, s);
+    pk.Bp[((((size_t)nt * pk.taps + tap) * pk.ncg + (c >> 3)) * pk.NT + n) * 8 + (c & 7)] = __float2bfloat16_rn(r);
+  }
+}
+
 constexpr int FUSED_THREADS = 512;
 constexpr int FUSED_R = 8;    // 16-byte vectors held per thread
 
@@ -502,7 +521,11 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_kernel(const uint4* __res
                                                               unsigned int* zero_count, double* sse,
                                                               float* __restrict__ scale_out,
                                                               int64_t n, int bits, int fsr, int mode,
-                                                              int flavor, Workspace* ws, int cluster) {
+                                                              int flavor, Workspace* ws, int cluster,
+                                                              PackArgs pk) {
+  // a kernel launched behind us with programmatic stream serialization (the conv that consumes the
+  // packed operand) may start its prologue now; it executes griddepcontrol.wait before reading Bp
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __shared__ LevelTab T;
   __shared__ uint32_t sm[32];
   __shared__ float smf[32];
@@ -568,7 +591,11 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_kernel(const uint4* __res
 #pragma unroll
     for (int r = 0; r < FUSED_R; ++r) {
       const int64_t i = gtid + r * total;
-      if (i < n_vec) stg_stream(y + i, quant_vec_t<DT, CODES, SSE>(v[r], T, nlev_m1, sshift, codes4, codes, i, acc));
+      if (i < n_vec) {
+        const uint4 o = quant_vec_t<DT, CODES, SSE>(v[r], T, nlev_m1, sshift, codes4, codes, i, acc);
+        stg_stream(y + i, o);
+        if (DT == PO2_F32 && pk.Bp) pack_vec(pk, o, (int)i * 4, s);
+      }
     }
     if (blockIdx.x == 0 && threadIdx.x < EPV / 2) {
       const int64_t ip = n_vec * (EPV / 2) + threadIdx.x;
@@ -577,6 +604,9 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_kernel(const uint4* __res
   } else {
     const int64_t n_pair = (n + 1) / 2;
     for (int64_t i = gtid; i < n_pair; i += total) quant_pair<DT>(x, y, codes, i, n, T, bits, acc, false);
+    if (DT == PO2_F32 && pk.Bp)                             // NaN / Inf weights: the operand is NaN, like y
+      for (int64_t i = gtid; i < n_vec; i += total)
+        pack_vec(pk, make_uint4(0x7FC00000u, 0x7FC00000u, 0x7FC00000u, 0x7FC00000u), (int)i * 4, 1.0f);
   }
   flush_acc(acc, zero_count, sse, smf);
 }
@@ -751,6 +781,52 @@ static int launch_quantize(const void* x, void* y, void* codes, unsigned int* zc
   return (int)cudaGetLastError();
 }
 
+// fp32 weights -> y, scale and the conv's packed operand in one launch (see PackArgs)
+int fused_quantize_pack(const void* w, void* y, float* scale_out, int64_t n, int bits, int fsr, int mode,
+                        int flavor, void* workspace, const PackArgs& pk_in, cudaStream_t st) {
+  if (int e = check_common(n, PO2_F32)) return e;
+  if (int e = check_quant(bits, fsr, mode, flavor)) return e;
+  if (!w || !y || !scale_out || !pk_in.Bp) return PO2_E_NULL;
+  if (!workspace) return PO2_E_WORKSPACE;
+  if (n % 4 || !aligned16(w) || !aligned16(y) || n >= (1ll << 31)) return PO2_E_UNSUPPORTED;
+  const DevInfo* I = dev_info();
+  if (!I) return (int)cudaErrorInvalidDevice;
+  const int64_t n_vec = n / 4;
+  const int64_t per_block = (int64_t)FUSED_THREADS * FUSED_R;
+  const int64_t max_blocks = (int64_t)I->sms * I->fused_blocks_per_sm[PO2_F32];
+  if (max_blocks <= 0 || n_vec > max_blocks * per_block) return PO2_E_UNSUPPORTED;
+  int64_t blocks = (n_vec + FUSED_THREADS - 1) / FUSED_THREADS;
+  int cluster = 0;
+  if (n_vec <= per_block) blocks = 1;
+  else if (n_vec <= 8 * per_block) { if (blocks > 8) blocks = 8; cluster = 1; }
+  else if (blocks > max_blocks) blocks = max_blocks;
+  Workspace* ws = (Workspace*)workspace;
+  const uint4* xv = (const uint4*)w; uint4* yv = (uint4*)y; uint8_t* cp = nullptr;
+  unsigned int* zc = nullptr; double* sse = nullptr;
+  PackArgs pk = pk_in;
+  void* args[] = {&xv, &yv, &cp, &zc, &sse, &scale_out, &n, &bits, &fsr, &mode, &flavor, &ws, &cluster, &pk};
+  cudaError_t err;
+  if (blocks == 1) {
+    fused_kernel<PO2_F32, false, false><<<1, FUSED_THREADS, 0, st>>>(xv, yv, cp, zc, sse, scale_out, n, bits, fsr, mode, flavor, ws, 0, pk);
+    err = cudaGetLastError();
+  } else if (cluster) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(FUSED_THREADS);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)blocks; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    err = cudaLaunchKernelEx(&cfg, fused_kernel<PO2_F32, false, false>, xv, yv, cp, zc, sse, scale_out, n, bits, fsr, mode, flavor, ws, 1, pk);
+  } else {
+    err = cudaLaunchCooperativeKernel((const void*)fused_kernel<PO2_F32, false, false>, dim3((unsigned)blocks),
+                                      dim3(FUSED_THREADS), args, 0, st);
+  }
+  return (int)err;
+}
+
 }  // namespace po2
 
 using namespace po2;
@@ -833,11 +909,12 @@ int po2_quantize_fused(const void* x, void* y, void* codes, unsigned int* zero_c
     else if (blocks > max_blocks) blocks = max_blocks;
     Workspace* ws = (Workspace*)workspace;
     const uint4* xv = (const uint4*)x; uint4* yv = (uint4*)y; uint8_t* cp = (uint8_t*)codes;
-    void* args[] = {&xv, &yv, &cp, &zero_count, &sse, &scale_out, &n, &bits, &fsr, &mode, &flavor, &ws, &cluster};
+    PackArgs pk = {};
+    void* args[] = {&xv, &yv, &cp, &zero_count, &sse, &scale_out, &n, &bits, &fsr, &mode, &flavor, &ws, &cluster, &pk};
     cudaError_t err;
     if (blocks == 1) {
       PO2_DISPATCH(dtype, PO2_VARIANT(codes, sse, fused_kernel<DT, CODES, SSE><<<1, FUSED_THREADS, 0, st>>>(
-          xv, yv, cp, zero_count, sse, scale_out, n, bits, fsr, mode, flavor, ws, 0)));
+          xv, yv, cp, zero_count, sse, scale_out, n, bits, fsr, mode, flavor, ws, 0, pk)));
       err = cudaGetLastError();
     } else if (cluster) {
       cudaLaunchConfig_t cfg = {};
@@ -850,7 +927,7 @@ int po2_quantize_fused(const void* x, void* y, void* codes, unsigned int* zero_c
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       PO2_DISPATCH(dtype, PO2_VARIANT(codes, sse, err = cudaLaunchKernelEx(
-          &cfg, fused_kernel<DT, CODES, SSE>, xv, yv, cp, zero_count, sse, scale_out, n, bits, fsr, mode, flavor, ws, 1)));
+          &cfg, fused_kernel<DT, CODES, SSE>, xv, yv, cp, zero_count, sse, scale_out, n, bits, fsr, mode, flavor, ws, 1, pk)));
     } else {
       PO2_DISPATCH(dtype, PO2_VARIANT(codes, sse, err = cudaLaunchCooperativeKernel(
           (const void*)fused_kernel<DT, CODES, SSE>, dim3((unsigned)blocks), dim3(FUSED_THREADS), args, 0, st)));

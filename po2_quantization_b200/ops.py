@@ -352,3 +352,72 @@ def _quantize_scaled_bwd(ctx, gy, gscale):
 
 
 quantize_scaled.register_autograd(_quantize_scaled_bwd)
+
+
+# ------------------------------------------------------------------------------------------------
+# QAT forward as one op: quantize the master weight + convolve (models/quantized_conv.py:34-36)
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("po2::qconv2d", mutates_args=(), device_types="cuda")
+def qconv2d(x: torch.Tensor, weight: torch.Tensor, bits: int, fsr: int, plus: bool, stride: int, pad: int,
+            groups: int, compute: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(out, quantized weight, scale) = conv2d(x, Q(weight)).  The quantizer kernel emits the conv's
+    packed bf16 operand directly where the shape allows, so the forward is two kernel launches."""
+    global LAUNCHES
+    _require_cuda(x, "po2::qconv2d")
+    if x.dtype != torch.float32 or weight.dtype != torch.float32:
+        raise TypeError("po2::qconv2d: fp32 NCHW activations and fp32 weights only")
+    x = x.contiguous()
+    w = weight.contiguous()
+    lib = _lib.load()
+    B, C, H, W_ = x.shape
+    K, _, R, S = w.shape
+    out = torch.empty(_conv_out_shape(x, w, stride, pad), dtype=torch.float32, device=x.device)
+    qw = torch.empty_like(w)
+    scale = torch.empty((), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        need = lib.po2_conv2d_workspace(B, C, H, W_, K, R, S, stride, pad, groups, compute)
+        ws = torch.empty(max(int(need), 16), dtype=torch.uint8, device=x.device)
+        LAUNCHES += 3 if (C % 16 or K % 16 or groups != 1) else 2
+        _lib.check(lib.po2_qconv2d_fwd(x.data_ptr(), w.data_ptr(), qw.data_ptr(), scale.data_ptr(), out.data_ptr(),
+                                       B, C, H, W_, K, R, S, stride, pad, groups, bits, fsr, int(plus), _flavor,
+                                       compute, ws.data_ptr(), ws.numel(), _workspace(x.device).data_ptr(),
+                                       _stream_ptr(x.device)), "po2_qconv2d_fwd")
+    return out, qw, scale
+
+
+@qconv2d.register_fake
+def _(x, weight, bits, fsr, plus, stride, pad, groups, compute):
+    return (x.new_empty(_conv_out_shape(x, weight, stride, pad)), torch.empty_like(weight, memory_format=torch.contiguous_format),
+            x.new_empty((), dtype=torch.float32))
+
+
+def _qconv2d_setup(ctx, inputs, output):
+    x, weight, bits, fsr, plus, stride, pad, groups, compute = inputs
+    out, qw, scale = output
+    ctx.save_for_backward(x, qw, scale)
+    ctx.cfg = (stride, pad, groups, compute)
+
+
+def _qconv2d_bwd(ctx, g, g_qw, g_scale):
+    x, qw, scale = ctx.saved_tensors
+    stride, pad, groups, compute = ctx.cfg
+    need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+    g = g.contiguous()
+    gx = None
+    if need_x and _dgrad_mode == "tc" and compute == 0 and stride == 1 and groups == 1 and g.dtype == torch.float32:
+        cand = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            if conv2d_dgrad_out(g, qw, scale, cand, pad):
+                gx = cand
+    gx2, gw, _ = torch.ops.aten.convolution_backward(
+        g, x, qw, None, [stride, stride], [pad, pad], [1, 1], False, [0, 0], groups,
+        [need_x and gx is None, need_w, False])
+    if g_qw is not None and gw is not None:
+        gw = gw + g_qw                       # someone also used the returned quantized weight
+    elif g_qw is not None:
+        gw = g_qw
+    # straight-through estimator (utils/quantizers.py:34-36): d/d weight == d/d quantized weight
+    return (gx if gx is not None else gx2), gw, None, None, None, None, None, None, None
+
+
+qconv2d.register_autograd(_qconv2d_bwd, setup_context=_qconv2d_setup)

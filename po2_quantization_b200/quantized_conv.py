@@ -49,9 +49,11 @@ class QuantizedConv2d(nn.Conv2d):
         if self.quantize_fn is not None:
             plus = getattr(self.quantize_fn, "_PLUS", None)
             if plus is not None and self._po2_conv_ok(input):
-                # PO2 / PO2+: quantizer kernel (y, scale) -> tensor-core conv on the exact +-2^q operand
-                qw, scale = ops.quantize_scaled(self.weight, int(self.bits), 1, bool(plus))
-                return self._po2_conv(input, qw, scale)
+                # PO2 / PO2+: one op = quantizer kernel (which also emits the packed +-2^q tensor-core
+                # operand) + conv kernel; the straight-through gradient reaches self.weight
+                out, _qw, _scale = ops.qconv2d(input, self.weight, int(self.bits), 1, bool(plus), self.stride[0],
+                                               self.padding[0], self.groups, 0 if ops.get_conv_mode() == "tc" else 1)
+                return out
             quantized_weight = self.quantize_fn.apply(self.weight, self.bits)
             return self._conv_forward(input, quantized_weight, self.bias)
         tag = getattr(self, "_po2_ptq", None)

@@ -281,3 +281,32 @@ def test_ptq_forward_mobilevit_8bit_matches_oracle(img, patch, batch):
         assert ops.LAUNCHES >= 33
         ref = ref_model(x)
     assert _rel(logits, ref.double()) < TOL_TC
+
+
+@pytest.mark.parametrize("case", [RESNET[0], RESNET[1], RESNET[3], RESNET[6], MOBILENET[1], MOBILENET[3], MOBILENET[9], ODD[5]], ids=lambda c: c[0])
+@pytest.mark.parametrize("plus", [False, True])
+def test_fused_qat_forward_op_equals_quantize_then_conv(case, plus):
+    """po2::qconv2d (quantizer kernel emits the packed operand itself) == quantize, then conv:
+    bitwise the same quantized weight, scale and output, and the same gradients."""
+    name, B, C, H, W, K, k, stride, pad, groups = case
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(min(B, 16), C, H, W, device="cuda", generator=g, requires_grad=True)
+    w = (torch.randn(K, C // groups, k, k, device="cuda", generator=g) * 0.1).requires_grad_(True)
+    out, qw, scale = torch.ops.po2.qconv2d(x, w, 4, 1, plus, stride, pad, groups, 0)
+    y2, s2 = torch.ops.po2.quantize_scaled(w, 4, 1, plus)
+    out2 = torch.ops.po2.conv2d(x, y2, s2, stride, pad, groups, 0)
+    assert torch.equal(qw, y2) and scale.item() == s2.item()
+    assert torch.equal(out, out2), name
+    go = torch.randn_like(out)
+    gx1, gw1 = torch.autograd.grad(out, (x, w), go)
+    gx2, gw2 = torch.autograd.grad(out2, (x, w), go)
+    assert torch.allclose(gx1, gx2, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(gw1, gw2, rtol=1e-3, atol=1e-3)      # cuDNN wgrad accumulates with atomics
+
+
+def test_fused_qat_forward_nan_weight_propagates():
+    x = torch.randn(2, 16, 8, 8, device="cuda")
+    w = torch.randn(16, 16, 3, 3, device="cuda")
+    w[3, 2, 1, 1] = float("nan")
+    out, qw, scale = torch.ops.po2.qconv2d(x, w, 4, 1, False, 1, 1, 1, 0)
+    assert torch.isnan(qw).all() and torch.isnan(out).all()      # the reference: any NaN -> all NaN
