@@ -107,6 +107,17 @@ int po2_conv2d_fwd(const void* x, const void* w, const float* scale, void* out, 
                    int w_format, int bits, int fsr, int compute, void* workspace,
                    size_t workspace_bytes, void* stream);
 
+/* Static weights (post-training-quantized models, test.py:118-130): build the packed bf16 operand of the
+ * tensor-core kernel once (po2_conv2d_pack) and run every forward from it (po2_conv2d_fwd_packed: one
+ * launch).  The packed layout depends on the full conv geometry including the batch size; pack_bytes
+ * returns 0 when the shape is not taken by the tensor-core kernel. */
+size_t po2_conv2d_pack_bytes(int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups);
+int po2_conv2d_pack(const void* w, const float* scale, void* packed, size_t packed_bytes, int B, int C, int H,
+                    int W, int K, int R, int S, int stride, int pad, int groups, int w_format, int bits,
+                    int fsr, void* stream);
+int po2_conv2d_fwd_packed(const void* x, const void* packed, const float* scale, void* out, int B, int C,
+                          int H, int W, int K, int R, int S, int stride, int pad, int groups, void* stream);
+
 /* QuantizedConv2d.forward in QAT mode as one call -- models/quantized_conv.py:34-36: quantize the fp32
  * master weight w (K, C/groups, R, S) with PO2 (mode 0) / PO2+ (mode 1), then convolve.  qw_out receives
  * the quantized weight (what quantize_fn.apply returns), scale_out its scale.  Where the shape allows,

@@ -732,8 +732,13 @@ static bool plan_umma(ConvGeom& g) {
 
 static size_t umma_pack_bytes(const ConvGeom& g) { return (size_t)g.ntiles_n * g.b_slab_bytes; }
 
+// transpose: 0/1 = run pack_weights_kernel first (forward / data-gradient orientation); -1 = pack_buf
+// already holds the operand.  pdl: launch the conv with programmatic stream serialization -- ONLY
+// legal when the kernel directly in front of it in the stream is one of ours that was launched
+// with a full dependency (pack_weights_kernel, fused_kernel): the conv's producers read x without a
+// griddepcontrol.wait, which is safe only if x's producer finished before that kernel started.
 static int launch_umma(const void* x, const void* w, const float* scale, void* out, ConvGeom& g, int w_format,
-                       int bits, int fsr, int transpose, void* pack_buf, cudaStream_t st) {
+                       int bits, int fsr, int transpose, void* pack_buf, cudaStream_t st, bool pdl = true) {
   {
     __nv_bfloat16* Bp = reinterpret_cast<__nv_bfloat16*>(pack_buf);
     cudaError_t e = cudaSuccess;
@@ -763,7 +768,7 @@ static int launch_umma(const void* x, const void* w, const float* scale, void* o
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // overlap our prologue with the pack kernel
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl ? 1 : 0;
     const float* xf = (const float*)x;
     const __nv_bfloat16* bpc = Bp;
     float* of = (float*)out;
@@ -865,6 +870,43 @@ int po2_conv2d_dgrad(const void* g_out, const void* w, const float* scale, void*
   const size_t need = umma_pack_bytes(g) + 256;
   if (!workspace || workspace_bytes < need) return PO2_E_WORKSPACE;
   return launch_umma(g_out, w, scale, gx, g, w_format, bits, fsr, 1, workspace, (cudaStream_t)stream);
+}
+
+// Static weights (PTQ / eval): build the packed tensor-core operand once, reuse it every forward.
+// po2_conv2d_pack_bytes == 0 means the shape does not run on the tensor-core kernel.
+size_t po2_conv2d_pack_bytes(int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups) {
+  ConvGeom g;
+  if (!fill_geom(g, B, C, H, W, K, R, S, stride, pad, groups) || !umma_eligible(g) || !plan_umma(g)) return 0;
+  return (umma_pack_bytes(g) + 255) / 256 * 256;
+}
+
+int po2_conv2d_pack(const void* w, const float* scale, void* packed, size_t packed_bytes, int B, int C, int H,
+                    int W, int K, int R, int S, int stride, int pad, int groups, int w_format, int bits,
+                    int fsr, void* stream) {
+  if (!w || !packed) return PO2_E_NULL;
+  if (w_format != PO2_W_F32_PO2 && w_format != PO2_W_CODES) return PO2_E_UNSUPPORTED;
+  if (w_format == PO2_W_CODES && (!scale || bits < 2 || bits > 8)) return PO2_E_BITS;
+  ConvGeom g;
+  if (!fill_geom(g, B, C, H, W, K, R, S, stride, pad, groups)) return PO2_E_SHAPE;
+  if (!umma_eligible(g) || !plan_umma(g)) return PO2_E_UNSUPPORTED;
+  if (packed_bytes < umma_pack_bytes(g)) return PO2_E_WORKSPACE;
+  const int64_t total = (int64_t)umma_pack_bytes(g) / 2;
+  const int pblocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+  pack_weights_kernel<<<pblocks, 256, 0, (cudaStream_t)stream>>>(
+      w_format == PO2_W_CODES ? nullptr : (const float*)w, w_format == PO2_W_CODES ? (const uint8_t*)w : nullptr,
+      w_format == PO2_W_CODES ? nullptr : scale, reinterpret_cast<__nv_bfloat16*>(packed), g, bits, fsr, 0);
+  return (int)cudaGetLastError();
+}
+
+int po2_conv2d_fwd_packed(const void* x, const void* packed, const float* scale, void* out, int B, int C, int H,
+                          int W, int K, int R, int S, int stride, int pad, int groups, void* stream) {
+  if (!x || !packed || !out) return PO2_E_NULL;
+  ConvGeom g;
+  if (!fill_geom(g, B, C, H, W, K, R, S, stride, pad, groups)) return PO2_E_SHAPE;
+  if (!umma_eligible(g) || !plan_umma(g)) return PO2_E_UNSUPPORTED;
+  if ((int64_t)B * C * H * W >= (1ll << 31) || (int64_t)B * K * g.P * g.Q >= (1ll << 31)) return PO2_E_SIZE;
+  return launch_umma(x, nullptr, scale, out, g, PO2_W_F32_PO2, 4, 1, -1, const_cast<void*>(packed), (cudaStream_t)stream,
+                     /*pdl=*/false);
 }
 
 // QuantizedConv2d.forward in QAT mode as ONE call (models/quantized_conv.py:34-36): quantize the fp32

@@ -421,3 +421,50 @@ def _qconv2d_bwd(ctx, g, g_qw, g_scale):
 
 
 qconv2d.register_autograd(_qconv2d_bwd, setup_context=_qconv2d_setup)
+
+
+# ------------------------------------------------------------------------------------------------
+# static weights: pack once, then one launch per forward
+# ------------------------------------------------------------------------------------------------
+def conv2d_pack(w: torch.Tensor, scale: Optional[torch.Tensor], xshape, stride: int, pad: int, groups: int):
+    """Packed bf16 tensor-core operand for conv2d(x of shape xshape, w), or None if that shape does not
+    run on the tensor-core kernel."""
+    global LAUNCHES
+    lib = _lib.load()
+    B, C, H, W_ = xshape
+    K, _, R, S = w.shape
+    nbytes = lib.po2_conv2d_pack_bytes(B, C, H, W_, K, R, S, stride, pad, groups)
+    if nbytes == 0:
+        return None
+    packed = torch.empty(int(nbytes), dtype=torch.uint8, device=w.device)
+    with torch.cuda.device(w.device):
+        LAUNCHES += 1
+        _lib.check(lib.po2_conv2d_pack(w.data_ptr(), scale.data_ptr() if scale is not None else None, packed.data_ptr(),
+                                       packed.numel(), B, C, H, W_, K, R, S, stride, pad, groups, _lib.W_F32_PO2, 4, 1,
+                                       _stream_ptr(w.device)), "po2_conv2d_pack")
+    return packed
+
+
+@torch.library.custom_op("po2::conv2d_packed", mutates_args=(), device_types="cuda")
+def conv2d_packed(x: torch.Tensor, packed: torch.Tensor, scale: Optional[torch.Tensor], K: int, R: int, S: int,
+                  stride: int, pad: int, groups: int) -> torch.Tensor:
+    """conv2d from a pre-packed weight operand (inference with static weights): one kernel launch."""
+    global LAUNCHES
+    _require_cuda(x, "po2::conv2d_packed")
+    x = x.contiguous()
+    B, C, H, W_ = x.shape
+    out = torch.empty((B, K, (H + 2 * pad - R) // stride + 1, (W_ + 2 * pad - S) // stride + 1),
+                      dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        LAUNCHES += 1
+        _lib.check(_lib.load().po2_conv2d_fwd_packed(x.data_ptr(), packed.data_ptr(),
+                                                     scale.data_ptr() if scale is not None else None, out.data_ptr(),
+                                                     B, C, H, W_, K, R, S, stride, pad, groups, _stream_ptr(x.device)),
+                   "po2_conv2d_fwd_packed")
+    return out
+
+
+@conv2d_packed.register_fake
+def _(x, packed, scale, K, R, S, stride, pad, groups):
+    B, C, H, W_ = x.shape
+    return x.new_empty((B, K, (H + 2 * pad - R) // stride + 1, (W_ + 2 * pad - S) // stride + 1))

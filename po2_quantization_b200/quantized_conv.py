@@ -26,7 +26,7 @@ class QuantizedConv2d(nn.Conv2d):
         # (non-persistent) PTQ tag is re-keyed to the copy instead of silently going stale
         new = self.__class__.__new__(self.__class__)
         memo[id(self)] = new
-        new.__dict__ = {k: copy.deepcopy(v, memo) for k, v in self.__dict__.items()}
+        new.__dict__ = {k: copy.deepcopy(v, memo) for k, v in self.__dict__.items() if k != "_po2_pack_cache"}
         tag = self.__dict__.get("_po2_ptq")
         if tag is not None and tag[0] == self.weight._version:
             new.__dict__["_po2_ptq"] = (new.weight._version, new.__dict__["_po2_ptq"][1])
@@ -59,6 +59,19 @@ class QuantizedConv2d(nn.Conv2d):
         tag = getattr(self, "_po2_ptq", None)
         if tag is not None and tag[0] == self.weight._version and self._po2_conv_ok(input):
             # post-training-quantized weights (quantize_model): already on the grid +-scale*2^q
+            if ops.get_conv_mode() == "tc" and not (torch.is_grad_enabled() and (input.requires_grad or self.weight.requires_grad)):
+                # static weights, no autograd: pack the tensor-core operand once per (weight version,
+                # input shape) and run each forward as a single launch
+                key = (tag[0], tuple(input.shape), input.device)
+                cache = self.__dict__.get("_po2_pack_cache")
+                if cache is None or cache[0] != key:
+                    packed = ops.conv2d_pack(self.weight.detach(), tag[1], tuple(input.shape), self.stride[0],
+                                             self.padding[0], self.groups)
+                    cache = (key, packed)
+                    self.__dict__["_po2_pack_cache"] = cache
+                if cache[1] is not None:
+                    K, _, R, S = self.weight.shape
+                    return ops.conv2d_packed(input, cache[1], tag[1], K, R, S, self.stride[0], self.padding[0], self.groups)
             return self._po2_conv(input, self.weight, tag[1])
         return self._conv_forward(input, self.weight, self.bias)
 

@@ -310,3 +310,28 @@ def test_fused_qat_forward_nan_weight_propagates():
     w[3, 2, 1, 1] = float("nan")
     out, qw, scale = torch.ops.po2.qconv2d(x, w, 4, 1, False, 1, 1, 1, 0)
     assert torch.isnan(qw).all() and torch.isnan(out).all()      # the reference: any NaN -> all NaN
+
+
+def test_static_weight_pack_cache_single_launch():
+    """PTQ-tagged module in no-grad mode: the packed operand is built once per (weight version, input
+    shape) and every later forward is one launch with bitwise the same result."""
+    import po2_quantization_b200 as P
+    from po2_quantization_b200 import ops
+    torch.manual_seed(1)
+    seq = torch.nn.Sequential(P.QuantizedConv2d(32, 64, 3, 1, 1), P.QuantizedConv2d(64, 48, 1, 1, 0)).cuda()
+    P.quantize_model(seq, P.PowerOfTwoPlusQuantizer, 4)
+    x = torch.randn(8, 32, 16, 16, device="cuda")
+    ref = seq[1](seq[0](x))                                   # grad mode on: regular path (pack + conv)
+    with torch.no_grad():
+        ops.LAUNCHES = 0
+        a = seq(x)
+        first = ops.LAUNCHES
+        ops.LAUNCHES = 0
+        b = seq(x)
+        assert ops.LAUNCHES == 2 and first == 4               # 2 packs + 2 convs, then 2 convs only
+        assert torch.equal(a, b) and torch.equal(a, ref.detach())
+        c = seq(x[:4])                                        # new input shape -> new plan, re-packed
+        assert torch.equal(c, ref.detach()[:4])
+        seq[0].weight.mul_(2.0)                               # weight changed: tag invalid -> nn.Conv2d path
+        d = seq(x)
+        assert not torch.equal(d, a)
