@@ -233,7 +233,8 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
   uint64_t* tfull = bars + 2 * K3_MAX_STAGES;   // [2]     MMA (commit) -> epilogue
   uint64_t* tempty = tfull + 2;                 // [2]     epilogue -> MMA
   uint64_t* bfull = tempty + 2;                 // weight slab landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
+  uint64_t* tready = bfull + 1;                 // TMEM allocated, address published
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tready + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #ifdef PO2_K3_TRACE
@@ -246,19 +247,30 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
   uint32_t ncols = 32;
   while ((int)ncols < 2 * g.NT) ncols <<= 1;
 
+  // Only the barrier initialisation sits in front of the CTA-wide sync; TMEM allocation is taken
+  // off the producers' critical path: the first issuer warp allocates after the sync and publishes
+  // the address through `tready`, which its consumers (second issuer, epilogue warps) wait on.
+  if (warp == K3_EPI_WARPS + 1 && lane == 0) {
+    for (int i = 0; i < g.nst; ++i) { mbar_init(full + i, K3_PROD_WARPS / g.prod_groups); mbar_init(empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, K3_EPI_WARPS); }
+    mbar_init(bfull, 1);
+    mbar_init(tready, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t tmem_base = 0;
   if (warp == K3_EPI_WARPS) {
     tmem_alloc(tmem_slot, ncols);
-    if (lane == 0) {
-      for (int i = 0; i < g.nst; ++i) { mbar_init(full + i, K3_PROD_WARPS / g.prod_groups); mbar_init(empty + i, 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, K3_EPI_WARPS); }
-      mbar_init(bfull, 1);
-      fence_mbar_init();
-    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tready);
+    tc_fence_after();
+    tmem_base = *tmem_slot;
+  } else if (warp < K3_EPI_WARPS + K3_MMA_WARPS) {
+    mbar_wait(tready, 0);
+    tc_fence_after();
+    tmem_base = *tmem_slot;
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
   if (tid == 0) K3_TRACE(6, 1);
   const int HW = g.H * g.W, PQ = g.P * g.Q;
   const int ngrpCC = g.CC / 8;
@@ -535,20 +547,75 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4: depthwise 3x3 (groups == C == K), any stride/pad; one thread per output element
+// K4: depthwise 3x3 (groups == C == K), stride 1 or 2, pad 1: CUDA cores, HBM/L2-bound.
+// One thread = 4 consecutive outputs of one row (128-bit store); per input row it issues one or two
+// 128-bit loads plus the halo scalars instead of 3 (or 9) scalar loads per output.  32-bit index
+// arithmetic with mul-hi divisions.  Other depthwise shapes take the scalar kernel below.
 // ------------------------------------------------------------------------------------------------
+struct DwGeom {
+  int C, H, W, P, Q, Q4, stride;
+  int total;                 // B*C*P*Q4 threads' worth of work
+  FastDiv div_q4, div_p, div_c;
+};
+
+template <int STRIDE>
+__global__ void __launch_bounds__(256) conv_depthwise_vec_kernel(const float* __restrict__ x,
+                                                                 const float* __restrict__ w,
+                                                                 float* __restrict__ out, DwGeom g) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.total; i += gridDim.x * blockDim.x) {
+    int t = fdiv(i, g.div_q4);
+    const int q0 = (i - t * g.Q4) * 4;
+    int u = fdiv(t, g.div_p);
+    const int p = t - u * g.P;
+    const int plane = u;                                   // n * C + c
+    const int c = plane - fdiv(plane, g.div_c) * g.C;
+    const float* px = x + (size_t)plane * g.H * g.W;
+    const float* pw = w + c * 9;
+    float wk[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wk[k] = __ldg(pw + k);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    constexpr int NIN = STRIDE == 1 ? 6 : 9;               // input columns feeding 4 outputs
+    const int iw0 = q0 * STRIDE - 1;                       // leftmost input column (may be -1)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ih = p * STRIDE - 1 + r;
+      if (ih < 0 || ih >= g.H) continue;
+      const float* row = px + ih * g.W;
+      float in[NIN];
+      // columns iw0+1 .. iw0+4 (and +5..+8 for stride 2) are 16-byte aligned groups inside the row
+      const float4 a = __ldg(reinterpret_cast<const float4*>(row + iw0 + 1));
+      in[0] = iw0 >= 0 ? __ldg(row + iw0) : 0.f;
+      in[1] = a.x; in[2] = a.y; in[3] = a.z; in[4] = a.w;
+      if (STRIDE == 1) {
+        in[5] = (iw0 + 5 < g.W) ? __ldg(row + iw0 + 5) : 0.f;
+      } else {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(row + iw0 + 5));
+        in[5] = b.x; in[6] = b.y; in[7] = b.z; in[8] = b.w;
+      }
+#pragma unroll
+      for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int s2 = 0; s2 < 3; ++s2) acc[o] = fmaf(in[o * STRIDE + s2], wk[r * 3 + s2], acc[o]);
+    }
+    *reinterpret_cast<float4*>(out + ((size_t)plane * g.P + p) * g.Q + q0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  }
+}
+
+// any other depthwise shape: one thread per output element
 __global__ void __launch_bounds__(256) conv_depthwise_kernel(const float* __restrict__ x,
                                                              const float* __restrict__ w,
-                                                             float* __restrict__ out, ConvGeom g) {
-  const int64_t total = (int64_t)g.B * g.C * g.P * g.Q;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int q = (int)(i % g.Q);
-    int64_t t = i / g.Q;
-    const int p = (int)(t % g.P); t /= g.P;
-    const int c = (int)(t % g.C);
-    const int n = (int)(t / g.C);
-    const float* px = x + ((int64_t)n * g.C + c) * g.H * g.W;
-    const float* pw = w + (int64_t)c * g.R * g.S;
+                                                             float* __restrict__ out, ConvGeom g,
+                                                             FastDiv div_q, FastDiv div_p, FastDiv div_c) {
+  const int total = g.B * g.C * g.P * g.Q;                 // < 2^31 (checked on the host)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int t = fdiv(i, div_q);
+    const int q = i - t * g.Q;
+    const int plane = fdiv(t, div_p);
+    const int p = t - plane * g.P;
+    const int c = plane - fdiv(plane, div_c) * g.C;
+    const float* px = x + (size_t)plane * g.H * g.W;
+    const float* pw = w + (size_t)c * g.R * g.S;
     float acc = 0.0f;
     for (int r = 0; r < g.R; ++r) {
       const int ih = p * g.stride - g.pad + r;
@@ -654,7 +721,7 @@ static bool umma_eligible(const ConvGeom& g) {
 }
 
 static size_t umma_smem_bytes(const ConvGeom& g) {
-  return (size_t)g.b_slab_bytes + (size_t)g.nst * g.a_stage_bytes + (3 * K3_MAX_STAGES + 8) * 8 + 16;
+  return (size_t)g.b_slab_bytes + (size_t)g.nst * g.a_stage_bytes + (3 * K3_MAX_STAGES + 8) * 8 + 32;
 }
 
 // returns false if the shape does not fit the kernel's shared-memory plan
@@ -831,8 +898,21 @@ int po2_conv2d_fwd(const void* x, const void* w, const float* scale, void* out, 
   }
   if (groups == C && groups == K) {
     const int64_t total = (int64_t)B * C * g.P * g.Q;
+    // vector kernel: 3x3 pad 1, stride 1 or 2, rows and outputs in whole 16-byte groups
+    if (R == 3 && S == 3 && pad == 1 && (stride == 1 || stride == 2) && W % 4 == 0 && g.Q % 4 == 0 &&
+        (stride == 1 || W == 2 * g.Q) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+      DwGeom d;
+      d.C = C; d.H = H; d.W = W; d.P = g.P; d.Q = g.Q; d.Q4 = g.Q / 4; d.stride = stride;
+      d.total = (int)(total / 4);
+      d.div_q4 = make_fastdiv((uint32_t)d.Q4); d.div_p = make_fastdiv((uint32_t)g.P); d.div_c = make_fastdiv((uint32_t)C);
+      const int blocks = (int)((d.total + 255) / 256 < sm_count() * 16 ? (d.total + 255) / 256 : sm_count() * 16);
+      if (stride == 1) conv_depthwise_vec_kernel<1><<<blocks, 256, 0, st>>>((const float*)x, wf, (float*)out, d);
+      else conv_depthwise_vec_kernel<2><<<blocks, 256, 0, st>>>((const float*)x, wf, (float*)out, d);
+      return (int)cudaGetLastError();
+    }
     const int blocks = (int)((total + 255) / 256 < (int64_t)sm_count() * 16 ? (total + 255) / 256 : (int64_t)sm_count() * 16);
-    conv_depthwise_kernel<<<blocks, 256, 0, st>>>((const float*)x, wf, (float*)out, g);
+    conv_depthwise_kernel<<<blocks, 256, 0, st>>>((const float*)x, wf, (float*)out, g, make_fastdiv((uint32_t)g.Q),
+                                                  make_fastdiv((uint32_t)g.P), make_fastdiv((uint32_t)C));
     return (int)cudaGetLastError();
   }
   const int Cg = C / groups, Kg = K / groups;
