@@ -335,3 +335,52 @@ def test_static_weight_pack_cache_single_launch():
         seq[0].weight.mul_(2.0)                               # weight changed: tag invalid -> nn.Conv2d path
         d = seq(x)
         assert not torch.equal(d, a)
+
+
+def test_conv_tensor_core_path_random_shapes():
+    """Shape fuzz of the tcgen05 kernel: channel counts that need padding, K chunks, N tiles, strips
+    spanning several images, widths that do / do not take the 128-bit producer path, both strides."""
+    import random
+    rnd = random.Random(1234)
+    for it in range(60):
+        k = rnd.choice([1, 3])
+        stride = rnd.choice([1, 1, 2])
+        B = rnd.choice([1, 2, 3, 7, 16])
+        C = rnd.choice([3, 8, 16, 24, 40, 72, 100, 144, 200])
+        K = rnd.choice([5, 16, 24, 40, 72, 136, 272, 300])
+        H = rnd.choice([1, 2, 3, 4, 7, 8, 12, 16, 20, 33])
+        W = rnd.choice([1, 2, 4, 5, 8, 12, 16, 28, 36])
+        pad = 1 if k == 3 else 0
+        if (H + 2 * pad - k) // stride + 1 <= 0 or (W + 2 * pad - k) // stride + 1 <= 0:
+            continue
+        g = torch.Generator(device="cuda").manual_seed(it)
+        x = torch.randn(B, C, H, W, device="cuda", generator=g)
+        w = torch.randn(K, C, k, k, device="cuda", generator=g) * 0.1
+        y, codes, scale, _, _ = torch.ops.po2.quantize_full(w, 4, 1, bool(it & 1))
+        out = torch.ops.po2.conv2d(x, y, scale, stride, pad, 1, 0)
+        ref = _ref(x, y, stride, pad, 1)
+        assert out.shape == ref.shape, (it, B, C, H, W, K, k, stride)
+        err = _rel(out, ref)
+        assert err < TOL_TC, (it, B, C, H, W, K, k, stride, err)
+        if stride == 1:                                       # data gradient on the same kernel
+            from po2_quantization_b200 import ops
+            go = torch.randn_like(out)
+            gx = torch.empty_like(x)
+            if ops.conv2d_dgrad_out(go, y, scale, gx, pad):
+                gref = torch.nn.grad.conv2d_input(x.shape, y.double(), go.double(), stride=1, padding=pad)
+                assert _rel(gx, gref) < TOL_TC, (it, "dgrad", B, C, H, W, K, k)
+
+
+def test_depthwise_random_shapes():
+    import random
+    rnd = random.Random(99)
+    for it in range(30):
+        stride = rnd.choice([1, 2])
+        B, C = rnd.choice([1, 3, 8]), rnd.choice([3, 16, 96, 130])
+        H, W = rnd.choice([1, 2, 4, 7, 8, 16, 28]), rnd.choice([1, 2, 4, 6, 8, 16, 28])
+        x = torch.randn(B, C, H, W, device="cuda")
+        w = torch.randn(C, 1, 3, 3, device="cuda") * 0.2
+        y, _, scale, _, _ = torch.ops.po2.quantize_full(w, 4, 1, True)
+        out = torch.ops.po2.conv2d(x, y, scale, stride, 1, C, 0)
+        ref = _ref(x, y, stride, 1, C)
+        assert _rel(out, ref) < TOL_FP32, (it, B, C, H, W, stride)
