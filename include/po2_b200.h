@@ -99,7 +99,9 @@ int po2_ste_backward(const void* g, void* gx, int64_t n, int dtype, int accumula
 
 /* out = conv2d(x, W)  -- models/quantized_conv.py:36,38 (nn.Conv2d._conv_forward, bias=None,
  * dilation=1, zero padding).  x: fp32 NCHW (B,C,H,W); out: fp32 NCHW (B,K,P,Q); W: (K,C/groups,R,S)
- * in `w_format`.  compute = 0: bf16 tensor cores where the shape allows, 1: fp32 CUDA cores. */
+ * in `w_format`.  compute = 0: tensor cores with bf16 operands where the shape allows (weights exact,
+ * activations rounded to bf16), 2: tensor cores with tf32 operands (activations keep 10 mantissa bits --
+ * the precision of the reference's own cuDNN default), 1: fp32 CUDA cores everywhere. */
 size_t po2_conv2d_workspace(int B, int C, int H, int W, int K, int R, int S, int stride, int pad,
                             int groups, int compute);
 int po2_conv2d_fwd(const void* x, const void* w, const float* scale, void* out, int B, int C,
@@ -111,12 +113,14 @@ int po2_conv2d_fwd(const void* x, const void* w, const float* scale, void* out, 
  * tensor-core kernel once (po2_conv2d_pack) and run every forward from it (po2_conv2d_fwd_packed: one
  * launch).  The packed layout depends on the full conv geometry including the batch size; pack_bytes
  * returns 0 when the shape is not taken by the tensor-core kernel. */
-size_t po2_conv2d_pack_bytes(int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups);
+size_t po2_conv2d_pack_bytes(int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups,
+                             int compute);
 int po2_conv2d_pack(const void* w, const float* scale, void* packed, size_t packed_bytes, int B, int C, int H,
                     int W, int K, int R, int S, int stride, int pad, int groups, int w_format, int bits,
-                    int fsr, void* stream);
+                    int fsr, int compute, void* stream);
 int po2_conv2d_fwd_packed(const void* x, const void* packed, const float* scale, void* out, int B, int C,
-                          int H, int W, int K, int R, int S, int stride, int pad, int groups, void* stream);
+                          int H, int W, int K, int R, int S, int stride, int pad, int groups, int compute,
+                          void* stream);
 
 /* QuantizedConv2d.forward in QAT mode as one call -- models/quantized_conv.py:34-36: quantize the fp32
  * master weight w (K, C/groups, R, S) with PO2 (mode 0) / PO2+ (mode 1), then convolve.  qw_out receives
@@ -132,10 +136,10 @@ int po2_qconv2d_fwd(const void* x, const void* w, void* qw_out, float* scale_out
  * for the stride-1 dense shapes (3x3 pad 1, 1x1 pad 0), on the tensor-core kernel with the
  * channel-transposed, 180-degree-rotated PO2 weights (exact in bf16; g is rounded to bf16).
  * Returns PO2_E_UNSUPPORTED for other shapes (the caller keeps aten.convolution_backward). */
-size_t po2_conv2d_dgrad_workspace(int B, int C, int H, int W, int K, int R, int S, int pad);
+size_t po2_conv2d_dgrad_workspace(int B, int C, int H, int W, int K, int R, int S, int pad, int compute);
 int po2_conv2d_dgrad(const void* g, const void* w, const float* scale, void* gx, int B, int C, int H,
                      int W, int K, int R, int S, int stride, int pad, int groups, int w_format,
-                     int bits, int fsr, void* workspace, size_t workspace_bytes, void* stream);
+                     int bits, int fsr, int compute, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

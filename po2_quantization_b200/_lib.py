@@ -32,12 +32,12 @@ SIGNATURES = {
     "po2_ste_backward": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     "po2_conv2d_workspace": (_sz, [_i] * 11),
     "po2_conv2d_fwd": (_i, [_vp, _vp, _vp, _vp] + [_i] * 14 + [_vp, _sz, _vp]),
-    "po2_conv2d_pack_bytes": (_sz, [_i] * 10),
-    "po2_conv2d_pack": (_i, [_vp, _vp, _vp, _sz] + [_i] * 13 + [_vp]),
-    "po2_conv2d_fwd_packed": (_i, [_vp] * 4 + [_i] * 10 + [_vp]),
+    "po2_conv2d_pack_bytes": (_sz, [_i] * 11),
+    "po2_conv2d_pack": (_i, [_vp, _vp, _vp, _sz] + [_i] * 14 + [_vp]),
+    "po2_conv2d_fwd_packed": (_i, [_vp] * 4 + [_i] * 11 + [_vp]),
     "po2_qconv2d_fwd": (_i, [_vp] * 5 + [_i] * 15 + [_vp, _sz, _vp, _vp]),
-    "po2_conv2d_dgrad_workspace": (_sz, [_i] * 8),
-    "po2_conv2d_dgrad": (_i, [_vp, _vp, _vp, _vp] + [_i] * 13 + [_vp, _sz, _vp]),
+    "po2_conv2d_dgrad_workspace": (_sz, [_i] * 9),
+    "po2_conv2d_dgrad": (_i, [_vp, _vp, _vp, _vp] + [_i] * 14 + [_vp, _sz, _vp]),
 }
 
 _lock = threading.Lock()

@@ -103,11 +103,12 @@ inline FastDiv make_fastdiv(uint32_t d) {
 }
 
 // Optional epilogue of the fused quantizer: besides y it emits the conv's tensor-core B operand
-// Bp[nt][tap][c/8][n][8] = bf16(y / scale) = exact +-2^q (layout: csrc/po2_conv.cu).  Only for
+// Bp[nt][tap][c/G][n][G] = y / scale = exact +-2^q as bf16 or tf32 (layout: csrc/po2_conv.cu).  Only for
 // weights whose C and K need no padding, so that every Bp entry is written.
 struct PackArgs {
-  __nv_bfloat16* Bp;         // nullptr: off
-  int C, K, taps, NT, ncg;   // ncg = C / 8
+  void* Bp;                  // nullptr: off
+  int G;                     // 8: bf16 operand, 4: tf32 (fp32) operand -- channels per 16-byte plane entry
+  int C, K, taps, NT, ncg;   // ncg = C / G
   FastDiv div_ct, div_t, div_nt;   // by C*taps, taps, NT
 };
 

@@ -57,20 +57,29 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 x bf16 -> fp32
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+// D[tmem] (+)= A[smem desc] * B[smem desc] -> fp32; operands bf16 (kind::f16, K = 16 per instruction)
+// or fp32 read as tf32 (kind::tf32, K = 8 per instruction)
+template <bool TF32>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (TF32)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void umma_bf16_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.eq.b32 p, 0, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+template <bool TF32>
+__device__ __forceinline__ void umma_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  if (TF32)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -91,9 +100,20 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
-// instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, M=128, N
-__device__ __forceinline__ uint32_t make_idesc(uint32_t n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor: D=f32, A=B=bf16 (format 1) or tf32 (format 2), both K-major, M=128, N
+__device__ __forceinline__ uint32_t make_idesc(uint32_t n, bool tf32) {
+  const uint32_t fmt = tf32 ? 2u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// 16 bytes of one strip position: G channels, as 8 x bf16 or 4 x fp32(tf32)
+template <bool TF32>
+__device__ __forceinline__ uint4 pack_channels(const float* v) {
+  if (TF32) return make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+  return make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                    *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -112,7 +132,8 @@ struct ConvGeom {
   int ntaps;
   int tap_phase[9];      // which phase plane set a tap reads
   int tap_off[9];        // strip index of the tap's row for tile row 0 (>= 0)
-  int Cpad, CC, nchunk;  // channels padded to 16; channels per pipeline stage; stages per item
+  int tf32, G;           // operand kind: bf16 (G = 8 channels per 16-byte plane entry) or tf32 (G = 4)
+  int Cpad, CC, nchunk;  // channels padded to 2G (one MMA k-step); channels per pipeline stage; stages per item
   int NT, ntiles_n;      // out-channel tile (multiple of 16, <= 256) and their count
   int nitems_m, m_step;  // 128-position items; items advance by m_step per CTA iteration
   int nst;               // A pipeline stages
@@ -120,6 +141,7 @@ struct ConvGeom {
   FastDiv div_pitch, div_rows, div_strip, div_ipr, div_NT, div_ncg, div_taps;
   int vec4, items_per_row;   // producer fast path: float4 loads along W
   int prod_groups;           // independent producer groups (stages in flight per CTA)
+  int dual_issue;            // two MMA issuers alternate tiles (only when a tile is one stage)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -127,7 +149,7 @@ struct ConvGeom {
 //   Bp[nt][tap][cg][n][8]   (cg: group of 8 input channels, n: out channel inside the N tile)
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_weights_kernel(const float* __restrict__ w, const uint8_t* __restrict__ codes,
-                                    const float* __restrict__ scale, __nv_bfloat16* __restrict__ Bp,
+                                    const float* __restrict__ scale, void* __restrict__ Bp,
                                     ConvGeom g, int bits, int fsr, int transpose) {
   // programmatic dependent launch: the conv kernel behind us may start now; its MMA warp executes
   // griddepcontrol.wait before it touches Bp, everything else (TMEM alloc, barrier init, the
@@ -135,17 +157,18 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const uint8_t* 
   // (full) dependency on its predecessor, so everything earlier in the stream -- in particular the
   // kernel that produced the conv's input x -- has completed and is visible before either starts.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  const int taps = g.ntaps, ncg = g.Cpad / 8;
-  const int total = g.ntiles_n * taps * ncg * g.NT * 8;           // < 2^31 (weights)
+  const int G = g.G, lgG = (G == 8) ? 3 : 2;
+  const int taps = g.ntaps, ncg = g.Cpad / G;
+  const int total = g.ntiles_n * taps * ncg * g.NT * G;           // < 2^31 (weights)
   const float s = scale ? *scale : 1.0f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    // i = (((nt * taps + tap) * ncg + cg) * NT + n) * 8 + j, decoded with mul-hi divisions
-    const int j = i & 7;
-    int t = i >> 3;
+    // i = (((nt * taps + tap) * ncg + cg) * NT + n) * G + j, decoded with mul-hi divisions
+    const int j = i & (G - 1);
+    int t = i >> lgG;
     int q = fdiv(t, g.div_NT);  const int n = t - q * g.NT;  t = q;
     q = fdiv(t, g.div_ncg);     const int cg = t - q * ncg;   t = q;
     q = fdiv(t, g.div_taps);    const int tap = t - q * taps; const int nt = q;
-    const int c = cg * 8 + j;
+    const int c = cg * G + j;
     const int k = nt * g.NT + n;
     float v = 0.0f;
     if (c < g.C && k < g.K) {
@@ -164,7 +187,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const uint8_t* 
         v = (s == 1.0f) ? w[wi] : __fdiv_rn(w[wi], s);
       }
     }
-    Bp[i] = __float2bfloat16_rn(v);
+    if (g.tf32) reinterpret_cast<float*>(Bp)[i] = v;       // +-2^q is exact in tf32 as well
+    else reinterpret_cast<__nv_bfloat16*>(Bp)[i] = __float2bfloat16_rn(v);
   }
 }
 
@@ -219,9 +243,9 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-template <int NTAPS>
+template <int NTAPS, bool TF32>
 __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* __restrict__ x,
-                                                                  const __nv_bfloat16* __restrict__ Bp,
+                                                                  const uint8_t* __restrict__ Bp,
                                                                   const float* __restrict__ scale,
                                                                   float* __restrict__ out, ConvGeom g) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -234,7 +258,8 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
   uint64_t* tempty = tfull + 2;                 // [2]     epilogue -> MMA
   uint64_t* bfull = tempty + 2;                 // weight slab landed
   uint64_t* tready = bfull + 1;                 // TMEM allocated, address published
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tready + 1);
+  uint64_t* turn = tready + 1;                  // [2]     issuer hand-over (dual-issuer mode)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(turn + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #ifdef PO2_K3_TRACE
@@ -255,6 +280,8 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
     for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, K3_EPI_WARPS); }
     mbar_init(bfull, 1);
     mbar_init(tready, 1);
+    mbar_init(turn, 1);
+    mbar_init(turn + 1, 1);
     fence_mbar_init();
   }
   __syncthreads();
@@ -273,7 +300,9 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
   }
   if (tid == 0) K3_TRACE(6, 1);
   const int HW = g.H * g.W, PQ = g.P * g.Q;
-  const int ngrpCC = g.CC / 8;
+  constexpr int G = TF32 ? 4 : 8;                 // channels per 16-byte plane entry
+  constexpr int KCH = 2 * G;                      // channels per MMA k-step (two planes)
+  const int ngrpCC = g.CC / G;
 
   if (warp >= K3_EPI_WARPS && warp < K3_EPI_WARPS + K3_MMA_WARPS) {
     // =========================== MMA issuers ===========================
@@ -285,17 +314,17 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
     if (leader && me == 0) {
       asm volatile("griddepcontrol.wait;" ::: "memory");       // the weight-pack kernel has completed and flushed
       mbar_expect_tx(bfull, g.b_slab_bytes);
-      bulk_g2s(sB, reinterpret_cast<const uint8_t*>(Bp) + (size_t)nt * g.b_slab_bytes, g.b_slab_bytes, bfull);
+      bulk_g2s(sB, Bp + (size_t)nt * g.b_slab_bytes, g.b_slab_bytes, bfull);
     }
     mbar_wait(bfull, 0);
-    const uint32_t idesc = make_idesc((uint32_t)g.NT);
+    const uint32_t idesc = make_idesc((uint32_t)g.NT, TF32);
     const uint32_t a_plane16 = (uint32_t)g.strip, b_plane16 = (uint32_t)g.NT;     // plane strides in 16-byte units
     // descriptor words: lo = start>>4 | LBO>>4 << 16 ; hi = SBO>>4 (=8) | version 1 << 14
     const uint32_t desc_hi = 8u | (1u << 14);
     const uint32_t a_lo_fixed = a_plane16 << 16, b_lo_fixed = b_plane16 << 16;
     const uint32_t b0_16 = smem_u32(sB) >> 4, a0_16 = smem_u32(sA) >> 4;
     const uint32_t a_stage16 = g.a_stage_bytes >> 4;
-    const int ncg = g.Cpad / 8, nchunk = g.nchunk, nst = g.nst, CC = g.CC, Cpad = g.Cpad, NT = g.NT;
+    const int ncg = g.Cpad / G, nchunk = g.nchunk, nst = g.nst, CC = g.CC, Cpad = g.Cpad, NT = g.NT;
     uint32_t a_tap16[NTAPS], b_tap16[NTAPS];
 #pragma unroll
     for (int tap = 0; tap < NTAPS; ++tap) {
@@ -303,24 +332,31 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
       b_tap16[tap] = (uint32_t)(tap * ncg) * b_plane16;
     }
     const int nitems = g.nitems_m, m_step = g.m_step;
-    uint32_t s = 0, sphase = 0, aphase = 0;                        // A-stage ring position / my accumulator's phase
-    const uint32_t acc = me;
-    const uint32_t d = tmem_base + acc * (uint32_t)NT;
+    // mbarrier phases are one bit: a waiter must never target a phase more than one ahead of the
+    // barrier's current one.  Hence (1) two issuers alternate tiles only when a tile is a single
+    // stage (g.dual_issue), and then hand a token to each other so that the `full` waits of the whole
+    // CTA happen in stage order; (2) otherwise issuer 0 does everything.
+    const bool dual = g.dual_issue != 0;
+    uint32_t s = 0, sphase = 0, tkphase = 0;                       // A-stage ring position, token phase
+    uint32_t aph0 = 0, aph1 = 0;                                   // phase of each accumulator's `tempty`
     uint32_t tile = 0;
-    for (int m = m_first; m < nitems; m += m_step, ++tile) {
-      if ((tile & 1u) != me) {                                   // the other issuer's tile: just advance the ring
-        for (int chunk = 0; chunk < nchunk; ++chunk)
-          if (++s == (uint32_t)nst) { s = 0; sphase ^= 1; }
+    for (int m = m_first; m < nitems && (dual || me == 0); m += m_step, ++tile) {
+      if (dual && (tile & 1u) != me) {                           // the other issuer's tile: just advance the ring
+        if (++s == (uint32_t)nst) { s = 0; sphase ^= 1; }
         continue;
       }
-      mbar_wait(tempty + acc, aphase ^ 1);                       // epilogue has drained this accumulator
+      const uint32_t acc = tile & 1u;
+      const uint32_t d = tmem_base + acc * (uint32_t)NT;
+      if (dual && tile > 0) { mbar_wait(turn + me, tkphase); tkphase ^= 1; }   // stages < mine have been waited for
+      mbar_wait(tempty + acc, (acc ? aph1 : aph0) ^ 1);          // epilogue has drained this accumulator
       for (int chunk = 0; chunk < nchunk; ++chunk) {
         mbar_wait(full + s, sphase);
         tc_fence_after();                                        // orders the MMAs after both waits above
+        if (dual && leader) mbar_arrive(turn + (me ^ 1u));       // hand over: the other issuer may wait for the next stage
         if (leader) K3_TRACE((int)me * 7, 2 * (int)((tile >> 1) * nchunk + chunk));
         const uint32_t a_s16 = a0_16 + s * a_stage16;
         const uint32_t b_c16 = b0_16 + (uint32_t)(chunk * ngrpCC) * b_plane16;
-        const int ksteps = min(CC, Cpad - chunk * CC) / 16;
+        const int ksteps = min(CC, Cpad - chunk * CC) / KCH;
         if (leader) {
           // k-step outer (1-4 iterations), taps inner and fully unrolled: straight-line MMA issue with
           // per-tap descriptor words that only need the stage / k-step offset added
@@ -330,10 +366,10 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
             for (int tap = 0; tap < NTAPS; ++tap) {
               const uint64_t ad = ((uint64_t)desc_hi << 32) | (a_off + a_tap16[tap]);
               const uint64_t bd = ((uint64_t)desc_hi << 32) | (b_off + b_tap16[tap]);
-              if (tap == 0) umma_bf16(d, ad, bd, idesc, (uint32_t)((chunk | ks) != 0));
-              else umma_bf16_acc(d, ad, bd, idesc);
+              if (tap == 0) umma<TF32>(d, ad, bd, idesc, (uint32_t)((chunk | ks) != 0));
+              else umma_acc<TF32>(d, ad, bd, idesc);
             }
-            a_off += 2 * a_plane16;                              // next 16 channels: two planes on
+            a_off += 2 * a_plane16;                              // next k-step: two planes on
             b_off += 2 * b_plane16;
           }
           umma_commit(empty + s);                                // stage reusable once these MMAs retire
@@ -343,11 +379,16 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
         __syncwarp();
         if (++s == (uint32_t)nst) { s = 0; sphase ^= 1; }
       }
-      aphase ^= 1;
+      if (acc) aph1 ^= 1; else aph0 ^= 1;
     }
   } else if (warp < K3_EPI_WARPS) {
     // =========================== epilogue: TMEM -> scale -> NCHW fp32 ===========================
-    const float sc = scale ? *scale : 1.0f;
+    // `scale` may be written by the kernel this one was launched behind with programmatic dependent
+    // launch (the fused quantize+pack kernel of po2_qconv2d_fwd): like the weight slab it must not be
+    // read before that grid has completed.  The wait costs nothing here -- the first accumulator
+    // cannot be ready before the slab, which sits behind the same wait in the issuer.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const float sc = scale ? *reinterpret_cast<const volatile float*>(scale) : 1.0f;
     const int K = g.K, NT = g.NT, m_step = g.m_step, nitems = g.nitems_m;
     const int kbase = nt * NT;
     uint32_t item = 0, acc = 0, aphase = 0;
@@ -412,7 +453,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
         if (gt == 0) K3_TRACE(2 + grp_id, 2 * (int)(it / ngroups));
         uint8_t* stage = sA + (size_t)s_cur * a_stage_bytes;
         const int cbase = chunk * CC;
-        const int ngrp = min(CC, Cpad - cbase) / 8;
+        const int ngrp = min(CC, Cpad - cbase) / G;
         const int nitem = ngrp * strip;                    // (channel group, position) items per phase
         if (g.vec4) {
           // ---- fast path (stride 1, W % 4 == 0): one item = 4 consecutive pixels of one image row x
@@ -427,7 +468,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
           const int nall = ngrp * nrow_items;                 // (channel group, row item) pairs of this stage
           const float inv_items = 1.0f / (float)nrow_items;
           for (int i0 = gt; i0 < nall; i0 += 2 * NPG) {
-            float4 v[2][8];
+            float4 v[2][G];
             int lbase[2], npos[2], gsel[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {                // 16 x 128-bit loads in flight per thread
@@ -443,7 +484,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
                 const int rr = fdiv(j, g.div_ipr);
                 const int q4 = j - rr * ipr;
                 const int row = rowA + rr;
-                const int c0 = cbase + grp * 8;
+                const int c0 = cbase + grp * G;
                 gsel[u] = grp;
                 cvalid = C - c0;
                 lbase[u] = row * pitch + q4 * 4 - Ls;                       // strip index of pixel 0 of the item
@@ -457,7 +498,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
               }
               const float4* px = reinterpret_cast<const float4*>(x + idx);
 #pragma unroll
-              for (int c = 0; c < 8; ++c)
+              for (int c = 0; c < G; ++c)
                 v[u][c] = (ok && c < cvalid) ? __ldg(px + (size_t)c * (HW >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
@@ -468,14 +509,11 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
                 const int lloc = lbase[u] + e;
                 if (e < npos[u] && lloc >= 0 && lloc < strip) {
 #define PO2_C4(q, e_) ((e_) == 0 ? (q).x : (e_) == 1 ? (q).y : (e_) == 2 ? (q).z : (q).w)
-                  __nv_bfloat162 p0 = __floats2bfloat162_rn(PO2_C4(v[u][0], e), PO2_C4(v[u][1], e));
-                  __nv_bfloat162 p1 = __floats2bfloat162_rn(PO2_C4(v[u][2], e), PO2_C4(v[u][3], e));
-                  __nv_bfloat162 p2 = __floats2bfloat162_rn(PO2_C4(v[u][4], e), PO2_C4(v[u][5], e));
-                  __nv_bfloat162 p3 = __floats2bfloat162_rn(PO2_C4(v[u][6], e), PO2_C4(v[u][7], e));
+                  float ch[G];                                    // pixel e of every channel of the item
+#pragma unroll
+                  for (int c = 0; c < G; ++c) ch[c] = PO2_C4(v[u][c], e);
 #undef PO2_C4
-                  *reinterpret_cast<uint4*>(sgrp + (size_t)lloc * 16) =
-                      make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
-                                 *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+                  *reinterpret_cast<uint4*>(sgrp + (size_t)lloc * 16) = pack_channels<TF32>(ch);
                 }
               }
             }
@@ -485,8 +523,8 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
           const int pr = ph >> 1, pc = ph & 1;
           uint8_t* sph = stage + (size_t)ph * ngrpCC * strip * 16;
           for (int i0 = gt; i0 < nitem; i0 += PU * NPG) {
-            // PU items (PU*8 independent loads) in flight per thread before the first conversion
-            float v[PU][8];
+            // PU items (PU*G independent loads) in flight per thread before the first conversion
+            float v[PU][G];
 #pragma unroll
             for (int u = 0; u < PU; ++u) {
               const int i = i0 + u * NPG;
@@ -498,32 +536,30 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
                 if (decode_pos(g, Ls + lloc, img, a, b)) {
                   const int ih = a * stride + pr, iw = b * stride + pc;
                   if (ih < H && iw < W) {
-                    const int c0 = cbase + grp * 8;
+                    const int c0 = cbase + grp * G;
                     cvalid = C - c0;
                     idx = ((img * C + c0) * H + ih) * W + iw;
                   }
                 }
               }
               const float* px = x + idx;
-              if (hw1) {                                   // 1x1 feature map: the 8 channels are 32 contiguous bytes
+              if (hw1) {                                   // 1x1 feature map: the G channels are contiguous bytes
                 const float4 lo = cvalid > 0 ? __ldg(reinterpret_cast<const float4*>(px)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 hi = cvalid > 4 ? __ldg(reinterpret_cast<const float4*>(px) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
                 v[u][0] = lo.x; v[u][1] = lo.y; v[u][2] = lo.z; v[u][3] = lo.w;
-                v[u][4] = hi.x; v[u][5] = hi.y; v[u][6] = hi.z; v[u][7] = hi.w;
+                if (G == 8) {
+                  const float4 hi = cvalid > 4 ? __ldg(reinterpret_cast<const float4*>(px) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  v[u][G - 4] = hi.x; v[u][G - 3] = hi.y; v[u][G - 2] = hi.z; v[u][G - 1] = hi.w;
+                }
               } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[u][j] = (j < cvalid) ? __ldg(px + j * HW) : 0.0f;
+                for (int j = 0; j < G; ++j) v[u][j] = (j < cvalid) ? __ldg(px + j * HW) : 0.0f;
               }
             }
 #pragma unroll
             for (int u = 0; u < PU; ++u) {
               const int i = i0 + u * NPG;
               if (i < nitem) {
-                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[u][0], v[u][1]), p1 = __floats2bfloat162_rn(v[u][2], v[u][3]);
-                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[u][4], v[u][5]), p3 = __floats2bfloat162_rn(v[u][6], v[u][7]);
-                *reinterpret_cast<uint4*>(sph + (size_t)i * 16) =           // i == grp*strip + lloc
-                    make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
-                               *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+                *reinterpret_cast<uint4*>(sph + (size_t)i * 16) = pack_channels<TF32>(v[u]);   // i == grp*strip + lloc
               }
             }
           }
@@ -721,12 +757,15 @@ static bool umma_eligible(const ConvGeom& g) {
 }
 
 static size_t umma_smem_bytes(const ConvGeom& g) {
-  return (size_t)g.b_slab_bytes + (size_t)g.nst * g.a_stage_bytes + (3 * K3_MAX_STAGES + 8) * 8 + 32;
+  return (size_t)g.b_slab_bytes + (size_t)g.nst * g.a_stage_bytes + (3 * K3_MAX_STAGES + 8) * 8 + 64;
 }
 
 // returns false if the shape does not fit the kernel's shared-memory plan
-static bool plan_umma(ConvGeom& g) {
+static bool plan_umma(ConvGeom& g, bool tf32) {
   const bool k3 = (g.R == 3);
+  g.tf32 = tf32 ? 1 : 0;
+  g.G = tf32 ? 4 : 8;
+  const int G = g.G, KCH = 2 * G;                   // channels per plane entry / per MMA k-step
   if (!k3 && g.stride == 1) {
     // a 1x1 stride-1 conv has no spatial structure: view each image as ONE row of H*W pixels, which
     // makes 2x2 / 4x4 feature maps eligible for the 128-bit producer path (W % 4 == 0)
@@ -756,12 +795,13 @@ static bool plan_umma(ConvGeom& g) {
     }
   }
   g.strip = 128 + g.halo_before + halo_after;
-  g.Cpad = (g.C + 15) / 16 * 16;
+  g.Cpad = (g.C + KCH - 1) / KCH * KCH;
   // N tile: the whole-K weight slab of one tile must fit its smem budget
   const int Kp = (g.K + 15) / 16 * 16;
   int NT = Kp < 256 ? Kp : 256;
-  while (NT > 16 && (size_t)g.ntaps * g.Cpad * NT * 2 > K3_B_BUDGET) NT -= 16;
-  if ((size_t)g.ntaps * g.Cpad * NT * 2 > K3_B_BUDGET) return false;
+  const size_t eb = tf32 ? 4 : 2;                   // operand element bytes
+  while (NT > 16 && (size_t)g.ntaps * g.Cpad * NT * eb > K3_B_BUDGET) NT -= 16;
+  if ((size_t)g.ntaps * g.Cpad * NT * eb > K3_B_BUDGET) return false;
   g.ntiles_n = (Kp + NT - 1) / NT;
   g.nitems_m = (g.Ltot + 127) / 128;
   // too few (M item, N tile) pairs to occupy the SMs: narrow the N tile (each CTA then moves a
@@ -769,13 +809,13 @@ static bool plan_umma(ConvGeom& g) {
   while (NT > 16 && g.nitems_m * ((Kp + (NT - 16) - 1) / (NT - 16)) <= sm_count()) NT -= 16;
   g.ntiles_n = (Kp + NT - 1) / NT;
   g.NT = ((Kp + g.ntiles_n - 1) / g.ntiles_n + 15) / 16 * 16;
-  g.b_slab_bytes = (uint32_t)g.ntaps * g.Cpad * g.NT * 2;
+  g.b_slab_bytes = (uint32_t)((size_t)g.ntaps * g.Cpad * g.NT * eb);
   // channels per A stage: keep a stage <= 32 KB so that >= 3 stages fit beside the slab
   int CC = g.Cpad;
-  while (CC > 16 && (size_t)g.nphase * CC * g.strip * 2 > 32 * 1024) CC -= 16;
+  while (CC > KCH && (size_t)g.nphase * CC * g.strip * eb > 32 * 1024) CC -= KCH;
   g.CC = CC;
   g.nchunk = (g.Cpad + CC - 1) / CC;
-  g.a_stage_bytes = (uint32_t)g.nphase * CC * g.strip * 2;
+  g.a_stage_bytes = (uint32_t)((size_t)g.nphase * CC * g.strip * eb);
   int nst = (int)((K3_SMEM_BUDGET - g.b_slab_bytes - 512) / g.a_stage_bytes);
   if (nst > K3_MAX_STAGES) nst = K3_MAX_STAGES;
   if (nst < 2) return false;
@@ -784,12 +824,17 @@ static bool plan_umma(ConvGeom& g) {
   if (per_n < 1) per_n = 1;
   g.m_step = g.nitems_m < per_n ? g.nitems_m : per_n;
   const int stages_per_cta = ((g.nitems_m + g.m_step - 1) / g.m_step) * g.nchunk;
-  g.prod_groups = stages_per_cta >= 4 ? 4 : (stages_per_cta >= 2 ? 2 : 1);
+  g.dual_issue = (g.nchunk == 1) ? 1 : 0;
+  // a producer group skips the other groups' stages, so it can run ahead of the consumer; with one-bit
+  // mbarrier phases it must stay within one wrap of the ring: groups (+ the one-tile reordering two
+  // issuers can introduce) <= stages
+  const int max_groups = g.nst - g.dual_issue;
+  g.prod_groups = (stages_per_cta >= 4 && max_groups >= 4) ? 4 : ((stages_per_cta >= 2 && max_groups >= 2) ? 2 : 1);
   g.div_pitch = make_fastdiv((uint32_t)g.pitch);
   g.div_rows = make_fastdiv((uint32_t)g.rows_img);
   g.div_strip = make_fastdiv((uint32_t)g.strip);
   g.div_NT = make_fastdiv((uint32_t)g.NT);
-  g.div_ncg = make_fastdiv((uint32_t)(g.Cpad / 8));
+  g.div_ncg = make_fastdiv((uint32_t)(g.Cpad / G));
   g.div_taps = make_fastdiv((uint32_t)g.ntaps);
   g.vec4 = (g.stride == 1 && g.W % 4 == 0) ? 1 : 0;
   g.items_per_row = g.W / 4 + (g.pitch > g.W ? 1 : 0);
@@ -807,10 +852,10 @@ static size_t umma_pack_bytes(const ConvGeom& g) { return (size_t)g.ntiles_n * g
 static int launch_umma(const void* x, const void* w, const float* scale, void* out, ConvGeom& g, int w_format,
                        int bits, int fsr, int transpose, void* pack_buf, cudaStream_t st, bool pdl = true) {
   {
-    __nv_bfloat16* Bp = reinterpret_cast<__nv_bfloat16*>(pack_buf);
+    uint8_t* Bp = reinterpret_cast<uint8_t*>(pack_buf);
     cudaError_t e = cudaSuccess;
     if (transpose >= 0) {                                  // transpose < 0: the operand is already packed
-      const int64_t total = (int64_t)umma_pack_bytes(g) / 2;
+      const int64_t total = (int64_t)umma_pack_bytes(g) / (g.tf32 ? 4 : 2);
       const int pblocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
       pack_weights_kernel<<<pblocks, 256, 0, st>>>(
           w_format == PO2_W_CODES ? nullptr : (const float*)w, w_format == PO2_W_CODES ? (const uint8_t*)w : nullptr,
@@ -820,9 +865,11 @@ static int launch_umma(const void* x, const void* w, const float* scale, void* o
     }
     static bool attr_set = false;
     if (!attr_set) {
-      e = cudaFuncSetAttribute(conv_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_SMEM_BUDGET + 1024);
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(conv_umma_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_SMEM_BUDGET + 1024);
+      const int smax = (int)K3_SMEM_BUDGET + 1024;
+      e = cudaFuncSetAttribute(conv_umma_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel<9, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel<9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
       if (e != cudaSuccess) return (int)e;
       attr_set = true;
     }
@@ -837,10 +884,15 @@ static int launch_umma(const void* x, const void* w, const float* scale, void* o
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     const float* xf = (const float*)x;
-    const __nv_bfloat16* bpc = Bp;
+    const uint8_t* bpc = Bp;
     float* of = (float*)out;
-    if (g.ntaps == 1) e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<1>, xf, bpc, scale, of, g);
-    else e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<9>, xf, bpc, scale, of, g);
+    if (g.tf32) {
+      if (g.ntaps == 1) e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, true>, xf, bpc, scale, of, g);
+      else e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<9, true>, xf, bpc, scale, of, g);
+    } else {
+      if (g.ntaps == 1) e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, false>, xf, bpc, scale, of, g);
+      else e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<9, false>, xf, bpc, scale, of, g);
+    }
     return (int)e;
   }
 }
@@ -863,7 +915,7 @@ size_t po2_conv2d_workspace(int B, int C, int H, int W, int K, int R, int S, int
   ConvGeom g;
   if (!fill_geom(g, B, C, H, W, K, R, S, stride, pad, groups)) return 0;
   size_t bytes = (size_t)K * (C / groups) * R * S * sizeof(float);       // decoded fp32 weights (codes input)
-  if (compute == 0 && umma_eligible(g) && plan_umma(g)) bytes += umma_pack_bytes(g) + 256;
+  if (compute != 1 && umma_eligible(g) && plan_umma(g, compute == 2)) bytes += umma_pack_bytes(g) + 256;
   return (bytes + 255) / 256 * 256;
 }
 
@@ -882,7 +934,7 @@ int po2_conv2d_fwd(const void* x, const void* w, const float* scale, void* out, 
   const int64_t wn = (int64_t)K * (C / groups) * R * S;
   const size_t wbytes = ((size_t)wn * sizeof(float) + 255) / 256 * 256;
 
-  if (compute == 0 && umma_eligible(g) && plan_umma(g)) {
+  if (compute != 1 && umma_eligible(g) && plan_umma(g, compute == 2)) {
     if (!workspace || workspace_bytes < need) return PO2_E_WORKSPACE;
     return launch_umma(x, w, scale, out, g, w_format, bits, fsr, 0, reinterpret_cast<char*>(workspace) + wbytes, st);
   }
@@ -938,15 +990,16 @@ int po2_conv2d_fwd(const void* x, const void* w, const float* scale, void* out, 
 // g: (B, K, P, Q) fp32, gx: (B, C, H, W) fp32, w: the FORWARD weight (K, C, R, S).
 int po2_conv2d_dgrad(const void* g_out, const void* w, const float* scale, void* gx, int B, int C, int H,
                      int W, int K, int R, int S, int stride, int pad, int groups, int w_format, int bits,
-                     int fsr, void* workspace, size_t workspace_bytes, void* stream) {
+                     int fsr, int compute, void* workspace, size_t workspace_bytes, void* stream) {
   if (!g_out || !w || !gx) return PO2_E_NULL;
+  if (compute == 1) return PO2_E_UNSUPPORTED;
   if (stride != 1 || groups != 1) return PO2_E_UNSUPPORTED;
   if (!((R == 3 && S == 3 && pad == 1) || (R == 1 && S == 1 && pad == 0))) return PO2_E_UNSUPPORTED;
   if (w_format != PO2_W_F32_PO2 && w_format != PO2_W_CODES) return PO2_E_UNSUPPORTED;
   ConvGeom g;
   if (!fill_geom(g, B, K, H, W, C, R, S, 1, pad, 1)) return PO2_E_SHAPE;      // in = K channels, out = C channels
   if ((int64_t)B * C * H * W >= (1ll << 31) || (int64_t)B * K * H * W >= (1ll << 31)) return PO2_E_SIZE;
-  if (!plan_umma(g)) return PO2_E_UNSUPPORTED;
+  if (!plan_umma(g, compute == 2)) return PO2_E_UNSUPPORTED;
   const size_t need = umma_pack_bytes(g) + 256;
   if (!workspace || workspace_bytes < need) return PO2_E_WORKSPACE;
   return launch_umma(g_out, w, scale, gx, g, w_format, bits, fsr, 1, workspace, (cudaStream_t)stream);
@@ -954,36 +1007,38 @@ int po2_conv2d_dgrad(const void* g_out, const void* w, const float* scale, void*
 
 // Static weights (PTQ / eval): build the packed tensor-core operand once, reuse it every forward.
 // po2_conv2d_pack_bytes == 0 means the shape does not run on the tensor-core kernel.
-size_t po2_conv2d_pack_bytes(int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups) {
+size_t po2_conv2d_pack_bytes(int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups,
+                             int compute) {
   ConvGeom g;
-  if (!fill_geom(g, B, C, H, W, K, R, S, stride, pad, groups) || !umma_eligible(g) || !plan_umma(g)) return 0;
+  if (compute == 1 || !fill_geom(g, B, C, H, W, K, R, S, stride, pad, groups) || !umma_eligible(g) ||
+      !plan_umma(g, compute == 2)) return 0;
   return (umma_pack_bytes(g) + 255) / 256 * 256;
 }
 
 int po2_conv2d_pack(const void* w, const float* scale, void* packed, size_t packed_bytes, int B, int C, int H,
                     int W, int K, int R, int S, int stride, int pad, int groups, int w_format, int bits,
-                    int fsr, void* stream) {
+                    int fsr, int compute, void* stream) {
   if (!w || !packed) return PO2_E_NULL;
   if (w_format != PO2_W_F32_PO2 && w_format != PO2_W_CODES) return PO2_E_UNSUPPORTED;
   if (w_format == PO2_W_CODES && (!scale || bits < 2 || bits > 8)) return PO2_E_BITS;
   ConvGeom g;
   if (!fill_geom(g, B, C, H, W, K, R, S, stride, pad, groups)) return PO2_E_SHAPE;
-  if (!umma_eligible(g) || !plan_umma(g)) return PO2_E_UNSUPPORTED;
+  if (compute == 1 || !umma_eligible(g) || !plan_umma(g, compute == 2)) return PO2_E_UNSUPPORTED;
   if (packed_bytes < umma_pack_bytes(g)) return PO2_E_WORKSPACE;
-  const int64_t total = (int64_t)umma_pack_bytes(g) / 2;
+  const int64_t total = (int64_t)umma_pack_bytes(g) / (g.tf32 ? 4 : 2);
   const int pblocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
   pack_weights_kernel<<<pblocks, 256, 0, (cudaStream_t)stream>>>(
       w_format == PO2_W_CODES ? nullptr : (const float*)w, w_format == PO2_W_CODES ? (const uint8_t*)w : nullptr,
-      w_format == PO2_W_CODES ? nullptr : scale, reinterpret_cast<__nv_bfloat16*>(packed), g, bits, fsr, 0);
+      w_format == PO2_W_CODES ? nullptr : scale, packed, g, bits, fsr, 0);
   return (int)cudaGetLastError();
 }
 
 int po2_conv2d_fwd_packed(const void* x, const void* packed, const float* scale, void* out, int B, int C, int H,
-                          int W, int K, int R, int S, int stride, int pad, int groups, void* stream) {
+                          int W, int K, int R, int S, int stride, int pad, int groups, int compute, void* stream) {
   if (!x || !packed || !out) return PO2_E_NULL;
   ConvGeom g;
   if (!fill_geom(g, B, C, H, W, K, R, S, stride, pad, groups)) return PO2_E_SHAPE;
-  if (!umma_eligible(g) || !plan_umma(g)) return PO2_E_UNSUPPORTED;
+  if (compute == 1 || !umma_eligible(g) || !plan_umma(g, compute == 2)) return PO2_E_UNSUPPORTED;
   if ((int64_t)B * C * H * W >= (1ll << 31) || (int64_t)B * K * g.P * g.Q >= (1ll << 31)) return PO2_E_SIZE;
   return launch_umma(x, nullptr, scale, out, g, PO2_W_F32_PO2, 4, 1, -1, const_cast<void*>(packed), (cudaStream_t)stream,
                      /*pdl=*/false);
@@ -1004,14 +1059,14 @@ int po2_qconv2d_fwd(const void* x, const void* w_master, void* qw_out, float* sc
   if (!fill_geom(g, B, C, H, W, K, R, S, stride, pad, groups)) return PO2_E_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t wn = (int64_t)K * (C / groups) * R * S;
-  if (compute == 0 && umma_eligible(g) && plan_umma(g) && g.Cpad == C && g.ntiles_n * g.NT == K) {
+  if (compute != 1 && umma_eligible(g) && plan_umma(g, compute == 2) && g.Cpad == C && g.ntiles_n * g.NT == K) {
     const size_t need = po2_conv2d_workspace(B, C, H, W, K, R, S, stride, pad, groups, compute);
     const size_t wbytes = ((size_t)wn * sizeof(float) + 255) / 256 * 256;
     if (!workspace || workspace_bytes < need) return PO2_E_WORKSPACE;
     if ((int64_t)B * C * H * W >= (1ll << 31) || (int64_t)B * K * g.P * g.Q >= (1ll << 31)) return PO2_E_SIZE;
     PackArgs pk;
-    pk.Bp = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(workspace) + wbytes);
-    pk.C = C; pk.K = K; pk.taps = g.ntaps; pk.NT = g.NT; pk.ncg = C / 8;
+    pk.Bp = reinterpret_cast<char*>(workspace) + wbytes;
+    pk.G = g.G; pk.C = C; pk.K = K; pk.taps = g.ntaps; pk.NT = g.NT; pk.ncg = C / g.G;
     pk.div_ct = make_fastdiv((uint32_t)(C * g.ntaps));
     pk.div_t = make_fastdiv((uint32_t)g.ntaps);
     pk.div_nt = make_fastdiv((uint32_t)g.NT);
@@ -1025,9 +1080,9 @@ int po2_qconv2d_fwd(const void* x, const void* w_master, void* qw_out, float* sc
                         fsr, compute, workspace, workspace_bytes, stream);
 }
 
-size_t po2_conv2d_dgrad_workspace(int B, int C, int H, int W, int K, int R, int S, int pad) {
+size_t po2_conv2d_dgrad_workspace(int B, int C, int H, int W, int K, int R, int S, int pad, int compute) {
   ConvGeom g;
-  if (!fill_geom(g, B, K, H, W, C, R, S, 1, pad, 1) || !plan_umma(g)) return 0;
+  if (compute == 1 || !fill_geom(g, B, K, H, W, C, R, S, 1, pad, 1) || !plan_umma(g, compute == 2)) return 0;
   return (umma_pack_bytes(g) + 256 + 255) / 256 * 256;
 }
 

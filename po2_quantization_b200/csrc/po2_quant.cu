@@ -508,7 +508,10 @@ __device__ __forceinline__ void pack_vec(const PackArgs& pk, const uint4& o, int
     const int n = k - nt * pk.NT;
     const float yv = __uint_as_float(ob[j]);
     const float r = (s == 1.0f) ? yv : __fdiv_rn(yv, s);
-    pk.Bp[((((size_t)nt * pk.taps + tap) * pk.ncg + (c >> 3)) * pk.NT + n) * 8 + (c & 7)] = __float2bfloat16_rn(r);
+    const int cg = pk.G == 8 ? (c >> 3) : (c >> 2), cj = c & (pk.G - 1);
+    const size_t idx = ((((size_t)nt * pk.taps + tap) * pk.ncg + cg) * pk.NT + n) * pk.G + cj;
+    if (pk.G == 8) reinterpret_cast<__nv_bfloat16*>(pk.Bp)[idx] = __float2bfloat16_rn(r);
+    else reinterpret_cast<float*>(pk.Bp)[idx] = r;
   }
 }
 

@@ -45,15 +45,18 @@ _workspaces = {}
 LAUNCHES = 0
 
 
-# "tc": bf16 tcgen05 tensor cores where the shape allows (default); "fp32": CUDA-core fp32 FMA
-# everywhere (the fp32-accumulate parity mode); "cudnn": leave the convolution to F.conv2d.
+# "tc": tcgen05 tensor cores with bf16 operands where the shape allows (default); "tf32": the same
+# kernel with tf32 operands (activations keep 10 mantissa bits, the precision of the reference's own
+# cuDNN default); "fp32": CUDA-core fp32 FMA everywhere (the fp32-accumulate parity mode); "cudnn":
+# leave the convolution to F.conv2d.
+COMPUTE = {"tc": 0, "fp32": 1, "tf32": 2}
 _conv_mode = os.environ.get("PO2_CONV", "tc")
 
 
 def set_conv_mode(mode: str) -> None:
     global _conv_mode
-    if mode not in ("tc", "fp32", "cudnn"):
-        raise ValueError("conv mode must be 'tc', 'fp32' or 'cudnn'")
+    if mode not in ("tc", "tf32", "fp32", "cudnn"):
+        raise ValueError("conv mode must be 'tc', 'tf32', 'fp32' or 'cudnn'")
     _conv_mode = mode
 
 
@@ -64,6 +67,7 @@ def get_conv_mode() -> str:
 def conv_backend_name() -> str:
     """Which kernel QuantizedConv2d's convolution runs on (reported by bench.py)."""
     return {"tc": "po2::conv_umma_kernel (tcgen05 bf16 implicit GEMM) / po2 depthwise+direct fp32 for the rest",
+            "tf32": "po2::conv_umma_kernel (tcgen05 tf32 implicit GEMM) / po2 depthwise+direct fp32 for the rest",
             "fp32": "po2 CUDA-core fp32 kernels (depthwise / direct)",
             "cudnn": "cudnn (torch F.conv2d on the po2-quantized weight)"}[_conv_mode]
 
@@ -275,18 +279,18 @@ def set_dgrad_mode(mode: str) -> None:
     _dgrad_mode = mode
 
 
-def conv2d_dgrad_out(g, w, scale, gx, pad) -> bool:
+def conv2d_dgrad_out(g, w, scale, gx, pad, compute: int = 0) -> bool:
     """gx = dL/dx of conv2d(x, w) (stride 1, dense) from g = dL/dout.  False if the shape is not taken."""
     global LAUNCHES
     lib = _lib.load()
     B, C, H, W_ = gx.shape
     K, _, R, S = w.shape
-    need = lib.po2_conv2d_dgrad_workspace(B, C, H, W_, K, R, S, pad)
+    need = lib.po2_conv2d_dgrad_workspace(B, C, H, W_, K, R, S, pad, compute)
     if need == 0:
         return False
     ws = torch.empty(int(need), dtype=torch.uint8, device=g.device)
     rc = lib.po2_conv2d_dgrad(g.data_ptr(), w.data_ptr(), scale.data_ptr() if scale is not None else None,
-                              gx.data_ptr(), B, C, H, W_, K, R, S, 1, pad, 1, _lib.W_F32_PO2, 4, 1,
+                              gx.data_ptr(), B, C, H, W_, K, R, S, 1, pad, 1, _lib.W_F32_PO2, 4, 1, compute,
                               ws.data_ptr(), ws.numel(), _stream_ptr(g.device))
     if rc == -10:                      # PO2_E_UNSUPPORTED
         return False
@@ -312,11 +316,11 @@ def _conv2d_bwd(ctx, g):
     need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
     g = g.contiguous()
     gx = None
-    if (need_x and _dgrad_mode == "tc" and compute == 0 and stride == 1 and groups == 1 and scale is not None
+    if (need_x and _dgrad_mode == "tc" and compute != 1 and stride == 1 and groups == 1 and scale is not None
             and g.dtype == torch.float32):
         cand = torch.empty_like(x)
         with torch.cuda.device(x.device):
-            if conv2d_dgrad_out(g, w, scale, cand, pad):
+            if conv2d_dgrad_out(g, w, scale, cand, pad, compute):
                 gx = cand
     gx2, gw, _ = torch.ops.aten.convolution_backward(
         g, x, w, None, [stride, stride], [pad, pad], [1, 1], False, [0, 0], groups,
@@ -404,10 +408,10 @@ def _qconv2d_bwd(ctx, g, g_qw, g_scale):
     need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
     g = g.contiguous()
     gx = None
-    if need_x and _dgrad_mode == "tc" and compute == 0 and stride == 1 and groups == 1 and g.dtype == torch.float32:
+    if need_x and _dgrad_mode == "tc" and compute != 1 and stride == 1 and groups == 1 and g.dtype == torch.float32:
         cand = torch.empty_like(x)
         with torch.cuda.device(x.device):
-            if conv2d_dgrad_out(g, qw, scale, cand, pad):
+            if conv2d_dgrad_out(g, qw, scale, cand, pad, compute):
                 gx = cand
     gx2, gw, _ = torch.ops.aten.convolution_backward(
         g, x, qw, None, [stride, stride], [pad, pad], [1, 1], False, [0, 0], groups,
@@ -426,14 +430,15 @@ qconv2d.register_autograd(_qconv2d_bwd, setup_context=_qconv2d_setup)
 # ------------------------------------------------------------------------------------------------
 # static weights: pack once, then one launch per forward
 # ------------------------------------------------------------------------------------------------
-def conv2d_pack(w: torch.Tensor, scale: Optional[torch.Tensor], xshape, stride: int, pad: int, groups: int):
+def conv2d_pack(w: torch.Tensor, scale: Optional[torch.Tensor], xshape, stride: int, pad: int, groups: int,
+                compute: int = 0):
     """Packed bf16 tensor-core operand for conv2d(x of shape xshape, w), or None if that shape does not
     run on the tensor-core kernel."""
     global LAUNCHES
     lib = _lib.load()
     B, C, H, W_ = xshape
     K, _, R, S = w.shape
-    nbytes = lib.po2_conv2d_pack_bytes(B, C, H, W_, K, R, S, stride, pad, groups)
+    nbytes = lib.po2_conv2d_pack_bytes(B, C, H, W_, K, R, S, stride, pad, groups, compute)
     if nbytes == 0:
         return None
     packed = torch.empty(int(nbytes), dtype=torch.uint8, device=w.device)
@@ -441,13 +446,13 @@ def conv2d_pack(w: torch.Tensor, scale: Optional[torch.Tensor], xshape, stride: 
         LAUNCHES += 1
         _lib.check(lib.po2_conv2d_pack(w.data_ptr(), scale.data_ptr() if scale is not None else None, packed.data_ptr(),
                                        packed.numel(), B, C, H, W_, K, R, S, stride, pad, groups, _lib.W_F32_PO2, 4, 1,
-                                       _stream_ptr(w.device)), "po2_conv2d_pack")
+                                       compute, _stream_ptr(w.device)), "po2_conv2d_pack")
     return packed
 
 
 @torch.library.custom_op("po2::conv2d_packed", mutates_args=(), device_types="cuda")
 def conv2d_packed(x: torch.Tensor, packed: torch.Tensor, scale: Optional[torch.Tensor], K: int, R: int, S: int,
-                  stride: int, pad: int, groups: int) -> torch.Tensor:
+                  stride: int, pad: int, groups: int, compute: int) -> torch.Tensor:
     """conv2d from a pre-packed weight operand (inference with static weights): one kernel launch."""
     global LAUNCHES
     _require_cuda(x, "po2::conv2d_packed")
@@ -459,12 +464,13 @@ def conv2d_packed(x: torch.Tensor, packed: torch.Tensor, scale: Optional[torch.T
         LAUNCHES += 1
         _lib.check(_lib.load().po2_conv2d_fwd_packed(x.data_ptr(), packed.data_ptr(),
                                                      scale.data_ptr() if scale is not None else None, out.data_ptr(),
-                                                     B, C, H, W_, K, R, S, stride, pad, groups, _stream_ptr(x.device)),
+                                                     B, C, H, W_, K, R, S, stride, pad, groups, compute,
+                                                     _stream_ptr(x.device)),
                    "po2_conv2d_fwd_packed")
     return out
 
 
 @conv2d_packed.register_fake
-def _(x, packed, scale, K, R, S, stride, pad, groups):
+def _(x, packed, scale, K, R, S, stride, pad, groups, compute):
     B, C, H, W_ = x.shape
     return x.new_empty((B, K, (H + 2 * pad - R) // stride + 1, (W_ + 2 * pad - S) // stride + 1))

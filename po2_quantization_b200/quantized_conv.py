@@ -42,7 +42,7 @@ class QuantizedConv2d(nn.Conv2d):
 
     def _po2_conv(self, input, weight, scale):
         return ops.conv2d(input, weight, scale, self.stride[0], self.padding[0], self.groups,
-                          0 if ops.get_conv_mode() == "tc" else 1)
+                          ops.COMPUTE[ops.get_conv_mode()])
 
     def forward(self, input):
         # models/quantized_conv.py:32-38: quantize the weight on every forward (QAT), then conv
@@ -52,26 +52,28 @@ class QuantizedConv2d(nn.Conv2d):
                 # PO2 / PO2+: one op = quantizer kernel (which also emits the packed +-2^q tensor-core
                 # operand) + conv kernel; the straight-through gradient reaches self.weight
                 out, _qw, _scale = ops.qconv2d(input, self.weight, int(self.bits), 1, bool(plus), self.stride[0],
-                                               self.padding[0], self.groups, 0 if ops.get_conv_mode() == "tc" else 1)
+                                               self.padding[0], self.groups, ops.COMPUTE[ops.get_conv_mode()])
                 return out
             quantized_weight = self.quantize_fn.apply(self.weight, self.bits)
             return self._conv_forward(input, quantized_weight, self.bias)
         tag = getattr(self, "_po2_ptq", None)
         if tag is not None and tag[0] == self.weight._version and self._po2_conv_ok(input):
             # post-training-quantized weights (quantize_model): already on the grid +-scale*2^q
-            if ops.get_conv_mode() == "tc" and not (torch.is_grad_enabled() and (input.requires_grad or self.weight.requires_grad)):
+            mode = ops.get_conv_mode()
+            if mode in ("tc", "tf32") and not (torch.is_grad_enabled() and (input.requires_grad or self.weight.requires_grad)):
                 # static weights, no autograd: pack the tensor-core operand once per (weight version,
                 # input shape) and run each forward as a single launch
-                key = (tag[0], tuple(input.shape), input.device)
+                key = (tag[0], tuple(input.shape), input.device, mode)
                 cache = self.__dict__.get("_po2_pack_cache")
                 if cache is None or cache[0] != key:
                     packed = ops.conv2d_pack(self.weight.detach(), tag[1], tuple(input.shape), self.stride[0],
-                                             self.padding[0], self.groups)
+                                             self.padding[0], self.groups, ops.COMPUTE[mode])
                     cache = (key, packed)
                     self.__dict__["_po2_pack_cache"] = cache
                 if cache[1] is not None:
                     K, _, R, S = self.weight.shape
-                    return ops.conv2d_packed(input, cache[1], tag[1], K, R, S, self.stride[0], self.padding[0], self.groups)
+                    return ops.conv2d_packed(input, cache[1], tag[1], K, R, S, self.stride[0], self.padding[0], self.groups,
+                                             ops.COMPUTE[mode])
             return self._po2_conv(input, self.weight, tag[1])
         return self._conv_forward(input, self.weight, self.bias)
 
