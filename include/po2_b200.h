@@ -141,6 +141,37 @@ int po2_conv2d_dgrad(const void* g, const void* w, const float* scale, void* gx,
                      int W, int K, int R, int S, int stride, int pad, int groups, int w_format,
                      int bits, int fsr, int compute, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- batch normalisation around the quantized convs (SURVEY.md section 8f "next" #3) -----------------
+ * The reference models follow every QuantizedConv2d with nn.SyncBatchNorm (+ ReLU, + the residual add):
+ * models/resnet.py:38-61, models/mobilenet.py:29-33.  x, y, dy, dx are fp32 [B][C][HW] (NCHW), parameters
+ * and statistics fp32 [C].  act: 0 none, 1 ReLU.
+ *
+ * po2_bn_stats: this rank's batch statistics, stat[0..C) = mean, stat[C..2C) = sum (x-mean)^2,
+ *   stat[2C] = B*HW.  workspace: po2_bn_workspace_bytes(C) bytes, zero-initialised once (left zeroed).
+ * po2_bn_apply: y = act((x - mean) * invstd * gamma + beta [+ residual]).  stats = R entries of 2C+1
+ *   floats (R ranks' po2_bn_stats results, combined with the parallel-variance formula as
+ *   torch.batch_norm_gather_stats_with_counts does), or use_running != 0: the running statistics
+ *   (eval mode).  In train mode also updates running_mean / running_var (unbiased variance,
+ *   `momentum`) and num_batches_tracked when given, and writes save_mean / save_invstd for backward.
+ * po2_bn_bwd_reduce: sums[0..C) = sum g, sums[C..2C) = sum g*(x-mean) with g = dy (act 0) or
+ *   dy*(y>0) (act 1); dgamma = sums[C+c]*invstd, dbeta = sums[c] (local sums, as SyncBatchNorm).
+ * po2_bn_bwd_apply: dx = (g - sum_g/M - (x-mean)*invstd^2*sum_gx/M) * gamma*invstd, M = total count
+ *   over the R stats entries; `sums` all-reduced over ranks by the caller.  dres (optional): g, the
+ *   gradient of the residual branch behind the ReLU. */
+size_t po2_bn_workspace_bytes(int C);
+int po2_bn_stats(const void* x, int B, int C, int HW, float* stat, void* workspace, size_t workspace_bytes,
+                 void* stream);
+int po2_bn_apply(const void* x, const void* residual, void* y, const float* stats, int R, const float* gamma,
+                 const float* beta, float* running_mean, float* running_var, long long* num_batches_tracked,
+                 float momentum, float eps, int act, int use_running, float* save_mean, float* save_invstd, int B,
+                 int C, int HW, void* stream);
+int po2_bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* save_mean, const float* save_invstd,
+                      float* sums, float* dgamma, float* dbeta, int act, int B, int C, int HW, void* workspace,
+                      size_t workspace_bytes, void* stream);
+int po2_bn_bwd_apply(const void* dy, const void* x, const void* y, const float* save_mean, const float* save_invstd,
+                     const float* gamma, const float* sums, const float* stats, int R, void* dx, void* dres, int act,
+                     int B, int C, int HW, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,181 @@
+"""SyncBatchNorm (+ residual add) (+ ReLU) on the sm_100a kernels of csrc/po2_bn.cu.
+
+The reference models place an ``nn.SyncBatchNorm`` and usually a ReLU behind every QuantizedConv2d
+(models/resnet.py:38-61).  ``FusedSyncBatchNorm`` is that module -- same parameters, buffers and
+``state_dict`` -- whose ``forward`` also accepts the residual and the activation of the surrounding
+block so that ``relu(bn(x) + shortcut)`` is one streaming pass forward and one backward:
+
+    forward :  bn_stats  -> [all_gather of 2C+1 statistics when world_size > 1] -> bn_apply
+    backward:  bn_bwd_reduce -> [all_reduce of 2C sums]                         -> bn_bwd_apply
+
+The collective sits exactly where torch's SyncBatchNorm has it (same algebra: per-rank mean / M2 /
+count combined with the parallel-variance formula; gradient of the affine parameters from local
+sums).  Inputs the kernels do not cover (CPU tensors, non-fp32, eval mode under autograd,
+``momentum=None``) take ``nn.SyncBatchNorm.forward`` itself followed by the add and the ReLU.
+"""
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib, ops
+
+_bn_workspaces = {}
+
+
+def _bn_workspace(device: torch.device, C: int) -> torch.Tensor:
+    """Zero-initialised scratch (ticket counters + partial sums), one per (device, stream); the
+    kernels leave the counters at zero."""
+    stream = torch.cuda.current_stream(device)
+    key = (device.index, stream.cuda_stream)
+    ws = _bn_workspaces.get(key)
+    need = int(_lib.load().po2_bn_workspace_bytes(C))
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(max(need, 1 << 16), dtype=torch.uint8, device=device)
+        _bn_workspaces[key] = ws
+    return ws
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return t.data_ptr() if t is not None else None
+
+
+# ------------------------------------------------------------------------------------------------
+# raw launchers
+# ------------------------------------------------------------------------------------------------
+def bn_stats_out(x: torch.Tensor, stat: torch.Tensor) -> None:
+    """stat[0:C] = mean, stat[C:2C] = sum of squared deviations, stat[2C] = B*H*W (this rank)."""
+    B, C = x.shape[0], x.shape[1]
+    HW = x.numel() // (B * C)
+    ws = _bn_workspace(x.device, C)
+    ops.LAUNCHES += 1
+    _lib.check(_lib.load().po2_bn_stats(x.data_ptr(), B, C, HW, stat.data_ptr(), ws.data_ptr(), ws.numel(),
+                                        ops._stream_ptr(x.device)), "po2_bn_stats")
+
+
+def bn_apply_out(x, residual, y, stats, weight, bias, running_mean, running_var, num_batches_tracked,
+                 momentum, eps, relu, use_running, save_mean, save_invstd) -> None:
+    B, C = x.shape[0], x.shape[1]
+    HW = x.numel() // (B * C)
+    R = 1 if stats is None else stats.numel() // (2 * C + 1)
+    ops.LAUNCHES += 1
+    _lib.check(_lib.load().po2_bn_apply(
+        x.data_ptr(), _ptr(residual), y.data_ptr(), _ptr(stats), R, _ptr(weight), _ptr(bias), _ptr(running_mean),
+        _ptr(running_var), _ptr(num_batches_tracked), float(momentum), float(eps), int(relu), int(use_running),
+        _ptr(save_mean), _ptr(save_invstd), B, C, HW, ops._stream_ptr(x.device)), "po2_bn_apply")
+
+
+def bn_bwd_reduce_out(dy, x, y, save_mean, save_invstd, sums, dgamma, dbeta, relu) -> None:
+    B, C = x.shape[0], x.shape[1]
+    HW = x.numel() // (B * C)
+    ws = _bn_workspace(x.device, C)
+    ops.LAUNCHES += 1
+    _lib.check(_lib.load().po2_bn_bwd_reduce(
+        dy.data_ptr(), x.data_ptr(), _ptr(y), save_mean.data_ptr(), save_invstd.data_ptr(), sums.data_ptr(),
+        _ptr(dgamma), _ptr(dbeta), int(relu), B, C, HW, ws.data_ptr(), ws.numel(), ops._stream_ptr(x.device)),
+        "po2_bn_bwd_reduce")
+
+
+def bn_bwd_apply_out(dy, x, y, save_mean, save_invstd, weight, sums, stats, dx, dres, relu) -> None:
+    B, C = x.shape[0], x.shape[1]
+    HW = x.numel() // (B * C)
+    R = stats.numel() // (2 * C + 1)
+    ops.LAUNCHES += 1
+    _lib.check(_lib.load().po2_bn_bwd_apply(
+        dy.data_ptr(), x.data_ptr(), _ptr(y), save_mean.data_ptr(), save_invstd.data_ptr(), _ptr(weight),
+        sums.data_ptr(), stats.data_ptr(), R, dx.data_ptr(), _ptr(dres), int(relu), B, C, HW,
+        ops._stream_ptr(x.device)), "po2_bn_bwd_apply")
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd
+# ------------------------------------------------------------------------------------------------
+class _BatchNormTrain(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, residual, weight, bias, running_mean, running_var, num_batches_tracked, momentum, eps,
+                relu, group, world):
+        x = x.contiguous()
+        if residual is not None:
+            residual = residual.contiguous()
+        C = x.shape[1]
+        with torch.cuda.device(x.device):
+            stat = torch.empty(2 * C + 1, dtype=torch.float32, device=x.device)
+            bn_stats_out(x, stat)
+            if world > 1:
+                stats = torch.empty(world, 2 * C + 1, dtype=torch.float32, device=x.device)
+                dist.all_gather_into_tensor(stats.view(-1), stat, group=group)
+            else:
+                stats = stat.view(1, -1)
+            y = torch.empty_like(x)
+            save_mean = torch.empty(C, dtype=torch.float32, device=x.device)
+            save_invstd = torch.empty(C, dtype=torch.float32, device=x.device)
+            bn_apply_out(x, residual, y, stats, weight, bias, running_mean, running_var, num_batches_tracked,
+                         momentum, eps, relu, False, save_mean, save_invstd)
+        ctx.relu, ctx.has_res, ctx.group, ctx.world = relu, residual is not None, group, world
+        ctx.save_for_backward(x, y if relu else None, weight, save_mean, save_invstd, stats)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, weight, save_mean, save_invstd, stats = ctx.saved_tensors
+        dy = dy.contiguous()
+        C = x.shape[1]
+        need_x, need_res, need_w, need_b = ctx.needs_input_grad[:4]
+        with torch.cuda.device(x.device):
+            sums = torch.empty(2 * C, dtype=torch.float32, device=x.device)
+            dgamma = torch.empty(C, dtype=torch.float32, device=x.device) if weight is not None else None
+            dbeta = torch.empty(C, dtype=torch.float32, device=x.device) if weight is not None else None
+            bn_bwd_reduce_out(dy, x, y, save_mean, save_invstd, sums, dgamma, dbeta, ctx.relu)
+            if ctx.world > 1:
+                dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=ctx.group)
+            dx = torch.empty_like(x)
+            dres = None
+            if ctx.has_res and need_res:
+                dres = torch.empty_like(x) if ctx.relu else dy       # without the ReLU the branch gets dy itself
+            bn_bwd_apply_out(dy, x, y, save_mean, save_invstd, weight, sums, stats, dx,
+                             dres if ctx.relu else None, ctx.relu)
+        return (dx if need_x else None, dres, dgamma if need_w else None, dbeta if need_b else None,
+                None, None, None, None, None, None, None, None)
+
+
+def _kernel_ok(x: torch.Tensor) -> bool:
+    return x.is_cuda and x.dtype == torch.float32 and x.dim() >= 2 and x.numel() > 0 and x.shape[1] <= 4096
+
+
+class FusedSyncBatchNorm(nn.SyncBatchNorm):
+    """``nn.SyncBatchNorm`` whose forward can absorb the residual add and the ReLU that follow it."""
+
+    fused_residual_relu = True
+
+    def forward(self, input: torch.Tensor, residual: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
+        use_batch_stats = self.training or (self.running_mean is None and self.running_var is None)
+        fast = _kernel_ok(input) and (residual is None or (residual.shape == input.shape and _kernel_ok(residual)))
+        if fast and use_batch_stats and (self.momentum is not None or self.running_mean is None):
+            if input.numel() // input.shape[1] <= 1:
+                raise ValueError(f"Expected more than 1 value per channel when training, got input size {input.size()}")
+            world, group = 1, None
+            if self.training and dist.is_available() and dist.is_initialized():
+                group = self.process_group if self.process_group is not None else dist.group.WORLD
+                world = dist.get_world_size(group)
+            track = self.training and self.track_running_stats
+            return _BatchNormTrain.apply(
+                input, residual, self.weight, self.bias, self.running_mean if track else None,
+                self.running_var if track else None, self.num_batches_tracked if track else None,
+                self.momentum if self.momentum is not None else 0.0, self.eps, bool(relu), group, world)
+        if fast and not use_batch_stats and not (torch.is_grad_enabled() and (
+                input.requires_grad or (residual is not None and residual.requires_grad) or
+                (self.weight is not None and self.weight.requires_grad))):
+            x = input.contiguous()
+            y = torch.empty_like(x)
+            with torch.cuda.device(x.device):
+                bn_apply_out(x, residual.contiguous() if residual is not None else None, y, None, self.weight,
+                             self.bias, self.running_mean, self.running_var, None, 0.0, self.eps, bool(relu), True,
+                             None, None)
+            return y
+        # stock path (CPU tensors, other dtypes, eval mode under autograd, cumulative-average momentum)
+        out = super().forward(input)
+        if residual is not None:
+            out = out + residual
+        return F.relu(out) if relu else out

@@ -1,0 +1,501 @@
+// Batch normalisation around the quantized convs: train-mode batch
+// statistics, normalise (+ residual add) (+ ReLU) and the matching backward, for fp32 NCHW tensors.
+//
+// The reference models put an nn.SyncBatchNorm (+ ReLU, + the residual add) behind every
+// QuantizedConv2d (models/resnet.py:38-61, :100-141).  On one GPU torch sends that to cuDNN's
+// bn_fw_tr / bn_bw kernels, which take 44 / 84 us for an 8.4 MB tensor -- 49 % of a ResNet-56 QAT
+// step (profiles/r01_launches_resnet56_qat_step_po2_conv.csv).  These kernels are HBM/L2-bound
+// streaming passes with 128-bit accesses:
+//
+//   bn_stats_kernel       x -> per-channel (mean, M2, count)          reads x once
+//   bn_apply_kernel       y = act((x-mean)*invstd*gamma+beta [+res])  reads x (L2), [res], writes y
+//   bn_bwd_reduce_kernel  per-channel sum(g), sum(g*(x-mean)), g = dy masked by y>0 for ReLU
+//   bn_bwd_apply_kernel   dx (and the masked gradient for the residual branch)
+//
+// The split between the two halves of each direction is where SyncBatchNorm's collective goes
+// (all_gather of the 2C+1 statistics forward, all_reduce of the 2C sums backward); with one rank the
+// second kernel consumes the first one's output directly.
+//
+// Layout: x[B][C][HW].  A reduce CTA (s, c) owns the slabs b = s, s+S, ... of channel c; its partial
+// sums go to a workspace and the last CTA of a channel to finish (ticket counter, self-resetting)
+// combines them in double precision.  Sums are shifted by the channel's first element so that
+// E[x^2]-E[x]^2 cancellation stays harmless when |mean| >> std.
+#include "po2_common.cuh"
+
+namespace po2 {
+
+constexpr int BN_THREADS = 256;
+constexpr int BN_MAX_SPLIT = 64;
+constexpr int BN_UNROLL = 4;
+constexpr int BN_MAX_C = 4096;           // per-channel parameters live in shared memory (16 B each)
+
+struct BnGeom {
+  int B, C, HW;
+  int L;          // vector lanes per slab: HW/4 (vec) or HW (scalar)
+  int S;          // reduce splits per channel
+  int total;      // B*C*L
+  FastDiv div_l, div_c;
+};
+
+struct BnWorkspace {              // caller-provided, zero-initialised once; kernels leave counters zero
+  unsigned int* ticket;           // [BN_MAX_C], first in the buffer
+  double2* partial;               // [C][BN_MAX_SPLIT]
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  return v;
+}
+
+// sum (a, b) over the CTA; valid in every thread of warp 0
+__device__ __forceinline__ void block_sum2(double& a, double& b, double (*sm)[2]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  a = warp_sum(a);
+  b = warp_sum(b);
+  __syncthreads();                                   // sm may still be read from a previous call
+  if (lane == 0) { sm[warp][0] = a; sm[warp][1] = b; }
+  __syncthreads();
+  if (warp == 0) {
+    a = lane < BN_THREADS / 32 ? sm[lane][0] : 0.0;
+    b = lane < BN_THREADS / 32 ? sm[lane][1] : 0.0;
+    a = warp_sum(a);
+    b = warp_sum(b);
+  }
+}
+
+// publish this CTA's partial, and tell whether it is the last CTA of channel c to do so
+__device__ __forceinline__ bool publish_partial(double a, double b, const BnWorkspace& ws, int c, int s, int S,
+                                                int* flag) {
+  if (threadIdx.x == 0) {
+    ws.partial[c * BN_MAX_SPLIT + s] = make_double2(a, b);
+    __threadfence();
+    const unsigned int t = atomicAdd(ws.ticket + c, 1u);
+    *flag = (t == (unsigned int)(S - 1));
+    if (*flag) { ws.ticket[c] = 0; __threadfence(); }
+  }
+  __syncthreads();
+  return *flag != 0;
+}
+
+// MODE 0: forward statistics (p = x - shift, q = p);  1: backward sums (p = dy, q = x - mean);
+// MODE 2: backward sums behind a ReLU (p = y > 0 ? dy : 0).
+template <bool VEC, int MODE>
+__global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const float* __restrict__ x,
+                                                               const float* __restrict__ dy,
+                                                               const float* __restrict__ y,
+                                                               const float* __restrict__ mean,
+                                                               const float* __restrict__ invstd,
+                                                               float* __restrict__ out,      // MODE 0: stat[2C+1]; else sums[2C]
+                                                               float* __restrict__ dgamma,
+                                                               float* __restrict__ dbeta, BnGeom g,
+                                                               BnWorkspace ws) {
+  __shared__ double sm[BN_THREADS / 32][2];
+  __shared__ int flag;
+  const int s = blockIdx.x, c = blockIdx.y;
+  const int L = g.L, C = g.C;
+  const int nslab = (g.B - s + g.S - 1) / g.S;                 // slabs b = s, s+S, ...
+  const int n = nslab * L;
+  const float shift = MODE == 0 ? __ldg(x + (size_t)c * g.HW) : __ldg(mean + c);
+  float s1 = 0.f, s2 = 0.f;
+  for (int i0 = threadIdx.x; i0 < n; i0 += BN_UNROLL * BN_THREADS) {
+    if (VEC) {
+      float4 vx[BN_UNROLL], vd[BN_UNROLL], vy[BN_UNROLL];
+#pragma unroll
+      for (int u = 0; u < BN_UNROLL; ++u) {
+        const int i = i0 + u * BN_THREADS;
+        vx[u] = vd[u] = vy[u] = make_float4(shift, shift, shift, shift);
+        if (MODE != 0) vd[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n) {
+          const int k = fdiv(i, g.div_l);
+          const size_t off = ((size_t)(s + k * g.S) * C + c) * L + (i - k * L);
+          vx[u] = __ldg(reinterpret_cast<const float4*>(x) + off);
+          if (MODE != 0) vd[u] = __ldg(reinterpret_cast<const float4*>(dy) + off);
+          if (MODE == 2) vy[u] = __ldg(reinterpret_cast<const float4*>(y) + off);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < BN_UNROLL; ++u) {
+        const float xs[4] = {vx[u].x, vx[u].y, vx[u].z, vx[u].w};
+        const float ds[4] = {vd[u].x, vd[u].y, vd[u].z, vd[u].w};
+        const float ys[4] = {vy[u].x, vy[u].y, vy[u].z, vy[u].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float q = xs[e] - shift;
+          if (MODE == 0) { s1 += q; s2 = fmaf(q, q, s2); }
+          else {
+            const float p = (MODE == 2 && !(ys[e] > 0.f)) ? 0.f : ds[e];
+            s1 += p; s2 = fmaf(p, q, s2);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < BN_UNROLL; ++u) {
+        const int i = i0 + u * BN_THREADS;
+        if (i < n) {
+          const int k = fdiv(i, g.div_l);
+          const size_t off = ((size_t)(s + k * g.S) * C + c) * L + (i - k * L);
+          const float q = __ldg(x + off) - shift;
+          if (MODE == 0) { s1 += q; s2 = fmaf(q, q, s2); }
+          else {
+            float p = __ldg(dy + off);
+            if (MODE == 2 && !(__ldg(y + off) > 0.f)) p = 0.f;
+            s1 += p; s2 = fmaf(p, q, s2);
+          }
+        }
+      }
+    }
+  }
+  double a = (double)s1, b = (double)s2;
+  block_sum2(a, b, sm);
+  if (!publish_partial(a, b, ws, c, s, g.S, &flag)) return;
+  // last CTA of this channel: combine the S partials
+  double pa = 0.0, pb = 0.0;
+  if ((int)threadIdx.x < g.S) {
+    const double2 p = __ldcg(ws.partial + c * BN_MAX_SPLIT + threadIdx.x);
+    pa = p.x; pb = p.y;
+  }
+  block_sum2(pa, pb, sm);
+  if (threadIdx.x == 0) {
+    if (MODE == 0) {
+      const double cnt = (double)g.B * (double)g.HW;
+      const double m = pa / cnt;
+      out[c] = (float)((double)shift + m);
+      out[C + c] = (float)fmax(pb - pa * m, 0.0);               // M2 = sum (x-mean)^2
+      if (c == 0) out[2 * C] = (float)cnt;
+    } else {
+      out[c] = (float)pa;                                        // sum g
+      out[C + c] = (float)pb;                                    // sum g*(x-mean)
+      if (dbeta) dbeta[c] = (float)pa;
+      if (dgamma) dgamma[c] = (float)(pb * (double)__ldg(invstd + c));
+    }
+  }
+}
+
+// ---- per-channel parameters in shared memory ----------------------------------------------------
+// forward: {mean, gamma*invstd, beta, -};  statistics = R entries of [mean[C] | M2[C] | count] (train)
+// or the running statistics (eval).
+__device__ __forceinline__ void combine_stats(const float* __restrict__ stats, int R, int C, int c, double& mean,
+                                              double& var_biased, double& count) {
+  double n = 0.0, m = 0.0;
+  for (int r = 0; r < R; ++r) {
+    const float* st = stats + (size_t)r * (2 * C + 1);
+    const double nr = (double)st[2 * C];
+    n += nr;
+    m += nr * (double)st[c];
+  }
+  m /= n;
+  double m2 = 0.0;
+  for (int r = 0; r < R; ++r) {
+    const float* st = stats + (size_t)r * (2 * C + 1);
+    const double d = (double)st[c] - m;
+    m2 += (double)st[C + c] + (double)st[2 * C] * d * d;
+  }
+  mean = m; var_biased = m2 / n; count = n;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const float* __restrict__ x,
+                                                              const float* __restrict__ res,
+                                                              float* __restrict__ y,
+                                                              const float* __restrict__ stats, int R,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta,
+                                                              float* running_mean, float* running_var,
+                                                              long long* num_batches_tracked, float momentum,
+                                                              float eps, int act, int use_running,
+                                                              float* __restrict__ save_mean,
+                                                              float* __restrict__ save_invstd, BnGeom g) {
+  extern __shared__ float4 prm[];
+  const int C = g.C;
+  for (int c = threadIdx.x; c < C; c += BN_THREADS) {
+    double mean, var, cnt = 0.0;
+    if (use_running) { mean = (double)running_mean[c]; var = (double)running_var[c]; }
+    else combine_stats(stats, R, C, c, mean, var, cnt);
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float ga = gamma ? gamma[c] : 1.0f, be = beta ? beta[c] : 0.0f;
+    prm[c] = make_float4((float)mean, ga * invstd, be, 0.f);
+    if (blockIdx.x == 0 && !use_running) {
+      if (save_mean) save_mean[c] = (float)mean;
+      if (save_invstd) save_invstd[c] = invstd;
+      if (running_mean) {
+        const double unbiased = var * cnt / fmax(cnt - 1.0, 1.0);
+        running_mean[c] = (float)((1.0 - (double)momentum) * (double)running_mean[c] + (double)momentum * mean);
+        running_var[c] = (float)((1.0 - (double)momentum) * (double)running_var[c] + (double)momentum * unbiased);
+      }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && !use_running && num_batches_tracked) *num_batches_tracked += 1;
+  __syncthreads();
+  const int L = g.L;
+  for (int i0 = blockIdx.x * (BN_UNROLL * BN_THREADS) + threadIdx.x; i0 < g.total;
+       i0 += gridDim.x * (BN_UNROLL * BN_THREADS)) {
+    if (VEC) {
+      float4 vx[BN_UNROLL], vr[BN_UNROLL];
+#pragma unroll
+      for (int u = 0; u < BN_UNROLL; ++u) {
+        const int i = i0 + u * BN_THREADS;
+        if (i < g.total) {
+          vx[u] = __ldg(reinterpret_cast<const float4*>(x) + i);
+          if (res) vr[u] = __ldg(reinterpret_cast<const float4*>(res) + i);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < BN_UNROLL; ++u) {
+        const int i = i0 + u * BN_THREADS;
+        if (i < g.total) {
+          const int slab = fdiv(i, g.div_l);
+          const int c = slab - fdiv(slab, g.div_c) * C;
+          const float4 p = prm[c];
+          float4 o;
+          o.x = fmaf(vx[u].x - p.x, p.y, p.z); o.y = fmaf(vx[u].y - p.x, p.y, p.z);
+          o.z = fmaf(vx[u].z - p.x, p.y, p.z); o.w = fmaf(vx[u].w - p.x, p.y, p.z);
+          if (res) { o.x += vr[u].x; o.y += vr[u].y; o.z += vr[u].z; o.w += vr[u].w; }
+          if (act == 1) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          reinterpret_cast<float4*>(y)[i] = o;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < BN_UNROLL; ++u) {
+        const int i = i0 + u * BN_THREADS;
+        if (i < g.total) {
+          const int slab = fdiv(i, g.div_l);
+          const int c = slab - fdiv(slab, g.div_c) * C;
+          const float4 p = prm[c];
+          float o = fmaf(__ldg(x + i) - p.x, p.y, p.z);
+          if (res) o += __ldg(res + i);
+          if (act == 1) o = fmaxf(o, 0.f);
+          y[i] = o;
+        }
+      }
+    }
+  }
+}
+
+// backward: dx = (g - sum_g/M - (x-mean) * invstd^2 * sum_gx/M) * gamma*invstd;  dres = g (masked dy)
+template <bool VEC>
+__global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const float* __restrict__ dy,
+                                                                  const float* __restrict__ x,
+                                                                  const float* __restrict__ y,
+                                                                  const float* __restrict__ mean,
+                                                                  const float* __restrict__ invstd,
+                                                                  const float* __restrict__ gamma,
+                                                                  const float* __restrict__ sums,
+                                                                  const float* __restrict__ stats, int R,
+                                                                  float* __restrict__ dx,
+                                                                  float* __restrict__ dres, int act, BnGeom g) {
+  extern __shared__ float4 prm[];
+  const int C = g.C;
+  double M = 0.0;
+  for (int r = 0; r < R; ++r) M += (double)stats[(size_t)r * (2 * C + 1) + 2 * C];
+  for (int c = threadIdx.x; c < C; c += BN_THREADS) {
+    const double is = (double)invstd[c];
+    const float ga = gamma ? gamma[c] : 1.0f;
+    prm[c] = make_float4(mean[c], (float)((double)sums[c] / M), (float)(is * is * (double)sums[C + c] / M),
+                         (float)((double)ga * is));
+  }
+  __syncthreads();
+  const bool relu = act == 1;
+  for (int i0 = blockIdx.x * (BN_UNROLL * BN_THREADS) + threadIdx.x; i0 < g.total;
+       i0 += gridDim.x * (BN_UNROLL * BN_THREADS)) {
+    if (VEC) {
+      float4 vd[BN_UNROLL], vx[BN_UNROLL], vy[BN_UNROLL];
+#pragma unroll
+      for (int u = 0; u < BN_UNROLL; ++u) {
+        const int i = i0 + u * BN_THREADS;
+        if (i < g.total) {
+          vd[u] = __ldg(reinterpret_cast<const float4*>(dy) + i);
+          vx[u] = __ldg(reinterpret_cast<const float4*>(x) + i);
+          if (relu) vy[u] = __ldg(reinterpret_cast<const float4*>(y) + i);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < BN_UNROLL; ++u) {
+        const int i = i0 + u * BN_THREADS;
+        if (i < g.total) {
+          const int slab = fdiv(i, g.div_l);
+          const int c = slab - fdiv(slab, g.div_c) * C;
+          const float4 p = prm[c];
+          float4 gr = vd[u];
+          if (relu) {
+            gr.x = vy[u].x > 0.f ? gr.x : 0.f; gr.y = vy[u].y > 0.f ? gr.y : 0.f;
+            gr.z = vy[u].z > 0.f ? gr.z : 0.f; gr.w = vy[u].w > 0.f ? gr.w : 0.f;
+          }
+          float4 o;
+          o.x = (gr.x - p.y - (vx[u].x - p.x) * p.z) * p.w; o.y = (gr.y - p.y - (vx[u].y - p.x) * p.z) * p.w;
+          o.z = (gr.z - p.y - (vx[u].z - p.x) * p.z) * p.w; o.w = (gr.w - p.y - (vx[u].w - p.x) * p.z) * p.w;
+          reinterpret_cast<float4*>(dx)[i] = o;
+          if (dres) reinterpret_cast<float4*>(dres)[i] = gr;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < BN_UNROLL; ++u) {
+        const int i = i0 + u * BN_THREADS;
+        if (i < g.total) {
+          const int slab = fdiv(i, g.div_l);
+          const int c = slab - fdiv(slab, g.div_c) * C;
+          const float4 p = prm[c];
+          float gr = __ldg(dy + i);
+          if (relu && !(__ldg(y + i) > 0.f)) gr = 0.f;
+          dx[i] = (gr - p.y - (__ldg(x + i) - p.x) * p.z) * p.w;
+          if (dres) dres[i] = gr;
+        }
+      }
+    }
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+static int bn_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+static bool aligned16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int bn_geom(BnGeom& g, int B, int C, int HW, bool vec_ok) {
+  if (B <= 0 || C <= 0 || HW <= 0) return PO2_E_SIZE;
+  if ((int64_t)B * C * HW >= (int64_t)1 << 31) return PO2_E_SIZE;
+  if (C > BN_MAX_C) return PO2_E_UNSUPPORTED;
+  g.B = B; g.C = C; g.HW = HW;
+  const bool vec = vec_ok && (HW % 4 == 0);
+  g.L = vec ? HW / 4 : HW;
+  g.total = B * C * g.L;
+  int S = (4 * bn_sms() + C - 1) / C;                         // ~4 reduce CTAs per SM over all channels
+  const int per_cta = BN_UNROLL * BN_THREADS;                 // do not split below one full pass per CTA
+  const int max_useful = (int)(((int64_t)B * g.L + per_cta - 1) / per_cta);
+  if (S > max_useful) S = max_useful;
+  if (S > B) S = B;
+  if (S > BN_MAX_SPLIT) S = BN_MAX_SPLIT;
+  if (S < 1) S = 1;
+  g.S = S;
+  g.div_l = make_fastdiv((uint32_t)g.L);
+  g.div_c = make_fastdiv((uint32_t)C);
+  return vec ? 1 : 0;
+}
+
+static BnWorkspace bn_ws(void* workspace, int C) {
+  // the ticket counters sit at a FIXED place (they must stay zero between calls of any C); the
+  // partial sums behind them are scratch
+  BnWorkspace ws;
+  (void)C;
+  ws.ticket = reinterpret_cast<unsigned int*>(workspace);
+  ws.partial = reinterpret_cast<double2*>(reinterpret_cast<uint8_t*>(workspace) + BN_MAX_C * sizeof(unsigned int));
+  return ws;
+}
+
+static int elementwise_grid(const BnGeom& g) {
+  const int per_cta = BN_UNROLL * BN_THREADS;
+  int64_t ctas = ((int64_t)g.total + per_cta - 1) / per_cta;
+  const int64_t cap = (int64_t)bn_sms() * 16;
+  if (ctas > cap) ctas = cap;
+  return (int)(ctas < 1 ? 1 : ctas);
+}
+
+}  // namespace po2
+
+using namespace po2;
+
+extern "C" {
+
+size_t po2_bn_workspace_bytes(int C) {
+  if (C <= 0) return 0;
+  return (size_t)BN_MAX_C * sizeof(unsigned int) + (size_t)C * BN_MAX_SPLIT * sizeof(double2);
+}
+
+int po2_bn_stats(const void* x, int B, int C, int HW, float* stat, void* workspace, size_t workspace_bytes,
+                 void* stream) {
+  if (!x || !stat || !workspace) return PO2_E_NULL;
+  if (workspace_bytes < po2_bn_workspace_bytes(C)) return PO2_E_WORKSPACE;
+  if (!aligned16(workspace)) return PO2_E_ALIGN;
+  BnGeom g;
+  const int v = bn_geom(g, B, C, HW, aligned16(x));
+  if (v < 0) return v;
+  const BnWorkspace ws = bn_ws(workspace, C);
+  const dim3 grid(g.S, C);
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* xf = (const float*)x;
+  if (v) bn_reduce_kernel<true, 0><<<grid, BN_THREADS, 0, st>>>(xf, nullptr, nullptr, nullptr, nullptr, stat, nullptr, nullptr, g, ws);
+  else bn_reduce_kernel<false, 0><<<grid, BN_THREADS, 0, st>>>(xf, nullptr, nullptr, nullptr, nullptr, stat, nullptr, nullptr, g, ws);
+  return (int)cudaGetLastError();
+}
+
+int po2_bn_apply(const void* x, const void* residual, void* y, const float* stats, int R, const float* gamma,
+                 const float* beta, float* running_mean, float* running_var, long long* num_batches_tracked,
+                 float momentum, float eps, int act, int use_running, float* save_mean, float* save_invstd, int B,
+                 int C, int HW, void* stream) {
+  if (!x || !y) return PO2_E_NULL;
+  if (use_running ? (!running_mean || !running_var) : (!stats || R < 1)) return PO2_E_NULL;
+  if (act != 0 && act != 1) return PO2_E_MODE;
+  BnGeom g;
+  const int v = bn_geom(g, B, C, HW, aligned16(x) && aligned16(y) && aligned16(residual));
+  if (v < 0) return v;
+  const size_t smem = (size_t)C * sizeof(float4);
+  cudaStream_t st = (cudaStream_t)stream;
+  auto kern = v ? bn_apply_kernel<true> : bn_apply_kernel<false>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  kern<<<elementwise_grid(g), BN_THREADS, smem, st>>>((const float*)x, (const float*)residual, (float*)y, stats, R,
+                                                      gamma, beta, running_mean, running_var, num_batches_tracked,
+                                                      momentum, eps, act, use_running, save_mean, save_invstd, g);
+  return (int)cudaGetLastError();
+}
+
+int po2_bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* save_mean, const float* save_invstd,
+                      float* sums, float* dgamma, float* dbeta, int act, int B, int C, int HW, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  if (!dy || !x || !save_mean || !save_invstd || !sums || !workspace) return PO2_E_NULL;
+  if (act != 0 && act != 1) return PO2_E_MODE;
+  if (act == 1 && !y) return PO2_E_NULL;
+  if (workspace_bytes < po2_bn_workspace_bytes(C)) return PO2_E_WORKSPACE;
+  if (!aligned16(workspace)) return PO2_E_ALIGN;
+  BnGeom g;
+  const int v = bn_geom(g, B, C, HW, aligned16(dy) && aligned16(x) && aligned16(y));
+  if (v < 0) return v;
+  const BnWorkspace ws = bn_ws(workspace, C);
+  const dim3 grid(g.S, C);
+  cudaStream_t st = (cudaStream_t)stream;
+  const float *xf = (const float*)x, *df = (const float*)dy, *yf = (const float*)y;
+  if (act == 1) {
+    if (v) bn_reduce_kernel<true, 2><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws);
+    else bn_reduce_kernel<false, 2><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws);
+  } else {
+    if (v) bn_reduce_kernel<true, 1><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws);
+    else bn_reduce_kernel<false, 1><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws);
+  }
+  return (int)cudaGetLastError();
+}
+
+int po2_bn_bwd_apply(const void* dy, const void* x, const void* y, const float* save_mean, const float* save_invstd,
+                     const float* gamma, const float* sums, const float* stats, int R, void* dx, void* dres, int act,
+                     int B, int C, int HW, void* stream) {
+  if (!dy || !x || !save_mean || !save_invstd || !sums || !stats || !dx || R < 1) return PO2_E_NULL;
+  if (act != 0 && act != 1) return PO2_E_MODE;
+  if (act == 1 && !y) return PO2_E_NULL;
+  BnGeom g;
+  const int v = bn_geom(g, B, C, HW, aligned16(dy) && aligned16(x) && aligned16(y) && aligned16(dx) && aligned16(dres));
+  if (v < 0) return v;
+  const size_t smem = (size_t)C * sizeof(float4);
+  cudaStream_t st = (cudaStream_t)stream;
+  auto kern = v ? bn_bwd_apply_kernel<true> : bn_bwd_apply_kernel<false>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  kern<<<elementwise_grid(g), BN_THREADS, smem, st>>>((const float*)dy, (const float*)x, (const float*)y, save_mean,
+                                                      save_invstd, gamma, sums, stats, R, (float*)dx, (float*)dres,
+                                                      act, g);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

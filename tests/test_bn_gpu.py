@@ -1,0 +1,202 @@
+"""FusedSyncBatchNorm (csrc/po2_bn.cu) against torch's own batch norm -- what the reference's
+nn.SyncBatchNorm layers (models/resnet.py:38-61) compute -- in fp64 on the CPU.
+
+Tolerance: fp32 elementwise work on fp32 statistics accumulated in double: rel 1e-5 (the
+fp32-accumulate bar of BASELINE.json's north_star)."""
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+def _ref_forward_backward(x, res, w, b, relu, go, eps=1e-5):
+    """fp64 CPU reference: returns y, dx, dres, dw, db, batch mean, biased var"""
+    xd = x.detach().double().cpu().requires_grad_(True)
+    rd = res.detach().double().cpu().requires_grad_(True) if res is not None else None
+    wd = w.detach().double().cpu().requires_grad_(True)
+    bd = b.detach().double().cpu().requires_grad_(True)
+    y = F.batch_norm(xd, None, None, wd, bd, True, 0.0, eps)
+    if rd is not None:
+        y = y + rd
+    if relu:
+        y = F.relu(y)
+    y.backward(go.detach().double().cpu())
+    dims = [0] + list(range(2, xd.dim()))
+    return y, xd.grad, rd.grad if rd is not None else None, wd.grad, bd.grad, xd.mean(dims), xd.var(dims, unbiased=False)
+
+
+SHAPES = [(128, 16, 32, 32), (128, 32, 16, 16), (128, 64, 8, 8), (16, 3, 5, 7), (9, 130, 3, 3), (64, 960, 1, 1),
+          (2, 8, 1, 1), (5, 24, 6, 6), (128, 16, 32, 32)]
+
+
+@pytest.mark.parametrize("shape", SHAPES[:8], ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("relu,with_res", [(False, False), (True, False), (True, True), (False, True)])
+def test_train_forward_backward_matches_torch_fp64(shape, relu, with_res):
+    import po2_quantization_b200 as P
+    g = torch.Generator(device="cuda").manual_seed(sum(shape))
+    x = (torch.randn(shape, device="cuda", generator=g) * 1.7 + 0.6).requires_grad_(True)
+    res = torch.randn(shape, device="cuda", generator=g).requires_grad_(True) if with_res else None
+    bn = P.FusedSyncBatchNorm(shape[1]).cuda().train()
+    with torch.no_grad():
+        bn.weight.copy_(torch.randn(shape[1], generator=torch.Generator().manual_seed(1)) * 0.5 + 1.0)
+        bn.bias.copy_(torch.randn(shape[1], generator=torch.Generator().manual_seed(2)) * 0.3)
+    go = torch.randn(shape, device="cuda", generator=g)
+    y = bn(x, res, relu)
+    y.backward(go)
+    yr, dxr, drr, dwr, dbr, mean, var = _ref_forward_backward(x, res, bn.weight, bn.bias, relu, go)
+    assert _rel(y, yr) < TOL
+    n = x.numel() // shape[1]
+    if n >= 8:          # with 2 values per channel dx is eps-sized cancellation noise on any implementation
+        assert _rel(x.grad, dxr) < 5 * TOL
+    else:
+        assert (x.grad.double().cpu() - dxr).abs().max().item() < 1e-6
+    assert _rel(bn.weight.grad, dwr) < 5 * TOL and _rel(bn.bias.grad, dbr) < 5 * TOL
+    if with_res:
+        assert _rel(res.grad, drr) < TOL
+    assert _rel(bn.running_mean, 0.1 * mean) < TOL
+    assert _rel(bn.running_var, 0.9 + 0.1 * var * n / (n - 1)) < TOL
+    assert bn.num_batches_tracked.item() == 1
+
+
+def test_statistics_survive_large_mean():
+    """|mean| >> std: shifted sums keep the variance accurate (E[x^2]-E[x]^2 in fp32 would not)."""
+    import po2_quantization_b200 as P
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(64, 8, 16, 16, device="cuda", generator=g) * 0.01 + 300.0
+    bn = P.FusedSyncBatchNorm(8).cuda().train()
+    y = bn(x)
+    ref = F.batch_norm(x.double().cpu(), None, None, bn.weight.double().cpu(), bn.bias.double().cpu(), True, 0.0, bn.eps)
+    assert _rel(y, ref) < 2e-3          # x itself carries only ~3e-5/0.01 relative precision around its mean
+    var = x.double().var(dim=(0, 2, 3), unbiased=False).mean().item()
+    assert abs(y.std().item() - (var / (var + bn.eps)) ** 0.5) < 1e-3
+
+
+def test_matches_stock_module_state_and_eval_mode():
+    import po2_quantization_b200 as P
+    torch.manual_seed(4)
+    stock = nn.BatchNorm2d(24).cuda().train()
+    mine = P.FusedSyncBatchNorm(24).cuda().train()
+    assert set(stock.state_dict()) == set(mine.state_dict())
+    mine.load_state_dict(stock.state_dict())
+    for it in range(3):
+        x = torch.randn(32, 24, 8, 8, device="cuda") * (1 + it) + it
+        assert _rel(mine(x), stock(x)) < TOL
+    for k, v in stock.state_dict().items():
+        assert _rel(mine.state_dict()[k].float(), v.float()) < TOL, k
+    stock.eval(), mine.eval()
+    x = torch.randn(32, 24, 8, 8, device="cuda")
+    res = torch.randn_like(x)
+    with torch.no_grad():
+        assert _rel(mine(x), stock(x)) < TOL
+        assert _rel(mine(x, res, True), F.relu(stock(x) + res)) < TOL
+    # eval mode under autograd: the stock path, still correct and differentiable
+    x.requires_grad_(True)
+    out = mine(x, res, True)
+    out.sum().backward()
+    assert _rel(out, F.relu(stock(x) + res)) < TOL and x.grad is not None
+
+
+def test_two_rank_statistics_combine_like_sync_batchnorm():
+    """The multi-rank algebra on one GPU: statistics of two half-batches combined by bn_apply and the
+    summed backward partials must equal batch norm over the whole batch (what SyncBatchNorm does)."""
+    from po2_quantization_b200 import batchnorm as bnm
+    g = torch.Generator(device="cuda").manual_seed(5)
+    shape = (24, 16, 8, 8)
+    x = torch.randn(shape, device="cuda", generator=g) * 2 + 1
+    x[:10] += 3.0                                             # the two "ranks" see different distributions
+    go = torch.randn(shape, device="cuda", generator=g)
+    w = torch.rand(16, device="cuda", generator=g) + 0.5
+    b = torch.randn(16, device="cuda", generator=g)
+    parts = [(x[:10].contiguous(), go[:10].contiguous()), (x[10:].contiguous(), go[10:].contiguous())]
+    C = 16
+    stats = torch.empty(2, 2 * C + 1, device="cuda")
+    for r, (xr, _) in enumerate(parts):
+        bnm.bn_stats_out(xr, stats[r])
+    ys, dxs, sums, saves = [], [], [], []
+    for xr, _ in parts:
+        y = torch.empty_like(xr)
+        sm, si = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+        bnm.bn_apply_out(xr, None, y, stats, w, b, None, None, None, 0.1, 1e-5, True, False, sm, si)
+        ys.append(y), saves.append((sm, si))
+    for (xr, gr), y, (sm, si) in zip(parts, ys, saves):
+        s = torch.empty(2 * C, device="cuda")
+        bnm.bn_bwd_reduce_out(gr, xr, y, sm, si, s, None, None, True)
+        sums.append(s)
+    total = sums[0] + sums[1]                                  # the all_reduce
+    for (xr, gr), y, (sm, si) in zip(parts, ys, saves):
+        dx = torch.empty_like(xr)
+        bnm.bn_bwd_apply_out(gr, xr, y, sm, si, w, total, stats, dx, None, True)
+        dxs.append(dx)
+    yr, dxr, _, _, _, _, _ = _ref_forward_backward(x, None, w, b, True, go)
+    assert _rel(torch.cat(ys), yr) < TOL
+    assert _rel(torch.cat(dxs), dxr) < 5 * TOL
+
+
+def test_cuda_graph_capture_and_replay():
+    import po2_quantization_b200 as P
+    bn = P.FusedSyncBatchNorm(32).cuda().train()
+    x = torch.randn(16, 32, 8, 8, device="cuda", requires_grad=True)
+    res = torch.randn(16, 32, 8, 8, device="cuda")
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            bn(x, res, True).sum().backward()
+        x.grad = None
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=s):
+            y = bn(x, res, True)
+            y.sum().backward()
+    torch.cuda.current_stream().wait_stream(s)
+    nb = bn.num_batches_tracked.item()
+    with torch.no_grad():
+        x.copy_(torch.randn_like(x) * 3)
+    gr.replay()
+    torch.cuda.synchronize()
+    yr, dxr, *_ = _ref_forward_backward(x, res, bn.weight, bn.bias, True, torch.ones_like(x))
+    assert _rel(y, yr) < TOL and _rel(x.grad, dxr) < 5 * TOL
+    assert bn.num_batches_tracked.item() == nb + 1
+
+
+def test_resnet20_train_step_with_fused_norm_equals_stock_norm():
+    """Same model, same weights: FusedSyncBatchNorm vs nn.SyncBatchNorm in the block graph."""
+    import po2_quantization_b200 as P
+    from po2_quantization_b200 import ops
+    from workloads import resnet_cifar
+    torch.manual_seed(6)
+    ops.set_conv_mode("fp32")
+    ops.set_dgrad_mode("aten")
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        a = resnet_cifar(20, 10, P.PowerOfTwoQuantizer, 4).cuda().train()
+        b = resnet_cifar(20, 10, P.PowerOfTwoQuantizer, 4, norm_cls=nn.SyncBatchNorm).cuda().train()
+        b.load_state_dict(a.state_dict())
+        x = torch.randn(32, 3, 32, 32, device="cuda")
+        t = torch.randint(0, 10, (32,), device="cuda")
+        la = F.cross_entropy(a(x), t)
+        lb = F.cross_entropy(b(x), t)
+        la.backward(), lb.backward()
+        assert abs(la.item() - lb.item()) < 1e-4
+        pb = dict(b.named_parameters())
+        for n, p in a.named_parameters():
+            gb = pb[n].grad
+            if gb.abs().max() < 1e-6:
+                continue
+            assert _rel(p.grad, gb) < 2e-2, n                  # train-mode BN chains amplify fp32 rounding
+        for (n, va), vb in zip(a.state_dict().items(), b.state_dict().values()):
+            if "running" in n:
+                assert _rel(va, vb) < 1e-4, n
+    finally:
+        ops.set_conv_mode("tc")
+        ops.set_dgrad_mode("tc")
+        torch.backends.cudnn.allow_tf32 = old
