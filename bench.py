@@ -83,11 +83,29 @@ def build_training(device, world, local_rank, batch):
     torch.manual_seed(8)
     model = resnet_cifar(56, 10, P.PowerOfTwoQuantizer, 4).to(device).train()
     if world > 1:
-        model = nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])
+        if os.environ.get("PO2_DDP", "0") == "1":
+            # torch's DistributedDataParallel, as the reference wraps its model (train.py:153-155)
+            model = nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True,
+                                                        broadcast_buffers=False)
+        else:
+            # same arithmetic, one coalesced NCCL all-reduce(AVG) per step (distributed.BatchSharded)
+            from po2_quantization_b200.distributed import BatchSharded
+            model = BatchSharded(model)
     # reference train.py:51-56: SGD momentum 0.9, wd 1e-4, lr 0.1 * world
     opt = torch.optim.SGD(model.parameters(), lr=0.1 * world, momentum=0.9, weight_decay=1e-4)
     crit = nn.CrossEntropyLoss()
     return model, opt, crit
+
+
+def _parallelism_note():
+    from po2_quantization_b200 import batchnorm
+    grads = ("torch DDP buckets" if os.environ.get("PO2_DDP", "0") == "1"
+             else "one coalesced NCCL all-reduce(AVG) of the gradients per step")
+    ex = [e for e in batchnorm._exchanges.values()]
+    mode = os.environ.get("PO2_BN_EXCHANGE", "peer")
+    bn = ("SyncBatchNorm statistics exchanged inside the BN kernels over NVLink peer stores" if any(e is not None for e in ex)
+          else "per-rank BatchNorm statistics" if mode == "local" else "SyncBatchNorm statistics over NCCL all_gather/all_reduce")
+    return f" (batch-sharded; {grads}; {bn})"
 
 
 def activation_bytes_estimate(batch):
@@ -139,8 +157,34 @@ def _run_ours_on_stream(a, ops, world, rank, local_rank, device):
         opt.zero_grad()  # reference train.py:81 (set_to_none=True: no fill / accumulate kernels)
         loss = crit(model(x_dev), y_dev)
         loss.backward()
+        if hasattr(model, "average_gradients"):
+            model.average_gradients()
         opt.step()
         loss_buf.copy_(loss.detach())
+
+    if a.torch_profile:
+        # kernel-time table of eager steps from torch.profiler (works under torchrun, where ncu does not):
+        # rank 0 writes the per-kernel totals of 5 steps to the given path
+        from torch.profiler import ProfilerActivity, profile
+        for _ in range(12):
+            step()
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(5):
+                step()
+            torch.cuda.synchronize()
+        if rank == 0:
+            rows = [(e.key, e.count, e.device_time_total) for e in prof.key_averages() if e.device_time_total > 0]
+            rows.sort(key=lambda r: -r[2])
+            tot = sum(r[2] for r in rows)
+            with open(a.torch_profile, "w") as f:
+                f.write(f"# 5 eager steps, world={world}; total device time {tot / 5:.1f} us per step\n")
+                for k, c, t in rows:
+                    f.write(f"{t / 5:10.1f} us/step {c // 5:5d} x  {100 * t / tot:5.1f}%  {k[:110]}\n")
+            print(json.dumps({"torch_profile": a.torch_profile, "device_us_per_step": tot / 5}))
+        return
 
     if a.profile_step:
         # one eager step between cudaProfilerStart/Stop: `ncu --profile-from-start off` lists exactly
@@ -239,7 +283,7 @@ def _run_ours_on_stream(a, ops, world, rank, local_rank, device):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic (randn images 3x32x32, randint labels; kaiming-init weights, seed 8)",
         "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
-                   "parallelism": f"dp{world}" + (" (DDP + SyncBatchNorm, NCCL)" if world > 1 else ""),
+                   "parallelism": f"dp{world}" + (_parallelism_note() if world > 1 else ""),
                    "cuda_graph": graph is not None,
                    "l2": "working set per step ~%d MB of saved activations > 126 MB L2; no flush needed"
                          % (activation_bytes_estimate(B) // 2 ** 20),
@@ -451,6 +495,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep-log2", type=int, default=30)
+    ap.add_argument("--torch-profile", default=None, help="write a torch.profiler kernel table of eager steps and exit")
     ap.add_argument("--profile-step", action="store_true", help="run one eager step inside cudaProfilerStart/Stop and exit")
     a = ap.parse_args()
     if a.impl == "reference":

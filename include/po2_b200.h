@@ -160,17 +160,29 @@ int po2_conv2d_dgrad(const void* g, const void* w, const float* scale, void* gx,
  *   gradient of the residual branch behind the ReLU. */
 size_t po2_bn_workspace_bytes(int C);
 int po2_bn_stats(const void* x, int B, int C, int HW, float* stat, void* workspace, size_t workspace_bytes,
-                 void* stream);
-int po2_bn_apply(const void* x, const void* residual, void* y, const float* stats, int R, const float* gamma,
-                 const float* beta, float* running_mean, float* running_var, long long* num_batches_tracked,
-                 float momentum, float eps, int act, int use_running, float* save_mean, float* save_invstd, int B,
-                 int C, int HW, void* stream);
+                 void* const* peers, int rank, int world, void* stream);
+int po2_bn_apply(const void* x, const void* residual, void* y, const float* stats, int R, void* mailbox,
+                 float* stats_dense, const float* gamma, const float* beta, float* running_mean,
+                 float* running_var, long long* num_batches_tracked, float momentum, float eps, int act,
+                 int use_running, float* save_mean, float* save_invstd, int B, int C, int HW, void* stream);
 int po2_bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* save_mean, const float* save_invstd,
                       float* sums, float* dgamma, float* dbeta, int act, int B, int C, int HW, void* workspace,
-                      size_t workspace_bytes, void* stream);
+                      size_t workspace_bytes, void* const* peers, int rank, int world, void* stream);
 int po2_bn_bwd_apply(const void* dy, const void* x, const void* y, const float* save_mean, const float* save_invstd,
-                     const float* gamma, const float* sums, const float* stats, int R, void* dx, void* dres, int act,
-                     int B, int C, int HW, void* stream);
+                     const float* gamma, const float* sums, const float* stats, int R, void* mailbox, void* dx,
+                     void* dres, int act, int B, int C, int HW, void* stream);
+
+/* Peer exchange (one NVLink domain, <= 8 ranks): SyncBatchNorm's two collectives done by the kernels
+ * themselves.  Every rank allocates one zero-initialised mailbox of po2_bn_mailbox_bytes() in memory
+ * that its peers have mapped (torch.distributed._symmetric_memory); `peers` is a HOST array of
+ * `world` device pointers -- rank r's mailbox as mapped in this process.  With peers != NULL and
+ * world > 1, po2_bn_stats / po2_bn_bwd_reduce additionally store this rank's vector into every
+ * rank's mailbox (the all_gather / all_reduce over NVLink stores, flagged with an epoch number);
+ * po2_bn_apply / po2_bn_bwd_apply given mailbox = this rank's own mailbox (and R = world) wait for
+ * the R vectors of the current epoch instead of reading `stats` / `sums` (which may then be NULL;
+ * po2_bn_apply copies the gathered statistics to stats_dense[R][2C+1] for the backward call).
+ * All ranks must issue the same sequence of exchanges (the rule of any collective). */
+size_t po2_bn_mailbox_bytes(void);
 
 #ifdef __cplusplus
 }

@@ -39,11 +39,12 @@ SIGNATURES = {
     "po2_conv2d_dgrad_workspace": (_sz, [_i] * 9),
     "po2_conv2d_dgrad": (_i, [_vp, _vp, _vp, _vp] + [_i] * 14 + [_vp, _sz, _vp]),
     "po2_bn_workspace_bytes": (_sz, [_i]),
-    "po2_bn_stats": (_i, [_vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
-    "po2_bn_apply": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _c.c_float, _c.c_float, _i, _i,
-                          _vp, _vp, _i, _i, _i, _vp]),
-    "po2_bn_bwd_reduce": (_i, [_vp] * 8 + [_i] * 4 + [_vp, _sz, _vp]),
-    "po2_bn_bwd_apply": (_i, [_vp] * 8 + [_i, _vp, _vp] + [_i] * 4 + [_vp]),
+    "po2_bn_mailbox_bytes": (_sz, []),
+    "po2_bn_stats": (_i, [_vp, _i, _i, _i, _vp, _vp, _sz, _vp, _i, _i, _vp]),
+    "po2_bn_apply": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c.c_float, _c.c_float,
+                          _i, _i, _vp, _vp, _i, _i, _i, _vp]),
+    "po2_bn_bwd_reduce": (_i, [_vp] * 8 + [_i] * 4 + [_vp, _sz, _vp, _i, _i, _vp]),
+    "po2_bn_bwd_apply": (_i, [_vp] * 8 + [_i, _vp, _vp, _vp] + [_i] * 4 + [_vp]),
 }
 
 _lock = threading.Lock()

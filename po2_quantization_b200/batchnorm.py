@@ -10,9 +10,15 @@ block so that ``relu(bn(x) + shortcut)`` is one streaming pass forward and one b
 
 The collective sits exactly where torch's SyncBatchNorm has it (same algebra: per-rank mean / M2 /
 count combined with the parallel-variance formula; gradient of the affine parameters from local
-sums).  Inputs the kernels do not cover (CPU tensors, non-fp32, eval mode under autograd,
+sums).  Within one NVLink domain (<= 8 ranks) the bracketed collectives are not separate launches at
+all: the producing kernel stores this rank's vector into every rank's mailbox (symmetric memory,
+``PeerExchange``) and the consuming kernel waits for the R vectors -- see csrc/po2_bn.cu.  NCCL
+(``PO2_BN_EXCHANGE=nccl``, larger groups, or no symmetric memory) remains the other path.  Inputs the kernels do not cover (CPU tensors, non-fp32, eval mode under autograd,
 ``momentum=None``) take ``nn.SyncBatchNorm.forward`` itself followed by the add and the ReLU.
 """
+import ctypes
+import os
+import sys
 from typing import Optional
 
 import torch
@@ -43,50 +49,124 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 # ------------------------------------------------------------------------------------------------
+# peer exchange: the two SyncBatchNorm collectives done inside the kernels over NVLink stores
+# ------------------------------------------------------------------------------------------------
+class PeerExchange:
+    """This rank's mailbox (csrc/po2_bn.cu, BnMailbox) in symmetric memory plus the host array of
+    every rank's mailbox pointer as mapped here.  One per process group; at most 8 ranks."""
+
+    def __init__(self, peers, rank: int, world: int, keepalive=None):
+        self.peers = (ctypes.c_void_p * world)(*peers)
+        self.rank, self.world = rank, world
+        self.mailbox = peers[rank]
+        self._keepalive = keepalive
+
+    @classmethod
+    def create(cls, group) -> "PeerExchange":
+        import torch.distributed._symmetric_memory as symm_mem
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        buf = symm_mem.empty(int(_lib.load().po2_bn_mailbox_bytes()), dtype=torch.uint8, device=dev)
+        buf.zero_()
+        handle = symm_mem.rendezvous(buf, group)
+        peers = [int(p) for p in handle.buffer_ptrs]
+        if len(peers) != world or peers[rank] != buf.data_ptr():
+            raise RuntimeError("symmetric-memory rendezvous returned an unexpected pointer table")
+        torch.cuda.synchronize(dev)
+        return cls(peers, rank, world, keepalive=(buf, handle))
+
+    def error_flag(self) -> int:
+        """non-zero once a wait timed out (a peer stopped publishing)"""
+        buf = self._keepalive[0] if self._keepalive else None
+        return int(buf[4:8].view(torch.int32).item()) if buf is not None else 0
+
+
+_exchanges = {}
+
+
+def peer_exchange_for(group) -> Optional[PeerExchange]:
+    """The PeerExchange of `group`, created (collectively) on first use; None when the group spans
+    more than 8 ranks, PO2_BN_EXCHANGE=nccl, or symmetric memory cannot be set up on EVERY rank (the
+    ranks agree through one all_reduce, so either all use it or none does)."""
+    key = id(group)
+    if key in _exchanges:
+        return _exchanges[key]
+    ex = None
+    world = dist.get_world_size(group)
+    want = os.environ.get("PO2_BN_EXCHANGE", "peer") == "peer" and 1 < world <= 8
+    if want:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("the first multi-rank FusedSyncBatchNorm call sets up symmetric memory and must "
+                               "not happen inside a CUDA graph capture: run one eager step first")
+        try:
+            ex = PeerExchange.create(group)
+        except Exception as e:  # noqa: BLE001 -- any failure on any rank demotes every rank to NCCL
+            print(f"[po2] peer exchange unavailable on rank {dist.get_rank(group)} ({type(e).__name__}: {e}); "
+                  "SyncBatchNorm statistics go through NCCL", file=sys.stderr)
+            ex = None
+        ok = torch.tensor([1 if ex is not None else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if ok.item() == 0:
+            ex = None
+        dist.barrier(group)                      # every mailbox is zeroed and mapped before anyone publishes
+    _exchanges[key] = ex
+    return ex
+
+
+def _peer_args(exch):
+    return (exch.peers, exch.rank, exch.world) if exch is not None else (None, 0, 1)
+
+
+# ------------------------------------------------------------------------------------------------
 # raw launchers
 # ------------------------------------------------------------------------------------------------
-def bn_stats_out(x: torch.Tensor, stat: torch.Tensor) -> None:
-    """stat[0:C] = mean, stat[C:2C] = sum of squared deviations, stat[2C] = B*H*W (this rank)."""
+def bn_stats_out(x: torch.Tensor, stat: torch.Tensor, exch: Optional[PeerExchange] = None) -> None:
+    """stat[0:C] = mean, stat[C:2C] = sum of squared deviations, stat[2C] = B*H*W (this rank); with
+    `exch` the vector is also stored into every rank's mailbox."""
     B, C = x.shape[0], x.shape[1]
     HW = x.numel() // (B * C)
     ws = _bn_workspace(x.device, C)
     ops.LAUNCHES += 1
     _lib.check(_lib.load().po2_bn_stats(x.data_ptr(), B, C, HW, stat.data_ptr(), ws.data_ptr(), ws.numel(),
-                                        ops._stream_ptr(x.device)), "po2_bn_stats")
+                                        *_peer_args(exch), ops._stream_ptr(x.device)), "po2_bn_stats")
 
 
 def bn_apply_out(x, residual, y, stats, weight, bias, running_mean, running_var, num_batches_tracked,
-                 momentum, eps, relu, use_running, save_mean, save_invstd) -> None:
+                 momentum, eps, relu, use_running, save_mean, save_invstd, exch=None, stats_dense=None) -> None:
     B, C = x.shape[0], x.shape[1]
     HW = x.numel() // (B * C)
-    R = 1 if stats is None else stats.numel() // (2 * C + 1)
+    if exch is not None:
+        R = exch.world
+    else:
+        R = 1 if stats is None else stats.numel() // (2 * C + 1)
     ops.LAUNCHES += 1
     _lib.check(_lib.load().po2_bn_apply(
-        x.data_ptr(), _ptr(residual), y.data_ptr(), _ptr(stats), R, _ptr(weight), _ptr(bias), _ptr(running_mean),
-        _ptr(running_var), _ptr(num_batches_tracked), float(momentum), float(eps), int(relu), int(use_running),
+        x.data_ptr(), _ptr(residual), y.data_ptr(), _ptr(stats), R, exch.mailbox if exch is not None else None,
+        _ptr(stats_dense), _ptr(weight), _ptr(bias), _ptr(running_mean), _ptr(running_var),
+        _ptr(num_batches_tracked), float(momentum), float(eps), int(relu), int(use_running),
         _ptr(save_mean), _ptr(save_invstd), B, C, HW, ops._stream_ptr(x.device)), "po2_bn_apply")
 
 
-def bn_bwd_reduce_out(dy, x, y, save_mean, save_invstd, sums, dgamma, dbeta, relu) -> None:
+def bn_bwd_reduce_out(dy, x, y, save_mean, save_invstd, sums, dgamma, dbeta, relu, exch=None) -> None:
     B, C = x.shape[0], x.shape[1]
     HW = x.numel() // (B * C)
     ws = _bn_workspace(x.device, C)
     ops.LAUNCHES += 1
     _lib.check(_lib.load().po2_bn_bwd_reduce(
         dy.data_ptr(), x.data_ptr(), _ptr(y), save_mean.data_ptr(), save_invstd.data_ptr(), sums.data_ptr(),
-        _ptr(dgamma), _ptr(dbeta), int(relu), B, C, HW, ws.data_ptr(), ws.numel(), ops._stream_ptr(x.device)),
-        "po2_bn_bwd_reduce")
+        _ptr(dgamma), _ptr(dbeta), int(relu), B, C, HW, ws.data_ptr(), ws.numel(), *_peer_args(exch),
+        ops._stream_ptr(x.device)), "po2_bn_bwd_reduce")
 
 
-def bn_bwd_apply_out(dy, x, y, save_mean, save_invstd, weight, sums, stats, dx, dres, relu) -> None:
+def bn_bwd_apply_out(dy, x, y, save_mean, save_invstd, weight, sums, stats, dx, dres, relu, exch=None) -> None:
     B, C = x.shape[0], x.shape[1]
     HW = x.numel() // (B * C)
     R = stats.numel() // (2 * C + 1)
     ops.LAUNCHES += 1
     _lib.check(_lib.load().po2_bn_bwd_apply(
         dy.data_ptr(), x.data_ptr(), _ptr(y), save_mean.data_ptr(), save_invstd.data_ptr(), _ptr(weight),
-        sums.data_ptr(), stats.data_ptr(), R, dx.data_ptr(), _ptr(dres), int(relu), B, C, HW,
-        ops._stream_ptr(x.device)), "po2_bn_bwd_apply")
+        _ptr(sums), stats.data_ptr(), R, exch.mailbox if exch is not None else None, dx.data_ptr(), _ptr(dres),
+        int(relu), B, C, HW, ops._stream_ptr(x.device)), "po2_bn_bwd_apply")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -95,25 +175,32 @@ def bn_bwd_apply_out(dy, x, y, save_mean, save_invstd, weight, sums, stats, dx, 
 class _BatchNormTrain(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, residual, weight, bias, running_mean, running_var, num_batches_tracked, momentum, eps,
-                relu, group, world):
+                relu, group, world, exch):
         x = x.contiguous()
         if residual is not None:
             residual = residual.contiguous()
         C = x.shape[1]
         with torch.cuda.device(x.device):
             stat = torch.empty(2 * C + 1, dtype=torch.float32, device=x.device)
-            bn_stats_out(x, stat)
-            if world > 1:
-                stats = torch.empty(world, 2 * C + 1, dtype=torch.float32, device=x.device)
-                dist.all_gather_into_tensor(stats.view(-1), stat, group=group)
-            else:
-                stats = stat.view(1, -1)
             y = torch.empty_like(x)
             save_mean = torch.empty(C, dtype=torch.float32, device=x.device)
             save_invstd = torch.empty(C, dtype=torch.float32, device=x.device)
-            bn_apply_out(x, residual, y, stats, weight, bias, running_mean, running_var, num_batches_tracked,
-                         momentum, eps, relu, False, save_mean, save_invstd)
-        ctx.relu, ctx.has_res, ctx.group, ctx.world = relu, residual is not None, group, world
+            if world > 1 and exch is not None:
+                # all_gather inside the kernels: stats publishes to every rank's mailbox, apply waits for R vectors
+                bn_stats_out(x, stat, exch)
+                stats = torch.empty(world, 2 * C + 1, dtype=torch.float32, device=x.device)
+                bn_apply_out(x, residual, y, None, weight, bias, running_mean, running_var, num_batches_tracked,
+                             momentum, eps, relu, False, save_mean, save_invstd, exch=exch, stats_dense=stats)
+            else:
+                bn_stats_out(x, stat)
+                if world > 1:
+                    stats = torch.empty(world, 2 * C + 1, dtype=torch.float32, device=x.device)
+                    dist.all_gather_into_tensor(stats.view(-1), stat, group=group)
+                else:
+                    stats = stat.view(1, -1)
+                bn_apply_out(x, residual, y, stats, weight, bias, running_mean, running_var, num_batches_tracked,
+                             momentum, eps, relu, False, save_mean, save_invstd)
+        ctx.relu, ctx.has_res, ctx.group, ctx.world, ctx.exch = relu, residual is not None, group, world, exch
         ctx.save_for_backward(x, y if relu else None, weight, save_mean, save_invstd, stats)
         return y
 
@@ -123,21 +210,22 @@ class _BatchNormTrain(torch.autograd.Function):
         dy = dy.contiguous()
         C = x.shape[1]
         need_x, need_res, need_w, need_b = ctx.needs_input_grad[:4]
+        exch = ctx.exch if ctx.world > 1 else None
         with torch.cuda.device(x.device):
             sums = torch.empty(2 * C, dtype=torch.float32, device=x.device)
             dgamma = torch.empty(C, dtype=torch.float32, device=x.device) if weight is not None else None
             dbeta = torch.empty(C, dtype=torch.float32, device=x.device) if weight is not None else None
-            bn_bwd_reduce_out(dy, x, y, save_mean, save_invstd, sums, dgamma, dbeta, ctx.relu)
-            if ctx.world > 1:
+            bn_bwd_reduce_out(dy, x, y, save_mean, save_invstd, sums, dgamma, dbeta, ctx.relu, exch)
+            if ctx.world > 1 and exch is None:
                 dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=ctx.group)
             dx = torch.empty_like(x)
             dres = None
             if ctx.has_res and need_res:
                 dres = torch.empty_like(x) if ctx.relu else dy       # without the ReLU the branch gets dy itself
             bn_bwd_apply_out(dy, x, y, save_mean, save_invstd, weight, sums, stats, dx,
-                             dres if ctx.relu else None, ctx.relu)
+                             dres if ctx.relu else None, ctx.relu, exch)
         return (dx if need_x else None, dres, dgamma if need_w else None, dbeta if need_b else None,
-                None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None)
 
 
 def _kernel_ok(x: torch.Tensor) -> bool:
@@ -155,15 +243,19 @@ class FusedSyncBatchNorm(nn.SyncBatchNorm):
         if fast and use_batch_stats and (self.momentum is not None or self.running_mean is None):
             if input.numel() // input.shape[1] <= 1:
                 raise ValueError(f"Expected more than 1 value per channel when training, got input size {input.size()}")
-            world, group = 1, None
+            world, group, exch = 1, None, None
             if self.training and dist.is_available() and dist.is_initialized():
                 group = self.process_group if self.process_group is not None else dist.group.WORLD
                 world = dist.get_world_size(group)
+                if os.environ.get("PO2_BN_EXCHANGE") == "local":     # nn.BatchNorm2d semantics: per-rank statistics
+                    world = 1
+                if world > 1:
+                    exch = peer_exchange_for(group)
             track = self.training and self.track_running_stats
             return _BatchNormTrain.apply(
                 input, residual, self.weight, self.bias, self.running_mean if track else None,
                 self.running_var if track else None, self.num_batches_tracked if track else None,
-                self.momentum if self.momentum is not None else 0.0, self.eps, bool(relu), group, world)
+                self.momentum if self.momentum is not None else 0.0, self.eps, bool(relu), group, world, exch)
         if fast and not use_batch_stats and not (torch.is_grad_enabled() and (
                 input.requires_grad or (residual is not None and residual.requires_grad) or
                 (self.weight is not None and self.weight.requires_grad))):

@@ -38,9 +38,106 @@ struct BnGeom {
 };
 
 struct BnWorkspace {              // caller-provided, zero-initialised once; kernels leave counters zero
-  unsigned int* ticket;           // [BN_MAX_C], first in the buffer
+  unsigned int* ticket;           // [BN_MAX_C + 1] (per channel + one for the whole grid), first in the buffer
   double2* partial;               // [C][BN_MAX_SPLIT]
 };
+
+// ---- peer exchange: SyncBatchNorm's collectives inside the kernels ---------------------------------
+// Every rank owns one BnMailbox in memory that all ranks of the NVLink domain have mapped (symmetric
+// allocation; box[r] is rank r's mailbox in THIS rank's address space).  An exchange moves one small
+// vector per rank (2C+1 statistics forward, 2C sums backward) with a flag-less low-latency protocol:
+// every value travels as ONE 8-byte store {value bits, epoch tag} (8-byte stores are single
+// transactions on the GPU and over NVLink), so there is no separate flag, no system-scope fence and
+// no round trip on the producer -- the CTA that finishes channel c stores that channel's values
+// straight into slot [epoch % BN_SLOTS].ll[rank] of EVERY rank's mailbox and is done.  The
+// consuming kernel (apply / backward apply), next in the stream, polls the R tagged copies of each
+// value it needs in its own mailbox until the tag equals the current epoch.  No collective launch,
+// no host involvement, CUDA-graph replayable (the epoch lives in device memory; the last CTA of the
+// producing grid advances it).  All ranks perform the same sequence of exchanges, so their epochs
+// agree; a rank can be at most one exchange ahead of a peer (it needs the peer's values to get
+// past the consumer), so with BN_SLOTS >= 2 a slot is never overwritten while it is being read, and
+// a stale tag (epoch - BN_SLOTS) can never be mistaken for the current one.
+constexpr int BN_MAX_RANKS = 8;
+constexpr int BN_SLOTS = 4;
+constexpr int BN_PAYLOAD = 2 * BN_MAX_C + 32;      // values per rank per slot (>= 2C+1)
+struct BnMailSlot {
+  uint2 ll[BN_MAX_RANKS][BN_PAYLOAD];              // {value bits, epoch tag}
+};
+struct BnMailbox {
+  uint32_t epoch;                                  // exchanges this rank has completed producing
+  uint32_t error;                                  // set when a poll timed out (a peer died)
+  uint32_t pad[14];
+  BnMailSlot slot[BN_SLOTS];
+};
+struct BnPeers {
+  BnMailbox* box[BN_MAX_RANKS];
+  int rank, world;                                 // world <= 1: no exchange
+};
+
+__device__ __forceinline__ void st_ll(uint2* p, float v, uint32_t tag) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" :: "l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// poll one tagged value of this rank's own mailbox
+__device__ __forceinline__ float ld_ll(const uint2* p, uint32_t tag, BnMailbox* me) {
+  uint32_t v, t;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(t) : "l"(p) : "memory");
+  if (t != tag) {
+    const unsigned long long t0 = global_ns();
+    do {
+      __nanosleep(64);
+      asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(t) : "l"(p) : "memory");
+      if (global_ns() - t0 > 20000000000ull) { me->error = 1; break; }      // 20 s: a peer is gone
+    } while (t != tag);
+  }
+  return __uint_as_float(v);
+}
+
+// R vectors of the current exchange: dense rows (stats != nullptr) or this rank's mailbox.
+// fetch<N>: values idx[0..N) of every rank at once -- all loads are issued before the first tag is
+// looked at (N*R independent L2 reads instead of a chain of dependent polls); a value whose tag is
+// not there yet falls to the polling loop.
+struct BnGather {
+  const float* dense; int stride;
+  const uint2* ll; uint32_t tag; BnMailbox* me;
+  template <int N>
+  __device__ __forceinline__ void fetch(int R, const int (&idx)[N], float (&out)[N][BN_MAX_RANKS]) const {
+    if (ll) {
+      uint2 raw[N][BN_MAX_RANKS];
+#pragma unroll
+      for (int r = 0; r < BN_MAX_RANKS; ++r)
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+          if (r < R) raw[k][r] = __ldcv(ll + (size_t)r * BN_PAYLOAD + idx[k]);
+#pragma unroll
+      for (int r = 0; r < BN_MAX_RANKS; ++r)
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+          if (r < R)
+            out[k][r] = raw[k][r].y == tag ? __uint_as_float(raw[k][r].x)
+                                           : ld_ll(ll + (size_t)r * BN_PAYLOAD + idx[k], tag, me);
+    } else {
+#pragma unroll
+      for (int r = 0; r < BN_MAX_RANKS; ++r)
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+          if (r < R) out[k][r] = __ldcg(dense + (size_t)r * stride + idx[k]);
+    }
+  }
+};
+__device__ __forceinline__ BnGather gather_from(const float* dense, int stride, BnMailbox* mailbox) {
+  BnGather g;
+  g.dense = dense; g.stride = stride; g.ll = nullptr; g.tag = 0; g.me = mailbox;
+  if (mailbox) {
+    g.tag = *reinterpret_cast<volatile uint32_t*>(&mailbox->epoch);       // advanced by the producing grid
+    g.ll = &mailbox->slot[g.tag % BN_SLOTS].ll[0][0];
+  }
+  return g;
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -89,14 +186,20 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const float* __re
                                                                float* __restrict__ out,      // MODE 0: stat[2C+1]; else sums[2C]
                                                                float* __restrict__ dgamma,
                                                                float* __restrict__ dbeta, BnGeom g,
-                                                               BnWorkspace ws) {
+                                                               BnWorkspace ws, BnPeers peers) {
   __shared__ double sm[BN_THREADS / 32][2];
   __shared__ int flag;
+  __shared__ uint32_t s_epoch;
+  __shared__ float s_val[2];
   const int s = blockIdx.x, c = blockIdx.y;
   const int L = g.L, C = g.C;
   const int nslab = (g.B - s + g.S - 1) / g.S;                 // slabs b = s, s+S, ...
   const int n = nslab * L;
   const float shift = MODE == 0 ? __ldg(x + (size_t)c * g.HW) : __ldg(mean + c);
+  // tag of the exchange this grid produces; read before any CTA can have advanced it (the advance
+  // needs every CTA's ticket, taken below), visible to the CTA after the first barrier in block_sum2
+  if (threadIdx.x == 0 && peers.world > 1)
+    s_epoch = *reinterpret_cast<volatile uint32_t*>(&peers.box[peers.rank]->epoch) + 1;
   float s1 = 0.f, s2 = 0.f;
   for (int i0 = threadIdx.x; i0 < n; i0 += BN_UNROLL * BN_THREADS) {
     if (VEC) {
@@ -158,17 +261,40 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const float* __re
   }
   block_sum2(pa, pb, sm);
   if (threadIdx.x == 0) {
+    float v0, v1;
     if (MODE == 0) {
       const double cnt = (double)g.B * (double)g.HW;
       const double m = pa / cnt;
-      out[c] = (float)((double)shift + m);
-      out[C + c] = (float)fmax(pb - pa * m, 0.0);               // M2 = sum (x-mean)^2
+      v0 = (float)((double)shift + m);
+      v1 = (float)fmax(pb - pa * m, 0.0);                        // M2 = sum (x-mean)^2
       if (c == 0) out[2 * C] = (float)cnt;
     } else {
-      out[c] = (float)pa;                                        // sum g
-      out[C + c] = (float)pb;                                    // sum g*(x-mean)
-      if (dbeta) dbeta[c] = (float)pa;
+      v0 = (float)pa;                                            // sum g
+      v1 = (float)pb;                                            // sum g*(x-mean)
+      if (dbeta) dbeta[c] = v0;
       if (dgamma) dgamma[c] = (float)(pb * (double)__ldg(invstd + c));
+    }
+    out[c] = v0;
+    out[C + c] = v1;
+    s_val[0] = v0; s_val[1] = v1;
+  }
+  if (peers.world <= 1) return;
+  __syncthreads();
+  // this channel's values go straight to every rank's mailbox (one thread per destination)
+  if ((int)threadIdx.x < peers.world) {
+    const uint32_t tag = s_epoch;
+    uint2* dst = peers.box[threadIdx.x]->slot[tag % BN_SLOTS].ll[peers.rank];
+    st_ll(dst + c, s_val[0], tag);
+    st_ll(dst + C + c, s_val[1], tag);
+    if (MODE == 0 && c == 0) st_ll(dst + 2 * C, (float)((double)g.B * (double)g.HW), tag);
+  }
+  // the CTA that finishes the last channel advances this rank's epoch for the consuming kernel
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(ws.ticket + BN_MAX_C, 1u);
+    if (t == (unsigned int)(C - 1)) {
+      ws.ticket[BN_MAX_C] = 0;
+      peers.box[peers.rank]->epoch = s_epoch;
     }
   }
 }
@@ -176,30 +302,31 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const float* __re
 // ---- per-channel parameters in shared memory ----------------------------------------------------
 // forward: {mean, gamma*invstd, beta, -};  statistics = R entries of [mean[C] | M2[C] | count] (train)
 // or the running statistics (eval).
-__device__ __forceinline__ void combine_stats(const float* __restrict__ stats, int R, int C, int c, double& mean,
+__device__ __forceinline__ void combine_stats(const BnGather& src, int R, int C, int c, double& mean,
                                               double& var_biased, double& count) {
+  const int idx[3] = {c, C + c, 2 * C};
+  float v[3][BN_MAX_RANKS];                          // mean, M2, count of every rank
+  src.fetch<3>(R, idx, v);
   double n = 0.0, m = 0.0;
   for (int r = 0; r < R; ++r) {
-    const float* st = stats + (size_t)r * (2 * C + 1);
-    const double nr = (double)st[2 * C];
-    n += nr;
-    m += nr * (double)st[c];
+    n += (double)v[2][r];
+    m += (double)v[2][r] * (double)v[0][r];
   }
   m /= n;
   double m2 = 0.0;
   for (int r = 0; r < R; ++r) {
-    const float* st = stats + (size_t)r * (2 * C + 1);
-    const double d = (double)st[c] - m;
-    m2 += (double)st[C + c] + (double)st[2 * C] * d * d;
+    const double d = (double)v[0][r] - m;
+    m2 += (double)v[1][r] + (double)v[2][r] * d * d;
   }
   mean = m; var_biased = m2 / n; count = n;
 }
 
 template <bool VEC>
-__global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const float* __restrict__ x,
+__global__ void __launch_bounds__(BN_THREADS, 4) bn_apply_kernel(const float* __restrict__ x,
                                                               const float* __restrict__ res,
                                                               float* __restrict__ y,
-                                                              const float* __restrict__ stats, int R,
+                                                              const float* stats, int R, BnMailbox* mailbox,
+                                                              float* __restrict__ stats_dense,
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta,
                                                               float* running_mean, float* running_var,
@@ -209,10 +336,18 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const float* __res
                                                               float* __restrict__ save_invstd, BnGeom g) {
   extern __shared__ float4 prm[];
   const int C = g.C;
+  const BnGather src = gather_from(stats, 2 * C + 1, use_running ? nullptr : mailbox);
+  if (src.ll && blockIdx.x == 0 && stats_dense)          // dense copy of the gathered statistics for backward
+    for (int i = threadIdx.x; i < 2 * C + 1; i += BN_THREADS) {
+      const int idx[1] = {i};
+      float v[1][BN_MAX_RANKS];
+      src.fetch<1>(R, idx, v);
+      for (int r = 0; r < R; ++r) stats_dense[(size_t)r * (2 * C + 1) + i] = v[0][r];
+    }
   for (int c = threadIdx.x; c < C; c += BN_THREADS) {
     double mean, var, cnt = 0.0;
     if (use_running) { mean = (double)running_mean[c]; var = (double)running_var[c]; }
-    else combine_stats(stats, R, C, c, mean, var, cnt);
+    else combine_stats(src, R, C, c, mean, var, cnt);
     const float invstd = (float)(1.0 / sqrt(var + (double)eps));
     const float ga = gamma ? gamma[c] : 1.0f, be = beta ? beta[c] : 0.0f;
     prm[c] = make_float4((float)mean, ga * invstd, be, 0.f);
@@ -276,25 +411,35 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const float* __res
 
 // backward: dx = (g - sum_g/M - (x-mean) * invstd^2 * sum_gx/M) * gamma*invstd;  dres = g (masked dy)
 template <bool VEC>
-__global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const float* __restrict__ dy,
+__global__ void __launch_bounds__(BN_THREADS, 4) bn_bwd_apply_kernel(const float* __restrict__ dy,
                                                                   const float* __restrict__ x,
                                                                   const float* __restrict__ y,
                                                                   const float* __restrict__ mean,
                                                                   const float* __restrict__ invstd,
                                                                   const float* __restrict__ gamma,
-                                                                  const float* __restrict__ sums,
+                                                                  const float* sums,
                                                                   const float* __restrict__ stats, int R,
+                                                                  BnMailbox* mailbox,
                                                                   float* __restrict__ dx,
                                                                   float* __restrict__ dres, int act, BnGeom g) {
   extern __shared__ float4 prm[];
   const int C = g.C;
   double M = 0.0;
   for (int r = 0; r < R; ++r) M += (double)stats[(size_t)r * (2 * C + 1) + 2 * C];
+  const BnGather src = gather_from(nullptr, 0, mailbox);          // R ranks' sums: add them here, in rank order
   for (int c = threadIdx.x; c < C; c += BN_THREADS) {
     const double is = (double)invstd[c];
     const float ga = gamma ? gamma[c] : 1.0f;
-    prm[c] = make_float4(mean[c], (float)((double)sums[c] / M), (float)(is * is * (double)sums[C + c] / M),
-                         (float)((double)ga * is));
+    double sg, sgx;
+    if (src.ll) {
+      const int idx[2] = {c, C + c};
+      float v[2][BN_MAX_RANKS];
+      src.fetch<2>(R, idx, v);
+      float a = 0.f, b = 0.f;                                      // fp32 adds in rank order == all_reduce(SUM) semantics
+      for (int r = 0; r < R; ++r) { a += v[0][r]; b += v[1][r]; }
+      sg = (double)a; sgx = (double)b;
+    } else { sg = (double)sums[c]; sgx = (double)sums[C + c]; }
+    prm[c] = make_float4(mean[c], (float)(sg / M), (float)(is * is * sgx / M), (float)((double)ga * is));
   }
   __syncthreads();
   const bool relu = act == 1;
@@ -388,8 +533,22 @@ static BnWorkspace bn_ws(void* workspace, int C) {
   BnWorkspace ws;
   (void)C;
   ws.ticket = reinterpret_cast<unsigned int*>(workspace);
-  ws.partial = reinterpret_cast<double2*>(reinterpret_cast<uint8_t*>(workspace) + BN_MAX_C * sizeof(unsigned int));
+  ws.partial = reinterpret_cast<double2*>(reinterpret_cast<uint8_t*>(workspace) + (BN_MAX_C + 4) * sizeof(unsigned int));
   return ws;
+}
+
+// peers: host array of `world` device pointers (every rank's mailbox as mapped in this process)
+static int make_peers(BnPeers& p, void* const* peers, int rank, int world) {
+  p.rank = 0; p.world = 0;
+  for (int i = 0; i < BN_MAX_RANKS; ++i) p.box[i] = nullptr;
+  if (!peers || world <= 1) return 0;
+  if (world > BN_MAX_RANKS || rank < 0 || rank >= world) return PO2_E_SIZE;
+  for (int i = 0; i < world; ++i) {
+    if (!peers[i]) return PO2_E_NULL;
+    p.box[i] = reinterpret_cast<BnMailbox*>(peers[i]);
+  }
+  p.rank = rank; p.world = world;
+  return 0;
 }
 
 static int elementwise_grid(const BnGeom& g) {
@@ -408,32 +567,38 @@ extern "C" {
 
 size_t po2_bn_workspace_bytes(int C) {
   if (C <= 0) return 0;
-  return (size_t)BN_MAX_C * sizeof(unsigned int) + (size_t)C * BN_MAX_SPLIT * sizeof(double2);
+  return (size_t)(BN_MAX_C + 4) * sizeof(unsigned int) + (size_t)C * BN_MAX_SPLIT * sizeof(double2);
 }
 
+size_t po2_bn_mailbox_bytes(void) { return sizeof(BnMailbox); }
+
 int po2_bn_stats(const void* x, int B, int C, int HW, float* stat, void* workspace, size_t workspace_bytes,
-                 void* stream) {
+                 void* const* peers, int rank, int world, void* stream) {
   if (!x || !stat || !workspace) return PO2_E_NULL;
   if (workspace_bytes < po2_bn_workspace_bytes(C)) return PO2_E_WORKSPACE;
   if (!aligned16(workspace)) return PO2_E_ALIGN;
   BnGeom g;
   const int v = bn_geom(g, B, C, HW, aligned16(x));
   if (v < 0) return v;
+  BnPeers pr;
+  const int pe = make_peers(pr, peers, rank, world);
+  if (pe) return pe;
   const BnWorkspace ws = bn_ws(workspace, C);
   const dim3 grid(g.S, C);
   cudaStream_t st = (cudaStream_t)stream;
   const float* xf = (const float*)x;
-  if (v) bn_reduce_kernel<true, 0><<<grid, BN_THREADS, 0, st>>>(xf, nullptr, nullptr, nullptr, nullptr, stat, nullptr, nullptr, g, ws);
-  else bn_reduce_kernel<false, 0><<<grid, BN_THREADS, 0, st>>>(xf, nullptr, nullptr, nullptr, nullptr, stat, nullptr, nullptr, g, ws);
+  if (v) bn_reduce_kernel<true, 0><<<grid, BN_THREADS, 0, st>>>(xf, nullptr, nullptr, nullptr, nullptr, stat, nullptr, nullptr, g, ws, pr);
+  else bn_reduce_kernel<false, 0><<<grid, BN_THREADS, 0, st>>>(xf, nullptr, nullptr, nullptr, nullptr, stat, nullptr, nullptr, g, ws, pr);
   return (int)cudaGetLastError();
 }
 
-int po2_bn_apply(const void* x, const void* residual, void* y, const float* stats, int R, const float* gamma,
-                 const float* beta, float* running_mean, float* running_var, long long* num_batches_tracked,
-                 float momentum, float eps, int act, int use_running, float* save_mean, float* save_invstd, int B,
-                 int C, int HW, void* stream) {
+int po2_bn_apply(const void* x, const void* residual, void* y, const float* stats, int R, void* mailbox,
+                 float* stats_dense, const float* gamma, const float* beta, float* running_mean,
+                 float* running_var, long long* num_batches_tracked, float momentum, float eps, int act,
+                 int use_running, float* save_mean, float* save_invstd, int B, int C, int HW, void* stream) {
   if (!x || !y) return PO2_E_NULL;
-  if (use_running ? (!running_mean || !running_var) : (!stats || R < 1)) return PO2_E_NULL;
+  if (use_running ? (!running_mean || !running_var) : ((!stats && !mailbox) || R < 1)) return PO2_E_NULL;
+  if (R > BN_MAX_RANKS && mailbox) return PO2_E_SIZE;
   if (act != 0 && act != 1) return PO2_E_MODE;
   BnGeom g;
   const int v = bn_geom(g, B, C, HW, aligned16(x) && aligned16(y) && aligned16(residual));
@@ -446,14 +611,15 @@ int po2_bn_apply(const void* x, const void* residual, void* y, const float* stat
     if (e != cudaSuccess) return (int)e;
   }
   kern<<<elementwise_grid(g), BN_THREADS, smem, st>>>((const float*)x, (const float*)residual, (float*)y, stats, R,
-                                                      gamma, beta, running_mean, running_var, num_batches_tracked,
-                                                      momentum, eps, act, use_running, save_mean, save_invstd, g);
+                                                      (BnMailbox*)mailbox, stats_dense, gamma, beta, running_mean,
+                                                      running_var, num_batches_tracked, momentum, eps, act,
+                                                      use_running, save_mean, save_invstd, g);
   return (int)cudaGetLastError();
 }
 
 int po2_bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* save_mean, const float* save_invstd,
                       float* sums, float* dgamma, float* dbeta, int act, int B, int C, int HW, void* workspace,
-                      size_t workspace_bytes, void* stream) {
+                      size_t workspace_bytes, void* const* peers, int rank, int world, void* stream) {
   if (!dy || !x || !save_mean || !save_invstd || !sums || !workspace) return PO2_E_NULL;
   if (act != 0 && act != 1) return PO2_E_MODE;
   if (act == 1 && !y) return PO2_E_NULL;
@@ -462,24 +628,28 @@ int po2_bn_bwd_reduce(const void* dy, const void* x, const void* y, const float*
   BnGeom g;
   const int v = bn_geom(g, B, C, HW, aligned16(dy) && aligned16(x) && aligned16(y));
   if (v < 0) return v;
+  BnPeers pr;
+  const int pe = make_peers(pr, peers, rank, world);
+  if (pe) return pe;
   const BnWorkspace ws = bn_ws(workspace, C);
   const dim3 grid(g.S, C);
   cudaStream_t st = (cudaStream_t)stream;
   const float *xf = (const float*)x, *df = (const float*)dy, *yf = (const float*)y;
   if (act == 1) {
-    if (v) bn_reduce_kernel<true, 2><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws);
-    else bn_reduce_kernel<false, 2><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws);
+    if (v) bn_reduce_kernel<true, 2><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr);
+    else bn_reduce_kernel<false, 2><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr);
   } else {
-    if (v) bn_reduce_kernel<true, 1><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws);
-    else bn_reduce_kernel<false, 1><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws);
+    if (v) bn_reduce_kernel<true, 1><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr);
+    else bn_reduce_kernel<false, 1><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr);
   }
   return (int)cudaGetLastError();
 }
 
 int po2_bn_bwd_apply(const void* dy, const void* x, const void* y, const float* save_mean, const float* save_invstd,
-                     const float* gamma, const float* sums, const float* stats, int R, void* dx, void* dres, int act,
-                     int B, int C, int HW, void* stream) {
-  if (!dy || !x || !save_mean || !save_invstd || !sums || !stats || !dx || R < 1) return PO2_E_NULL;
+                     const float* gamma, const float* sums, const float* stats, int R, void* mailbox, void* dx,
+                     void* dres, int act, int B, int C, int HW, void* stream) {
+  if (!dy || !x || !save_mean || !save_invstd || (!sums && !mailbox) || !stats || !dx || R < 1) return PO2_E_NULL;
+  if (R > BN_MAX_RANKS && mailbox) return PO2_E_SIZE;
   if (act != 0 && act != 1) return PO2_E_MODE;
   if (act == 1 && !y) return PO2_E_NULL;
   BnGeom g;
@@ -493,8 +663,8 @@ int po2_bn_bwd_apply(const void* dy, const void* x, const void* y, const float* 
     if (e != cudaSuccess) return (int)e;
   }
   kern<<<elementwise_grid(g), BN_THREADS, smem, st>>>((const float*)dy, (const float*)x, (const float*)y, save_mean,
-                                                      save_invstd, gamma, sums, stats, R, (float*)dx, (float*)dres,
-                                                      act, g);
+                                                      save_invstd, gamma, sums, stats, R, (BnMailbox*)mailbox,
+                                                      (float*)dx, (float*)dres, act, g);
   return (int)cudaGetLastError();
 }
 

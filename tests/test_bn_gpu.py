@@ -141,6 +141,49 @@ def test_two_rank_statistics_combine_like_sync_batchnorm():
     assert _rel(torch.cat(dxs), dxr) < 5 * TOL
 
 
+def test_peer_exchange_protocol_two_ranks_emulated_on_one_gpu():
+    """The mailbox protocol (publish into every rank's mailbox, epoch flags, slot rotation) with both
+    "ranks" on one device: producers of both ranks are enqueued before the consumers, so nothing has to
+    spin.  Six exchanges (> BN_SLOTS) so slots get reused.  Real cross-GPU runs: tools/check_sync_bn.py."""
+    from po2_quantization_b200 import _lib, batchnorm as bnm
+    g = torch.Generator(device="cuda").manual_seed(11)
+    C, shape = 24, (20, 24, 6, 6)
+    boxes = [torch.zeros(int(_lib.load().po2_bn_mailbox_bytes()), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    ptrs = [b.data_ptr() for b in boxes]
+    ex = [bnm.PeerExchange(ptrs, r, 2) for r in range(2)]
+    w = torch.rand(C, device="cuda", generator=g) + 0.5
+    b = torch.randn(C, device="cuda", generator=g)
+    for it in range(3):
+        x = torch.randn(shape, device="cuda", generator=g) * (1 + it) + it
+        go = torch.randn(shape, device="cuda", generator=g)
+        parts = [(x[:8].contiguous(), go[:8].contiguous()), (x[8:].contiguous(), go[8:].contiguous())]
+        stat = [torch.empty(2 * C + 1, device="cuda") for _ in range(2)]
+        for r in range(2):
+            bnm.bn_stats_out(parts[r][0], stat[r], ex[r])
+        ys, saves, dense = [], [], []
+        for r in range(2):
+            y = torch.empty_like(parts[r][0])
+            sm, si = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+            d = torch.empty(2, 2 * C + 1, device="cuda")
+            bnm.bn_apply_out(parts[r][0], None, y, None, w, b, None, None, None, 0.1, 1e-5, True, False, sm, si,
+                             exch=ex[r], stats_dense=d)
+            ys.append(y), saves.append((sm, si)), dense.append(d)
+        assert torch.equal(dense[0], dense[1]) and torch.equal(dense[0][0], stat[0]) and torch.equal(dense[0][1], stat[1])
+        sums = [torch.empty(2 * C, device="cuda") for _ in range(2)]
+        for r in range(2):
+            bnm.bn_bwd_reduce_out(parts[r][1], parts[r][0], ys[r], *saves[r], sums[r], None, None, True, ex[r])
+        dxs = []
+        for r in range(2):
+            dx = torch.empty_like(parts[r][0])
+            bnm.bn_bwd_apply_out(parts[r][1], parts[r][0], ys[r], *saves[r], w, None, dense[r], dx, None, True, ex[r])
+            dxs.append(dx)
+        yr, dxr, *_ = _ref_forward_backward(x, None, w, b, True, go)
+        assert _rel(torch.cat(ys), yr) < TOL, it
+        assert _rel(torch.cat(dxs), dxr) < 5 * TOL, it
+    for bx in boxes:
+        assert bx[0:4].view(torch.int32).item() == 6 and bx[4:8].view(torch.int32).item() == 0   # epoch, error flag
+
+
 def test_cuda_graph_capture_and_replay():
     import po2_quantization_b200 as P
     bn = P.FusedSyncBatchNorm(32).cuda().train()
