@@ -141,6 +141,18 @@ int po2_conv2d_dgrad(const void* g, const void* w, const float* scale, void* gx,
                      int W, int K, int R, int S, int stride, int pad, int groups, int w_format,
                      int bits, int fsr, int compute, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Weight gradient of the same conv (SURVEY.md section 8f "next" #2, second half): gw (K, C, R, S) = dL/dW
+ * given g = dL/dout (B, K, P, Q) and the forward input x (B, C, H, W).  QuantizedConv2d's quantizer is
+ * a straight-through estimator (utils/quantizers.py:34-36), so this is the gradient of the fp32
+ * master weight.  Dense stride-1 shapes (3x3 pad 1, 1x1 pad 0), K <= 128, compute 0 (bf16 operands:
+ * x and g rounded to bf16, fp32 accumulation in TMEM, per-CTA partials summed in a fixed order ->
+ * deterministic).  PO2_E_UNSUPPORTED for anything else (the caller keeps aten.convolution_backward). */
+size_t po2_conv2d_wgrad_workspace(int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups,
+                                  int compute);
+int po2_conv2d_wgrad(const void* g, const void* x, void* gw, int B, int C, int H, int W, int K, int R, int S,
+                     int stride, int pad, int groups, int compute, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
 /* ---- batch normalisation around the quantized convs (SURVEY.md section 8f "next" #3) -----------------
  * The reference models follow every QuantizedConv2d with nn.SyncBatchNorm (+ ReLU, + the residual add):
  * models/resnet.py:38-61, models/mobilenet.py:29-33.  x, y, dy, dx are fp32 [B][C][HW] (NCHW), parameters

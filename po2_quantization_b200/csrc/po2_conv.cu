@@ -897,6 +897,293 @@ static int launch_umma(const void* x, const void* w, const float* scale, void* o
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// K5: weight gradient of the dense stride-1 convs on the tensor cores (SURVEY.md section 8f "next" #2:
+// the gradient lands in the fp32 master weight through the straight-through estimator, so this IS the
+// STE backward of QuantizedConv2d).
+//
+//   gw[k][c][r][s] = sum over (n, p, q) of  go[n][k][p][q] * x[n][c][p + r - pad][q + s - pad]
+//
+// A GEMM whose reduction dimension is the pixel index: D[k][(tap, c)] += go^T x_tap.  Both operands
+// are staged exactly like the forward kernel's activation strips -- planes [channel / 8][flat padded
+// position][8 channels] of bf16, 16 bytes per position -- which is UMMA's MN-major no-swizzle
+// canonical layout with the reduction (position) index running along K: 8 consecutive positions
+// form a core matrix (LBO = 128 B between K blocks, SBO = plane stride between 8-channel blocks).  A
+// filter tap is again nothing but a shift of the x descriptor's start address by (r*pitch + s)
+// positions; go's pad positions are zero, so the shared zero column / row contribute nothing.
+//   * one CTA accumulates ALL its 128-position tiles into TMEM (M = 128 rows = out channels, of which
+//     K are real; one N = Cpad column block per tap) and runs the epilogue once;
+//   * per-CTA partial results go to a workspace, conv_wgrad_reduce_kernel adds them in a fixed order
+//     (deterministic, unlike atomics) and writes gw[K][C][R][S];
+//   * taps are split over blockIdx.y when 9 * Cpad columns exceed TMEM's 512.
+// ------------------------------------------------------------------------------------------------
+struct WgGeom {
+  int K, Kplanes;            // out channels (<= 128), ceil(K / 8)
+  int Cplanes;               // Cpad / 8
+  int ntaps, taps_per_cta, tap_splits;
+  int m_ctas;                // CTAs along the position dimension
+  int nst, prod_groups;
+  uint32_t go_bytes, x_bytes, stage_bytes;
+  uint32_t ncols;            // TMEM columns
+};
+constexpr uint32_t WG_A_SPAN = 16 * 128 * 16;      // the A descriptor always spans M/8 = 16 planes of 128 positions
+
+// idesc: D=f32, A=B=bf16, both MN-major ("transposed"), M=128, N
+__device__ __forceinline__ uint32_t make_idesc_mn(uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// fill planes [ngrp][strip][8 x bf16] of `stage` with channels [0, 8*ngrp) of src (fp32 NCHW, nC
+// channels, zero beyond) at flat positions [Ls, Ls + strip); stride-1 geometry of g
+__device__ __forceinline__ void produce_planes_bf16(const ConvGeom& g, const float* __restrict__ src, int nC, int ngrp,
+                                                    int strip, int Ls, uint8_t* stage, int gt, int NPG) {
+  const int H = g.H, W = g.W, HW = H * W;
+  if (g.vec4) {
+    const int pitch = g.pitch, W4 = W >> 2, ipr = g.items_per_row;
+    const int rowA = Ls >= 0 ? fdiv(Ls, g.div_pitch) : -((-Ls + pitch - 1) / pitch);
+    const int rowB = fdiv(Ls + strip - 1, g.div_pitch);
+    const int jA = min((Ls - rowA * pitch) >> 2, ipr - 1);
+    const int jB = (rowB - rowA) * ipr + min((Ls + strip - 1 - rowB * pitch) >> 2, ipr - 1);
+    const int nrow_items = jB - jA + 1;
+    const int nall = ngrp * nrow_items;
+    const float inv_items = 1.0f / (float)nrow_items;
+    for (int i = gt; i < nall; i += NPG) {
+      int grp = (int)(((float)i + 0.5f) * inv_items);
+      int j = i - grp * nrow_items;
+      if (j < 0) { --grp; j += nrow_items; } else if (j >= nrow_items) { ++grp; j -= nrow_items; }
+      j += jA;
+      const int rr = fdiv(j, g.div_ipr);
+      const int q4 = j - rr * ipr;
+      const int row = rowA + rr;
+      const int c0 = grp * 8;
+      const int cvalid = nC - c0;
+      const int lbase = row * pitch + q4 * 4 - Ls;
+      const int npos = q4 < W4 ? 4 : pitch - W;
+      bool ok = false;
+      int idx = 0;
+      const int r0 = row - g.top;
+      if (q4 < W4 && r0 >= 0) {
+        const int img = fdiv(r0, g.div_rows);
+        const int a = r0 - img * g.rows_img;
+        if (a < H && img < g.B) { ok = true; idx = ((img * nC + c0) * H + a) * W + q4 * 4; }
+      }
+      float4 v[8];
+      const float4* px = reinterpret_cast<const float4*>(src + idx);
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        v[c] = (ok && c < cvalid) ? __ldg(px + (size_t)c * (HW >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      uint8_t* sgrp = stage + (size_t)grp * strip * 16;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int lloc = lbase + e;
+        if (e < npos && lloc >= 0 && lloc < strip) {
+          float ch[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) ch[c] = e == 0 ? v[c].x : e == 1 ? v[c].y : e == 2 ? v[c].z : v[c].w;
+          *reinterpret_cast<uint4*>(sgrp + (size_t)lloc * 16) = pack_channels<false>(ch);
+        }
+      }
+    }
+  } else {
+    const int nitem = ngrp * strip;
+    for (int i = gt; i < nitem; i += NPG) {
+      const int grp = i / strip;
+      const int lloc = i - grp * strip;
+      float v[8];
+      int img, a, b, cvalid = 0, idx = 0;
+      if (decode_pos(g, Ls + lloc, img, a, b) && a < H && b < W) {
+        cvalid = nC - grp * 8;
+        idx = ((img * nC + grp * 8) * H + a) * W + b;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (j < cvalid) ? __ldg(src + idx + j * HW) : 0.0f;
+      *reinterpret_cast<uint4*>(stage + (size_t)i * 16) = pack_channels<false>(v);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(K3_THREADS, 1) conv_wgrad_umma_kernel(const float* __restrict__ x,
+                                                                        const float* __restrict__ go,
+                                                                        float* __restrict__ partial, ConvGeom g,
+                                                                        WgGeom wg) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  // stage = [go planes | x planes]; WG_A_SPAN bytes of slack behind the ring keep the 16-plane A
+  // descriptor of the last stage inside the allocation (rows >= K of D are garbage and never read)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)wg.nst * wg.stage_bytes + WG_A_SPAN);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + K3_MAX_STAGES;
+  uint64_t* tfull = bars + 2 * K3_MAX_STAGES;
+  uint64_t* tready = tfull + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tready + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m_first = blockIdx.x, m_step = wg.m_ctas, nitems = g.nitems_m, nst = wg.nst;
+  const int tap0 = blockIdx.y * wg.taps_per_cta;
+  const int ntap = min(wg.taps_per_cta, wg.ntaps - tap0);
+  const int Cpad = wg.Cplanes * 8;
+
+  if (warp == K3_EPI_WARPS + 1 && lane == 0) {
+    for (int i = 0; i < nst; ++i) { mbar_init(full + i, K3_PROD_WARPS / wg.prod_groups); mbar_init(empty + i, 1); }
+    mbar_init(tfull, 1);
+    mbar_init(tready, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t tmem_base = 0;
+  if (warp == K3_EPI_WARPS) {
+    tmem_alloc(tmem_slot, wg.ncols);
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tready);
+    tc_fence_after();
+    tmem_base = *tmem_slot;
+  } else if (warp < K3_EPI_WARPS) {
+    mbar_wait(tready, 0);
+    tc_fence_after();
+    tmem_base = *tmem_slot;
+  }
+
+  if (warp == K3_EPI_WARPS) {
+    // =========================== MMA issuer ===========================
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_mn((uint32_t)Cpad);
+    // descriptor words: lo = start>>4 | LBO>>4 << 16 (K-block stride: 8 positions = 128 B);
+    //                   hi = SBO>>4 (MN-block stride: one plane) | version 1 << 14
+    const uint32_t a_hi = (uint32_t)(128 * 16 >> 4) | (1u << 14);
+    const uint32_t b_hi = (uint32_t)g.strip | (1u << 14);
+    const uint32_t lo_fixed = 8u << 16;
+    const uint32_t s0_16 = smem_u32(smem) >> 4, stage16 = wg.stage_bytes >> 4, go16 = wg.go_bytes >> 4;
+    uint32_t s = 0, sphase = 0, tile = 0;
+    for (int m = m_first; m < nitems; m += m_step, ++tile) {
+      mbar_wait(full + s, sphase);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t a16 = s0_16 + s * stage16, b16 = a16 + go16;
+        for (int t = 0; t < ntap; ++t) {
+          const uint32_t d = tmem_base + (uint32_t)(t * Cpad);
+          const uint32_t boff = b16 + (uint32_t)g.tap_off[tap0 + t];
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {                       // 16 positions per MMA
+            const uint64_t ad = ((uint64_t)a_hi << 32) | (lo_fixed | ((a16 + ks * 16) & 0x3FFFu));
+            const uint64_t bd = ((uint64_t)b_hi << 32) | (lo_fixed | ((boff + ks * 16) & 0x3FFFu));
+            umma<false>(d, ad, bd, idesc, (uint32_t)((tile | ks) != 0));
+          }
+        }
+        umma_commit(empty + s);
+      }
+      __syncwarp();
+      if (++s == (uint32_t)nst) { s = 0; sphase ^= 1; }
+    }
+    if (leader) umma_commit(tfull);
+    __syncwarp();
+  } else if (warp < K3_EPI_WARPS) {
+    // =========================== epilogue: TMEM -> partial[cta][tap][c][k] ===========================
+    const int K = wg.K, C = g.C;
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    if (warp * 32 < K) {                                         // this warp's TMEM lanes hold real out channels
+      const int k = warp * 32 + lane;
+      float* pbase = partial + (size_t)blockIdx.x * wg.ntaps * C * K;
+      for (int t = 0; t < ntap; ++t)
+        for (int cb = 0; cb < Cpad / 16; ++cb) {
+          uint32_t r[16];
+          tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * Cpad + cb * 16), r);
+          if (k < K) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int c = cb * 16 + j;
+              if (c < C) pbase[((size_t)(tap0 + t) * C + c) * K + k] = __uint_as_float(r[j]);
+            }
+          }
+        }
+    }
+    tc_fence_before();
+  } else if (warp >= K3_EPI_WARPS + K3_MMA_WARPS) {
+    // =========================== producers: go tile + x strip of every stage ===========================
+    const int ngroups = wg.prod_groups;
+    const int WPG = K3_PROD_WARPS / ngroups, NPG = 32 * WPG;
+    const int pw = warp - (K3_EPI_WARPS + K3_MMA_WARPS);
+    const int grp_id = pw / WPG;
+    const int gt = tid - 32 * (K3_EPI_WARPS + K3_MMA_WARPS) - grp_id * NPG;
+    uint32_t s = 0, sphase = 0;
+    int turn = 0;
+    for (int m = m_first; m < nitems; m += m_step) {
+      const uint32_t s_cur = s, ph_cur = sphase;
+      const bool mine = (turn == grp_id);
+      if (++s == (uint32_t)nst) { s = 0; sphase ^= 1; }
+      if (++turn == ngroups) turn = 0;
+      if (!mine) continue;
+      mbar_wait(empty + s_cur, ph_cur ^ 1);
+      uint8_t* stage = smem + (size_t)s_cur * wg.stage_bytes;
+      produce_planes_bf16(g, go, wg.K, wg.Kplanes, 128, m * 128, stage, gt, NPG);
+      produce_planes_bf16(g, x, g.C, wg.Cplanes, g.strip, m * 128 - g.halo_before, stage + wg.go_bytes, gt, NPG);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full + s_cur);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == K3_EPI_WARPS) tmem_dealloc(tmem_base, wg.ncols);
+}
+
+// gw[(k*C + c)*ntaps + tap] = sum over CTAs of partial[cta][tap][c][k], in CTA order
+__global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ gw,
+                                                                int nparts, int K, int C, int ntaps) {
+  __shared__ float sm[8][32];
+  const int n = ntaps * C * K;
+  const int o = blockIdx.x * 32 + (threadIdx.x & 31);           // index in the partial layout [tap][c][k]
+  const int j = threadIdx.x >> 5;
+  float acc = 0.f;
+  if (o < n)
+    for (int p = j; p < nparts; p += 8) acc += __ldcg(partial + (size_t)p * n + o);
+  sm[j][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (j == 0 && o < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += sm[q][threadIdx.x];
+    const int k = o % K, tc = o / K, c = tc % C, tap = tc / C;
+    gw[((size_t)k * C + c) * ntaps + tap] = t;
+  }
+}
+
+static bool plan_wgrad(ConvGeom& g, WgGeom& wg) {
+  // g: forward geometry already through plan_umma(g, false) (flat padded space, tap offsets, producer fast path)
+  if (g.K > 128 || g.Cpad > 256) return false;
+  wg.K = g.K;
+  wg.Kplanes = (g.K + 7) / 8;
+  wg.Cplanes = g.Cpad / 8;
+  wg.ntaps = g.ntaps;
+  wg.taps_per_cta = 512 / g.Cpad;
+  if (wg.taps_per_cta > wg.ntaps) wg.taps_per_cta = wg.ntaps;
+  if (wg.taps_per_cta < 1) return false;
+  wg.tap_splits = (wg.ntaps + wg.taps_per_cta - 1) / wg.taps_per_cta;
+  wg.taps_per_cta = (wg.ntaps + wg.tap_splits - 1) / wg.tap_splits;        // balance the splits
+  uint32_t ncols = 32;
+  while ((int)ncols < wg.taps_per_cta * g.Cpad) ncols <<= 1;
+  wg.ncols = ncols;
+  wg.go_bytes = (uint32_t)wg.Kplanes * 128 * 16;
+  wg.x_bytes = (uint32_t)wg.Cplanes * g.strip * 16;
+  wg.stage_bytes = wg.go_bytes + wg.x_bytes;
+  int nst = (int)((K3_SMEM_BUDGET - WG_A_SPAN - 512) / wg.stage_bytes);
+  if (nst > K3_MAX_STAGES) nst = K3_MAX_STAGES;
+  if (nst < 2) return false;
+  wg.nst = nst;
+  int m_ctas = sm_count() / wg.tap_splits;
+  if (m_ctas < 1) m_ctas = 1;
+  if (m_ctas > g.nitems_m) m_ctas = g.nitems_m;
+  wg.m_ctas = m_ctas;
+  const int stages_per_cta = (g.nitems_m + m_ctas - 1) / m_ctas;
+  wg.prod_groups = (stages_per_cta >= 4 && nst >= 4) ? 4 : ((stages_per_cta >= 2 && nst >= 2) ? 2 : 1);
+  // the 14-bit descriptor start field (>> 4) covers 256 KB: every stage address fits
+  return true;
+}
+
+static size_t wgrad_partial_bytes(const ConvGeom& g, const WgGeom& wg) {
+  return (size_t)wg.m_ctas * wg.ntaps * g.C * g.K * sizeof(float);
+}
+
 }  // namespace po2
 
 using namespace po2;
@@ -1084,6 +1371,56 @@ size_t po2_conv2d_dgrad_workspace(int B, int C, int H, int W, int K, int R, int 
   ConvGeom g;
   if (compute == 1 || !fill_geom(g, B, K, H, W, C, R, S, 1, pad, 1) || !plan_umma(g, compute == 2)) return 0;
   return (umma_pack_bytes(g) + 256 + 255) / 256 * 256;
+}
+
+
+// Weight gradient of the same conv (SURVEY.md section 8f "next" #2, second half): gw = dL/dW given
+// g = dL/dout and the forward input x -- through the straight-through estimator this is the gradient
+// of the fp32 master weight.  Dense stride-1 shapes (3x3 pad 1, 1x1 pad 0) with K <= 128, bf16
+// operands; returns PO2_E_UNSUPPORTED otherwise (the caller keeps aten.convolution_backward).
+static bool wgrad_plan(ConvGeom& g, WgGeom& wg, int B, int C, int H, int W, int K, int R, int S, int stride, int pad,
+                       int groups, int compute) {
+  if (compute != 0 || stride != 1 || groups != 1) return false;
+  if (!((R == 3 && S == 3 && pad == 1) || (R == 1 && S == 1 && pad == 0))) return false;
+  if (!fill_geom(g, B, C, H, W, K, R, S, stride, pad, groups)) return false;
+  if ((int64_t)B * C * H * W >= (1ll << 31) || (int64_t)B * K * g.P * g.Q >= (1ll << 31)) return false;
+  if (!umma_eligible(g) || !plan_umma(g, false)) return false;
+  return plan_wgrad(g, wg);
+}
+
+size_t po2_conv2d_wgrad_workspace(int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups,
+                                  int compute) {
+  ConvGeom g;
+  WgGeom wg;
+  if (!wgrad_plan(g, wg, B, C, H, W, K, R, S, stride, pad, groups, compute)) return 0;
+  return (wgrad_partial_bytes(g, wg) + 255) / 256 * 256;
+}
+
+int po2_conv2d_wgrad(const void* g_out, const void* x, void* gw, int B, int C, int H, int W, int K, int R, int S,
+                     int stride, int pad, int groups, int compute, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+  if (!g_out || !x || !gw) return PO2_E_NULL;
+  ConvGeom g;
+  WgGeom wg;
+  if (!wgrad_plan(g, wg, B, C, H, W, K, R, S, stride, pad, groups, compute)) return PO2_E_UNSUPPORTED;
+  const size_t need = wgrad_partial_bytes(g, wg);
+  if (!workspace || workspace_bytes < need) return PO2_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)K3_SMEM_BUDGET + 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const size_t smem = (size_t)wg.nst * wg.stage_bytes + WG_A_SPAN + 512;
+  conv_wgrad_umma_kernel<<<dim3(wg.m_ctas, wg.tap_splits), K3_THREADS, smem, st>>>((const float*)x, (const float*)g_out,
+                                                                                   (float*)workspace, g, wg);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  const int n = wg.ntaps * C * K;
+  conv_wgrad_reduce_kernel<<<(n + 31) / 32, 256, 0, st>>>((const float*)workspace, (float*)gw, wg.m_ctas, K, C, wg.ntaps);
+  return (int)cudaGetLastError();
 }
 
 }  // extern "C"

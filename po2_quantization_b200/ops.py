@@ -299,6 +299,62 @@ def conv2d_dgrad_out(g, w, scale, gx, pad, compute: int = 0) -> bool:
     return True
 
 
+# "tc": weight gradient of stride-1 dense convs (K <= 128) on the tensor-core kernel (x and grad rounded
+# to bf16, fp32 accumulation, deterministic); "aten": aten.convolution_backward (cuDNN)
+_wgrad_mode = os.environ.get("PO2_CONV_WGRAD", "tc")
+
+
+def set_wgrad_mode(mode: str) -> None:
+    global _wgrad_mode
+    if mode not in ("tc", "aten"):
+        raise ValueError("wgrad mode must be 'tc' or 'aten'")
+    _wgrad_mode = mode
+
+
+def conv2d_wgrad_out(g, x, gw, pad, compute: int = 0) -> bool:
+    """gw = dL/dW of conv2d(x, W) (stride 1, dense) from g = dL/dout.  False if the shape is not taken."""
+    global LAUNCHES
+    lib = _lib.load()
+    B, C, H, W_ = x.shape
+    K, _, R, S = gw.shape
+    need = lib.po2_conv2d_wgrad_workspace(B, C, H, W_, K, R, S, 1, pad, 1, compute)
+    if need == 0:
+        return False
+    ws = torch.empty(int(need), dtype=torch.uint8, device=g.device)
+    rc = lib.po2_conv2d_wgrad(g.data_ptr(), x.data_ptr(), gw.data_ptr(), B, C, H, W_, K, R, S, 1, pad, 1, compute,
+                              ws.data_ptr(), ws.numel(), _stream_ptr(g.device))
+    if rc == -10:                      # PO2_E_UNSUPPORTED
+        return False
+    _lib.check(rc, "po2_conv2d_wgrad")
+    LAUNCHES += 2
+    return True
+
+
+def _conv_backward(g, x, w, scale, stride, pad, groups, compute, need_x, need_w):
+    """(gx, gw) of conv2d(x, w): the stride-1 dense layers on the tcgen05 kernels (data gradient:
+    forward kernel with transposed weights; weight gradient: conv_wgrad_umma_kernel), everything else
+    through aten.convolution_backward."""
+    g = g.contiguous()
+    gx = gw = None
+    ours = compute != 1 and stride == 1 and groups == 1 and g.dtype == torch.float32 and x.dtype == torch.float32
+    with torch.cuda.device(x.device):
+        if need_x and ours and _dgrad_mode == "tc" and scale is not None:
+            cand = torch.empty_like(x)
+            if conv2d_dgrad_out(g, w, scale, cand, pad, compute):
+                gx = cand
+        if need_w and ours and _wgrad_mode == "tc" and compute == 0:
+            cand = torch.empty_like(w)
+            if conv2d_wgrad_out(g, x.contiguous(), cand, pad, compute):
+                gw = cand
+    if (need_x and gx is None) or (need_w and gw is None):
+        gx2, gw2, _ = torch.ops.aten.convolution_backward(
+            g, x, w, None, [stride, stride], [pad, pad], [1, 1], False, [0, 0], groups,
+            [need_x and gx is None, need_w and gw is None, False])
+        gx = gx if gx is not None else gx2
+        gw = gw if gw is not None else gw2
+    return gx, gw
+
+
 def _conv2d_setup(ctx, inputs, output):
     x, w, scale, stride, pad, groups, compute = inputs
     ctx.save_for_backward(x, w, scale) if scale is not None else ctx.save_for_backward(x, w)
@@ -307,25 +363,13 @@ def _conv2d_setup(ctx, inputs, output):
 
 
 def _conv2d_bwd(ctx, g):
-    # weight gradient stays on ATen/cuDNN (SURVEY.md section 8f "next" #2); the data gradient of the
-    # stride-1 dense layers runs on the same tcgen05 kernel as the forward, with transposed weights
     saved = ctx.saved_tensors
     x, w = saved[0], saved[1]
     scale = saved[2] if ctx.has_scale else None
     stride, pad, groups, compute = ctx.cfg
-    need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-    g = g.contiguous()
-    gx = None
-    if (need_x and _dgrad_mode == "tc" and compute != 1 and stride == 1 and groups == 1 and scale is not None
-            and g.dtype == torch.float32):
-        cand = torch.empty_like(x)
-        with torch.cuda.device(x.device):
-            if conv2d_dgrad_out(g, w, scale, cand, pad, compute):
-                gx = cand
-    gx2, gw, _ = torch.ops.aten.convolution_backward(
-        g, x, w, None, [stride, stride], [pad, pad], [1, 1], False, [0, 0], groups,
-        [need_x and gx is None, need_w, False])
-    return (gx if gx is not None else gx2), gw, None, None, None, None, None
+    gx, gw = _conv_backward(g, x, w, scale, stride, pad, groups, compute, ctx.needs_input_grad[0],
+                            ctx.needs_input_grad[1])
+    return gx, gw, None, None, None, None, None
 
 
 conv2d.register_autograd(_conv2d_bwd, setup_context=_conv2d_setup)
@@ -406,22 +450,13 @@ def _qconv2d_bwd(ctx, g, g_qw, g_scale):
     x, qw, scale = ctx.saved_tensors
     stride, pad, groups, compute = ctx.cfg
     need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-    g = g.contiguous()
-    gx = None
-    if need_x and _dgrad_mode == "tc" and compute != 1 and stride == 1 and groups == 1 and g.dtype == torch.float32:
-        cand = torch.empty_like(x)
-        with torch.cuda.device(x.device):
-            if conv2d_dgrad_out(g, qw, scale, cand, pad, compute):
-                gx = cand
-    gx2, gw, _ = torch.ops.aten.convolution_backward(
-        g, x, qw, None, [stride, stride], [pad, pad], [1, 1], False, [0, 0], groups,
-        [need_x and gx is None, need_w, False])
+    gx, gw = _conv_backward(g, x, qw, scale, stride, pad, groups, compute, need_x, need_w)
     if g_qw is not None and gw is not None:
         gw = gw + g_qw                       # someone also used the returned quantized weight
     elif g_qw is not None:
         gw = g_qw
     # straight-through estimator (utils/quantizers.py:34-36): d/d weight == d/d quantized weight
-    return (gx if gx is not None else gx2), gw, None, None, None, None, None, None, None
+    return gx, gw, None, None, None, None, None, None, None
 
 
 qconv2d.register_autograd(_qconv2d_bwd, setup_context=_qconv2d_setup)

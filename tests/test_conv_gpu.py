@@ -130,6 +130,7 @@ def test_conv_dgrad_tensor_core_path(case):
 def test_conv_autograd_matches_aten():
     from po2_quantization_b200 import ops
     ops.set_dgrad_mode("aten")                    # this test pins the ATen formula; dgrad-on-K3 is tested above
+    ops.set_wgrad_mode("aten")
     torch.backends.cudnn.allow_tf32 = False       # both backward passes in true fp32
     x, y, codes, scale = _make(RESNET[3])
     x1 = x.clone().requires_grad_(True)
@@ -149,6 +150,44 @@ def test_conv_autograd_matches_aten():
     torch.ops.po2.conv2d(x3, w3, scale, 1, 1, 1, 0).backward(g)
     assert torch.allclose(w3.grad, w2.grad, rtol=1e-4, atol=1e-3)
     assert _rel(x3.grad, x2.grad.double()) < TOL_TC
+    # and with the tensor-core weight gradient too: both operands rounded to bf16
+    ops.set_wgrad_mode("tc")
+    x4 = x.clone().requires_grad_(True)
+    w4 = y.clone().requires_grad_(True)
+    torch.ops.po2.conv2d(x4, w4, scale, 1, 1, 1, 0).backward(g)
+    assert _rel(w4.grad, w2.grad.double()) < TOL_TC
+
+
+WGRAD_CASES = [RESNET[0], RESNET[3], RESNET[6], MOBILENET[1], MOBILENET[4], ODD[1],
+               ("wg 24->40 3x3 @12x20", 5, 24, 12, 20, 40, 3, 1, 1, 1), ("wg 128->128 3x3 @8", 8, 128, 8, 8, 128, 3, 1, 1, 1),
+               ("wg 100->72 1x1 @7x9", 3, 100, 7, 9, 72, 1, 1, 0, 1), ("wg 16->16 3x3 @32 B=128", 128, 16, 32, 32, 16, 3, 1, 1, 1)]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES, ids=lambda c: c[0])
+def test_conv_wgrad_tensor_core_path(case):
+    """Weight gradient on the tcgen05 kernel (x and grad rounded to bf16, fp32 accumulation over all
+    pixels in TMEM, fixed-order partial sums) against fp64: rel 1e-2 like the forward, deterministic."""
+    from po2_quantization_b200 import ops
+    name, B, C, H, W, K, k, stride, pad, groups = case
+    if stride != 1 or groups != 1 or K > 128:
+        pytest.skip("shape not taken by the wgrad kernel")
+    g0 = torch.Generator(device="cuda").manual_seed(B + C + K)
+    x = torch.randn(B, C, H, W, device="cuda", generator=g0)
+    gout = torch.randn(B, K, H, W, device="cuda", generator=g0)
+    gw = torch.full((K, C, k, k), float("nan"), device="cuda")
+    assert ops.conv2d_wgrad_out(gout, x, gw, pad)
+    ref = torch.nn.grad.conv2d_weight(x.double(), (K, C, k, k), gout.double(), stride=1, padding=pad)
+    assert _rel(gw, ref) < TOL_TC, (name, _rel(gw, ref))
+    rms = ((gw.double() - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+    assert rms < 4e-3, (name, rms)
+    gw2 = torch.empty_like(gw)
+    assert ops.conv2d_wgrad_out(gout, x, gw2, pad)
+    assert torch.equal(gw, gw2), "wgrad must be deterministic"
+    # operands that are exact in bf16 make the result exact up to fp32 accumulation order
+    xb, gb = x.bfloat16().float(), gout.bfloat16().float()
+    assert ops.conv2d_wgrad_out(gb, xb, gw2, pad)
+    ref_b = torch.nn.grad.conv2d_weight(xb.double(), (K, C, k, k), gb.double(), stride=1, padding=pad)
+    assert _rel(gw2, ref_b) < 1e-5, (name, _rel(gw2, ref_b))
 
 
 @pytest.mark.parametrize("plus", [False, True])
@@ -172,8 +211,18 @@ def test_module_qat_forward_backward_vs_oracle(plus):
     g = torch.randn_like(ref)
     out.backward(g.cuda())
     ref.backward(g)
-    assert torch.allclose(m.weight.grad.cpu(), o.weight.grad, rtol=2e-3, atol=2e-3)
+    # weight gradient (straight-through): x and grad rounded to bf16 on the tensor-core kernel
+    assert _rel(m.weight.grad.cpu(), o.weight.grad.double()) < TOL_TC
     assert _rel(xg.grad.cpu(), xc.grad.double()) < TOL_TC      # data gradient: grad rounded to bf16, PO2 weights exact
+    # ... and exactly ATen's when the tensor-core gradient kernels are switched off
+    from po2_quantization_b200 import ops
+    ops.set_wgrad_mode("aten")
+    try:
+        m.weight.grad = None
+        m(xg).backward(g.cuda())
+        assert torch.allclose(m.weight.grad.cpu(), o.weight.grad, rtol=2e-3, atol=2e-3)
+    finally:
+        ops.set_wgrad_mode("tc")
     e1, n1 = m.get_quantization_error()
     ref_e = torch.sum((PO2_PLUS if plus else PO2).forward(None, o.weight.detach()) - o.weight.detach()).item()
     assert n1 == o.weight.numel() and np.isfinite(e1.item()) and np.isfinite(ref_e)
