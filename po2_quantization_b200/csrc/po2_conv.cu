@@ -920,24 +920,40 @@ static int launch_umma(const void* x, const void* w, const float* scale, void* o
 // ------------------------------------------------------------------------------------------------
 struct WgGeom {
   int K, Kplanes;            // out channels (<= 128), ceil(K / 8)
+  int M;                     // MMA M: 64 (K <= 64) or 128 -- rows >= K are garbage and never read
   int Cplanes;               // Cpad / 8
   int ntaps, taps_per_cta, tap_splits;
+  int copies;                // 3: x is staged as three column-shifted copies, one MMA covers the taps (r, 0..2)
+  int groups_per_cta;        // MMA groups (taps, or filter rows when copies == 3) per CTA = taps_per_cta / copies
   int m_ctas;                // CTAs along the position dimension
   int nst, prod_groups;
   uint32_t go_bytes, x_bytes, stage_bytes;
   uint32_t ncols;            // TMEM columns
 };
-constexpr uint32_t WG_A_SPAN = 16 * 128 * 16;      // the A descriptor always spans M/8 = 16 planes of 128 positions
+constexpr uint32_t WG_A_SPAN = 16 * 128 * 16;      // the A descriptor spans M/8 <= 16 planes of 128 positions
 
 // idesc: D=f32, A=B=bf16, both MN-major ("transposed"), M=128, N
-__device__ __forceinline__ uint32_t make_idesc_mn(uint32_t n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc_mn(uint32_t m, uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 // fill planes [ngrp][strip][8 x bf16] of `stage` with channels [0, 8*ngrp) of src (fp32 NCHW, nC
 // channels, zero beyond) at flat positions [Ls, Ls + strip); stride-1 geometry of g
+// copies == 3: the planes are written three times, copy s shifted by (s - 1) positions
+// (copy_s[i] = strip[i + s - 1]; copy stride = ngrp * strip * 16 bytes), so that the three taps of a
+// filter row become ONE MMA with N = 3 * channels.
+__device__ __forceinline__ void store_copies(uint8_t* plane, int lloc, int strip, const uint4& val, int copies,
+                                             size_t copy_bytes) {
+  if (copies == 1) { *reinterpret_cast<uint4*>(plane + (size_t)lloc * 16) = val; return; }
+  if (lloc + 1 < strip) *reinterpret_cast<uint4*>(plane + (size_t)(lloc + 1) * 16) = val;                // s = 0
+  *reinterpret_cast<uint4*>(plane + copy_bytes + (size_t)lloc * 16) = val;                               // s = 1
+  if (lloc >= 1) *reinterpret_cast<uint4*>(plane + 2 * copy_bytes + (size_t)(lloc - 1) * 16) = val;      // s = 2
+}
+
 __device__ __forceinline__ void produce_planes_bf16(const ConvGeom& g, const float* __restrict__ src, int nC, int ngrp,
-                                                    int strip, int Ls, uint8_t* stage, int gt, int NPG) {
+                                                    int strip, int Ls, uint8_t* stage, int gt, int NPG,
+                                                    int copies = 1) {
+  const size_t copy_bytes = (size_t)ngrp * strip * 16;
   const int H = g.H, W = g.W, HW = H * W;
   if (g.vec4) {
     const int pitch = g.pitch, W4 = W >> 2, ipr = g.items_per_row;
@@ -948,40 +964,52 @@ __device__ __forceinline__ void produce_planes_bf16(const ConvGeom& g, const flo
     const int nrow_items = jB - jA + 1;
     const int nall = ngrp * nrow_items;
     const float inv_items = 1.0f / (float)nrow_items;
-    for (int i = gt; i < nall; i += NPG) {
-      int grp = (int)(((float)i + 0.5f) * inv_items);
-      int j = i - grp * nrow_items;
-      if (j < 0) { --grp; j += nrow_items; } else if (j >= nrow_items) { ++grp; j -= nrow_items; }
-      j += jA;
-      const int rr = fdiv(j, g.div_ipr);
-      const int q4 = j - rr * ipr;
-      const int row = rowA + rr;
-      const int c0 = grp * 8;
-      const int cvalid = nC - c0;
-      const int lbase = row * pitch + q4 * 4 - Ls;
-      const int npos = q4 < W4 ? 4 : pitch - W;
-      bool ok = false;
-      int idx = 0;
-      const int r0 = row - g.top;
-      if (q4 < W4 && r0 >= 0) {
-        const int img = fdiv(r0, g.div_rows);
-        const int a = r0 - img * g.rows_img;
-        if (a < H && img < g.B) { ok = true; idx = ((img * nC + c0) * H + a) * W + q4 * 4; }
+    for (int i0 = gt; i0 < nall; i0 += 2 * NPG) {
+      float4 v[2][8];
+      int lbase[2], npos[2], gsel[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {                    // 16 x 128-bit loads in flight per thread
+        const int i = i0 + u * NPG;
+        lbase[u] = 0; npos[u] = 0; gsel[u] = 0;
+        bool ok = false;
+        int idx = 0, cvalid = 0;
+        if (i < nall) {
+          int grp = (int)(((float)i + 0.5f) * inv_items);
+          int j = i - grp * nrow_items;
+          if (j < 0) { --grp; j += nrow_items; } else if (j >= nrow_items) { ++grp; j -= nrow_items; }
+          j += jA;
+          const int rr = fdiv(j, g.div_ipr);
+          const int q4 = j - rr * ipr;
+          const int row = rowA + rr;
+          const int c0 = grp * 8;
+          gsel[u] = grp;
+          cvalid = nC - c0;
+          lbase[u] = row * pitch + q4 * 4 - Ls;
+          npos[u] = q4 < W4 ? 4 : pitch - W;
+          const int r0 = row - g.top;
+          if (q4 < W4 && r0 >= 0) {
+            const int img = fdiv(r0, g.div_rows);
+            const int a = r0 - img * g.rows_img;
+            if (a < H && img < g.B) { ok = true; idx = ((img * nC + c0) * H + a) * W + q4 * 4; }
+          }
+        }
+        const float4* px = reinterpret_cast<const float4*>(src + idx);
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          v[u][c] = (ok && c < cvalid) ? __ldg(px + (size_t)c * (HW >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      float4 v[8];
-      const float4* px = reinterpret_cast<const float4*>(src + idx);
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        v[c] = (ok && c < cvalid) ? __ldg(px + (size_t)c * (HW >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      uint8_t* sgrp = stage + (size_t)grp * strip * 16;
+      for (int u = 0; u < 2; ++u) {
+        uint8_t* sgrp = stage + (size_t)gsel[u] * strip * 16;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int lloc = lbase + e;
-        if (e < npos && lloc >= 0 && lloc < strip) {
-          float ch[8];
+        for (int e = 0; e < 4; ++e) {
+          const int lloc = lbase[u] + e;
+          if (e < npos[u] && lloc >= 0 && lloc < strip) {
+            float ch[8];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) ch[c] = e == 0 ? v[c].x : e == 1 ? v[c].y : e == 2 ? v[c].z : v[c].w;
-          *reinterpret_cast<uint4*>(sgrp + (size_t)lloc * 16) = pack_channels<false>(ch);
+            for (int c = 0; c < 8; ++c) ch[c] = e == 0 ? v[u][c].x : e == 1 ? v[u][c].y : e == 2 ? v[u][c].z : v[u][c].w;
+            store_copies(sgrp, lloc, strip, pack_channels<false>(ch), copies, copy_bytes);
+          }
         }
       }
     }
@@ -998,7 +1026,7 @@ __device__ __forceinline__ void produce_planes_bf16(const ConvGeom& g, const flo
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = (j < cvalid) ? __ldg(src + idx + j * HW) : 0.0f;
-      *reinterpret_cast<uint4*>(stage + (size_t)i * 16) = pack_channels<false>(v);
+      store_copies(stage + (size_t)grp * strip * 16, lloc, strip, pack_channels<false>(v), copies, copy_bytes);
     }
   }
 }
@@ -1021,6 +1049,11 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_wgrad_umma_kernel(const fl
   const int tap0 = blockIdx.y * wg.taps_per_cta;
   const int ntap = min(wg.taps_per_cta, wg.ntaps - tap0);
   const int Cpad = wg.Cplanes * 8;
+#ifdef PO2_K3_TRACE
+  for (int i = tid; i < 8 * 64; i += K3_THREADS) k3_trace_smem[i] = 0;
+  __syncthreads();
+#endif
+  if (tid == 0) K3_TRACE(6, 0);
 
   if (warp == K3_EPI_WARPS + 1 && lane == 0) {
     for (int i = 0; i < nst; ++i) { mbar_init(full + i, K3_PROD_WARPS / wg.prod_groups); mbar_init(empty + i, 1); }
@@ -1042,11 +1075,12 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_wgrad_umma_kernel(const fl
     tc_fence_after();
     tmem_base = *tmem_slot;
   }
+  if (tid == 0) K3_TRACE(6, 1);
 
   if (warp == K3_EPI_WARPS) {
     // =========================== MMA issuer ===========================
     const bool leader = elect_one();
-    const uint32_t idesc = make_idesc_mn((uint32_t)Cpad);
+    const uint32_t idesc = make_idesc_mn((uint32_t)wg.M, (uint32_t)(wg.copies * Cpad));
     // descriptor words: lo = start>>4 | LBO>>4 << 16 (K-block stride: 8 positions = 128 B);
     //                   hi = SBO>>4 (MN-block stride: one plane) | version 1 << 14
     const uint32_t a_hi = (uint32_t)(128 * 16 >> 4) | (1u << 14);
@@ -1057,11 +1091,14 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_wgrad_umma_kernel(const fl
     for (int m = m_first; m < nitems; m += m_step, ++tile) {
       mbar_wait(full + s, sphase);
       tc_fence_after();
+      if (leader) K3_TRACE(0, 2 * (int)tile);
       if (leader) {
         const uint32_t a16 = s0_16 + s * stage16, b16 = a16 + go16;
-        for (int t = 0; t < ntap; ++t) {
+        // one MMA group = one tap, or (copies == 3) one filter row: N = 3*Cpad columns (s, c) read from
+        // the three shifted copies at the CENTRE tap's offset -- the same column order tap*Cpad + c
+        for (int t = 0; t < ntap; t += wg.copies) {
           const uint32_t d = tmem_base + (uint32_t)(t * Cpad);
-          const uint32_t boff = b16 + (uint32_t)g.tap_off[tap0 + t];
+          const uint32_t boff = b16 + (uint32_t)g.tap_off[tap0 + t + (wg.copies == 3 ? 1 : 0)];
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {                       // 16 positions per MMA
             const uint64_t ad = ((uint64_t)a_hi << 32) | (lo_fixed | ((a16 + ks * 16) & 0x3FFFu));
@@ -1070,6 +1107,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_wgrad_umma_kernel(const fl
           }
         }
         umma_commit(empty + s);
+        K3_TRACE(0, 2 * (int)tile + 1);
       }
       __syncwarp();
       if (++s == (uint32_t)nst) { s = 0; sphase ^= 1; }
@@ -1077,27 +1115,43 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_wgrad_umma_kernel(const fl
     if (leader) umma_commit(tfull);
     __syncwarp();
   } else if (warp < K3_EPI_WARPS) {
-    // =========================== epilogue: TMEM -> partial[cta][tap][c][k] ===========================
+    // =========================== epilogue: TMEM -> partial[cta][tap][k][c] ===========================
     const int K = wg.K, C = g.C;
     mbar_wait(tfull, 0);
     tc_fence_after();
-    if (warp * 32 < K) {                                         // this warp's TMEM lanes hold real out channels
-      const int k = warp * 32 + lane;
+    if (warp == 0 && lane == 0) K3_TRACE(1, 0);
+    // M = 128: D row i sits in TMEM lane i.  M = 64: each warp's 32-lane partition holds 16 rows in its
+    // lanes 0..15 (row = 16 * warp + lane)
+    const int rows_per_warp = wg.M == 64 ? 16 : 32;
+    if (warp * rows_per_warp < K) {                              // this warp's TMEM lanes hold real out channels
+      const int k = lane < rows_per_warp ? warp * rows_per_warp + lane : K;
+      // partial[cta][tap][k][c]: a lane owns row k and writes its 16 channels of a column block as four
+      // 128-bit stores (one warp runs this epilogue alone, so every instruction's latency is exposed:
+      // few, wide stores and 32-bit index arithmetic)
       float* pbase = partial + (size_t)blockIdx.x * wg.ntaps * C * K;
-      for (int t = 0; t < ntap; ++t)
+      const bool vec = (C & 3) == 0;
+      for (int t = 0; t < ntap; ++t) {
+        float* prow = pbase + ((tap0 + t) * K + k) * C;            // k == K for idle lanes: never dereferenced
         for (int cb = 0; cb < Cpad / 16; ++cb) {
           uint32_t r[16];
           tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * Cpad + cb * 16), r);
           if (k < K) {
+            const int c0 = cb * 16;
+            if (vec && c0 + 16 <= C) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int c = cb * 16 + j;
-              if (c < C) pbase[((size_t)(tap0 + t) * C + c) * K + k] = __uint_as_float(r[j]);
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(prow + c0 + 4 * q) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < C) prow[c0 + j] = __uint_as_float(r[j]);
             }
           }
         }
+      }
     }
     tc_fence_before();
+    if (warp == 0 && lane == 0) K3_TRACE(1, 1);
   } else if (warp >= K3_EPI_WARPS + K3_MMA_WARPS) {
     // =========================== producers: go tile + x strip of every stage ===========================
     const int ngroups = wg.prod_groups;
@@ -1105,45 +1159,64 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_wgrad_umma_kernel(const fl
     const int pw = warp - (K3_EPI_WARPS + K3_MMA_WARPS);
     const int grp_id = pw / WPG;
     const int gt = tid - 32 * (K3_EPI_WARPS + K3_MMA_WARPS) - grp_id * NPG;
-    uint32_t s = 0, sphase = 0;
+    uint32_t s = 0, sphase = 0, it = 0;
     int turn = 0;
-    for (int m = m_first; m < nitems; m += m_step) {
+    for (int m = m_first; m < nitems; m += m_step, ++it) {
       const uint32_t s_cur = s, ph_cur = sphase;
       const bool mine = (turn == grp_id);
       if (++s == (uint32_t)nst) { s = 0; sphase ^= 1; }
       if (++turn == ngroups) turn = 0;
       if (!mine) continue;
       mbar_wait(empty + s_cur, ph_cur ^ 1);
+      if (gt == 0) K3_TRACE(2 + grp_id, 2 * (int)(it / ngroups));
       uint8_t* stage = smem + (size_t)s_cur * wg.stage_bytes;
       produce_planes_bf16(g, go, wg.K, wg.Kplanes, 128, m * 128, stage, gt, NPG);
-      produce_planes_bf16(g, x, g.C, wg.Cplanes, g.strip, m * 128 - g.halo_before, stage + wg.go_bytes, gt, NPG);
+      produce_planes_bf16(g, x, g.C, wg.Cplanes, g.strip, m * 128 - g.halo_before, stage + wg.go_bytes, gt, NPG,
+                          wg.copies);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(full + s_cur);
+      if (gt == 0) K3_TRACE(2 + grp_id, 2 * (int)(it / ngroups) + 1);
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) K3_TRACE(6, 2);
+#ifdef PO2_K3_TRACE
+  __syncthreads();
+  if (g_k3_trace && blockIdx.x < 4 && blockIdx.y == 0)
+    for (int i = tid; i < 8 * 64; i += K3_THREADS) g_k3_trace[blockIdx.x * 8 * 64 + i] = k3_trace_smem[i];
+#endif
   if (warp == K3_EPI_WARPS) tmem_dealloc(tmem_base, wg.ncols);
 }
 
-// gw[(k*C + c)*ntaps + tap] = sum over CTAs of partial[cta][tap][c][k], in CTA order
+// gw[(k*C + c)*ntaps + tap] = sum over CTAs of partial[cta][tap][k][c], in CTA order
 __global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ gw,
                                                                 int nparts, int K, int C, int ntaps) {
   __shared__ float sm[8][32];
   const int n = ntaps * C * K;
-  const int o = blockIdx.x * 32 + (threadIdx.x & 31);           // index in the partial layout [tap][c][k]
+  const int o = blockIdx.x * 32 + (threadIdx.x & 31);           // index in the partial layout [tap][k][c]
   const int j = threadIdx.x >> 5;
   float acc = 0.f;
-  if (o < n)
-    for (int p = j; p < nparts; p += 8) acc += __ldcg(partial + (size_t)p * n + o);
+  if (o < n) {
+    // four independent loads per round (an in-order warp would otherwise pay one L2 latency per partial);
+    // the summation order stays fixed: p = j, j+8, j+16, ...
+    const float* src = partial + o;
+    int p = j;
+    for (; p + 24 < nparts; p += 32) {
+      const float v0 = __ldcg(src + (size_t)p * n), v1 = __ldcg(src + (size_t)(p + 8) * n);
+      const float v2 = __ldcg(src + (size_t)(p + 16) * n), v3 = __ldcg(src + (size_t)(p + 24) * n);
+      acc += v0; acc += v1; acc += v2; acc += v3;
+    }
+    for (; p < nparts; p += 8) acc += __ldcg(src + (size_t)p * n);
+  }
   sm[j][threadIdx.x & 31] = acc;
   __syncthreads();
   if (j == 0 && o < n) {
     float t = 0.f;
 #pragma unroll
     for (int q = 0; q < 8; ++q) t += sm[q][threadIdx.x];
-    const int k = o % K, tc = o / K, c = tc % C, tap = tc / C;
+    const int c = o % C, tk = o / C, k = tk % K, tap = tk / K;
     gw[((size_t)k * C + c) * ntaps + tap] = t;
   }
 }
@@ -1152,19 +1225,26 @@ static bool plan_wgrad(ConvGeom& g, WgGeom& wg) {
   // g: forward geometry already through plan_umma(g, false) (flat padded space, tap offsets, producer fast path)
   if (g.K > 128 || g.Cpad > 256) return false;
   wg.K = g.K;
+  wg.M = g.K <= 64 ? 64 : 128;
   wg.Kplanes = (g.K + 7) / 8;
   wg.Cplanes = g.Cpad / 8;
   wg.ntaps = g.ntaps;
-  wg.taps_per_cta = 512 / g.Cpad;
-  if (wg.taps_per_cta > wg.ntaps) wg.taps_per_cta = wg.ntaps;
-  if (wg.taps_per_cta < 1) return false;
-  wg.tap_splits = (wg.ntaps + wg.taps_per_cta - 1) / wg.taps_per_cta;
-  wg.taps_per_cta = (wg.ntaps + wg.tap_splits - 1) / wg.tap_splits;        // balance the splits
+  // three shifted copies triple the producers' shared-memory stores: a win while the MMAs are tiny
+  // (N = 16 / 32 per tap), a loss from 64 channels on (measured, profiles/r01_wgrad_layers_*.json)
+  wg.copies = (g.ntaps == 9 && g.Cpad <= 32) ? 3 : 1;
+  const int ngroups = wg.ntaps / wg.copies;                                // MMA groups: taps or filter rows
+  int gpc = 512 / (wg.copies * g.Cpad);                                    // groups whose columns fit TMEM
+  if (gpc > ngroups) gpc = ngroups;
+  if (gpc < 1) return false;
+  wg.tap_splits = (ngroups + gpc - 1) / gpc;
+  gpc = (ngroups + wg.tap_splits - 1) / wg.tap_splits;                     // balance the splits
+  wg.groups_per_cta = gpc;
+  wg.taps_per_cta = gpc * wg.copies;
   uint32_t ncols = 32;
   while ((int)ncols < wg.taps_per_cta * g.Cpad) ncols <<= 1;
   wg.ncols = ncols;
   wg.go_bytes = (uint32_t)wg.Kplanes * 128 * 16;
-  wg.x_bytes = (uint32_t)wg.Cplanes * g.strip * 16;
+  wg.x_bytes = (uint32_t)wg.copies * wg.Cplanes * g.strip * 16;
   wg.stage_bytes = wg.go_bytes + wg.x_bytes;
   int nst = (int)((K3_SMEM_BUDGET - WG_A_SPAN - 512) / wg.stage_bytes);
   if (nst > K3_MAX_STAGES) nst = K3_MAX_STAGES;
@@ -1174,7 +1254,9 @@ static bool plan_wgrad(ConvGeom& g, WgGeom& wg) {
   if (m_ctas < 1) m_ctas = 1;
   if (m_ctas > g.nitems_m) m_ctas = g.nitems_m;
   wg.m_ctas = m_ctas;
-  const int stages_per_cta = (g.nitems_m + m_ctas - 1) / m_ctas;
+  // producer groups fill different stages concurrently; a CTA with a single tile wants all eight
+  // warps on that one stage, so size the groups for the typical (floor) number of tiles per CTA
+  const int stages_per_cta = g.nitems_m / m_ctas;
   wg.prod_groups = (stages_per_cta >= 4 && nst >= 4) ? 4 : ((stages_per_cta >= 2 && nst >= 2) ? 2 : 1);
   // the 14-bit descriptor start field (>> 4) covers 256 KB: every stage address fits
   return true;

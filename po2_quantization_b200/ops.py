@@ -444,12 +444,17 @@ def _qconv2d_setup(ctx, inputs, output):
     out, qw, scale = output
     ctx.save_for_backward(x, qw, scale)
     ctx.cfg = (stride, pad, groups, compute)
+    # qw / scale are normally unused downstream: do not let autograd manufacture zero gradients for
+    # them (two fill kernels and an add per layer and step)
+    ctx.set_materialize_grads(False)
 
 
 def _qconv2d_bwd(ctx, g, g_qw, g_scale):
     x, qw, scale = ctx.saved_tensors
     stride, pad, groups, compute = ctx.cfg
     need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+    if g is None:                            # only the quantized weight was used: straight-through
+        return None, g_qw, None, None, None, None, None, None, None
     gx, gw = _conv_backward(g, x, qw, scale, stride, pad, groups, compute, need_x, need_w)
     if g_qw is not None and gw is not None:
         gw = gw + g_qw                       # someone also used the returned quantized weight

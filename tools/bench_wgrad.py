@@ -24,6 +24,7 @@ SHAPES = [("r56 16->16 3x3 @32", 16, 32, 32, 16, 3, 1, 18), ("r56 32->32 3x3 @16
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
+    ap.add_argument("--profile", action="store_true", help="also print per-kernel durations (torch.profiler)")
     a = ap.parse_args()
     REPS = 20
     rows = []
@@ -41,6 +42,17 @@ def main():
             torch.ops.aten.convolution_backward(go, x, w, None, [1, 1], [pad, pad], [1, 1], False, [0, 0], 1,
                                                 [False, True, False])
 
+        if a.profile:
+            from torch.profiler import ProfilerActivity, profile
+            ours()
+            torch.cuda.synchronize()
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                for _ in range(10):
+                    ours()
+                torch.cuda.synchronize()
+            for e in prof.key_averages():
+                if e.device_time_total > 0:
+                    print(f"   {name}: {e.key[:60]:60s} {e.device_time_total / e.count:8.2f} us x{e.count}")
         t_o = graph_time(ours, REPS) / REPS * 1e3
         t_a = graph_time(aten, REPS) / REPS * 1e3
         flops = 2.0 * B * H * W * C * K * k * k
