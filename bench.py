@@ -82,6 +82,10 @@ def build_training(device, world, local_rank, batch):
     from workloads import resnet_cifar
     torch.manual_seed(8)
     model = resnet_cifar(56, 10, P.PowerOfTwoQuantizer, 4).to(device).train()
+    if os.environ.get("PO2_PREFETCH", "1") == "1":
+        # quantize all 56 weights in ONE multi-tensor launch at the start of each forward instead of one
+        # by one in front of each conv (po2_quantization_b200/prefetch.py); same arithmetic, same results
+        P.enable_weight_prefetch(model)
     if world > 1:
         if os.environ.get("PO2_DDP", "0") == "1":
             # torch's DistributedDataParallel, as the reference wraps its model (train.py:153-155)

@@ -132,6 +132,27 @@ int po2_qconv2d_fwd(const void* x, const void* w, void* qw_out, float* scale_out
                     int mode, int flavor, int compute, void* workspace, size_t workspace_bytes,
                     void* quant_workspace, void* stream);
 
+/* The first half of po2_qconv2d_fwd on its own: quantize the master weight (qw_out, scale_out) and emit
+ * the packed tensor-core operand (`packed`, po2_conv2d_pack_bytes(...) bytes) for inputs of shape
+ * (B, C, H, W).  Weight quantization does not depend on the activations, so a caller can run it for
+ * every layer of a model ahead of time on another stream and feed po2_conv2d_fwd_packed.
+ * PO2_E_UNSUPPORTED when the shape does not run on the tensor-core kernel. */
+int po2_quantize_pack(const void* w, void* qw_out, float* scale_out, void* packed, size_t packed_bytes, int B, int C,
+                      int H, int W, int K, int R, int S, int stride, int pad, int groups, int bits, int fsr, int mode,
+                      int flavor, int compute, void* quant_workspace, void* stream);
+
+/* Multi-tensor form (SURVEY.md section 8f "next" #4): ONE launch quantizes and packs many weight tensors
+ * (one thread-block cluster per tensor).  The caller builds a table of po2_multi_desc_bytes()-sized
+ * descriptors in HOST memory with po2_multi_desc_fill (same arguments as po2_quantize_pack; returns the
+ * cluster size 1/2/4/8 this tensor needs, or PO2_E_UNSUPPORTED when the layer must take
+ * po2_quantize_pack), copies it to the device once, and calls po2_quantize_pack_multi every step with
+ * cluster_size = the largest value po2_multi_desc_fill returned. */
+size_t po2_multi_desc_bytes(void);
+int po2_multi_desc_fill(void* host_table, int index, const void* w, void* qw_out, float* scale_out, void* packed,
+                        size_t packed_bytes, int B, int C, int H, int W, int K, int R, int S, int stride, int pad,
+                        int groups, int bits, int fsr, int mode, int flavor, int compute);
+int po2_quantize_pack_multi(const void* device_table, int ntensors, int cluster_size, void* stream);
+
 /* Data gradient of the same conv (SURVEY.md section 8f "next" #2, first half): gx = dL/dx given g = dL/dout,
  * for the stride-1 dense shapes (3x3 pad 1, 1x1 pad 0), on the tensor-core kernel with the
  * channel-transposed, 180-degree-rotated PO2 weights (exact in bf16; g is rounded to bf16).

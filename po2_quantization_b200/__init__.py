@@ -6,6 +6,7 @@ Public surface mirrors the reference (utils/quantizers.py, models/quantized_conv
 """
 from . import _lib, ops  # noqa: F401
 from .batchnorm import FusedSyncBatchNorm  # noqa: F401
+from .prefetch import enable_weight_prefetch, prefetch_weights  # noqa: F401
 from .ops import get_log2_flavor, set_log2_flavor  # noqa: F401
 from .quantized_conv import QuantizedConv2d  # noqa: F401
 from .quantizers import (LinearPowerOfTwoPlusQuantizer, LinearPowerOfTwoQuantizer,  # noqa: F401

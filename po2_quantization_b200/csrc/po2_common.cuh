@@ -116,4 +116,15 @@ struct PackArgs {
 int fused_quantize_pack(const void* w, void* y, float* scale_out, int64_t n, int bits, int fsr, int mode,
                         int flavor, void* workspace, const PackArgs& pk, cudaStream_t st);
 
+// one tensor of the multi-tensor quantize+pack kernel (fp32 weights)
+struct MultiDesc {
+  const uint4* x; uint4* y; float* scale_out;
+  int64_t n;
+  int bits, fsr, mode, flavor;
+  PackArgs pk;
+};
+int multi_fused_capacity();
+int multi_fused_launch(const MultiDesc* descs_dev, int ntensors, int csize, cudaStream_t st);
+int check_quant_args(int bits, int fsr, int mode, int flavor);
+
 }  // namespace po2

@@ -1449,6 +1449,72 @@ int po2_qconv2d_fwd(const void* x, const void* w_master, void* qw_out, float* sc
                         fsr, compute, workspace, workspace_bytes, stream);
 }
 
+// The first half of po2_qconv2d_fwd on its own: quantize the master weight and emit the packed
+// tensor-core operand of conv2d(x of shape (B, C, H, W), Q(w)).  Lets a caller quantize all layers of a
+// model ahead of the activations (on another stream), then run each conv with po2_conv2d_fwd_packed.
+int po2_quantize_pack(const void* w_master, void* qw_out, float* scale_out, void* packed, size_t packed_bytes, int B,
+                      int C, int H, int W, int K, int R, int S, int stride, int pad, int groups, int bits, int fsr,
+                      int mode, int flavor, int compute, void* quant_workspace, void* stream) {
+  if (!w_master || !qw_out || !scale_out || !packed) return PO2_E_NULL;
+  if (!quant_workspace) return PO2_E_WORKSPACE;
+  ConvGeom g;
+  if (!fill_geom(g, B, C, H, W, K, R, S, stride, pad, groups)) return PO2_E_SHAPE;
+  if (compute == 1 || !umma_eligible(g) || !plan_umma(g, compute == 2)) return PO2_E_UNSUPPORTED;
+  if (packed_bytes < umma_pack_bytes(g)) return PO2_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t wn = (int64_t)K * (C / groups) * R * S;
+  if (g.Cpad == C && g.ntiles_n * g.NT == K) {
+    PackArgs pk;
+    pk.Bp = packed;
+    pk.G = g.G; pk.C = C; pk.K = K; pk.taps = g.ntaps; pk.NT = g.NT; pk.ncg = C / g.G;
+    pk.div_ct = make_fastdiv((uint32_t)(C * g.ntaps));
+    pk.div_t = make_fastdiv((uint32_t)g.ntaps);
+    pk.div_nt = make_fastdiv((uint32_t)g.NT);
+    const int rc = fused_quantize_pack(w_master, qw_out, scale_out, wn, bits, fsr, mode, flavor, quant_workspace, pk, st);
+    if (rc != PO2_E_UNSUPPORTED) return rc;
+  }
+  if (int e = po2_quantize_fused(w_master, qw_out, nullptr, nullptr, nullptr, scale_out, wn, PO2_F32, bits, fsr, mode,
+                                 flavor, quant_workspace, stream)) return e;
+  return po2_conv2d_pack(qw_out, scale_out, packed, packed_bytes, B, C, H, W, K, R, S, stride, pad, groups,
+                         PO2_W_F32_PO2, bits, fsr, compute, stream);
+}
+
+// ---- multi-tensor quantize + pack: one launch for all QAT weights of a model --------------------------
+size_t po2_multi_desc_bytes(void) { return sizeof(MultiDesc); }
+
+int po2_multi_desc_fill(void* host_table, int index, const void* w_master, void* qw_out, float* scale_out, void* packed,
+                        size_t packed_bytes, int B, int C, int H, int W, int K, int R, int S, int stride, int pad,
+                        int groups, int bits, int fsr, int mode, int flavor, int compute) {
+  if (!host_table || index < 0 || !w_master || !qw_out || !scale_out || !packed) return PO2_E_NULL;
+  if (int e = check_quant_args(bits, fsr, mode, flavor)) return e;
+  ConvGeom g;
+  if (!fill_geom(g, B, C, H, W, K, R, S, stride, pad, groups)) return PO2_E_SHAPE;
+  if (compute == 1 || !umma_eligible(g) || !plan_umma(g, compute == 2)) return PO2_E_UNSUPPORTED;
+  if (!(g.Cpad == C && g.ntiles_n * g.NT == K)) return PO2_E_UNSUPPORTED;        // the packed operand has no padding
+  if (packed_bytes < umma_pack_bytes(g)) return PO2_E_WORKSPACE;
+  const int64_t wn = (int64_t)K * (C / groups) * R * S;
+  if (wn % 4 || (reinterpret_cast<uintptr_t>(w_master) & 15) || (reinterpret_cast<uintptr_t>(qw_out) & 15))
+    return PO2_E_UNSUPPORTED;
+  const int cap = multi_fused_capacity();
+  int csize = 1;
+  while (csize < 8 && (int64_t)csize * cap < wn) csize <<= 1;
+  if ((int64_t)csize * cap < wn) return PO2_E_UNSUPPORTED;                        // does not fit one cluster
+  MultiDesc d;
+  d.x = (const uint4*)w_master; d.y = (uint4*)qw_out; d.scale_out = scale_out; d.n = wn;
+  d.bits = bits; d.fsr = fsr; d.mode = mode; d.flavor = flavor;
+  d.pk.Bp = packed;
+  d.pk.G = g.G; d.pk.C = C; d.pk.K = K; d.pk.taps = g.ntaps; d.pk.NT = g.NT; d.pk.ncg = C / g.G;
+  d.pk.div_ct = make_fastdiv((uint32_t)(C * g.ntaps));
+  d.pk.div_t = make_fastdiv((uint32_t)g.ntaps);
+  d.pk.div_nt = make_fastdiv((uint32_t)g.NT);
+  reinterpret_cast<MultiDesc*>(host_table)[index] = d;
+  return csize;
+}
+
+int po2_quantize_pack_multi(const void* device_table, int ntensors, int cluster_size, void* stream) {
+  return multi_fused_launch((const MultiDesc*)device_table, ntensors, cluster_size, (cudaStream_t)stream);
+}
+
 size_t po2_conv2d_dgrad_workspace(int B, int C, int H, int W, int K, int R, int S, int pad, int compute) {
   ConvGeom g;
   if (compute == 1 || !fill_geom(g, B, K, H, W, C, R, S, 1, pad, 1) || !plan_umma(g, compute == 2)) return 0;

@@ -519,24 +519,24 @@ constexpr int FUSED_THREADS = 512;
 constexpr int FUSED_R = 8;    // 16-byte vectors held per thread
 
 template <int DT, bool CODES, bool SSE>
-__global__ void __launch_bounds__(FUSED_THREADS) fused_kernel(const uint4* __restrict__ x,
+__device__ __forceinline__ void fused_body(const uint4* __restrict__ x,
                                                               uint4* __restrict__ y, uint8_t* codes,
                                                               unsigned int* zero_count, double* sse,
                                                               float* __restrict__ scale_out,
                                                               int64_t n, int bits, int fsr, int mode,
                                                               int flavor, Workspace* ws, int cluster,
-                                                              PackArgs pk) {
-  // a kernel launched behind us with programmatic stream serialization (the conv that consumes the
-  // packed operand) may start its prologue now; it executes griddepcontrol.wait before reading Bp
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+                                                              const PackArgs& pk, const uint32_t lgrid,
+                                                              const uint32_t lblock) {
+  // lgrid / lblock: number and index of the CTAs working on THIS tensor (the whole grid for the
+  // single-tensor kernel, one cluster for the multi-tensor kernel)
   __shared__ LevelTab T;
   __shared__ uint32_t sm[32];
   __shared__ float smf[32];
   __shared__ uint32_t cl_max;                            // this CTA's max, read by its cluster peers
   constexpr int EPV = Tr<DT>::EPV;
   const int64_t n_vec = n / EPV;
-  const int64_t total = (int64_t)gridDim.x * blockDim.x;
-  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)lgrid * blockDim.x;
+  const int64_t gtid = (int64_t)lblock * blockDim.x + threadIdx.x;
   const uint32_t pre_b = prefetch_bound(DT, bits, fsr, mode, flavor);   // in flight together with the data
   uint4 v[FUSED_R];
   uint32_t m = 0;
@@ -548,18 +548,18 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_kernel(const uint4* __res
 #pragma unroll
   for (int r = 0; r < FUSED_R; ++r) m = vec_absmax<DT>(v[r], m);
   m = absmax_finish<DT>(m);
-  if (blockIdx.x == 0)
+  if (lblock == 0)
     for (int64_t k = n_vec * EPV + threadIdx.x; k < n; k += blockDim.x)
       m = max(m, load_pat<DT>(x, k) & Tr<DT>::MAG);
   m = block_max_u32(m, sm);
-  if (gridDim.x > 1 && cluster) {
+  if (lgrid > 1 && cluster) {
     // the whole grid is one thread-block cluster: exchange the per-CTA maxima through distributed
     // shared memory (two cluster barriers) instead of global atomics and a spin
     if (threadIdx.x == 0) cl_max = m;
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     uint32_t mm = 0;
     const uint32_t laddr = (uint32_t)__cvta_generic_to_shared(&cl_max);
-    for (uint32_t r = 0; r < gridDim.x; ++r) {
+    for (uint32_t r = 0; r < lgrid; ++r) {
       uint32_t raddr, val;
       asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(r));
       asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(val) : "r"(raddr) : "memory");
@@ -567,16 +567,16 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_kernel(const uint4* __res
     }
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     m = mm;
-  } else if (gridDim.x > 1) {
+  } else if (lgrid > 1) {
     if (threadIdx.x == 0) {
       atomicMax(&ws->absmax, m);
       __threadfence();
       atomicAdd(&ws->arrive, 1u);
-      while (*reinterpret_cast<volatile unsigned int*>(&ws->arrive) < gridDim.x) __nanosleep(20);
+      while (*reinterpret_cast<volatile unsigned int*>(&ws->arrive) < lgrid) __nanosleep(20);
       __threadfence();
       sm[0] = *reinterpret_cast<volatile unsigned int*>(&ws->absmax);
       const unsigned int d = atomicAdd(&ws->depart, 1u);
-      if (d == gridDim.x - 1) {                          // everyone has read it: re-zero
+      if (d == lgrid - 1) {                          // everyone has read it: re-zero
         ws->absmax = 0u; ws->arrive = 0u; ws->depart = 0u;
       }
     }
@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_kernel(const uint4* __res
         if (DT == PO2_F32 && pk.Bp) pack_vec(pk, o, (int)i * 4, s);
       }
     }
-    if (blockIdx.x == 0 && threadIdx.x < EPV / 2) {
+    if (lblock == 0 && threadIdx.x < EPV / 2) {
       const int64_t ip = n_vec * (EPV / 2) + threadIdx.x;
       if (2 * ip < n) quant_pair<DT>(x, y, codes, ip, n, T, bits, acc, want_sse);
     }
@@ -613,6 +613,31 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_kernel(const uint4* __res
   }
   flush_acc(acc, zero_count, sse, smf);
 }
+
+template <int DT, bool CODES, bool SSE>
+__global__ void __launch_bounds__(FUSED_THREADS) fused_kernel(const uint4* __restrict__ x,
+                                                              uint4* __restrict__ y, uint8_t* codes,
+                                                              unsigned int* zero_count, double* sse,
+                                                              float* __restrict__ scale_out,
+                                                              int64_t n, int bits, int fsr, int mode,
+                                                              int flavor, Workspace* ws, int cluster,
+                                                              PackArgs pk) {
+  // a kernel launched behind us with programmatic stream serialization (the conv that consumes the
+  // packed operand) may start its prologue now; it executes griddepcontrol.wait before reading Bp
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  fused_body<DT, CODES, SSE>(x, y, codes, zero_count, sse, scale_out, n, bits, fsr, mode, flavor, ws, cluster, pk,
+                             gridDim.x, blockIdx.x);
+}
+
+// Multi-tensor form (SURVEY.md section 8f "next" #4): ONE launch quantizes (and packs) many weight
+// tensors, one thread-block cluster per tensor.  Per-tensor arguments come from a device table.
+__global__ void __launch_bounds__(FUSED_THREADS) multi_fused_kernel(const MultiDesc* __restrict__ descs, int csize) {
+  const uint32_t t = blockIdx.x / (uint32_t)csize, lblock = blockIdx.x % (uint32_t)csize;
+  const MultiDesc d = descs[t];
+  fused_body<PO2_F32, false, false>(d.x, d.y, nullptr, nullptr, nullptr, d.scale_out, d.n, d.bits, d.fsr, d.mode, d.flavor,
+                                    nullptr, 1, d.pk, (uint32_t)csize, lblock);
+}
+
 
 // ------------------------------------------------------------------------------------------------
 // codes -> values
@@ -734,6 +759,11 @@ static int check_quant(int bits, int fsr, int mode, int flavor) {
   return 0;
 }
 
+int check_quant_args(int bits, int fsr, int mode, int flavor) {
+  if (flavor == PO2_FLAVOR_TORCH_CUDA && !po2_have_torch_cuda_table()) return PO2_E_FLAVOR;
+  return check_quant(bits, fsr, mode, flavor);
+}
+
 static int grid_for(int64_t work_items, int threads, int per_thread, int max_blocks) {
   int64_t b = (work_items + (int64_t)threads * per_thread - 1) / ((int64_t)threads * per_thread);
   if (b < 1) b = 1;
@@ -828,6 +858,24 @@ int fused_quantize_pack(const void* w, void* y, float* scale_out, int64_t n, int
                                       dim3(FUSED_THREADS), args, 0, st);
   }
   return (int)err;
+}
+
+int multi_fused_capacity() { return FUSED_THREADS * FUSED_R * 4; }      // elements one CTA holds in registers
+
+int multi_fused_launch(const MultiDesc* descs_dev, int ntensors, int csize, cudaStream_t st) {
+  if (!descs_dev) return PO2_E_NULL;
+  if (ntensors <= 0) return 0;
+  if (csize != 1 && csize != 2 && csize != 4 && csize != 8) return PO2_E_SIZE;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(ntensors * csize));
+  cfg.blockDim = dim3(FUSED_THREADS);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, multi_fused_kernel, descs_dev, csize);
 }
 
 }  // namespace po2

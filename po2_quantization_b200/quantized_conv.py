@@ -26,7 +26,8 @@ class QuantizedConv2d(nn.Conv2d):
         # (non-persistent) PTQ tag is re-keyed to the copy instead of silently going stale
         new = self.__class__.__new__(self.__class__)
         memo[id(self)] = new
-        new.__dict__ = {k: copy.deepcopy(v, memo) for k, v in self.__dict__.items() if k != "_po2_pack_cache"}
+        new.__dict__ = {k: copy.deepcopy(v, memo) for k, v in self.__dict__.items()
+                        if k not in ("_po2_pack_cache", "_po2_prefetch", "_po2_prefetch_single", "_po2_prefetch_static")}
         tag = self.__dict__.get("_po2_ptq")
         if tag is not None and tag[0] == self.weight._version:
             new.__dict__["_po2_ptq"] = (new.weight._version, new.__dict__["_po2_ptq"][1])
@@ -49,6 +50,15 @@ class QuantizedConv2d(nn.Conv2d):
         if self.quantize_fn is not None:
             plus = getattr(self.quantize_fn, "_PLUS", None)
             if plus is not None and self._po2_conv_ok(input):
+                mode = ops.get_conv_mode()
+                if mode in ("tc", "tf32"):
+                    # weights already quantized by the multi-tensor prefetch (prefetch.py)?  Then the conv
+                    # is a single launch; otherwise remember the input shape for the next prefetch
+                    from . import prefetch
+                    out = prefetch.try_prefetched_forward(self, input, mode)
+                    if out is not None:
+                        return out
+                    self.__dict__["_po2_xshape"] = tuple(input.shape)
                 # PO2 / PO2+: one op = quantizer kernel (which also emits the packed +-2^q tensor-core
                 # operand) + conv kernel; the straight-through gradient reaches self.weight
                 out, _qw, _scale = ops.qconv2d(input, self.weight, int(self.bits), 1, bool(plus), self.stride[0],

@@ -561,3 +561,53 @@ def test_tf32_mode_end_to_end_module_paths():
         assert torch.equal(a, b) and _rel(a, r2) < TOL_TF32
     finally:
         ops.set_conv_mode("tc")
+
+
+def test_weight_prefetch_equals_inline_quantization():
+    """enable_weight_prefetch: all weights quantized by one multi-tensor launch before the forward.
+    Same arithmetic as the inline path, so with deterministic cuDNN (the stem conv) the models stay
+    bitwise equal -- eagerly over optimizer steps (weights change, the prefetch must notice) and
+    under CUDA-graph replay."""
+    import po2_quantization_b200 as P
+    from workloads import resnet_cifar
+    torch.manual_seed(12)
+    torch.backends.cudnn.deterministic = True
+    a = resnet_cifar(20, 10, P.PowerOfTwoQuantizer, 4).cuda().train()
+    b = copy.deepcopy(a)
+    P.enable_weight_prefetch(b)
+    oa = torch.optim.SGD(a.parameters(), lr=0.05, momentum=0.9)
+    ob = torch.optim.SGD(b.parameters(), lr=0.05, momentum=0.9)
+    x = torch.randn(32, 3, 32, 32, device="cuda")
+    t = torch.randint(0, 10, (32,), device="cuda")
+    for it in range(3):                                   # step 0 records shapes, steps 1-2 run prefetched
+        for m, o in ((a, oa), (b, ob)):
+            o.zero_grad()
+            F.cross_entropy(m(x), t).backward()
+            o.step()
+        used = sum(1 for m in b.modules() if getattr(m, "_po2_prefetch", None))
+        assert (used > 0) == (it > 0), (it, used)
+        for (n, pa), pb in zip(a.named_parameters(), b.parameters()):
+            assert torch.equal(pa, pb), (it, n)
+    # CUDA-graph capture of a whole step with the side-stream fork inside
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        xs = x.clone()
+
+        def step(m, o):
+            o.zero_grad()
+            F.cross_entropy(m(xs), t).backward()
+            o.step()
+        step(b, ob), step(a, oa)
+        torch.cuda.current_stream().synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            step(b, ob)
+        for _ in range(2):
+            g.replay()
+            step(a, oa)
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    torch.backends.cudnn.deterministic = False
+    for (n, pa), pb in zip(a.named_parameters(), b.parameters()):
+        assert torch.equal(pa, pb), n
