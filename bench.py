@@ -104,7 +104,7 @@ def build_training(device, world, local_rank, batch):
 def _parallelism_note():
     from po2_quantization_b200 import batchnorm
     grads = ("torch DDP buckets" if os.environ.get("PO2_DDP", "0") == "1"
-             else "one coalesced NCCL all-reduce(AVG) of the gradients per step")
+             else "coalesced NCCL all-reduce(AVG) of the gradients in 4 buckets, issued from grad hooks under backward")
     ex = [e for e in batchnorm._exchanges.values()]
     mode = os.environ.get("PO2_BN_EXCHANGE", "peer")
     bn = ("SyncBatchNorm statistics exchanged inside the BN kernels over NVLink peer stores" if any(e is not None for e in ex)

@@ -187,6 +187,10 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const float* __re
                                                                float* __restrict__ dgamma,
                                                                float* __restrict__ dbeta, BnGeom g,
                                                                BnWorkspace ws, BnPeers peers) {
+  // the consuming kernel (apply / backward apply, launched with programmatic stream serialization) may
+  // be scheduled as soon as every CTA of this grid is running; it waits for this grid's completion
+  // (griddepcontrol.wait) before it reads anything this grid writes
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __shared__ double sm[BN_THREADS / 32][2];
   __shared__ int flag;
   __shared__ uint32_t s_epoch;
@@ -336,6 +340,9 @@ __global__ void __launch_bounds__(BN_THREADS, 4) bn_apply_kernel(const float* __
                                                               float* __restrict__ save_invstd, BnGeom g) {
   extern __shared__ float4 prm[];
   const int C = g.C;
+  // x / residual were complete before the statistics kernel started; the statistics (and the mailbox
+  // epoch) are that kernel's output
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const BnGather src = gather_from(stats, 2 * C + 1, use_running ? nullptr : mailbox);
   if (src.ll && blockIdx.x == 0 && stats_dense)          // dense copy of the gathered statistics for backward
     for (int i = threadIdx.x; i < 2 * C + 1; i += BN_THREADS) {
@@ -424,6 +431,7 @@ __global__ void __launch_bounds__(BN_THREADS, 4) bn_bwd_apply_kernel(const float
                                                                   float* __restrict__ dres, int act, BnGeom g) {
   extern __shared__ float4 prm[];
   const int C = g.C;
+  asm volatile("griddepcontrol.wait;" ::: "memory");            // sums / mailbox epoch come from the reduce kernel
   double M = 0.0;
   for (int r = 0; r < R; ++r) M += (double)stats[(size_t)r * (2 * C + 1) + 2 * C];
   const BnGather src = gather_from(nullptr, 0, mailbox);          // R ranks' sums: add them here, in rank order
@@ -610,11 +618,19 @@ int po2_bn_apply(const void* x, const void* residual, void* y, const float* stat
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  kern<<<elementwise_grid(g), BN_THREADS, smem, st>>>((const float*)x, (const float*)residual, (float*)y, stats, R,
-                                                      (BnMailbox*)mailbox, stats_dense, gamma, beta, running_mean,
-                                                      running_var, num_batches_tracked, momentum, eps, act,
-                                                      use_running, save_mean, save_invstd, g);
-  return (int)cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)elementwise_grid(g));
+  cfg.blockDim = dim3(BN_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_running ? 0 : 1;                       // train mode: directly behind po2_bn_stats
+  return (int)cudaLaunchKernelEx(&cfg, kern, (const float*)x, (const float*)residual, (float*)y, stats, R,
+                                 (BnMailbox*)mailbox, stats_dense, gamma, beta, running_mean, running_var,
+                                 num_batches_tracked, momentum, eps, act, use_running, save_mean, save_invstd, g);
 }
 
 int po2_bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* save_mean, const float* save_invstd,
@@ -662,10 +678,18 @@ int po2_bn_bwd_apply(const void* dy, const void* x, const void* y, const float* 
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  kern<<<elementwise_grid(g), BN_THREADS, smem, st>>>((const float*)dy, (const float*)x, (const float*)y, save_mean,
-                                                      save_invstd, gamma, sums, stats, R, (BnMailbox*)mailbox,
-                                                      (float*)dx, (float*)dres, act, g);
-  return (int)cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)elementwise_grid(g));
+  cfg.blockDim = dim3(BN_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // directly behind po2_bn_bwd_reduce
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, kern, (const float*)dy, (const float*)x, (const float*)y, save_mean, save_invstd,
+                                 gamma, sums, stats, R, (BnMailbox*)mailbox, (float*)dx, (float*)dres, act, g);
 }
 
 }  // extern "C"

@@ -1049,6 +1049,9 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_wgrad_umma_kernel(const fl
   const int tap0 = blockIdx.y * wg.taps_per_cta;
   const int ntap = min(wg.taps_per_cta, wg.ntaps - tap0);
   const int Cpad = wg.Cplanes * 8;
+  // conv_wgrad_reduce_kernel (launched with programmatic stream serialization) may be scheduled early;
+  // it waits for this grid's completion before reading the partials
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #ifdef PO2_K3_TRACE
   for (int i = tid; i < 8 * 64; i += K3_THREADS) k3_trace_smem[i] = 0;
   __syncthreads();
@@ -1194,6 +1197,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_wgrad_umma_kernel(const fl
 __global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ gw,
                                                                 int nparts, int K, int C, int ntaps) {
   __shared__ float sm[8][32];
+  asm volatile("griddepcontrol.wait;" ::: "memory");            // the partials are the main kernel's output
   const int n = ntaps * C * K;
   const int o = blockIdx.x * 32 + (threadIdx.x & 31);           // index in the partial layout [tap][k][c]
   const int j = threadIdx.x >> 5;
@@ -1567,8 +1571,17 @@ int po2_conv2d_wgrad(const void* g_out, const void* x, void* gw, int B, int C, i
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   const int n = wg.ntaps * C * K;
-  conv_wgrad_reduce_kernel<<<(n + 31) / 32, 256, 0, st>>>((const float*)workspace, (float*)gw, wg.m_ctas, K, C, wg.ntaps);
-  return (int)cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((n + 31) / 32));
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, conv_wgrad_reduce_kernel, (const float*)workspace, (float*)gw, wg.m_ctas, K, C,
+                                 wg.ntaps);
 }
 
 }  // extern "C"

@@ -56,31 +56,51 @@ class BatchSharded(torch.nn.Module):
 
     Same arithmetic as the reference's DistributedDataParallel (train.py:153-155) -- parameters and
     buffers broadcast from rank 0 at construction, gradients averaged every step -- but the exchange
-    is ONE coalesced NCCL all-reduce(AVG) over the gradient tensors where they lie, issued by
-    ``average_gradients()`` after ``backward()``.  DDP's reducer instead launches one scale-and-copy
-    kernel per parameter into its buckets (171 launches per ResNet-56 step, ~0.4 ms on a B200, as
-    long as the whole gradient all-reduce itself), which is what this avoids; with 3.4 MB of
-    gradients there is nothing worth overlapping with backward."""
+    is a few coalesced NCCL all-reduce(AVG) calls over the gradient tensors where they lie.  DDP's
+    reducer instead launches one scale-and-copy kernel per parameter into its buckets (171 launches
+    per ResNet-56 step, ~0.4 ms on a B200, as long as the whole gradient all-reduce itself), which is
+    what this avoids.  With ``overlap=True`` (CUDA) the parameters are split into ``buckets`` groups
+    in backward order; a group's all-reduce is issued from a post-accumulate-grad hook as soon as its
+    last gradient exists, on a side stream, so it runs under the rest of the backward pass (also inside
+    a CUDA-graph capture, where the side stream becomes a parallel branch).  ``average_gradients()``
+    after ``backward()`` reduces whatever is left and joins the side stream."""
 
-    def __init__(self, module: torch.nn.Module, group: Optional[dist.ProcessGroup] = None):
+    def __init__(self, module: torch.nn.Module, group: Optional[dist.ProcessGroup] = None, overlap: bool = True,
+                 buckets: int = 4):
         super().__init__()
         self.module = module
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self._buckets, self._pending, self._bucket_of, self._comm = [], [], {}, None
         if self.world > 1:
             src = dist.get_global_rank(group, 0) if group is not None else 0
             with torch.no_grad():
                 for t in list(module.parameters()) + list(module.buffers()):
                     dist.broadcast(t, src=src, group=group)
+            params = [p for p in module.parameters() if p.requires_grad]
+            if overlap and params and params[0].is_cuda and dist.get_backend(group) == "nccl":
+                self._comm = torch.cuda.Stream(params[0].device)
+                total = sum(p.numel() for p in params)
+                acc, cur = 0, []
+                for p in reversed(params):                      # gradients arrive in roughly this order
+                    cur.append(p)
+                    acc += p.numel()
+                    if acc * buckets >= total * (len(self._buckets) + 1) and len(self._buckets) < buckets - 1:
+                        self._buckets.append(cur)
+                        cur = []
+                if cur:
+                    self._buckets.append(cur)
+                for bi, bucket in enumerate(self._buckets):
+                    for p in bucket:
+                        self._bucket_of[id(p)] = bi
+                        p.register_post_accumulate_grad_hook(self._on_grad)
+                self._pending = [len(b) for b in self._buckets]
 
     def forward(self, *args, **kwargs):
         return self.module(*args, **kwargs)
 
-    def average_gradients(self) -> int:
-        """all-reduce(AVG) every existing .grad in one coalesced call; returns how many tensors"""
-        grads = [p.grad for p in self.module.parameters() if p.grad is not None]
-        if self.world <= 1 or not grads:
-            return len(grads)
+    # ---- gradient exchange ---------------------------------------------------------------------------
+    def _all_reduce(self, grads) -> None:
         if dist.get_backend(self.group) == "nccl":
             with dist._coalescing_manager(group=self.group, device=grads[0].device, async_ops=False):
                 for g in grads:
@@ -89,4 +109,41 @@ class BatchSharded(torch.nn.Module):
             for g in grads:
                 dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
             torch._foreach_div_(grads, float(self.world))
+
+    def _launch_bucket(self, bi: int) -> int:
+        grads = [p.grad for p in self._buckets[bi] if p.grad is not None]
+        self._pending[bi] = -1                  # done for this step
+        if grads:
+            cur = torch.cuda.current_stream(grads[0].device)
+            self._comm.wait_stream(cur)         # the gradients of this bucket are complete on the compute stream
+            with torch.cuda.stream(self._comm):
+                self._all_reduce(grads)
         return len(grads)
+
+    def _on_grad(self, p) -> None:
+        bi = self._bucket_of[id(p)]
+        if self._pending[bi] > 0:
+            self._pending[bi] -= 1
+            if self._pending[bi] == 0:
+                self._launch_bucket(bi)
+
+    def average_gradients(self) -> int:
+        """Average every existing .grad over the group (what was not already reduced from the hooks);
+        returns how many gradient tensors this step exchanged."""
+        if self.world <= 1:
+            return sum(1 for p in self.module.parameters() if p.grad is not None)
+        if self._comm is None:
+            grads = [p.grad for p in self.module.parameters() if p.grad is not None]
+            if grads:
+                self._all_reduce(grads)
+            return len(grads)
+        n = 0
+        for bi, bucket in enumerate(self._buckets):
+            if self._pending[bi] >= 0:          # a parameter of this bucket got no gradient this step
+                n += self._launch_bucket(bi)
+            else:
+                n += sum(1 for p in bucket if p.grad is not None)
+        dev = self._buckets[0][0].device
+        torch.cuda.current_stream(dev).wait_stream(self._comm)
+        self._pending = [len(b) for b in self._buckets]
+        return n

@@ -82,6 +82,34 @@ def main():
             print(json.dumps({"requested": mode, "used": used, "world": world, "max_rel_err": t[0].item(),
                               "graph_replay_max_rel_err": t[1].item(), "timeout_flag": err_flag}), flush=True)
         ok = ok and t[0].item() < 5e-5 and t[1].item() < 5e-5 and err_flag == 0 and (mode == "nccl" or True)
+    # BatchSharded: bucketed, overlapped gradient averaging == plain all_reduce(SUM) / world
+    from po2_quantization_b200.distributed import BatchSharded
+    torch.manual_seed(7 + rank)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(8, 8, 3, padding=1),
+                              torch.nn.Flatten(), torch.nn.Linear(8 * 8 * 8, 10)).cuda()
+    import copy
+    ref = copy.deepcopy(net)                              # un-wrapped replica: its gradients stay local
+    model = BatchSharded(net, buckets=3)
+    ref.load_state_dict(net.state_dict())                 # rank 0's parameters, as broadcast by the wrapper
+    xb = torch.randn(4, 3, 8, 8, device="cuda")
+    worst = 0.0
+    for it in range(3):
+        net.zero_grad()
+        ref.zero_grad()
+        model(xb * (it + 1)).square().mean().backward()   # all-reduces start from the hooks, under backward
+        nred = model.average_gradients()
+        ref(xb * (it + 1)).square().mean().backward()
+        local = [p.grad.clone() for p in ref.parameters()]
+        torch.cuda.synchronize()
+        for g in local:
+            dist.all_reduce(g)
+        for p, g in zip(net.parameters(), local):
+            worst = max(worst, ((p.grad - g / world).abs().max() / (g.abs().max() / world + 1e-30)).item())
+    t = torch.tensor([worst], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({"batch_sharded_grad_avg_max_rel_err": t.item(), "tensors": nred, "buckets": len(model._buckets)}), flush=True)
+    ok = ok and t.item() < 1e-6
     dist.barrier()
     torch.cuda.synchronize()
     os._exit(0 if ok else 1)
