@@ -200,7 +200,7 @@ class _BatchNormTrain(torch.autograd.Function):
                     stats = stat.view(1, -1)
                 bn_apply_out(x, residual, y, stats, weight, bias, running_mean, running_var, num_batches_tracked,
                              momentum, eps, relu, False, save_mean, save_invstd)
-        ctx.relu, ctx.has_res, ctx.group, ctx.world, ctx.exch = relu, residual is not None, group, world, exch
+        ctx.relu, ctx.has_res, ctx.group, ctx.world, ctx.exch = int(relu), residual is not None, group, world, exch
         ctx.save_for_backward(x, y if relu else None, weight, save_mean, save_invstd, stats)
         return y
 
@@ -232,12 +232,30 @@ def _kernel_ok(x: torch.Tensor) -> bool:
     return x.is_cuda and x.dtype == torch.float32 and x.dim() >= 2 and x.numel() > 0 and x.shape[1] <= 4096
 
 
+ACT = {None: 0, "none": 0, "relu": 1, "relu6": 2, "silu": 3}
+_ACT_FN = {0: lambda t: t, 1: F.relu, 2: F.relu6, 3: F.silu}
+
+
 class FusedSyncBatchNorm(nn.SyncBatchNorm):
-    """``nn.SyncBatchNorm`` whose forward can absorb the residual add and the ReLU that follow it."""
+    """``nn.SyncBatchNorm`` whose forward can absorb the residual add and the activation that follow it.
+
+    ``act`` ("relu", "relu6", "silu" or None) is the activation the model applies right after this norm
+    -- given at construction so that an ``nn.Sequential(conv, FusedSyncBatchNorm(c, act="relu6"),
+    nn.Identity())`` keeps the reference's ``state_dict`` keys -- or per call with ``relu=True``.
+    SiLU is fused in the forward-only (no-grad) path; under autograd it is applied by ``F.silu`` behind
+    the norm kernel."""
 
     fused_residual_relu = True
 
+    def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True,
+                 process_group=None, device=None, dtype=None, act=None):
+        super().__init__(num_features, eps, momentum, affine, track_running_stats, process_group, device, dtype)
+        if act not in ACT:
+            raise ValueError(f"act must be one of {sorted(k for k in ACT if k)} or None")
+        self.act = act
+
     def forward(self, input: torch.Tensor, residual: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
+        act = 1 if relu else ACT[getattr(self, "act", None)]
         use_batch_stats = self.training or (self.running_mean is None and self.running_var is None)
         fast = _kernel_ok(input) and (residual is None or (residual.shape == input.shape and _kernel_ok(residual)))
         if fast and use_batch_stats and (self.momentum is not None or self.running_mean is None):
@@ -252,10 +270,12 @@ class FusedSyncBatchNorm(nn.SyncBatchNorm):
                 if world > 1:
                     exch = peer_exchange_for(group)
             track = self.training and self.track_running_stats
-            return _BatchNormTrain.apply(
+            kact = act if act != 3 else 0                            # SiLU has no fused backward
+            out = _BatchNormTrain.apply(
                 input, residual, self.weight, self.bias, self.running_mean if track else None,
                 self.running_var if track else None, self.num_batches_tracked if track else None,
-                self.momentum if self.momentum is not None else 0.0, self.eps, bool(relu), group, world, exch)
+                self.momentum if self.momentum is not None else 0.0, self.eps, kact, group, world, exch)
+            return F.silu(out) if act == 3 else out
         if fast and not use_batch_stats and not (torch.is_grad_enabled() and (
                 input.requires_grad or (residual is not None and residual.requires_grad) or
                 (self.weight is not None and self.weight.requires_grad))):
@@ -263,11 +283,11 @@ class FusedSyncBatchNorm(nn.SyncBatchNorm):
             y = torch.empty_like(x)
             with torch.cuda.device(x.device):
                 bn_apply_out(x, residual.contiguous() if residual is not None else None, y, None, self.weight,
-                             self.bias, self.running_mean, self.running_var, None, 0.0, self.eps, bool(relu), True,
+                             self.bias, self.running_mean, self.running_var, None, 0.0, self.eps, act, True,
                              None, None)
             return y
         # stock path (CPU tensors, other dtypes, eval mode under autograd, cumulative-average momentum)
         out = super().forward(input)
         if residual is not None:
             out = out + residual
-        return F.relu(out) if relu else out
+        return _ACT_FN[act](out)

@@ -175,6 +175,16 @@ __device__ __forceinline__ bool publish_partial(double a, double b, const BnWork
   return *flag != 0;
 }
 
+// activations behind the norm: 0 none, 1 ReLU, 2 ReLU6 (hardtanh(0, 6): gradient passes for 0 < y < 6),
+// 3 SiLU (forward only)
+__device__ __forceinline__ float bn_act(float v, int act) {
+  if (act == 1) return fmaxf(v, 0.f);
+  if (act == 2) return fminf(fmaxf(v, 0.f), 6.f);
+  if (act == 3) return v / (1.f + __expf(-v));
+  return v;
+}
+__device__ __forceinline__ bool bn_act_open(float y, int act) { return y > 0.f && (act != 2 || y < 6.f); }
+
 // MODE 0: forward statistics (p = x - shift, q = p);  1: backward sums (p = dy, q = x - mean);
 // MODE 2: backward sums behind a ReLU (p = y > 0 ? dy : 0).
 template <bool VEC, int MODE>
@@ -186,7 +196,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const float* __re
                                                                float* __restrict__ out,      // MODE 0: stat[2C+1]; else sums[2C]
                                                                float* __restrict__ dgamma,
                                                                float* __restrict__ dbeta, BnGeom g,
-                                                               BnWorkspace ws, BnPeers peers) {
+                                                               BnWorkspace ws, BnPeers peers, int act) {
   // the consuming kernel (apply / backward apply, launched with programmatic stream serialization) may
   // be scheduled as soon as every CTA of this grid is running; it waits for this grid's completion
   // (griddepcontrol.wait) before it reads anything this grid writes
@@ -231,7 +241,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const float* __re
           const float q = xs[e] - shift;
           if (MODE == 0) { s1 += q; s2 = fmaf(q, q, s2); }
           else {
-            const float p = (MODE == 2 && !(ys[e] > 0.f)) ? 0.f : ds[e];
+            const float p = (MODE == 2 && !bn_act_open(ys[e], act)) ? 0.f : ds[e];
             s1 += p; s2 = fmaf(p, q, s2);
           }
         }
@@ -247,7 +257,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const float* __re
           if (MODE == 0) { s1 += q; s2 = fmaf(q, q, s2); }
           else {
             float p = __ldg(dy + off);
-            if (MODE == 2 && !(__ldg(y + off) > 0.f)) p = 0.f;
+            if (MODE == 2 && !bn_act_open(__ldg(y + off), act)) p = 0.f;
             s1 += p; s2 = fmaf(p, q, s2);
           }
         }
@@ -394,7 +404,7 @@ __global__ void __launch_bounds__(BN_THREADS, 4) bn_apply_kernel(const float* __
           o.x = fmaf(vx[u].x - p.x, p.y, p.z); o.y = fmaf(vx[u].y - p.x, p.y, p.z);
           o.z = fmaf(vx[u].z - p.x, p.y, p.z); o.w = fmaf(vx[u].w - p.x, p.y, p.z);
           if (res) { o.x += vr[u].x; o.y += vr[u].y; o.z += vr[u].z; o.w += vr[u].w; }
-          if (act == 1) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          if (act) { o.x = bn_act(o.x, act); o.y = bn_act(o.y, act); o.z = bn_act(o.z, act); o.w = bn_act(o.w, act); }
           reinterpret_cast<float4*>(y)[i] = o;
         }
       }
@@ -408,7 +418,7 @@ __global__ void __launch_bounds__(BN_THREADS, 4) bn_apply_kernel(const float* __
           const float4 p = prm[c];
           float o = fmaf(__ldg(x + i) - p.x, p.y, p.z);
           if (res) o += __ldg(res + i);
-          if (act == 1) o = fmaxf(o, 0.f);
+          o = bn_act(o, act);
           y[i] = o;
         }
       }
@@ -450,7 +460,7 @@ __global__ void __launch_bounds__(BN_THREADS, 4) bn_bwd_apply_kernel(const float
     prm[c] = make_float4(mean[c], (float)(sg / M), (float)(is * is * sgx / M), (float)((double)ga * is));
   }
   __syncthreads();
-  const bool relu = act == 1;
+  const bool relu = act != 0;                                  // masked by the activation's open interval
   for (int i0 = blockIdx.x * (BN_UNROLL * BN_THREADS) + threadIdx.x; i0 < g.total;
        i0 += gridDim.x * (BN_UNROLL * BN_THREADS)) {
     if (VEC) {
@@ -473,8 +483,8 @@ __global__ void __launch_bounds__(BN_THREADS, 4) bn_bwd_apply_kernel(const float
           const float4 p = prm[c];
           float4 gr = vd[u];
           if (relu) {
-            gr.x = vy[u].x > 0.f ? gr.x : 0.f; gr.y = vy[u].y > 0.f ? gr.y : 0.f;
-            gr.z = vy[u].z > 0.f ? gr.z : 0.f; gr.w = vy[u].w > 0.f ? gr.w : 0.f;
+            gr.x = bn_act_open(vy[u].x, act) ? gr.x : 0.f; gr.y = bn_act_open(vy[u].y, act) ? gr.y : 0.f;
+            gr.z = bn_act_open(vy[u].z, act) ? gr.z : 0.f; gr.w = bn_act_open(vy[u].w, act) ? gr.w : 0.f;
           }
           float4 o;
           o.x = (gr.x - p.y - (vx[u].x - p.x) * p.z) * p.w; o.y = (gr.y - p.y - (vx[u].y - p.x) * p.z) * p.w;
@@ -492,7 +502,7 @@ __global__ void __launch_bounds__(BN_THREADS, 4) bn_bwd_apply_kernel(const float
           const int c = slab - fdiv(slab, g.div_c) * C;
           const float4 p = prm[c];
           float gr = __ldg(dy + i);
-          if (relu && !(__ldg(y + i) > 0.f)) gr = 0.f;
+          if (relu && !bn_act_open(__ldg(y + i), act)) gr = 0.f;
           dx[i] = (gr - p.y - (__ldg(x + i) - p.x) * p.z) * p.w;
           if (dres) dres[i] = gr;
         }
@@ -595,8 +605,8 @@ int po2_bn_stats(const void* x, int B, int C, int HW, float* stat, void* workspa
   const dim3 grid(g.S, C);
   cudaStream_t st = (cudaStream_t)stream;
   const float* xf = (const float*)x;
-  if (v) bn_reduce_kernel<true, 0><<<grid, BN_THREADS, 0, st>>>(xf, nullptr, nullptr, nullptr, nullptr, stat, nullptr, nullptr, g, ws, pr);
-  else bn_reduce_kernel<false, 0><<<grid, BN_THREADS, 0, st>>>(xf, nullptr, nullptr, nullptr, nullptr, stat, nullptr, nullptr, g, ws, pr);
+  if (v) bn_reduce_kernel<true, 0><<<grid, BN_THREADS, 0, st>>>(xf, nullptr, nullptr, nullptr, nullptr, stat, nullptr, nullptr, g, ws, pr, 0);
+  else bn_reduce_kernel<false, 0><<<grid, BN_THREADS, 0, st>>>(xf, nullptr, nullptr, nullptr, nullptr, stat, nullptr, nullptr, g, ws, pr, 0);
   return (int)cudaGetLastError();
 }
 
@@ -607,7 +617,7 @@ int po2_bn_apply(const void* x, const void* residual, void* y, const float* stat
   if (!x || !y) return PO2_E_NULL;
   if (use_running ? (!running_mean || !running_var) : ((!stats && !mailbox) || R < 1)) return PO2_E_NULL;
   if (R > BN_MAX_RANKS && mailbox) return PO2_E_SIZE;
-  if (act != 0 && act != 1) return PO2_E_MODE;
+  if (act < 0 || act > 3) return PO2_E_MODE;
   BnGeom g;
   const int v = bn_geom(g, B, C, HW, aligned16(x) && aligned16(y) && aligned16(residual));
   if (v < 0) return v;
@@ -637,8 +647,8 @@ int po2_bn_bwd_reduce(const void* dy, const void* x, const void* y, const float*
                       float* sums, float* dgamma, float* dbeta, int act, int B, int C, int HW, void* workspace,
                       size_t workspace_bytes, void* const* peers, int rank, int world, void* stream) {
   if (!dy || !x || !save_mean || !save_invstd || !sums || !workspace) return PO2_E_NULL;
-  if (act != 0 && act != 1) return PO2_E_MODE;
-  if (act == 1 && !y) return PO2_E_NULL;
+  if (act < 0 || act > 2) return PO2_E_MODE;               // SiLU (3) has no backward here
+  if (act != 0 && !y) return PO2_E_NULL;
   if (workspace_bytes < po2_bn_workspace_bytes(C)) return PO2_E_WORKSPACE;
   if (!aligned16(workspace)) return PO2_E_ALIGN;
   BnGeom g;
@@ -651,12 +661,12 @@ int po2_bn_bwd_reduce(const void* dy, const void* x, const void* y, const float*
   const dim3 grid(g.S, C);
   cudaStream_t st = (cudaStream_t)stream;
   const float *xf = (const float*)x, *df = (const float*)dy, *yf = (const float*)y;
-  if (act == 1) {
-    if (v) bn_reduce_kernel<true, 2><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr);
-    else bn_reduce_kernel<false, 2><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr);
+  if (act != 0) {
+    if (v) bn_reduce_kernel<true, 2><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr, act);
+    else bn_reduce_kernel<false, 2><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr, act);
   } else {
-    if (v) bn_reduce_kernel<true, 1><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr);
-    else bn_reduce_kernel<false, 1><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr);
+    if (v) bn_reduce_kernel<true, 1><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr, act);
+    else bn_reduce_kernel<false, 1><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr, act);
   }
   return (int)cudaGetLastError();
 }
@@ -666,8 +676,8 @@ int po2_bn_bwd_apply(const void* dy, const void* x, const void* y, const float* 
                      void* dres, int act, int B, int C, int HW, void* stream) {
   if (!dy || !x || !save_mean || !save_invstd || (!sums && !mailbox) || !stats || !dx || R < 1) return PO2_E_NULL;
   if (R > BN_MAX_RANKS && mailbox) return PO2_E_SIZE;
-  if (act != 0 && act != 1) return PO2_E_MODE;
-  if (act == 1 && !y) return PO2_E_NULL;
+  if (act < 0 || act > 2) return PO2_E_MODE;               // SiLU (3) has no backward here
+  if (act != 0 && !y) return PO2_E_NULL;
   BnGeom g;
   const int v = bn_geom(g, B, C, HW, aligned16(dy) && aligned16(x) && aligned16(y) && aligned16(dx) && aligned16(dres));
   if (v < 0) return v;

@@ -243,3 +243,62 @@ def test_resnet20_train_step_with_fused_norm_equals_stock_norm():
         ops.set_conv_mode("tc")
         ops.set_dgrad_mode("tc")
         torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.parametrize("act", ["relu6", "silu"])
+@pytest.mark.parametrize("shape", [(32, 24, 8, 8), (16, 96, 3, 3), (64, 160, 1, 1)], ids=lambda s: "x".join(map(str, s)))
+def test_activation_variants_match_torch(act, shape):
+    """ReLU6 (MobileNetV2) and SiLU (MobileViT) behind the norm: train mode with backward (SiLU through
+    F.silu behind the kernel), and the fully fused eval / no-grad path."""
+    import po2_quantization_b200 as P
+    g = torch.Generator(device="cuda").manual_seed(sum(shape))
+    fn = {"relu6": F.relu6, "silu": F.silu}[act]
+    x = (torch.randn(shape, device="cuda", generator=g) * 2.5 + 0.5).requires_grad_(True)
+    go = torch.randn(shape, device="cuda", generator=g)
+    bn = P.FusedSyncBatchNorm(shape[1], act=act).cuda().train()
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(shape[1], device="cuda", generator=g) * 2 + 1)     # large gamma: ReLU6 clips at both ends
+        bn.bias.copy_(torch.randn(shape[1], device="cuda", generator=g) + 1)
+    y = bn(x)
+    y.backward(go)
+    xd = x.detach().double().cpu().requires_grad_(True)
+    yr = fn(F.batch_norm(xd, None, None, bn.weight.detach().double().cpu(), bn.bias.detach().double().cpu(), True, 0.0, bn.eps))
+    yr.backward(go.double().cpu())
+    assert _rel(y, yr) < TOL
+    n = x.numel() // shape[1]
+    if n >= 64:
+        assert _rel(x.grad, xd.grad) < 1e-4
+    bn.eval()
+    with torch.no_grad():
+        ye = bn(x.detach())
+        ref = fn(F.batch_norm(x.detach().double().cpu(), bn.running_mean.double().cpu(), bn.running_var.double().cpu(),
+                              bn.weight.double().cpu(), bn.bias.double().cpu(), False, 0.0, bn.eps))
+    assert _rel(ye, ref) < TOL
+
+
+def test_mobilenet_and_mobilevit_fused_norm_state_dict_and_forward():
+    """The fused-norm variants of the MobileNetV2 / MobileViT workloads keep the stock state_dict keys
+    and compute the same eval-mode forward."""
+    from po2_quantization_b200 import ops
+    from workloads import mobilenet_v2_cifar, mobilevit_xs
+    torch.manual_seed(3)
+    ops.set_conv_mode("fp32")            # keep bf16 / TF32 activation rounding out of a norm-vs-norm comparison
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        for build in (lambda f: mobilenet_v2_cifar(10, None, 4, fused_norm=f),
+                      lambda f: mobilevit_xs((32, 32), 10, (1, 1), None, 8, fused_norm=f)):
+            a, b = build(True).cuda(), build(False).cuda()
+            assert list(a.state_dict().keys()) == list(b.state_dict().keys())
+            b.load_state_dict(a.state_dict())
+            x = torch.randn(16, 3, 32, 32, device="cuda")
+            a.train(), b.train()             # one train-mode pass for non-trivial running statistics
+            with torch.no_grad():
+                a(x), b(x)
+            a.eval(), b.eval()
+            with torch.no_grad():
+                ya, yb = a(x), b(x)
+            assert _rel(ya, yb.double()) < 1e-3, _rel(ya, yb.double())
+    finally:
+        ops.set_conv_mode("tc")
+        torch.backends.cudnn.allow_tf32 = old_tf32

@@ -13,8 +13,20 @@ DIMS = (96, 120, 144)
 DEPTHS = (2, 4, 3)
 
 
+_FUSED_NORM = [False]       # set by the factory while it builds a model
+
+
+def _norm(c, act):
+    """[norm (, SiLU)]; the fused norm applies the SiLU itself (forward-only path) and an nn.Identity keeps
+    the reference's nn.Sequential indices, i.e. the state_dict keys"""
+    if _FUSED_NORM[0]:
+        from po2_quantization_b200 import FusedSyncBatchNorm
+        return [FusedSyncBatchNorm(c, act="silu" if act else None)] + ([nn.Identity()] if act else [])
+    return [nn.SyncBatchNorm(c)] + ([nn.SiLU()] if act else [])
+
+
 def _cbs(conv, c_out):
-    return nn.Sequential(conv, nn.SyncBatchNorm(c_out), nn.SiLU())
+    return nn.Sequential(conv, *_norm(c_out, True))
 
 
 class _FeedForward(nn.Module):
@@ -67,9 +79,9 @@ class _MV2(nn.Module):
         self.use_res_connect = stride == 1 and c_in == c_out
         layers = []
         if expansion != 1:
-            layers += [conv_cls(c_in, hid, 1, 1, 0, bias=False, **q), nn.SyncBatchNorm(hid), nn.SiLU()]
-        layers += [conv_cls(hid, hid, 3, stride, 1, groups=hid, bias=False, **q), nn.SyncBatchNorm(hid), nn.SiLU()]
-        layers += [conv_cls(hid, c_out, 1, 1, 0, bias=False, **q), nn.SyncBatchNorm(c_out)]
+            layers += [conv_cls(c_in, hid, 1, 1, 0, bias=False, **q)] + _norm(hid, True)
+        layers += [conv_cls(hid, hid, 3, stride, 1, groups=hid, bias=False, **q)] + _norm(hid, True)
+        layers += [conv_cls(hid, c_out, 1, 1, 0, bias=False, **q)] + _norm(c_out, False)
         self.conv = nn.Sequential(*layers)
 
     def forward(self, x):
@@ -131,7 +143,16 @@ class MobileViTXS(nn.Module):
         return self.to_logits(x)
 
 
-def mobilevit_xs(image_size=(224, 224), num_classes=1000, patch_size=(1, 1), quantize_fn=None, bits=8, conv_cls=None):
+def mobilevit_xs(image_size=(224, 224), num_classes=1000, patch_size=(1, 1), quantize_fn=None, bits=8, conv_cls=None,
+                 fused_norm=None):
+    """fused_norm: FusedSyncBatchNorm (norm + SiLU in one kernel when no gradient is needed) instead of
+    nn.SyncBatchNorm + nn.SiLU; default: on with this repo's conv class, off when another class is passed"""
+    if fused_norm is None:
+        fused_norm = conv_cls is None
     if conv_cls is None:
         from po2_quantization_b200 import QuantizedConv2d as conv_cls
-    return MobileViTXS(conv_cls, tuple(image_size), num_classes, tuple(patch_size), quantize_fn, bits)
+    _FUSED_NORM[0] = bool(fused_norm)
+    try:
+        return MobileViTXS(conv_cls, tuple(image_size), num_classes, tuple(patch_size), quantize_fn, bits)
+    finally:
+        _FUSED_NORM[0] = False
