@@ -174,6 +174,14 @@ int po2_conv2d_wgrad(const void* g, const void* x, void* gw, int B, int C, int H
                      int stride, int pad, int groups, int compute, void* workspace, size_t workspace_bytes,
                      void* stream);
 
+/* lin / lin+ quantizers (SURVEY.md section 8f "next" #1) -- utils/quantizers.py:59-96 (plus = 0), :99-136
+ * (plus = 1): per-input-channel uniform quantizer with a power-of-two step refined by num_iters rounds.
+ * w, y: fp32 (K, C, R*S) contiguous; one launch.  PO2_E_UNSUPPORTED when K*R*S exceeds
+ * po2_lin_max_channel_elems() (the caller keeps the op-by-op form). */
+int po2_lin_max_channel_elems(void);
+int po2_lin_quantize(const void* w, void* y, int K, int C, int RS, int bits, int num_iters, int plus, int flavor,
+                     void* stream);
+
 /* ---- batch normalisation around the quantized convs (SURVEY.md section 8f "next" #3) -----------------
  * The reference models follow every QuantizedConv2d with nn.SyncBatchNorm (+ ReLU, + the residual add):
  * models/resnet.py:38-61, models/mobilenet.py:29-33.  x, y, dy, dx are fp32 [B][C][HW] (NCHW), parameters

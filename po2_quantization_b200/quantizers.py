@@ -7,6 +7,8 @@ no CPU fallback on this path.
 """
 from typing import Callable, Optional
 
+import os
+
 import torch
 
 from . import ops
@@ -52,8 +54,8 @@ class PowerOfTwoPlusQuantizer(_Po2Base):
 
 # ------------------------------------------------------------------------------------------------
 # lin / lin+ (SURVEY.md section 8f "next" #1): per-input-channel uniform quantizer whose step is
-# constrained to a power of two.  Not on the accelerated path yet -- expressed with ATen ops in
-# the reference's op order (utils/quantizers.py:8-16, 59-136) so quantizer_dict stays complete.
+# constrained to a power of two (utils/quantizers.py:8-16, 59-136).  CUDA fp32 4-D weights take the
+# single-launch kernel of csrc/po2_lin.cu; everything else the op-by-op form below.
 # ------------------------------------------------------------------------------------------------
 def _uniform_per_in_channel(w: torch.Tensor, step: torch.Tensor, bits: int) -> torch.Tensor:
     s = step.view(-1, 1, 1)
@@ -61,7 +63,32 @@ def _uniform_per_in_channel(w: torch.Tensor, step: torch.Tensor, bits: int) -> t
     return s * torch.clamp(torch.round(w / s), min=-lim, max=lim)
 
 
+def _lin_forward_cuda(w: torch.Tensor, bits: int, num_iters: int, plus: bool):
+    """one launch of csrc/po2_lin.cu (one CTA per input channel), or None if the shape is not taken"""
+    from . import _lib
+    lib = _lib.load()
+    K, C = w.shape[0], w.shape[1]
+    RS = w.shape[2] * w.shape[3]
+    if K * RS > lib.po2_lin_max_channel_elems() or not 2 <= bits <= 16:
+        return None
+    x = w.contiguous()
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = lib.po2_lin_quantize(x.data_ptr(), y.data_ptr(), K, C, RS, int(bits), int(num_iters), int(plus), ops._flavor,
+                                  ops._stream_ptr(x.device))
+    if rc == -10:
+        return None
+    _lib.check(rc, "po2_lin_quantize")
+    ops.LAUNCHES += 1
+    return y
+
+
 def _lin_forward(w: torch.Tensor, bits: int, num_iters: int, plus: bool) -> torch.Tensor:
+    if w.is_cuda and w.dtype == torch.float32 and w.dim() == 4 and w.numel() > 0 and os.environ.get("PO2_LIN", "cuda") == "cuda":
+        y = _lin_forward_cuda(w.detach(), bits, num_iters, plus)
+        if y is not None:
+            return y
+    # op-by-op form in the reference's order (CPU tensors, other dtypes, very large channels)
     hi = torch.amax(w, dim=(0, 2, 3))
     lo = torch.amin(w, dim=(0, 2, 3))
     step = (hi - lo) / (2 ** bits - 1)

@@ -328,3 +328,59 @@ def test_ieee_vs_torch_cuda_flavor_difference_is_the_enumerated_boundaries(P):
     assert diffs[False] == []
     # cuda boundaries are 1 ulp below the cpu ones at k=-6..-4: exactly those three patterns flip
     assert sorted(diffs[True]) == [0x3C3FFFFE, 0x3CC00002, 0x3D3FFFFE], [hex(v) for v in diffs[True]]
+
+
+def test_lin_quantizers_cuda_kernel_matches_reference_vectors():
+    """lin / lin+ (utils/quantizers.py:59-136) on the single-launch kernel: bit-exact against the vectors
+    generated from the unmodified reference (tests/golden/lin_golden.npz)."""
+    import po2_quantization_b200 as P
+    from tests import golden_util as G
+    z = G.load("lin_golden.npz")
+    w = torch.from_numpy(z["w"]).cuda()
+    launches = P.ops.LAUNCHES
+    for name, cls in (("lin", P.LinearPowerOfTwoQuantizer), ("lin+", P.LinearPowerOfTwoPlusQuantizer)):
+        for bits in (3, 4):
+            got = cls.forward(None, w, bits=bits).cpu().numpy()
+            assert np.array_equal(got.view(np.uint32), z[f"{name}|{bits}"].view(np.uint32)), (name, bits)
+            g2 = cls.apply(w.clone().requires_grad_(True), bits)
+            assert np.array_equal(g2.detach().cpu().numpy().view(np.uint32), z[f"{name}|{bits}"].view(np.uint32))
+    assert P.ops.LAUNCHES == launches + 8            # one kernel launch per call
+
+
+@pytest.mark.parametrize("shape", [(16, 16, 3, 3), (64, 32, 3, 3), (96, 16, 1, 1), (320, 960, 1, 1), (64, 128, 3, 3), (8, 3, 5, 5)],
+                         ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("plus", [False, True])
+def test_lin_cuda_kernel_vs_op_by_op_form(shape, plus, monkeypatch):
+    """The kernel against the reference's own op sequence run by torch on the CPU (the oracle for this
+    quantizer).  The only licence: a channel whose <q,w>/<q,q> lands within rounding of a power-of-two
+    tie may pick the neighbouring step (torch's fp32 summation order decides there), so per-channel
+    disagreement must be rare and must be exactly a factor-of-two step."""
+    import po2_quantization_b200 as P
+    from po2_quantization_b200 import quantizers as Q
+    g = torch.Generator().manual_seed(sum(shape) + int(plus))
+    w = torch.randn(shape, generator=g) * 0.07
+    cls = P.LinearPowerOfTwoPlusQuantizer if plus else P.LinearPowerOfTwoQuantizer
+    for bits in (2, 4, 8):
+        got = cls.forward(None, w.cuda(), bits=bits).cpu()
+        monkeypatch.setenv("PO2_LIN", "aten")
+        ref = Q._lin_forward(w, bits, 10, plus)              # CPU, op by op
+        monkeypatch.setenv("PO2_LIN", "cuda")
+        same = (got.view(torch.int32) == ref.view(torch.int32)).all(dim=3).all(dim=2).all(dim=0)   # per input channel
+        assert same.float().mean().item() >= 0.97, (bits, same.float().mean().item())
+        for c in (~same).nonzero().flatten().tolist():
+            # both are k * 2^e grids; the steps differ by exactly one binade
+            sg = got[:, c][got[:, c] != 0].abs().min().item()
+            sr = ref[:, c][ref[:, c] != 0].abs().min().item()
+            assert sg in (2 * sr, sr / 2, sr), (bits, c, sg, sr)
+
+
+def test_lin_cuda_kernel_nan_and_constant_channels():
+    import po2_quantization_b200 as P
+    w = torch.randn(8, 4, 3, 3)
+    w[:, 1] = 0.25                      # constant channel: step 0 -> 0/0 -> NaN in the reference too
+    w[2, 2, 1, 1] = float("nan")        # NaN poisons its channel
+    ref = P.quantizers._lin_forward(w, 4, 10, False)
+    got = P.LinearPowerOfTwoQuantizer.forward(None, w.cuda(), bits=4).cpu()
+    assert torch.equal(torch.isnan(got), torch.isnan(ref))
+    ok = ~torch.isnan(ref)
+    assert torch.equal(got[ok], ref[ok])
