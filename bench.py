@@ -112,6 +112,12 @@ def _parallelism_note():
     return f" (batch-sharded; {grads}; {bn})"
 
 
+def _exchange_timeouts():
+    """number of peer mailboxes whose poll ever timed out (must be 0)"""
+    from po2_quantization_b200 import batchnorm
+    return sum(1 for e in batchnorm._exchanges.values() if e is not None and e.error_flag() != 0)
+
+
 def activation_bytes_estimate(batch):
     # saved activations of ResNet-56 at 32x32: 19 layer-1 convs+bn+relu at 16ch/32^2, 18 at 32ch/16^2, 18 at 64ch/8^2
     per_img = (19 * 16 * 32 * 32 + 18 * 32 * 16 * 16 + 18 * 64 * 8 * 8) * 4 * 3
@@ -291,7 +297,11 @@ def _run_ours_on_stream(a, ops, world, rank, local_rank, device):
                    "cuda_graph": graph is not None,
                    "l2": "working set per step ~%d MB of saved activations > 126 MB L2; no flush needed"
                          % (activation_bytes_estimate(B) // 2 ** 20),
-                   "conv_backend": ops.conv_backend_name(), "last_loss": last},
+                   "conv_backend": ops.conv_backend_name(), "last_loss": last,
+                   "norm_backend": "po2 FusedSyncBatchNorm kernels (norm + residual add + ReLU, forward and backward)",
+                   "weight_quantization": ("one multi-tensor launch per step (prefetch)"
+                                           if os.environ.get("PO2_PREFETCH", "1") == "1" else "one launch per layer"),
+                   "bn_exchange_timeouts": _exchange_timeouts()},
         "e2e": {"value": world * B * a.steps / (ms_e2e / 1e3), "unit": "images/s",
                 "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / a.steps},
