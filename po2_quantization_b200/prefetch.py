@@ -28,7 +28,7 @@ class _Slot:
 
 class _Table:
     """device table of MultiDesc entries for a fixed set of slots"""
-    __slots__ = ("ident", "dev", "n", "csize", "dev_single")
+    __slots__ = ("ident", "dev", "n", "csize")
 
 
 def _layer_key(m, xshape, mode):
@@ -111,11 +111,10 @@ def prefetch_weights(modules: Iterable[torch.nn.Module]) -> int:
             tab = _Table()
             tab.ident, tab.n, tab.csize = ident, len(multi), csize
             tab.dev = host[:max(len(multi), 1) * dbytes].to(dev)
-            tab.dev_single = None
             _tables[id(layers[0][0])] = tab
-            tab_single = {id(m) for m in single}
+            one_by_one = {id(m) for m in single}
             for m, slot, key in layers:
-                m.__dict__["_po2_prefetch_single"] = id(m) in tab_single
+                m.__dict__["_po2_prefetch_single"] = id(m) in one_by_one
         if tab.n:
             ops.LAUNCHES += 1
             _lib.check(lib.po2_quantize_pack_multi(tab.dev.data_ptr(), tab.n, tab.csize, stream), "po2_quantize_pack_multi")

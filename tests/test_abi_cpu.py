@@ -43,6 +43,31 @@ def test_argument_errors_are_return_codes():
     assert lib.po2_error_string(0) == b"success"
 
 
+def test_argument_errors_of_the_gradient_norm_and_lin_entry_points():
+    """wgrad / BatchNorm / lin / multi-tensor entry points: argument errors come back as PO2_E_* codes
+    before any launch (so this runs without a GPU), and the planning queries answer on the host."""
+    from po2_quantization_b200 import _lib
+    lib = _lib.load()
+    one = ctypes.c_void_p(4096)
+    conv = (8, 16, 32, 32, 16, 3, 3)
+    assert lib.po2_conv2d_wgrad_workspace(*conv, 2, 1, 1, 0) == 0                      # stride 2: not taken
+    assert lib.po2_conv2d_wgrad_workspace(*conv, 1, 1, 1, 0) > 0
+    assert lib.po2_conv2d_wgrad(None, one, one, *conv, 1, 1, 1, 0, one, 0, None) == -3            # PO2_E_NULL
+    assert lib.po2_conv2d_wgrad(one, one, one, *conv, 2, 1, 1, 0, one, 0, None) == -10            # PO2_E_UNSUPPORTED
+    assert lib.po2_conv2d_wgrad(one, one, one, *conv, 1, 1, 1, 0, None, 0, None) == -8            # PO2_E_WORKSPACE
+    assert lib.po2_bn_workspace_bytes(64) > 64 * 16 and lib.po2_bn_mailbox_bytes() > 1 << 20
+    assert lib.po2_bn_stats(None, 8, 16, 64, one, one, 1 << 20, None, 0, 1, None) == -3
+    assert lib.po2_bn_stats(one, 8, 16, 64, one, one, 16, None, 0, 1, None) == -8
+    assert lib.po2_bn_apply(one, None, one, one, 1, None, None, None, None, None, None, None, 0.1, 1e-5, 7, 0,
+                            None, None, 8, 16, 64, None) == -9                                      # unknown activation
+    assert lib.po2_bn_bwd_reduce(one, one, one, one, one, one, None, None, 3, 8, 16, 64, one, 1 << 20, None, 0, 1,
+                                 None) == -9                                                          # SiLU has no backward
+    assert lib.po2_lin_quantize(one, one, 4096, 4, 9, 4, 10, 0, 0, None) == -10                      # channel too large
+    assert lib.po2_lin_quantize(one, one, 16, 4, 9, 1, 10, 0, 0, None) == -2                         # bits
+    assert lib.po2_multi_desc_bytes() >= 64
+    assert lib.po2_quantize_pack(one, one, one, one, 1 << 20, *conv, 1, 1, 1, 4, 1, 0, 0, 1, one, None) == -10
+
+
 def test_cpu_tensors_are_rejected_not_emulated():
     import torch
     import po2_quantization_b200 as P
