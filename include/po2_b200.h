@@ -206,6 +206,16 @@ int po2_bn_apply(const void* x, const void* residual, void* y, const float* stat
                  float* stats_dense, const float* gamma, const float* beta, float* running_mean,
                  float* running_var, long long* num_batches_tracked, float momentum, float eps, int act,
                  int use_running, float* save_mean, float* save_invstd, int B, int C, int HW, void* stream);
+/* po2_bn_stats + po2_bn_apply in ONE launch for tensors whose per-channel slice fits the registers of
+ * the CTAs working on it (the CIFAR-scale layers): x is read once, the CTAs of a channel meet at a
+ * barrier in the workspace, statistics are combined (through the mailboxes when world > 1) and y is
+ * written from registers.  stats_dense (optional, [world][2C+1]) receives what po2_bn_bwd_apply needs.
+ * PO2_E_UNSUPPORTED when the tensor is too large / not 16-byte friendly: use the two-kernel form. */
+int po2_bn_fwd_fused(const void* x, const void* residual, void* y, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
+                     float eps, int act, float* save_mean, float* save_invstd, float* stats_dense, int B, int C,
+                     int HW, void* workspace, size_t workspace_bytes, void* const* peers, int rank, int world,
+                     void* stream);
 int po2_bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* save_mean, const float* save_invstd,
                       float* sums, float* dgamma, float* dbeta, int act, int B, int C, int HW, void* workspace,
                       size_t workspace_bytes, void* const* peers, int rank, int world, void* stream);

@@ -147,6 +147,26 @@ def bn_apply_out(x, residual, y, stats, weight, bias, running_mean, running_var,
         _ptr(save_mean), _ptr(save_invstd), B, C, HW, ops._stream_ptr(x.device)), "po2_bn_apply")
 
 
+def bn_fwd_fused_out(x, residual, y, weight, bias, running_mean, running_var, num_batches_tracked, momentum, eps,
+                     relu, save_mean, save_invstd, stats_dense, exch=None) -> bool:
+    """statistics + apply in one launch (tensors that fit the registers of their CTAs); False if the
+    shape is not taken"""
+    if os.environ.get("PO2_BN_FUSED", "1") != "1":
+        return False
+    B, C = x.shape[0], x.shape[1]
+    HW = x.numel() // (B * C)
+    ws = _bn_workspace(x.device, C)
+    rc = _lib.load().po2_bn_fwd_fused(
+        x.data_ptr(), _ptr(residual), y.data_ptr(), _ptr(weight), _ptr(bias), _ptr(running_mean), _ptr(running_var),
+        _ptr(num_batches_tracked), float(momentum), float(eps), int(relu), _ptr(save_mean), _ptr(save_invstd),
+        _ptr(stats_dense), B, C, HW, ws.data_ptr(), ws.numel(), *_peer_args(exch), ops._stream_ptr(x.device))
+    if rc == -10:
+        return False
+    _lib.check(rc, "po2_bn_fwd_fused")
+    ops.LAUNCHES += 1
+    return True
+
+
 def bn_bwd_reduce_out(dy, x, y, save_mean, save_invstd, sums, dgamma, dbeta, relu, exch=None) -> None:
     B, C = x.shape[0], x.shape[1]
     HW = x.numel() // (B * C)
@@ -185,7 +205,18 @@ class _BatchNormTrain(torch.autograd.Function):
             y = torch.empty_like(x)
             save_mean = torch.empty(C, dtype=torch.float32, device=x.device)
             save_invstd = torch.empty(C, dtype=torch.float32, device=x.device)
-            if world > 1 and exch is not None:
+            fused = False
+            if world == 1 or (exch is not None and os.environ.get("PO2_BN_FUSED_MULTI", "0") == "1"):
+                # small tensors: statistics + apply as ONE launch.  With several ranks the kernel can do the
+                # exchange inside too (verified by tools/check_sync_bn.py with PO2_BN_FUSED_MULTI=1), but its
+                # CTAs then sit on the SMs waiting for the peers with the NVLink latency fully exposed:
+                # measured 4.18 vs 4.07 ms per step at N=2, so the two-kernel form stays the default there
+                stats = torch.empty(world, 2 * C + 1, dtype=torch.float32, device=x.device)
+                fused = bn_fwd_fused_out(x, residual, y, weight, bias, running_mean, running_var, num_batches_tracked,
+                                         momentum, eps, relu, save_mean, save_invstd, stats, exch if world > 1 else None)
+            if fused:
+                pass
+            elif world > 1 and exch is not None:
                 # all_gather inside the kernels: stats publishes to every rank's mailbox, apply waits for R vectors
                 bn_stats_out(x, stat, exch)
                 stats = torch.empty(world, 2 * C + 1, dtype=torch.float32, device=x.device)

@@ -39,6 +39,7 @@ struct BnGeom {
 
 struct BnWorkspace {              // caller-provided, zero-initialised once; kernels leave counters zero
   unsigned int* ticket;           // [BN_MAX_C + 1] (per channel + one for the whole grid), first in the buffer
+  unsigned int* depart;           // [BN_MAX_C]     second counter of the fused kernel's per-channel barrier
   double2* partial;               // [C][BN_MAX_SPLIT]
 };
 
@@ -511,6 +512,178 @@ __global__ void __launch_bounds__(BN_THREADS, 4) bn_bwd_apply_kernel(const float
   }
 }
 
+// ---- fused forward for tensors that fit in registers ---------------------------------------------------
+// Statistics and apply in ONE launch: CTA (s, c) loads its slabs of channel c once (<= BN_FUSED_R
+// 128-bit vectors per thread, kept in registers), the S CTAs of a channel meet at a per-channel
+// barrier (two counters in the workspace, self-resetting; all CTAs are co-resident: the host caps the
+// grid at two CTAs per SM), the channel's statistics are combined -- through the peer mailboxes when
+// there are several ranks: CTA (0, c) publishes, every CTA of the channel polls -- and the CTA
+// normalises its registers and writes y.  Saves a launch and the second read of x per layer.
+constexpr int BN_FUSED_R = 8;
+
+__device__ __forceinline__ void channel_barrier(const BnWorkspace& ws, int c, int S, BnMailbox* errbox) {
+  __syncthreads();
+  if (threadIdx.x == 0 && S > 1) {
+    __threadfence();
+    atomicAdd(ws.ticket + c, 1u);
+    const unsigned long long t0 = global_ns();
+    while (*reinterpret_cast<volatile unsigned int*>(ws.ticket + c) < (unsigned int)S) {
+      if (global_ns() - t0 > 10000000000ull) { if (errbox) errbox->error = 2; break; }   // never hang the GPU
+      __nanosleep(32);
+    }
+    __threadfence();
+    const unsigned int d = atomicAdd(ws.depart + c, 1u);
+    if (d == (unsigned int)(S - 1)) { ws.ticket[c] = 0u; ws.depart[c] = 0u; __threadfence(); }   // everyone has passed
+  }
+  __syncthreads();
+}
+
+// thread 0 of a CTA: turn the channel's shifted sums into (mean, gamma*invstd, beta), with the peer
+// exchange when there are several ranks; CTA s == 0 of the channel also writes the per-channel outputs
+__device__ __noinline__ float4 fused_channel_finish(double pa, double pb, float shift, int s, int c, const BnGeom& g,
+                                                    const BnPeers& peers, BnMailbox* me, uint32_t tag, int R,
+                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                    float* running_mean, float* running_var,
+                                                    long long* num_batches_tracked, float momentum, float eps,
+                                                    float* __restrict__ save_mean, float* __restrict__ save_invstd,
+                                                    float* __restrict__ stats_dense) {
+  const int C = g.C;
+  float4 prm_out;
+    const double cnt = (double)g.B * (double)g.HW;
+    const double m = pa / cnt;
+    double mean = (double)shift + m, m2 = fmax(pb - pa * m, 0.0), n_tot = cnt;
+    if (me) {
+      // all_gather inside the kernel: CTA (0, c) stores this rank's values into every mailbox, every CTA polls
+      const float lmean = (float)mean, lm2 = (float)m2, lcnt = (float)cnt;
+      if (s == 0)
+        for (int p = 0; p < peers.world; ++p) {
+          uint2* dst = peers.box[p]->slot[tag % BN_SLOTS].ll[peers.rank];
+          st_ll(dst + c, lmean, tag);
+          st_ll(dst + C + c, lm2, tag);
+          if (c == 0) st_ll(dst + 2 * C, lcnt, tag);
+        }
+      BnGather src;
+      src.dense = nullptr; src.stride = 0; src.tag = tag; src.me = me;
+      src.ll = &me->slot[tag % BN_SLOTS].ll[0][0];
+      double var;
+      combine_stats(src, R, C, c, mean, var, n_tot);
+      m2 = var * n_tot;
+      if (s == 0 && stats_dense) {
+        const int idx[3] = {c, C + c, 2 * C};
+        float g3[3][BN_MAX_RANKS];
+        src.fetch<3>(R, idx, g3);
+        for (int r = 0; r < R; ++r) {
+          stats_dense[(size_t)r * (2 * C + 1) + c] = g3[0][r];
+          stats_dense[(size_t)r * (2 * C + 1) + C + c] = g3[1][r];
+          if (c == 0) stats_dense[(size_t)r * (2 * C + 1) + 2 * C] = g3[2][r];
+        }
+      }
+    } else if (s == 0 && stats_dense) {
+      stats_dense[c] = (float)mean;
+      stats_dense[C + c] = (float)m2;
+      if (c == 0) stats_dense[2 * C] = (float)cnt;
+    }
+    const double var = m2 / n_tot;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float ga = gamma ? gamma[c] : 1.0f, be = beta ? beta[c] : 0.0f;
+    prm_out = make_float4((float)mean, ga * invstd, be, 0.f);
+    if (s == 0) {
+      if (save_mean) save_mean[c] = (float)mean;
+      if (save_invstd) save_invstd[c] = invstd;
+      if (running_mean) {
+        const double unbiased = var * n_tot / fmax(n_tot - 1.0, 1.0);
+        running_mean[c] = (float)((1.0 - (double)momentum) * (double)running_mean[c] + (double)momentum * mean);
+        running_var[c] = (float)((1.0 - (double)momentum) * (double)running_var[c] + (double)momentum * unbiased);
+      }
+      if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
+    }
+  return prm_out;
+}
+
+__global__ void __launch_bounds__(BN_THREADS, 2) bn_fwd_fused_kernel(const float* __restrict__ x,
+                                                                     const float* __restrict__ res,
+                                                                     float* __restrict__ y,
+                                                                     const float* __restrict__ gamma,
+                                                                     const float* __restrict__ beta,
+                                                                     float* running_mean, float* running_var,
+                                                                     long long* num_batches_tracked, float momentum,
+                                                                     float eps, int act, float* __restrict__ save_mean,
+                                                                     float* __restrict__ save_invstd,
+                                                                     float* __restrict__ stats_dense, BnGeom g,
+                                                                     BnWorkspace ws, BnPeers peers) {
+  __shared__ double sm[BN_THREADS / 32][2];
+  __shared__ float4 s_prm;
+  const int s = blockIdx.x, c = blockIdx.y, C = g.C, L = g.L;
+  const int nslab = (g.B - s + g.S - 1) / g.S;
+  const int n = nslab * L;
+  const int R = peers.world > 1 ? peers.world : 1;
+  BnMailbox* me = peers.world > 1 ? peers.box[peers.rank] : nullptr;
+  const uint32_t tag = me ? *reinterpret_cast<volatile uint32_t*>(&me->epoch) + 1 : 0;   // read before anyone advances it
+  const float shift = __ldg(x + (size_t)c * g.HW);
+  // ---- phase 1: load into registers, shifted sums
+  float4 v[BN_FUSED_R];
+  int off[BN_FUSED_R];                                   // in 128-bit units (< 2^29, checked on the host)
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int u = 0; u < BN_FUSED_R; ++u) {
+    const int i = threadIdx.x + u * BN_THREADS;
+    v[u] = make_float4(shift, shift, shift, shift);
+    off[u] = 0;
+    if (i < n) {
+      const int k = fdiv(i, g.div_l);
+      off[u] = ((s + k * g.S) * C + c) * L + (i - k * L);
+      v[u] = __ldg(reinterpret_cast<const float4*>(x) + off[u]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < BN_FUSED_R; ++u) {
+    const float q0 = v[u].x - shift, q1 = v[u].y - shift, q2 = v[u].z - shift, q3 = v[u].w - shift;
+    s1 += (q0 + q1) + (q2 + q3);
+    s2 = fmaf(q0, q0, s2); s2 = fmaf(q1, q1, s2); s2 = fmaf(q2, q2, s2); s2 = fmaf(q3, q3, s2);
+  }
+  double a = (double)s1, b = (double)s2;
+  block_sum2(a, b, sm);
+  if (threadIdx.x == 0) ws.partial[c * BN_MAX_SPLIT + s] = make_double2(a, b);
+  channel_barrier(ws, c, g.S, me);
+  // ---- phase 2: this channel's statistics (every CTA of the channel computes the same numbers)
+  double pa = 0.0, pb = 0.0;
+  if ((int)threadIdx.x < g.S) {
+    const double2 p = __ldcg(ws.partial + c * BN_MAX_SPLIT + threadIdx.x);
+    pa = p.x; pb = p.y;
+  }
+  block_sum2(pa, pb, sm);
+  if (threadIdx.x == 0)
+    s_prm = fused_channel_finish(pa, pb, shift, s, c, g, peers, me, tag, R, gamma, beta, running_mean, running_var,
+                                 num_batches_tracked, momentum, eps, save_mean, save_invstd, stats_dense);
+  __syncthreads();
+  // ---- phase 3: normalise the registers
+  const float4 p = s_prm;
+#pragma unroll
+  for (int u = 0; u < BN_FUSED_R; ++u) {
+    const int i = threadIdx.x + u * BN_THREADS;
+    if (i < n) {
+      float4 o;
+      o.x = fmaf(v[u].x - p.x, p.y, p.z); o.y = fmaf(v[u].y - p.x, p.y, p.z);
+      o.z = fmaf(v[u].z - p.x, p.y, p.z); o.w = fmaf(v[u].w - p.x, p.y, p.z);
+      if (res) {
+        const float4 r4 = __ldg(reinterpret_cast<const float4*>(res) + off[u]);
+        o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+      }
+      if (act) { o.x = bn_act(o.x, act); o.y = bn_act(o.y, act); o.z = bn_act(o.z, act); o.w = bn_act(o.w, act); }
+      reinterpret_cast<float4*>(y)[off[u]] = o;
+    }
+  }
+  // the CTA that finishes the grid last advances this rank's epoch for the next exchange
+  if (me && threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(ws.ticket + BN_MAX_C, 1u);
+    if (t == gridDim.x * gridDim.y - 1) {
+      ws.ticket[BN_MAX_C] = 0;
+      me->epoch = tag;
+    }
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------
 static int bn_sms() {
   static int sms = 0;
@@ -551,7 +724,8 @@ static BnWorkspace bn_ws(void* workspace, int C) {
   BnWorkspace ws;
   (void)C;
   ws.ticket = reinterpret_cast<unsigned int*>(workspace);
-  ws.partial = reinterpret_cast<double2*>(reinterpret_cast<uint8_t*>(workspace) + (BN_MAX_C + 4) * sizeof(unsigned int));
+  ws.depart = ws.ticket + (BN_MAX_C + 4);
+  ws.partial = reinterpret_cast<double2*>(reinterpret_cast<uint8_t*>(workspace) + 2 * (BN_MAX_C + 4) * sizeof(unsigned int));
   return ws;
 }
 
@@ -585,7 +759,7 @@ extern "C" {
 
 size_t po2_bn_workspace_bytes(int C) {
   if (C <= 0) return 0;
-  return (size_t)(BN_MAX_C + 4) * sizeof(unsigned int) + (size_t)C * BN_MAX_SPLIT * sizeof(double2);
+  return (size_t)2 * (BN_MAX_C + 4) * sizeof(unsigned int) + (size_t)C * BN_MAX_SPLIT * sizeof(double2);
 }
 
 size_t po2_bn_mailbox_bytes(void) { return sizeof(BnMailbox); }
@@ -641,6 +815,40 @@ int po2_bn_apply(const void* x, const void* residual, void* y, const float* stat
   return (int)cudaLaunchKernelEx(&cfg, kern, (const float*)x, (const float*)residual, (float*)y, stats, R,
                                  (BnMailbox*)mailbox, stats_dense, gamma, beta, running_mean, running_var,
                                  num_batches_tracked, momentum, eps, act, use_running, save_mean, save_invstd, g);
+}
+
+int po2_bn_fwd_fused(const void* x, const void* residual, void* y, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
+                     float eps, int act, float* save_mean, float* save_invstd, float* stats_dense, int B, int C,
+                     int HW, void* workspace, size_t workspace_bytes, void* const* peers, int rank, int world,
+                     void* stream) {
+  if (!x || !y || !workspace) return PO2_E_NULL;
+  if (act < 0 || act > 3) return PO2_E_MODE;
+  if (workspace_bytes < po2_bn_workspace_bytes(C)) return PO2_E_WORKSPACE;
+  if (!aligned16(workspace)) return PO2_E_ALIGN;
+  BnGeom g;
+  const int v = bn_geom(g, B, C, HW, aligned16(x) && aligned16(y) && aligned16(residual));
+  if (v < 0) return v;
+  if (v == 0) return PO2_E_UNSUPPORTED;                                   // 128-bit path only
+  // one CTA holds at most BN_FUSED_R vectors per thread; all CTAs must be co-resident (2 per SM)
+  const int64_t per_cta = (int64_t)BN_FUSED_R * BN_THREADS;
+  const int64_t need_s = ((int64_t)B * g.L + per_cta - 1) / per_cta;
+  if (need_s > BN_MAX_SPLIT || need_s > B || need_s * C > 2 * (int64_t)bn_sms()) return PO2_E_UNSUPPORTED;
+  g.S = (int)need_s;
+  // slabs are dealt round-robin: the largest share must fit too
+  if ((int64_t)((B + g.S - 1) / g.S) * g.L > per_cta) {
+    if (g.S + 1 > BN_MAX_SPLIT || g.S + 1 > B || (int64_t)(g.S + 1) * C > 2 * (int64_t)bn_sms()) return PO2_E_UNSUPPORTED;
+    g.S += 1;
+    if ((int64_t)((B + g.S - 1) / g.S) * g.L > per_cta) return PO2_E_UNSUPPORTED;
+  }
+  BnPeers pr;
+  const int pe = make_peers(pr, peers, rank, world);
+  if (pe) return pe;
+  const BnWorkspace ws = bn_ws(workspace, C);
+  bn_fwd_fused_kernel<<<dim3(g.S, C), BN_THREADS, 0, (cudaStream_t)stream>>>(
+      (const float*)x, (const float*)residual, (float*)y, gamma, beta, running_mean, running_var, num_batches_tracked,
+      momentum, eps, act, save_mean, save_invstd, stats_dense, g, ws, pr);
+  return (int)cudaGetLastError();
 }
 
 int po2_bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* save_mean, const float* save_invstd,
