@@ -13,8 +13,11 @@ count combined with the parallel-variance formula; gradient of the affine parame
 sums).  Within one NVLink domain (<= 8 ranks) the bracketed collectives are not separate launches at
 all: the producing kernel stores this rank's vector into every rank's mailbox (symmetric memory,
 ``PeerExchange``) and the consuming kernel waits for the R vectors -- see csrc/po2_bn.cu.  NCCL
-(``PO2_BN_EXCHANGE=nccl``, larger groups, or no symmetric memory) remains the other path.  Inputs the kernels do not cover (CPU tensors, non-fp32, eval mode under autograd,
-``momentum=None``) take ``nn.SyncBatchNorm.forward`` itself followed by the add and the ReLU.
+(``PO2_BN_EXCHANGE=nccl``, larger groups, or no symmetric memory) remains the other path.  With one
+rank, tensors that fit the registers of their CTAs take the forward as a single launch
+(``po2_bn_fwd_fused``).  Inputs the kernels do not cover (CPU tensors, non-fp32, eval mode under
+autograd, ``momentum=None``) take ``nn.SyncBatchNorm.forward`` itself followed by the add and the
+activation.
 """
 import ctypes
 import os

@@ -7,14 +7,17 @@
 // step (profiles/r01_launches_resnet56_qat_step_po2_conv.csv).  These kernels are HBM/L2-bound
 // streaming passes with 128-bit accesses:
 //
-//   bn_stats_kernel       x -> per-channel (mean, M2, count)          reads x once
-//   bn_apply_kernel       y = act((x-mean)*invstd*gamma+beta [+res])  reads x (L2), [res], writes y
-//   bn_bwd_reduce_kernel  per-channel sum(g), sum(g*(x-mean)), g = dy masked by y>0 for ReLU
-//   bn_bwd_apply_kernel   dx (and the masked gradient for the residual branch)
+//   bn_reduce_kernel<0>    x -> per-channel (mean, M2, count)          reads x once
+//   bn_apply_kernel        y = act((x-mean)*invstd*gamma+beta [+res])  reads x (L2), [res], writes y
+//   bn_reduce_kernel<1|2>  per-channel sum(g), sum(g*(x-mean)), g = dy masked by the activation
+//   bn_bwd_apply_kernel    dx (and the masked gradient for the residual branch)
+//   bn_fwd_fused_kernel    the first two in ONE launch for tensors that fit in registers (one rank)
+//   act: none / ReLU / ReLU6 (forward + backward), SiLU (forward only)
 //
 // The split between the two halves of each direction is where SyncBatchNorm's collective goes
-// (all_gather of the 2C+1 statistics forward, all_reduce of the 2C sums backward); with one rank the
-// second kernel consumes the first one's output directly.
+// (all_gather of the 2C+1 statistics forward, all_reduce of the 2C sums backward) -- done by the
+// kernels themselves over NVLink peer stores (BnMailbox below), or by NCCL between the launches; with
+// one rank the second kernel consumes the first one's output directly.
 //
 // Layout: x[B][C][HW].  A reduce CTA (s, c) owns the slabs b = s, s+S, ... of channel c; its partial
 // sums go to a workspace and the last CTA of a channel to finish (ticket counter, self-resetting)
