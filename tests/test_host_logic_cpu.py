@@ -93,3 +93,42 @@ def test_flavor_and_mode_switches():
     P.set_log2_flavor("torch_cuda")
     assert P.get_log2_flavor() == "torch_cuda"
     P.set_log2_flavor("ieee")
+
+
+def test_fused_sync_batchnorm_cpu_fallback_and_state_dict():
+    """FusedSyncBatchNorm on CPU tensors takes nn.SyncBatchNorm's own path (+ add, + activation): same
+    numbers as the stock modules, same state_dict keys, every activation variant."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    x = torch.randn(6, 8, 5, 5)
+    res = torch.randn(6, 8, 5, 5)
+    for act, fn in ((None, lambda t: t), ("relu", F.relu), ("relu6", F.relu6), ("silu", F.silu)):
+        mine = P.FusedSyncBatchNorm(8, act=act)
+        stock = nn.BatchNorm2d(8)
+        assert list(mine.state_dict()) == list(stock.state_dict())
+        mine.load_state_dict(stock.state_dict())
+        for train in (True, False):
+            mine.train(train), stock.train(train)
+            assert torch.allclose(mine(x), fn(stock(x)), atol=1e-6), (act, train)
+        assert torch.allclose(mine(x, res), fn(stock(x) + res), atol=1e-6)
+    m = P.FusedSyncBatchNorm(8)
+    assert torch.allclose(m(x, res, True), F.relu(nn.BatchNorm2d(8)(x) + res), atol=1e-6)   # per-call relu=True
+    with pytest.raises(ValueError):
+        P.FusedSyncBatchNorm(8, act="gelu")
+
+
+def test_workloads_keep_state_dict_keys_with_fused_norms():
+    """The fused-norm variants of the three model families have exactly the stock variants' state_dict
+    keys and shapes (an nn.Identity keeps the nn.Sequential indices where an activation module was)."""
+    from workloads import mobilenet_v2_cifar, mobilevit_xs, resnet_cifar
+    import torch.nn as nn
+    pairs = [(resnet_cifar(20, 10, None, 4), resnet_cifar(20, 10, None, 4, norm_cls=nn.SyncBatchNorm)),
+             (mobilenet_v2_cifar(10, None, 4, fused_norm=True), mobilenet_v2_cifar(10, None, 4, fused_norm=False)),
+             (mobilevit_xs((32, 32), 10, (1, 1), None, 8, fused_norm=True), mobilevit_xs((32, 32), 10, (1, 1), None, 8, fused_norm=False))]
+    for a, b in pairs:
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa) == list(sb)
+        assert all(sa[k].shape == sb[k].shape for k in sa)
+        assert any(isinstance(m, P.FusedSyncBatchNorm) for m in a.modules())
+        assert not any(isinstance(m, P.FusedSyncBatchNorm) for m in b.modules())
