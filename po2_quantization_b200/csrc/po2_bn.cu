@@ -524,14 +524,17 @@ __global__ void __launch_bounds__(BN_THREADS, 4) bn_bwd_apply_kernel(const float
 // normalises its registers and writes y.  Saves a launch and the second read of x per layer.
 constexpr int BN_FUSED_R = 8;
 
-__device__ __forceinline__ void channel_barrier(const BnWorkspace& ws, int c, int S, BnMailbox* errbox) {
+// returns false if the barrier timed out (the CTAs of the channel were not co-resident for 10 s --
+// e.g. another stream held the SMs); the caller then poisons its output with NaN so the failure is loud
+__device__ __forceinline__ bool channel_barrier(const BnWorkspace& ws, int c, int S, BnMailbox* errbox, int* s_ok) {
+  if (threadIdx.x == 0) *s_ok = 1;
   __syncthreads();
   if (threadIdx.x == 0 && S > 1) {
     __threadfence();
     atomicAdd(ws.ticket + c, 1u);
     const unsigned long long t0 = global_ns();
     while (*reinterpret_cast<volatile unsigned int*>(ws.ticket + c) < (unsigned int)S) {
-      if (global_ns() - t0 > 10000000000ull) { if (errbox) errbox->error = 2; break; }   // never hang the GPU
+      if (global_ns() - t0 > 10000000000ull) { *s_ok = 0; if (errbox) errbox->error = 2; break; }   // never hang the GPU
       __nanosleep(32);
     }
     __threadfence();
@@ -539,6 +542,7 @@ __device__ __forceinline__ void channel_barrier(const BnWorkspace& ws, int c, in
     if (d == (unsigned int)(S - 1)) { ws.ticket[c] = 0u; ws.depart[c] = 0u; __threadfence(); }   // everyone has passed
   }
   __syncthreads();
+  return *s_ok != 0;
 }
 
 // thread 0 of a CTA: turn the channel's shifted sums into (mean, gamma*invstd, beta), with the peer
@@ -616,6 +620,7 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_fwd_fused_kernel(const float
                                                                      BnWorkspace ws, BnPeers peers) {
   __shared__ double sm[BN_THREADS / 32][2];
   __shared__ float4 s_prm;
+  __shared__ int s_ok;
   const int s = blockIdx.x, c = blockIdx.y, C = g.C, L = g.L;
   const int nslab = (g.B - s + g.S - 1) / g.S;
   const int n = nslab * L;
@@ -647,7 +652,7 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_fwd_fused_kernel(const float
   double a = (double)s1, b = (double)s2;
   block_sum2(a, b, sm);
   if (threadIdx.x == 0) ws.partial[c * BN_MAX_SPLIT + s] = make_double2(a, b);
-  channel_barrier(ws, c, g.S, me);
+  const bool barrier_ok = channel_barrier(ws, c, g.S, me, &s_ok);
   // ---- phase 2: this channel's statistics (every CTA of the channel computes the same numbers)
   double pa = 0.0, pb = 0.0;
   if ((int)threadIdx.x < g.S) {
@@ -660,7 +665,8 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_fwd_fused_kernel(const float
                                  num_batches_tracked, momentum, eps, save_mean, save_invstd, stats_dense);
   __syncthreads();
   // ---- phase 3: normalise the registers
-  const float4 p = s_prm;
+  float4 p = s_prm;
+  if (!barrier_ok) p.z = __uint_as_float(0x7FC00000u);     // incomplete statistics must not pass for a result
 #pragma unroll
   for (int u = 0; u < BN_FUSED_R; ++u) {
     const int i = threadIdx.x + u * BN_THREADS;
