@@ -3,14 +3,26 @@
 PO2 4-bit QAT forward + STE backward + SGD, batch 128 per GPU) and quantizer GB/s vs HBM peak.
 
     python bench.py --gpus N --steps K --warmup W            # our arm (N>1 under torchrun)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path
 
-One JSON line on rank 0.  `value` = whole-job images/s with inputs resident in HBM; `e2e` = the same
-step fed from pinned host memory with the loss read back every step; `roofline` = the quantizer's
-streaming kernel timed live with CUDA events against MEASURED_PEAKS.json; `cpu_baseline` = the
-oracle's torch-CPU restatement of the same training step on this box's host cores.
+One JSON line on rank 0.
+  value      whole-job images/s of the QAT step with inputs resident in HBM (CUDA-graph replay)
+  e2e        the same step fed from pinned host memory with the loss read back every step
+  roofline   the dominant kernel of the timed step (the tcgen05 conv forward) timed live per layer
+             class with CUDA events against MEASURED_PEAKS.json; `roofline_quantizer` is the same for
+             the quantizer's streaming kernels
+  cpu_baseline  the reference's step on this box's host cores (the unmodified reference files when
+             baseline/_ref is staged -- kind "reference" -- else the oracle's op-for-op port)
+At N=1 rank 0 also reports, under `extra` (none of it inside the timed region of `value`):
+  step variants   tf32 operands; the reference's OWN models/resnet.py (stock nn.SyncBatchNorm + ReLU
+                  around the drop-in QuantizedConv2d) -- what an unmodified checkout gets
+  gpu_oracle      the reference's torch code on this GPU (stock ATen / cuDNN, TF32 default), eager and
+                  CUDA-graph captured -- BASELINE.md section 3 (2), the same-box kernel to beat
+  configs         BASELINE.json configs[0], [2], [3] (ResNet-20 PTQ, MobileNetV2, MobileViT 224 B=256)
+  quantizer_sweep configs[4] compressed: 2^20..2^32 x {fp32, bf16} x bits {2,4,8} x {codes, no codes}
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -25,7 +37,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD = "resnet56_cifar10_po2_4bit_qat_fwd_bwd_sgd"
-METRIC = "quantized-conv images/sec (ResNet-56 PO2 4-bit QAT fwd+STE bwd); quantizer GB/s vs HBM peak in `roofline`"
+METRIC = "quantized-conv images/sec (ResNet-56 PO2 4-bit QAT fwd+STE bwd); quantizer GB/s vs HBM peak in `roofline_quantizer`"
+DATA = "synthetic (randn images 3x32x32, randint labels; kaiming-init weights, seed 8)"
+CONFIG_KEYS = ("workload", "batch_per_gpu", "global_batch", "parallelism", "device", "cuda_graph", "l2", "conv_backend",
+               "conv_operands", "norm_backend", "weight_quantization", "model_source", "top1_identity",
+               "bn_exchange_timeouts", "last_loss")
 
 
 def peaks():
@@ -34,6 +50,11 @@ def peaks():
         d = json.load(open(p))
         return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "source": "measured (MEASURED_PEAKS.json)"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def full_config(**kw):
+    """both arms emit the same config keys (the driver compares them)"""
+    return {k: kw.get(k) for k in CONFIG_KEYS}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -77,11 +98,25 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def build_training(device, world, local_rank, batch):
+# the QAT step (BASELINE.json configs[1])
+# ------------------------------------------------------------------------------------------------
+def build_training(device, world, local_rank, source="workload"):
+    """source "workload": workloads/resnet_cifar.py (FusedSyncBatchNorm takes add + ReLU);
+    "reference_files": the reference's own models/resnet.py, unmodified, on the drop-in classes."""
     import po2_quantization_b200 as P
-    from workloads import resnet_cifar
     torch.manual_seed(8)
-    model = resnet_cifar(56, 10, P.PowerOfTwoQuantizer, 4).to(device).train()
+    if source == "reference_files":
+        from workloads import reference_files as RF
+        ns = RF.load("dropin")
+        if ns is None:
+            return None
+        model = ns.get_model("resnet56", 10, P.PowerOfTwoQuantizer, 4, (32, 32)).to(device).train()
+    elif source == "workload_stock_norm":
+        from workloads import resnet_cifar
+        model = resnet_cifar(56, 10, P.PowerOfTwoQuantizer, 4, norm_cls=nn.SyncBatchNorm).to(device).train()
+    else:
+        from workloads import resnet_cifar
+        model = resnet_cifar(56, 10, P.PowerOfTwoQuantizer, 4).to(device).train()
     if os.environ.get("PO2_PREFETCH", "1") == "1":
         # quantize all 56 weights in ONE multi-tensor launch at the start of each forward instead of one
         # by one in front of each conv (po2_quantization_b200/prefetch.py); same arithmetic, same results
@@ -92,7 +127,7 @@ def build_training(device, world, local_rank, batch):
             model = nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True,
                                                         broadcast_buffers=False)
         else:
-            # same arithmetic, one coalesced NCCL all-reduce(AVG) per step (distributed.BatchSharded)
+            # same arithmetic, coalesced NCCL all-reduce(AVG) per bucket (distributed.BatchSharded)
             from po2_quantization_b200.distributed import BatchSharded
             model = BatchSharded(model)
     # reference train.py:51-56: SGD momentum 0.9, wd 1e-4, lr 0.1 * world
@@ -122,6 +157,125 @@ def activation_bytes_estimate(batch):
     # saved activations of ResNet-56 at 32x32: 19 layer-1 convs+bn+relu at 16ch/32^2, 18 at 32ch/16^2, 18 at 64ch/8^2
     per_img = (19 * 16 * 32 * 32 + 18 * 32 * 16 * 16 + 18 * 64 * 8 * 8) * 4 * 3
     return per_img * batch
+
+
+def operand_label(mode):
+    return {"tc": "bf16 operands (PO2 weights exact, activations/gradients rounded to bf16), f32 accumulate",
+            "tf32": "tf32 operands (PO2 weights exact, activations keep 10 mantissa bits), f32 accumulate",
+            "fp32": "f32 FMA", "cudnn": "cuDNN (TF32 by default)"}[mode]
+
+
+class StepHarness:
+    """One training configuration: model + optimiser + a CUDA graph of the whole step, on the current stream."""
+
+    def __init__(self, a, world, rank, local_rank, device, source="workload"):
+        from po2_quantization_b200 import ops
+        self.ops, self.world, self.rank, self.device, self.a = ops, world, rank, device, a
+        built = build_training(device, world, local_rank, source)
+        self.ok = built is not None
+        if not self.ok:
+            return
+        self.model, self.opt, self.crit = built
+        B = a.batch
+        g = torch.Generator().manual_seed(1000 + rank)
+        self.x_host = torch.randn(B, 3, 32, 32, generator=g).pin_memory()
+        self.y_host = torch.randint(0, 10, (B,), generator=g).pin_memory()
+        self.x_dev = self.x_host.to(device)
+        self.y_dev = self.y_host.to(device)
+        self.loss_buf = torch.zeros((), device=device)
+        self.graph = None
+        self.launches_per_step = None
+
+    def step(self):
+        self.opt.zero_grad()  # reference train.py:81 (set_to_none=True: no fill / accumulate kernels)
+        loss = self.crit(self.model(self.x_dev), self.y_dev)
+        loss.backward()
+        if hasattr(self.model, "average_gradients"):
+            self.model.average_gradients()
+        self.opt.step()
+        self.loss_buf.copy_(loss.detach())
+
+    def capture(self):
+        """CUDA graph of the whole step.  With N>1 the NCCL all-reduce and the SyncBatchNorm exchanges are
+        captured too; DDP needs its bucket rebuild (iteration 2) to have happened, hence the eager steps."""
+        ops, world = self.ops, self.world
+        for _ in range(3):
+            self.step()
+        torch.cuda.synchronize()
+        if not self.a.no_graph:
+            try:
+                for _ in range(11 if world > 1 else 3):
+                    self.step()
+                torch.cuda.current_stream().synchronize()
+                if world > 1:
+                    torch.distributed.barrier()
+                self.graph = torch.cuda.CUDAGraph()
+                ops.LAUNCHES = 0
+                with torch.cuda.graph(self.graph, stream=torch.cuda.current_stream()):
+                    self.step()
+                self.launches_per_step = ops.LAUNCHES
+                torch.cuda.synchronize()
+            except Exception as e:  # pragma: no cover
+                print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
+                self.graph = None
+        if self.launches_per_step is None:
+            ops.LAUNCHES = 0
+            self.step()
+            self.launches_per_step = ops.LAUNCHES
+        self.run = self.graph.replay if self.graph is not None else self.step
+
+    def barrier(self):
+        if self.world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.device, dtype=torch.float64)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    def time_resident(self, steps, warmup):
+        for _ in range(max(warmup, 3)):
+            self.run()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            self.run()
+        e1.record()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1))
+
+    def time_e2e(self, steps):
+        """pinned host -> device copy of the batch every step, loss read back every step"""
+        for _ in range(2):
+            self.x_dev.copy_(self.x_host, non_blocking=True); self.y_dev.copy_(self.y_host, non_blocking=True)
+            self.run(); self.loss_buf.item()
+        self.barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        last = 0.0
+        for _ in range(steps):
+            self.x_dev.copy_(self.x_host, non_blocking=True)
+            self.y_dev.copy_(self.y_host, non_blocking=True)
+            self.run()
+            last = self.loss_buf.item()            # device -> host read of the step's result
+        f1.record()
+        self.barrier()
+        return self.max_over_ranks(f0.elapsed_time(f1)), last
+
+    def weight_checksum(self):
+        """sum of all parameters in fp64: identical on every rank iff the replicas stayed in lock-step"""
+        with torch.no_grad():
+            return float(sum(p.double().sum() for p in self.model.parameters()).item())
+
+    def close(self):
+        self.graph = None
+        self.model = self.opt = None
+        gc.collect()
+        torch.cuda.empty_cache()
 
 
 def run_ours(a):
@@ -155,35 +309,21 @@ def run_ours(a):
 
 def _run_ours_on_stream(a, ops, world, rank, local_rank, device):
     B = a.batch
-    model, opt, crit = build_training(device, world, local_rank, B)
-    g = torch.Generator().manual_seed(1000 + rank)
-    x_host = torch.randn(B, 3, 32, 32, generator=g).pin_memory()
-    y_host = torch.randint(0, 10, (B,), generator=g).pin_memory()
-    x_dev = x_host.to(device)
-    y_dev = y_host.to(device)
-    loss_buf = torch.zeros((), device=device)
-
-    def step():
-        opt.zero_grad()  # reference train.py:81 (set_to_none=True: no fill / accumulate kernels)
-        loss = crit(model(x_dev), y_dev)
-        loss.backward()
-        if hasattr(model, "average_gradients"):
-            model.average_gradients()
-        opt.step()
-        loss_buf.copy_(loss.detach())
+    parts = set(a.parts.split(","))
+    h = StepHarness(a, world, rank, local_rank, device)
 
     if a.torch_profile:
         # kernel-time table of eager steps from torch.profiler (works under torchrun, where ncu does not):
         # rank 0 writes the per-kernel totals of 5 steps to the given path
         from torch.profiler import ProfilerActivity, profile
         for _ in range(12):
-            step()
+            h.step()
         torch.cuda.synchronize()
         if world > 1:
             torch.distributed.barrier()
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
             for _ in range(5):
-                step()
+                h.step()
             torch.cuda.synchronize()
         if rank == 0:
             rows = [(e.key, e.count, e.device_time_total) for e in prof.key_averages() if e.device_time_total > 0]
@@ -200,122 +340,318 @@ def _run_ours_on_stream(a, ops, world, rank, local_rank, device):
         # one eager step between cudaProfilerStart/Stop: `ncu --profile-from-start off` lists exactly
         # the kernels of a step (profiles/ launch list)
         for _ in range(3):
-            step()
+            h.step()
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStart()
-        step()
+        h.step()
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
         print(json.dumps({"profile_step": True, "launches_of_libpo2b200": ops.LAUNCHES}))
         return
 
-    # ---- CUDA graph of the whole step.  With DDP (N>1) the NCCL all-reduce and the SyncBatchNorm
-    # collectives are captured too (ProcessGroupNCCL supports capture); DDP needs its bucket rebuild
-    # (iteration 2) to have happened, hence 11 eager warm-up steps on the capture stream first.
-    graph = None
-    launches_per_step = None
-    for _ in range(3):
-        step()
-    torch.cuda.synchronize()
-    if not a.no_graph:
-        try:
-            for _ in range(11 if world > 1 else 3):
-                step()
-            torch.cuda.current_stream().synchronize()
-            if world > 1:
-                torch.distributed.barrier()
-            graph = torch.cuda.CUDAGraph()
-            ops.LAUNCHES = 0
-            with torch.cuda.graph(graph, stream=torch.cuda.current_stream()):
-                step()
-            launches_per_step = ops.LAUNCHES
-            torch.cuda.synchronize()
-        except Exception as e:  # pragma: no cover
-            print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
-            graph = None
-    if launches_per_step is None:
-        ops.LAUNCHES = 0
-        step()
-        launches_per_step = ops.LAUNCHES
-    run = graph.replay if graph is not None else step
-
-    def barrier():
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world > 1:
-            t = torch.tensor([ms], device=device, dtype=torch.float64)
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-            return float(t.item())
-        return ms
-
-    # ---- device-resident timing
-    for _ in range(max(a.warmup, 3)):
-        run()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h.capture()
     with ClockSampler(local_rank) as clk:
-        e0.record()
-        for _ in range(a.steps):
-            run()
-        e1.record()
-        barrier()
-        ms_total = max_over_ranks(e0.elapsed_time(e1))
-        # ---- end to end: pinned host -> device every step, loss read back every step
-        for _ in range(2):
-            x_dev.copy_(x_host, non_blocking=True); y_dev.copy_(y_host, non_blocking=True); run(); loss_buf.item()
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        last = 0.0
-        for _ in range(a.steps):
-            x_dev.copy_(x_host, non_blocking=True)
-            y_dev.copy_(y_host, non_blocking=True)
-            run()
-            last = loss_buf.item()            # device -> host read of the step's result
-        f1.record()
-        barrier()
-        ms_e2e = max_over_ranks(f0.elapsed_time(f1))
-        roof, extra = (quantizer_roofline(device, a) if rank == 0 else (None, None))
-        conv_roof = conv_forward_roofline(device, B) if rank == 0 else None
+        ms_total = h.time_resident(a.steps, a.warmup)
+        ms_e2e, last = h.time_e2e(a.steps)
     clocks = clk.summary()
+    checksum = h.weight_checksum()
     if world > 1:
+        # replicas must hold bit-identical weights after the timed steps (gradient averaging + SyncBatchNorm
+        # exchange correct on every rank): compare the fp64 checksums
+        t = torch.tensor([checksum, -checksum], device=device, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        replicas_identical = bool(t[0].item() == -t[1].item())
         torch.distributed.barrier()
-
+    else:
+        replicas_identical = True
+    timeouts = _exchange_timeouts()
     if rank != 0:
         return
+    mode = ops.get_conv_mode()
     ms_step = ms_total / a.steps
     out = {
         "metric": METRIC, "value": world * B * a.steps / (ms_total / 1e3), "unit": "images/s",
         "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic (randn images 3x32x32, randint labels; kaiming-init weights, seed 8)",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
-                   "parallelism": f"dp{world}" + (_parallelism_note() if world > 1 else ""),
-                   "cuda_graph": graph is not None,
-                   "l2": "working set per step ~%d MB of saved activations > 126 MB L2; no flush needed"
-                         % (activation_bytes_estimate(B) // 2 ** 20),
-                   "conv_backend": ops.conv_backend_name(), "last_loss": last,
-                   "norm_backend": "po2 FusedSyncBatchNorm kernels (norm + residual add + ReLU, forward and backward)",
-                   "weight_quantization": ("one multi-tensor launch per step (prefetch)"
-                                           if os.environ.get("PO2_PREFETCH", "1") == "1" else "one launch per layer"),
-                   "bn_exchange_timeouts": _exchange_timeouts()},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": operand_label(mode),
+        "data": DATA,
+        "config": full_config(
+            workload=WORKLOAD, batch_per_gpu=B, global_batch=B * world, device="cuda",
+            parallelism=f"dp{world}" + (_parallelism_note() if world > 1 else ""),
+            cuda_graph=h.graph is not None,
+            l2="working set per step ~%d MB of saved activations > 126 MB L2; no flush needed" % (activation_bytes_estimate(B) // 2 ** 20),
+            conv_backend=ops.conv_backend_name(), conv_operands=operand_label(mode), last_loss=last,
+            norm_backend="po2 FusedSyncBatchNorm kernels (norm + residual add + ReLU, forward and backward)",
+            weight_quantization=("one multi-tensor launch per step (prefetch)" if os.environ.get("PO2_PREFETCH", "1") == "1"
+                                 else "one launch per layer"),
+            model_source="workloads/resnet_cifar.py (layer graph of models/resnet.py; FusedSyncBatchNorm); the reference's "
+                         "own models/resnet.py is timed in extra.step_variants.reference_model_files",
+            top1_identity="asserted bit-for-bit in fp32-accumulate mode; bf16/tf32 operand modes are checked on decisive "
+                          "margins (tests/test_conv_gpu.py::test_ptq_quantize_model_and_forward_resnet20_top1)",
+            bn_exchange_timeouts=timeouts),
         "e2e": {"value": world * B * a.steps / (ms_e2e / 1e3), "unit": "images/s",
-                "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": 4,
+                "h2d_bytes_per_step": h.x_host.numel() * 4 + h.y_host.numel() * 8, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / a.steps},
-        "gpu_launches": launches_per_step * a.steps,
-        "gpu_launches_per_step": launches_per_step,
+        "gpu_launches": h.launches_per_step * a.steps,
+        "gpu_launches_per_step": h.launches_per_step,
         "clocks": clocks,
-        "roofline": roof, "roofline_extra": extra, "roofline_conv_forward": conv_roof,
+        "weights_fp64_checksum": checksum, "replicas_identical_after_timed_steps": replicas_identical,
     }
-    if world == 1 and not a.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(B, steps=2)
+    h.close()
+    if world == 1:
+        out["roofline"] = conv_forward_roofline(device, B) if "roofline" in parts else None
+        qroof, qrows = quantizer_roofline(device, a) if "roofline" in parts else (None, None)
+        out["roofline_quantizer"], out["roofline_quantizer_rows"] = qroof, qrows
+        extra = {}
+        if "variants" in parts:
+            extra["step_variants"] = step_variants(a, device, ms_step)
+        if "oracle" in parts:
+            extra["gpu_oracle"] = gpu_oracle_step(a, device, ms_step)
+        if "configs" in parts:
+            extra["configs"] = other_configs(device)
+        if "sweep" in parts:
+            extra["quantizer_sweep"] = quantizer_sweep(device, a.sweep_max_log2)
+        out["extra"] = extra
+        if not a.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(B, steps=2)
     print(json.dumps(out), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
+# step variants and the GPU oracle (N=1, outside the timed region of `value`)
+# ------------------------------------------------------------------------------------------------
+def step_variants(a, device, ms_main):
+    """The same QAT step (a) with tf32 operands, (b) on the reference's own models/resnet.py -- stock
+    nn.SyncBatchNorm + nn.ReLU modules around the drop-in QuantizedConv2d, which is what an unmodified
+    checkout of the reference gets from this library."""
+    from po2_quantization_b200 import ops
+    res = {"main_ms": ms_main}
+    prev = ops.get_conv_mode()
+    for name, mode, source in (("tf32_operands", "tf32", "workload"),
+                               ("reference_model_files", prev, "reference_files"),
+                               ("reference_model_files_tf32", "tf32", "reference_files")):
+        try:
+            ops.set_conv_mode(mode)
+            h = StepHarness(a, 1, 0, device.index or 0, device, source)
+            if not h.ok:
+                h = StepHarness(a, 1, 0, device.index or 0, device, "workload_stock_norm")
+                src = "workloads/resnet_cifar.py with stock nn.SyncBatchNorm (baseline/_ref not staged)"
+            else:
+                src = "models/resnet.py of the reference, unmodified (baseline/_ref)" if source == "reference_files" \
+                    else "workloads/resnet_cifar.py"
+            h.capture()
+            ms = h.time_resident(min(a.steps, 10), 3) / min(a.steps, 10)
+            res[name] = {"ms_per_step": ms, "images_per_s": a.batch / ms * 1e3, "conv_operands": operand_label(mode),
+                         "model": src, "cuda_graph": h.graph is not None, "launches_per_step": h.launches_per_step,
+                         "last_loss": float(h.loss_buf.item())}
+            h.close()
+        except Exception as e:  # pragma: no cover
+            res[name] = {"error": f"{type(e).__name__}: {e}"}
+        finally:
+            ops.set_conv_mode(prev)
+    return res
+
+
+def _reference_training_step(device, batch, seed_rank=0):
+    """The reference's own training step (train.py:79-92) on `device`: the unmodified reference files when
+    staged (kind "reference"), else the oracle's op-for-op torch restatement (kind "port")."""
+    from workloads import reference_files as RF
+    ns = RF.load("stock")
+    torch.manual_seed(8)
+    if ns is not None:
+        model = ns.get_model("resnet56", 10, ns.quantizers.PowerOfTwoQuantizer, 4, (32, 32))
+        kind, what = "reference", "unmodified reference files (baseline/_ref: models/resnet.py, utils/quantizers.py)"
+    else:
+        from oracle.po2_oracle_torch import PO2, QuantizedConv2dOracle
+        from workloads import resnet_cifar
+        model = resnet_cifar(56, 10, PO2, 4, conv_cls=QuantizedConv2dOracle)
+        kind, what = "port", "oracle/po2_oracle_torch.py (stock ATen ops == what the reference runs)"
+    model = model.to(device).train()
+    opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)
+    crit = nn.CrossEntropyLoss()
+    g = torch.Generator().manual_seed(1000 + seed_rank)
+    x = torch.randn(batch, 3, 32, 32, generator=g).to(device)
+    y = torch.randint(0, 10, (batch,), generator=g).to(device)
+    loss_buf = torch.zeros((), device=device)
+
+    def step():
+        opt.zero_grad()  # reference train.py:81
+        loss = crit(model(x), y)
+        loss.backward()
+        opt.step()
+        loss_buf.copy_(loss.detach())
+    return step, loss_buf, kind, what
+
+
+def _time_loop(fn, iters):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def gpu_oracle_step(a, device, ms_main):
+    """the reference's torch code on THIS GPU -- stock ATen elementwise
+    quantizer ops, cuDNN convolutions (allow_tf32 at torch's default, True), stock BatchNorm -- eager (how
+    train.py runs it) and CUDA-graph captured (launch overhead removed: the strongest same-box baseline)."""
+    try:
+        step, loss_buf, kind, what = _reference_training_step(device, a.batch)
+        for _ in range(5):
+            step()
+        iters = min(a.steps, 10)
+        eager = _time_loop(step, iters)
+        graph_ms = None
+        try:
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=torch.cuda.current_stream()):
+                step()
+            for _ in range(3):
+                g.replay()
+            graph_ms = _time_loop(g.replay, iters)
+        except Exception as e:  # pragma: no cover
+            print(f"[bench] gpu_oracle graph capture failed: {type(e).__name__}: {e}", file=sys.stderr)
+        res = {"kind": kind, "what": what, "device": torch.cuda.get_device_name(device),
+               "cudnn_allow_tf32": bool(torch.backends.cudnn.allow_tf32), "eager_ms_per_step": eager,
+               "eager_images_per_s": a.batch / eager * 1e3, "graph_ms_per_step": graph_ms,
+               "graph_images_per_s": (a.batch / graph_ms * 1e3) if graph_ms else None,
+               "ours_ms_per_step": ms_main, "speedup_vs_eager": eager / ms_main,
+               "speedup_vs_graph": (graph_ms / ms_main) if graph_ms else None, "last_loss": float(loss_buf.item())}
+        del g, step
+        gc.collect()
+        torch.cuda.empty_cache()
+        return res
+    except Exception as e:  # pragma: no cover
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[0], [2], [3]: inference forward, ours vs the reference's torch code on this GPU
+# ------------------------------------------------------------------------------------------------
+def _graph_forward_ms(model, x, iters=10):
+    with torch.no_grad():
+        for _ in range(3):
+            model(x)
+        torch.cuda.current_stream().synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=torch.cuda.current_stream()):
+            out = model(x)
+        for _ in range(2):
+            g.replay()
+        ms = _time_loop(g.replay, iters)
+    top1 = out.argmax(1).clone()
+    del g
+    return ms, top1, out
+
+
+def other_configs(device):
+    import po2_quantization_b200 as P
+    from po2_quantization_b200 import ops
+    from workloads import mobilenet_v2_cifar, mobilevit_xs, reference_files as RF, resnet_cifar
+    stock, dropin = RF.load("stock"), RF.load("dropin")
+    rows = {}
+
+    def oracle_model(name, bits, img, classes):
+        if stock is None:
+            return None
+        torch.manual_seed(8)
+        if name == "mobilevit224":
+            m = RF.mobilevit_224(stock, classes, None, bits)
+        else:
+            m = stock.get_model(name, classes, None, bits, img)
+        return m
+
+    cases = [
+        # (key, BASELINE config, ours builder, reference-file name, bits, batch, image, classes, flop per batch of quantized convs)
+        ("config0_resnet20_po2plus_4b_ptq_fwd_b128", lambda: resnet_cifar(20, 10, None, 4), "resnet20", 4, 128, (32, 32), 10, 10.34e9),
+        ("config2_mobilenetv2_po2plus_4b_ptq_fwd_b128", lambda: mobilenet_v2_cifar(10, None, 4), "mobilenet", 4, 128, (32, 32), 10, 1.40e9),
+        ("config3_mobilevit_xs_224_patch1_po2plus_8b_ptq_fwd_b256", lambda: mobilevit_xs((224, 224), 1000, (1, 1), None, 8),
+         "mobilevit224", 8, 256, (224, 224), 1000, 234.4e9),
+    ]
+    for key, build, refname, bits, B, img, classes, flop in cases:
+        r = {"batch": B, "image": list(img), "bits": bits, "qconv_flop_per_batch": flop}
+        try:
+            torch.manual_seed(8)
+            ref = oracle_model(refname, bits, img, classes)
+            torch.manual_seed(8)
+            m = build()
+            if ref is not None:
+                m.load_state_dict(ref.state_dict(), strict=True)       # same weights in all arms
+            m = m.to(device).eval()
+            mse = P.quantize_model(m, P.PowerOfTwoPlusQuantizer, bits)
+            x = torch.randn(B, 3, *img, generator=torch.Generator().manual_seed(0)).to(device)
+            ops.LAUNCHES = 0
+            ms, top1, out = _graph_forward_ms(m, x)
+            r.update({"ours_ms": ms, "ours_images_per_s": B / ms * 1e3, "ptq_mse": mse, "ours_launches_per_forward": ops.LAUNCHES // 4,
+                      "ours_qconv_TFLOPs_if_all_time_were_conv": flop / ms / 1e9})
+            # the same model object with its convs on cuDNN (isolates the conv kernels from the fused norms)
+            ops.set_conv_mode("cudnn")
+            try:
+                ms_c, _, _ = _graph_forward_ms(m, x)
+            finally:
+                ops.set_conv_mode("tc")
+            r.update({"ours_with_cudnn_convs_ms": ms_c, "speedup_vs_own_cudnn_convs": ms_c / ms})
+            if dropin is not None and refname != "mobilevit224":
+                # the reference's own model file on the drop-in classes (stock norms/activations)
+                torch.manual_seed(8)
+                md = dropin.get_model(refname, classes, None, bits, img)
+                md.load_state_dict(ref.state_dict(), strict=True)
+                md = md.to(device).eval()
+                P.quantize_model(md, P.PowerOfTwoPlusQuantizer, bits)
+                ms_d, top1_d, _ = _graph_forward_ms(md, x)
+                r.update({"reference_model_file_on_dropin_ms": ms_d, "reference_model_file_on_dropin_images_per_s": B / ms_d * 1e3})
+                del md
+            if ref is not None:
+                ref = ref.to(device).eval()
+                stock.quantizers.quantize_model(ref, stock.quantizers.PowerOfTwoPlusQuantizer, bits)
+                with torch.no_grad():
+                    for _ in range(3):
+                        ref(x)
+                    eager = _time_loop(lambda: ref(x), 5)
+                ms_o, top1_o, out_o = _graph_forward_ms(ref, x)
+                rel = ((out.double() - out_o.double()).abs().max() / out_o.double().abs().max()).item()
+                r.update({"gpu_oracle_eager_ms": eager, "gpu_oracle_graph_ms": ms_o, "gpu_oracle_images_per_s": B / ms_o * 1e3,
+                          "speedup_vs_gpu_oracle_graph": ms_o / ms, "speedup_vs_gpu_oracle_eager": eager / ms,
+                          "logits_rel_err_vs_gpu_oracle": rel,
+                          "top1_agreement_vs_gpu_oracle": float((top1 == top1_o).float().mean().item())})
+            if key.startswith("config2"):
+                # QAT-eval mode (test.py:133-159): the model keeps its quantizer and re-quantizes every forward
+                torch.manual_seed(8)
+                mq = mobilenet_v2_cifar(10, P.PowerOfTwoPlusQuantizer, 4).to(device).eval()
+                P.enable_weight_prefetch(mq)
+                ms_q, _, _ = _graph_forward_ms(mq, x)
+                r.update({"ours_qat_eval_ms": ms_q, "ours_qat_eval_images_per_s": B / ms_q * 1e3})
+                del mq
+            del m, ref, x, out
+        except Exception as e:  # pragma: no cover
+            r["error"] = f"{type(e).__name__}: {e}"
+        gc.collect()
+        torch.cuda.empty_cache()
+        rows[key] = r
+    return rows
+
+
+# ------------------------------------------------------------------------------------------------
+# quantizer: roofline at one size + the compressed sweep of BASELINE.json configs[4]
+# ------------------------------------------------------------------------------------------------
+def _timed_each(fn, iters=10, flush=None):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for p, q in ev:
+        if flush is not None:
+            flush.add_(1)
+        p.record(); fn(); q.record()
+    torch.cuda.synchronize()
+    ts = sorted(p.elapsed_time(q) for p, q in ev)
+    return sum(ts) / len(ts), ts[len(ts) // 2]
+
+
 def quantizer_roofline(device, a):
     """Quantizer streaming kernels at 2^log2n elements, timed one launch at a time with CUDA events
     on the launching stream.  Algorithmic bytes: absmax reads es, quantize reads es
@@ -328,20 +664,9 @@ def quantizer_roofline(device, a):
         x = torch.randn(n, device=device, dtype=torch.float32).to(dt)
         y = torch.empty_like(x)
         s = torch.empty((), dtype=torch.float32, device=device)
-
-        def timed(fn, iters=10):
-            for _ in range(3):
-                fn()
-            torch.cuda.synchronize()
-            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
-            for p, q in ev:
-                p.record(); fn(); q.record()
-            torch.cuda.synchronize()
-            return sum(p.elapsed_time(q) for p, q in ev) / iters
-
-        t_abs = timed(lambda: ops.absmax_out(x, s))
-        t_q = timed(lambda: ops.quantize_out(x, y, s, 4, 1, False))
-        t_all = timed(lambda: ops.quantize_fused_out(x, y, s, 4, 1, False))
+        t_abs, _ = _timed_each(lambda: ops.absmax_out(x, s))
+        t_q, _ = _timed_each(lambda: ops.quantize_out(x, y, s, 4, 1, False))
+        t_all, _ = _timed_each(lambda: ops.quantize_fused_out(x, y, s, 4, 1, False))
         res.append({"kernel": f"po2::quantize_kernel<{name}> (pass 2 of po2_quantize_fused)", "dtype": name,
                     "elements": n, "bytes_per_element": 2 * es, "ms": t_q,
                     "achieved": 2 * es * n / t_q / 1e6, "absmax_ms": t_abs,
@@ -355,17 +680,62 @@ def quantizer_roofline(device, a):
             # `ncu --set full` captures (profiles/r01_ncu_quantize_kernel_f32_2p28.csv: 1.074 + 1.028 GB;
             # profiles/r01_ncu_quantize_kernel_f32_2p30.csv: 4.295 + 4.248 GB)
             "traffic": {28: 2.102e9, 30: 8.543e9}.get(a.sweep_log2), "algorithmic_bytes": 8.0 * (1 << a.sweep_log2),
-            "peak_source": pk["source"],
+            "peak_source": pk["source"], "frac_of_nominal_8TBs": r0["achieved"] / 8000.0,
             "note": "algorithmic bytes = 8 B/element (4 read + 4 written) x 2^%d fp32 elements per launch; "
-                    "inputs (%.1f GB) larger than L2; BASELINE's sweep tops out at 2^32 elements, see "
-                    "profiles/r01_quantizer_sweep_2p30_2p32.json" % (a.sweep_log2, 4 * (1 << a.sweep_log2) / 1e9)}
+                    "inputs (%.1f GB) larger than L2" % (a.sweep_log2, 4 * (1 << a.sweep_log2) / 1e9)}
     for r in res:
         r["frac_quantize_pass"] = r["achieved"] / pk["hbm_gbs"]
         r["frac_both_passes"] = r["both_passes_GBs"] / pk["hbm_gbs"]
         r["frac_absmax_pass"] = r["absmax_GBs"] / pk["hbm_gbs"]
+    torch.cuda.empty_cache()
     return roof, res
 
 
+def quantizer_sweep(device, max_log2=32):
+    """BASELINE.json configs[4], compressed: N = 2^20, 2^22, ..., 2^max_log2; fp32 and bf16; bits 2, 4, 8;
+    with and without packed codes; po2 everywhere plus po2+ at 4 bits.  What `Q.forward` costs (both
+    passes): algorithmic bytes = 3*es (+ bits/8 with codes, rounded up to the packed byte) per element.
+    L2 is flushed between iterations while the tensors are smaller than 256 MB."""
+    from po2_quantization_b200 import ops
+    pk = peaks()
+    flush_buf = torch.zeros(320 * 1024 * 1024 // 4, dtype=torch.int32, device=device)
+    rows = []
+    for dt, es, name in ((torch.float32, 4, "f32"), (torch.bfloat16, 2, "bf16")):
+        for lg in range(20, max_log2 + 1, 2):
+            n = 1 << lg
+            try:
+                chunk = min(n, 1 << 28)
+                x = torch.empty(n, device=device, dtype=dt)
+                gen = torch.Generator(device=device).manual_seed(1234)
+                for i in range(0, n, chunk):            # randn in chunks: no 2x fp32 temporary for the 16 GiB case
+                    x[i:i + chunk] = torch.randn(chunk, device=device, dtype=torch.float32, generator=gen).to(dt)
+                y = torch.empty_like(x)
+                s = torch.empty((), dtype=torch.float32, device=device)
+                codes = torch.empty(n, dtype=torch.uint8, device=device)
+                flush = flush_buf if n * es < 256 * 1024 * 1024 else None
+                iters = 10 if lg <= 28 else 5
+                for bits, plus in ((2, False), (4, False), (4, True), (8, False)):
+                    mean, med = _timed_each(lambda: ops.quantize_fused_out(x, y, s, bits, 1, plus), iters, flush)
+                    cb = 0.5 if bits <= 4 else 1.0
+                    mean_c, med_c = _timed_each(lambda: ops.quantize_fused_out(x, y, s, bits, 1, plus, codes=codes[:int(n * cb)]),
+                                                iters, flush)
+                    rows.append({"dtype": name, "log2n": lg, "bits": bits, "quantizer": "po2+" if plus else "po2",
+                                 "ms": med, "GBs": 3 * es * n / med / 1e6, "frac": 3 * es * n / med / 1e6 / pk["hbm_gbs"],
+                                 "ms_codes": med_c, "GBs_codes": (3 * es + cb) * n / med_c / 1e6,
+                                 "frac_codes": (3 * es + cb) * n / med_c / 1e6 / pk["hbm_gbs"]})
+                del x, y, codes
+            except torch.cuda.OutOfMemoryError:  # pragma: no cover
+                rows.append({"dtype": name, "log2n": lg, "error": "out of memory"})
+            torch.cuda.empty_cache()
+    big = [r for r in rows if "frac" in r and r["log2n"] >= 28]
+    return {"peak_GBs": pk["hbm_gbs"], "peak_source": pk["source"], "bytes_per_element": "3*es (+0.5 or 1 with codes)",
+            "min_frac_at_2p28_and_up": min((r["frac"] for r in big), default=None),
+            "min_frac_codes_at_2p28_and_up": min((r["frac_codes"] for r in big), default=None), "rows": rows}
+
+
+# ------------------------------------------------------------------------------------------------
+# the dominant kernel of the step: tcgen05 conv forward, per ResNet-56 layer class
+# ------------------------------------------------------------------------------------------------
 def conv_forward_roofline(device, batch):
     """Quantized-conv FORWARD of the ResNet-56 layer classes, timed live in CUDA graphs (the pack +
     conv kernels of one QuantizedConv2d.forward), with a cold L2 (a 320 MB buffer is rewritten before
@@ -375,6 +745,7 @@ def conv_forward_roofline(device, batch):
     from po2_quantization_b200 import ops
     pk = peaks()
     flush = torch.zeros(320 * 1024 * 1024 // 4, dtype=torch.int32, device=device)
+    compute = ops.COMPUTE.get(ops.get_conv_mode(), 0)
 
     def graph_ms(body, reps=10, iters=5):
         body()
@@ -405,7 +776,7 @@ def conv_forward_roofline(device, batch):
 
         def ours():
             flush.add_(1)
-            ops.conv2d_out(x, y, scale, out, 1, 1, 1, 0)
+            ops.conv2d_out(x, y, scale, out, 1, 1, 1, compute)
 
         def cudnn():
             flush.add_(1)
@@ -417,85 +788,90 @@ def conv_forward_roofline(device, batch):
         rows.append({"layer": name, "count_in_resnet56": count, "us": us, "us_cudnn_tf32": us_c,
                      "TFLOPs": flop / us / 1e6, "io_GBs": byts / us / 1e3, "frac_hbm": byts / us / 1e3 / pk["hbm_gbs"]})
         tot_us += us * count; tot_cudnn += us_c * count; tot_flop += flop * count; tot_bytes += byts * count
+    del flush
+    torch.cuda.empty_cache()
     return {"bound": "hbm", "kernel": "po2::conv_umma_kernel<9> (+pack_weights_kernel)", "unit": "GB/s",
             "achieved": tot_bytes / tot_us / 1e3, "peak": pk["hbm_gbs"], "frac": tot_bytes / tot_us / 1e3 / pk["hbm_gbs"],
-            "traffic": None, "TFLOPs": tot_flop / tot_us / 1e6, "frac_of_bf16_peak": tot_flop / tot_us / 1e6 / pk["bf16_tflops"],
+            "traffic": 8.43e6, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the 16->16 @32x32 layer under "
+            "`ncu --set full` (profiles/r01_ncu_conv_umma_resnet56_16to16_3x3_at32_b128.csv): 8.43 MB read = the fp32 input exactly "
+            "once, 0 B written back during the kernel (the 8.39 MB output is still dirty in the 126 MB L2 when the kernel "
+            "ends); algorithmic bytes of that layer = 16.78 MB",
+            "peak_source": pk["source"],
+            "TFLOPs": tot_flop / tot_us / 1e6, "frac_of_bf16_peak": tot_flop / tot_us / 1e6 / pk["bf16_tflops"],
             "resnet56_3x3_forward_us": tot_us, "resnet56_3x3_forward_us_cudnn_tf32": tot_cudnn,
             "images_per_s_forward_qconv_only": batch / (tot_us * 1e-6), "layers": rows,
-            "note": "52 stride-1 3x3 quantized convs of ResNet-56 at batch %d, cold L2, CUDA-graph timed" % batch}
+            "conv_operands": operand_label(ops.get_conv_mode()),
+            "note": "the dominant kernel of the timed step (largest share of the launch list in profiles/); "
+                    "52 stride-1 3x3 quantized convs of ResNet-56 at batch %d, cold L2, CUDA-graph timed; algorithmic "
+                    "bytes per launch = 4*(B*C*H*W + B*K*P*Q)" % batch}
 
 
 # ------------------------------------------------------------------------------------------------
+# the reference's CPU path
+# ------------------------------------------------------------------------------------------------
 def cpu_training_step_fn(batch):
-    """The same training step on host cores through the oracle's torch-CPU restatement of the
-    reference (oracle/po2_oracle_torch.py): the one place bench.py executes oracle/."""
-    from oracle.po2_oracle_torch import PO2, QuantizedConv2dOracle
-    from workloads import resnet_cifar
+    """The reference's training step on host cores: the one place bench.py executes the oracle / the
+    staged reference files (as the baseline being timed, never as the product)."""
     torch.set_num_threads(os.cpu_count() or 1)
-    torch.manual_seed(8)
-    model = resnet_cifar(56, 10, PO2, 4, conv_cls=QuantizedConv2dOracle).train()
-    opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)
-    crit = nn.CrossEntropyLoss()
-    g = torch.Generator().manual_seed(1000)
-    x = torch.randn(batch, 3, 32, 32, generator=g)
-    y = torch.randint(0, 10, (batch,), generator=g)
-
-    def step():
-        opt.zero_grad()  # reference train.py:81 (set_to_none=True: no fill / accumulate kernels)
-        loss = crit(model(x), y)
-        loss.backward()
-        opt.step()
-        return float(loss.item())
-    return step
+    step, loss_buf, kind, what = _reference_training_step(torch.device("cpu"), batch)
+    return step, loss_buf, kind, what
 
 
 def cpu_baseline(batch, steps=2):
-    step = cpu_training_step_fn(batch)
-    step()
+    step, loss_buf, kind, what = cpu_training_step_fn(batch)
+    step(); step()                          # first step: oneDNN primitive creation, thread-pool start-up
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return {"value": batch * steps / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{steps} full training steps (fwd+bwd+SGD) of ResNet-56 PO2 4-bit QAT at batch {batch}, "
-                      f"oracle/po2_oracle_torch.py (stock ATen CPU ops == what the reference runs), 1 warm-up",
-            "ms_per_step": dt / steps * 1e3}
+    return {"value": batch * steps / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{steps} full training steps (fwd+bwd+SGD) of ResNet-56 PO2 4-bit QAT at batch {batch} after 2 warm-up "
+                      f"steps; {what}",
+            "ms_per_step": dt / steps * 1e3, "host_cpus": os.cpu_count()}
 
 
 def run_reference(a):
-    """--impl reference: the reference's own CPU implementation of the step.  The reference is
-    Python and cannot travel to the GPU box, so this is the oracle's op-for-op torch restatement
-    (pinned bit-exactly to the reference by tests/test_oracle_golden.py) on all host threads."""
+    """--impl reference: the reference's own CPU implementation of the step on all host threads -- the
+    unmodified reference files when baseline/_ref is staged, else the oracle's op-for-op torch port
+    (pinned bit-exactly to the reference by tests/test_oracle_golden.py).  Same batch, same warm-up
+    count and same config keys as our arm; only the NUMBER of timed steps is bounded (and reported) so
+    that a slow host still finishes within minutes."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     B = a.batch
-    step = cpu_training_step_fn(B)
+    step, loss_buf, kind, what = cpu_training_step_fn(B)
+    warm = max(a.warmup, 3)
+    step()                                   # cold step (library initialisation), never timed or probed
     t0 = time.perf_counter()
     step()
-    probe = time.perf_counter() - t0
-    sample = f"full batch {B}"
-    if probe > 6.0:                      # slow host: keep the whole run within a few minutes
-        B = 32
-        step = cpu_training_step_fn(B)
-        sample = f"reduced batch {B} (a batch-{a.batch} step took {probe:.1f} s on this host)"
-    for _ in range(max(0, min(a.warmup, 3) - 1)):
+    probe = time.perf_counter() - t0         # the SECOND step is the probe
+    budget = 240.0
+    steps = max(1, min(a.steps, int((budget - probe * warm) / max(probe, 1e-3))))
+    for _ in range(max(0, warm - 2)):
         step()
-    steps = max(1, min(a.steps, 20))
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
     v = B * steps / dt
+    sample = (f"{steps} training steps at the full batch {B} after {warm} warm-up steps" +
+              ("" if steps == a.steps else f" (fewer than the requested {a.steps}: a step takes {probe:.1f} s on this host)") +
+              f"; {what}")
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": world,
-           "steps": steps, "warmup": min(a.warmup, 3), "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-           "data": "synthetic (randn images 3x32x32, randint labels; kaiming-init weights, seed 8)",
-           "config": {"workload": WORKLOAD, "batch_per_gpu": B, "device": "cpu"},
-           "cpu_baseline": {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-                            "sample": f"{steps} training steps, {sample}; oracle/po2_oracle_torch.py on torch CPU kernels"},
-           "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+           "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32 (torch CPU kernels)",
+           "data": DATA,
+           "config": full_config(workload=WORKLOAD, batch_per_gpu=B, global_batch=B, device="cpu",
+                                 parallelism="one process, %d host threads" % torch.get_num_threads(), cuda_graph=False,
+                                 l2="n/a (CPU)", conv_backend="torch CPU (oneDNN) convolution", conv_operands="f32",
+                                 norm_backend="torch CPU batch norm", weight_quantization="one quantizer call per layer (11 ATen ops each)",
+                                 model_source=what, top1_identity="n/a (this arm is the reference)", bn_exchange_timeouts=0,
+                                 last_loss=float(loss_buf.item())),
+           "cpu_baseline": {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
+           "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
     print(json.dumps(out), flush=True)
 
 
@@ -508,7 +884,10 @@ def main():
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sweep-log2", type=int, default=30)
+    ap.add_argument("--sweep-log2", type=int, default=30, help="size of the quantizer roofline measurement")
+    ap.add_argument("--sweep-max-log2", type=int, default=32, help="largest size of the compressed quantizer sweep")
+    ap.add_argument("--parts", default="roofline,variants,oracle,configs,sweep",
+                    help="N=1 only: which of the untimed side measurements to run (comma separated)")
     ap.add_argument("--torch-profile", default=None, help="write a torch.profiler kernel table of eager steps and exit")
     ap.add_argument("--profile-step", action="store_true", help="run one eager step inside cudaProfilerStart/Stop and exit")
     a = ap.parse_args()

@@ -146,11 +146,14 @@ int po2_quantize_pack(const void* w, void* qw_out, float* scale_out, void* packe
  * descriptors in HOST memory with po2_multi_desc_fill (same arguments as po2_quantize_pack; returns the
  * cluster size 1/2/4/8 this tensor needs, or PO2_E_UNSUPPORTED when the layer must take
  * po2_quantize_pack), copies it to the device once, and calls po2_quantize_pack_multi every step with
- * cluster_size = the largest value po2_multi_desc_fill returned. */
+ * cluster_size = the largest value po2_multi_desc_fill returned.
+ * sse_out (device, fp64, may be NULL): receives sum((Q(w) - w)^2) of this tensor on every launch -- the
+ * value QuantizedConv2d.get_quantization_error returns (models/quantized_conv.py:40-45) and the models'
+ * error walkers sum (train.py:106), produced by the pass that quantizes instead of by 12 more launches. */
 size_t po2_multi_desc_bytes(void);
 int po2_multi_desc_fill(void* host_table, int index, const void* w, void* qw_out, float* scale_out, void* packed,
                         size_t packed_bytes, int B, int C, int H, int W, int K, int R, int S, int stride, int pad,
-                        int groups, int bits, int fsr, int mode, int flavor, int compute);
+                        int groups, int bits, int fsr, int mode, int flavor, int compute, double* sse_out);
 int po2_quantize_pack_multi(const void* device_table, int ntensors, int cluster_size, void* stream);
 
 /* Data gradient of the same conv (SURVEY.md section 8f "next" #2, first half): gx = dL/dx given g = dL/dout,

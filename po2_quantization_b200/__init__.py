@@ -10,6 +10,8 @@ from .prefetch import enable_weight_prefetch, prefetch_weights  # noqa: F401
 from .ops import get_log2_flavor, set_log2_flavor  # noqa: F401
 from .quantized_conv import QuantizedConv2d  # noqa: F401
 from .quantizers import (LinearPowerOfTwoPlusQuantizer, LinearPowerOfTwoQuantizer,  # noqa: F401
-                         PowerOfTwoPlusQuantizer, PowerOfTwoQuantizer, quantize_model, quantizer_dict)
+                         PowerOfTwoPlusQuantizer, PowerOfTwoQuantizer, model_quantization_error, quantize_model,
+                         quantizer_dict)
+from .checkpoint import load_packed_checkpoint, pack_state_dict, save_packed_checkpoint, unpack_state_dict  # noqa: F401
 
 __version__ = "0.1.0"

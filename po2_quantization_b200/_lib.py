@@ -38,7 +38,7 @@ SIGNATURES = {
     "po2_qconv2d_fwd": (_i, [_vp] * 5 + [_i] * 15 + [_vp, _sz, _vp, _vp]),
     "po2_quantize_pack": (_i, [_vp, _vp, _vp, _vp, _sz] + [_i] * 15 + [_vp, _vp]),
     "po2_multi_desc_bytes": (_sz, []),
-    "po2_multi_desc_fill": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _sz] + [_i] * 15),
+    "po2_multi_desc_fill": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _sz] + [_i] * 15 + [_vp]),
     "po2_quantize_pack_multi": (_i, [_vp, _i, _i, _vp]),
     "po2_conv2d_dgrad_workspace": (_sz, [_i] * 9),
     "po2_conv2d_dgrad": (_i, [_vp, _vp, _vp, _vp] + [_i] * 14 + [_vp, _sz, _vp]),

@@ -71,6 +71,9 @@ class PeerExchange:
         dev = torch.device("cuda", torch.cuda.current_device())
         buf = symm_mem.empty(int(_lib.load().po2_bn_mailbox_bytes()), dtype=torch.uint8, device=dev)
         buf.zero_()
+        # BnMailbox.timeout_s (csrc/po2_bn.cu): how long a kernel polls for a peer's values before it gives
+        # up, raises the error flag and poisons its output with NaN
+        buf[8:12].view(torch.int32).fill_(max(1, int(os.environ.get("PO2_BN_EXCHANGE_TIMEOUT_S", "60"))))
         handle = symm_mem.rendezvous(buf, group)
         peers = [int(p) for p in handle.buffer_ptrs]
         if len(peers) != world or peers[rank] != buf.data_ptr():
@@ -79,9 +82,36 @@ class PeerExchange:
         return cls(peers, rank, world, keepalive=(buf, handle))
 
     def error_flag(self) -> int:
-        """non-zero once a wait timed out (a peer stopped publishing)"""
+        """non-zero once a wait timed out (a peer stopped publishing); synchronises the device"""
         buf = self._keepalive[0] if self._keepalive else None
         return int(buf[4:8].view(torch.int32).item()) if buf is not None else 0
+
+    def check(self) -> None:
+        """Raise if an earlier exchange timed out.  Costs no synchronisation: each call looks at the
+        flag value that an EARLIER call copied to pinned host memory, then queues the next copy.  The
+        kernels themselves already made the failure loud on the device (NaN output, running statistics
+        left untouched); this is what turns it into a Python exception on the host, the way a stalled
+        NCCL collective would raise."""
+        buf = self._keepalive[0] if self._keepalive else None
+        if buf is None or torch.cuda.is_current_stream_capturing():
+            return
+        host = self.__dict__.get("_host_flag")
+        if host is None:
+            host = self.__dict__["_host_flag"] = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self.__dict__["_flag_event"] = None
+        ev = self.__dict__["_flag_event"]
+        if ev is not None:
+            if not ev.query():
+                return
+            if int(host[0]) != 0:
+                raise RuntimeError(
+                    f"FusedSyncBatchNorm: a peer of rank {self.rank} stopped publishing its statistics (mailbox error "
+                    f"{int(host[0])}: 1 = poll timed out after PO2_BN_EXCHANGE_TIMEOUT_S, 2 = channel barrier); the "
+                    "outputs of that step are NaN and the running statistics were not updated")
+        host.copy_(buf[4:8].view(torch.int32), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.__dict__["_flag_event"] = ev
 
 
 _exchanges = {}
@@ -303,6 +333,10 @@ class FusedSyncBatchNorm(nn.SyncBatchNorm):
                     world = 1
                 if world > 1:
                     exch = peer_exchange_for(group)
+                    if exch is not None:
+                        n = exch.__dict__["_calls"] = exch.__dict__.get("_calls", 0) + 1
+                        if n % 64 == 0:                              # about once per ResNet-56 step
+                            exch.check()
             track = self.training and self.track_running_stats
             kact = act if act != 3 else 0                            # SiLU has no fused backward
             out = _BatchNormTrain.apply(
@@ -320,7 +354,12 @@ class FusedSyncBatchNorm(nn.SyncBatchNorm):
                              self.bias, self.running_mean, self.running_var, None, 0.0, self.eps, act, True,
                              None, None)
             return y
-        # stock path (CPU tensors, other dtypes, eval mode under autograd, cumulative-average momentum)
+        # stock path (CPU tensors, other dtypes, eval mode under autograd, cumulative-average momentum):
+        # a library path, reported once per reason (an error under PO2_STRICT=1)
+        why = ("CPU tensor" if not input.is_cuda else f"dtype {input.dtype}" if input.dtype != torch.float32 else
+               "residual of another shape/dtype" if not fast else
+               "eval mode under autograd" if not use_batch_stats else "momentum=None (cumulative average)")
+        ops.note_library_path("bn:" + why, f"FusedSyncBatchNorm runs nn.SyncBatchNorm's own forward: {why}")
         out = super().forward(input)
         if residual is not None:
             out = out + residual

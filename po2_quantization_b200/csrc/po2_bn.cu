@@ -69,8 +69,9 @@ struct BnMailSlot {
 };
 struct BnMailbox {
   uint32_t epoch;                                  // exchanges this rank has completed producing
-  uint32_t error;                                  // set when a poll timed out (a peer died)
-  uint32_t pad[14];
+  uint32_t error;                                  // set when a poll timed out (a peer died); sticky
+  uint32_t timeout_s;                              // poll timeout in seconds, written by the host (0: 20 s)
+  uint32_t pad[13];
   BnMailSlot slot[BN_SLOTS];
 };
 struct BnPeers {
@@ -86,16 +87,30 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-// poll one tagged value of this rank's own mailbox
+// poll one tagged value of this rank's own mailbox.  A poll that times out (a peer stopped publishing:
+// stalled in its data loader, crashed, ...) must not pass for a result: it raises the sticky error flag
+// and returns NaN, so the statistics, the output and the loss of this step are NaN, the consumers skip
+// the running-statistics update, and the host-side check (PeerExchange.check) raises.
+__device__ __forceinline__ bool mailbox_failed(const BnMailbox* me) {
+  return me && *reinterpret_cast<const volatile uint32_t*>(&me->error) != 0u;
+}
 __device__ __forceinline__ float ld_ll(const uint2* p, uint32_t tag, BnMailbox* me) {
   uint32_t v, t;
   asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(t) : "l"(p) : "memory");
   if (t != tag) {
+    const uint32_t ts = *reinterpret_cast<const volatile uint32_t*>(&me->timeout_s);
+    const unsigned long long limit = (unsigned long long)(ts ? ts : 20u) * 1000000000ull;
     const unsigned long long t0 = global_ns();
     do {
+      // once any poll of this mailbox has failed, later polls give up quickly instead of each
+      // waiting the full timeout (2C+1 values per exchange)
+      if (global_ns() - t0 > (mailbox_failed(me) ? 1000000ull : limit)) {
+        me->error = 1;
+        __threadfence();
+        return __uint_as_float(0x7FC00000u);
+      }
       __nanosleep(64);
       asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(t) : "l"(p) : "memory");
-      if (global_ns() - t0 > 20000000000ull) { me->error = 1; break; }      // 20 s: a peer is gone
     } while (t != tag);
   }
   return __uint_as_float(v);
@@ -375,7 +390,7 @@ __global__ void __launch_bounds__(BN_THREADS, 4) bn_apply_kernel(const float* __
     if (blockIdx.x == 0 && !use_running) {
       if (save_mean) save_mean[c] = (float)mean;
       if (save_invstd) save_invstd[c] = invstd;
-      if (running_mean) {
+      if (running_mean && !mailbox_failed(src.ll ? mailbox : nullptr)) {   // a timed-out exchange must not reach the running statistics
         const double unbiased = var * cnt / fmax(cnt - 1.0, 1.0);
         running_mean[c] = (float)((1.0 - (double)momentum) * (double)running_mean[c] + (double)momentum * mean);
         running_var[c] = (float)((1.0 - (double)momentum) * (double)running_var[c] + (double)momentum * unbiased);
@@ -597,7 +612,7 @@ __device__ __noinline__ float4 fused_channel_finish(double pa, double pb, float 
     if (s == 0) {
       if (save_mean) save_mean[c] = (float)mean;
       if (save_invstd) save_invstd[c] = invstd;
-      if (running_mean) {
+      if (running_mean && !mailbox_failed(me)) {           // a timed-out exchange must not reach the running statistics
         const double unbiased = var * n_tot / fmax(n_tot - 1.0, 1.0);
         running_mean[c] = (float)((1.0 - (double)momentum) * (double)running_mean[c] + (double)momentum * mean);
         running_var[c] = (float)((1.0 - (double)momentum) * (double)running_var[c] + (double)momentum * unbiased);
@@ -694,15 +709,7 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_fwd_fused_kernel(const float
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
-static int bn_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  }
-  return sms;
-}
+static int bn_sms() { return device_sm_count(); }        // per device (po2_common.cuh)
 
 static bool aligned16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -854,10 +861,22 @@ int po2_bn_fwd_fused(const void* x, const void* residual, void* y, const float* 
   const int pe = make_peers(pr, peers, rank, world);
   if (pe) return pe;
   const BnWorkspace ws = bn_ws(workspace, C);
-  bn_fwd_fused_kernel<<<dim3(g.S, C), BN_THREADS, 0, (cudaStream_t)stream>>>(
-      (const float*)x, (const float*)residual, (float*)y, gamma, beta, running_mean, running_var, num_batches_tracked,
-      momentum, eps, act, save_mean, save_invstd, stats_dense, g, ws, pr);
-  return (int)cudaGetLastError();
+  // The CTAs of a channel wait for each other (channel_barrier): launch COOPERATIVELY, so the runtime
+  // guarantees that the whole grid is co-resident -- also when another stream (a NCCL kernel, another
+  // process under MPS) holds SMs -- or refuses the launch, in which case the caller takes the
+  // statistics + apply pair.
+  const float *xf = (const float*)x, *rf = (const float*)residual;
+  float* yf = (float*)y;
+  BnWorkspace wsv = ws;
+  void* args[] = {&xf, &rf, &yf, &gamma, &beta, &running_mean, &running_var, &num_batches_tracked, &momentum, &eps, &act,
+                  &save_mean, &save_invstd, &stats_dense, &g, &wsv, &pr};
+  const cudaError_t e = cudaLaunchCooperativeKernel((const void*)bn_fwd_fused_kernel, dim3(g.S, C), dim3(BN_THREADS), args, 0,
+                                                    (cudaStream_t)stream);
+  if (e == cudaErrorCooperativeLaunchTooLarge) {
+    (void)cudaGetLastError();
+    return PO2_E_UNSUPPORTED;
+  }
+  return (int)e;
 }
 
 int po2_bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* save_mean, const float* save_invstd,

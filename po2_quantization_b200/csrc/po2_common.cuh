@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "../../include/po2_b200.h"
 
 #define PO2_NEVER 0xFFFFFFFFu
@@ -119,6 +121,7 @@ int fused_quantize_pack(const void* w, void* y, float* scale_out, int64_t n, int
 // one tensor of the multi-tensor quantize+pack kernel (fp32 weights)
 struct MultiDesc {
   const uint4* x; uint4* y; float* scale_out;
+  double* sse_out;           // sum((y - x)^2) of this tensor (models/quantized_conv.py:43), or nullptr
   int64_t n;
   int bits, fsr, mode, flavor;
   PackArgs pk;
@@ -126,5 +129,27 @@ struct MultiDesc {
 int multi_fused_capacity();
 int multi_fused_launch(const MultiDesc* descs_dev, int ntensors, int csize, cudaStream_t st);
 int check_quant_args(int bits, int fsr, int mode, int flavor);
+
+// ---- per-device one-time host state ---------------------------------------------------------------
+// Kernel attributes (cudaFuncSetAttribute) and the SM count belong to a DEVICE, not to the process:
+// a process that drives several GPUs must set them once per device, and two host threads may race
+// to be first.  One std::once_flag per device ordinal; a failed initialisation stays failed (the
+// error is returned by every later call on that device).
+constexpr int PO2_MAX_DEVICES = 64;
+inline int current_device() {
+  int d = 0;
+  return (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < PO2_MAX_DEVICES) ? d : -1;
+}
+struct PerDeviceOnce {
+  std::once_flag flag[PO2_MAX_DEVICES];
+  cudaError_t err[PO2_MAX_DEVICES];
+  template <class F> cudaError_t run(F&& f) {
+    const int d = current_device();
+    if (d < 0) return cudaErrorInvalidDevice;
+    std::call_once(flag[d], [&] { err[d] = f(); });
+    return err[d];
+  }
+};
+int device_sm_count();          // SMs of the CURRENT device (cached per device; 148 if the query fails)
 
 }  // namespace po2

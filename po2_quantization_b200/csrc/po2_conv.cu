@@ -730,14 +730,7 @@ __global__ void decode_weights_kernel(const uint8_t* __restrict__ codes, const f
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static int g_sms = 0;
-static int sm_count() {
-  if (!g_sms) {
-    int d = 0, n = 0;
-    if (cudaGetDevice(&d) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d) == cudaSuccess) g_sms = n;
-  }
-  return g_sms > 0 ? g_sms : 148;
-}
+static int sm_count() { return device_sm_count(); }     // per device (po2_common.cuh)
 
 static bool fill_geom(ConvGeom& g, int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups) {
   if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0 || R <= 0 || S <= 0 || stride <= 0 || pad < 0 || groups <= 0) return false;
@@ -863,16 +856,16 @@ static int launch_umma(const void* x, const void* w, const float* scale, void* o
       e = cudaGetLastError();
       if (e != cudaSuccess) return (int)e;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;                       // the opt-in shared-memory size is a per-device attribute
+    e = attr_once.run([]() -> cudaError_t {
       const int smax = (int)K3_SMEM_BUDGET + 1024;
-      e = cudaFuncSetAttribute(conv_umma_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel<9, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel<9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
-      if (e != cudaSuccess) return (int)e;
-      attr_set = true;
-    }
+      cudaError_t a = cudaFuncSetAttribute(conv_umma_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+      if (a == cudaSuccess) a = cudaFuncSetAttribute(conv_umma_kernel<9, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+      if (a == cudaSuccess) a = cudaFuncSetAttribute(conv_umma_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+      if (a == cudaSuccess) a = cudaFuncSetAttribute(conv_umma_kernel<9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+      return a;
+    });
+    if (e != cudaSuccess) return (int)e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(g.ntiles_n * g.m_step));
     cfg.blockDim = dim3(K3_THREADS);
@@ -1343,12 +1336,10 @@ int po2_conv2d_fwd(const void* x, const void* w, const float* scale, void* out, 
   const int Cg = C / groups, Kg = K / groups;
   const size_t smem = (size_t)DK * Cg * R * S * sizeof(float);
   if (smem > 200 * 1024) return PO2_E_SHAPE;
-  static bool attr2 = false;
-  if (!attr2) {
-    cudaError_t e = cudaFuncSetAttribute(conv_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    attr2 = true;
-  }
+  static PerDeviceOnce direct_once;
+  if (cudaError_t e = direct_once.run([]() -> cudaError_t {
+        return cudaFuncSetAttribute(conv_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      })) return (int)e;
   const int64_t npix = (int64_t)B * g.P * g.Q;
   const int kblocks = groups * ((Kg + DK - 1) / DK);
   int bx = (int)((npix + 127) / 128);
@@ -1488,7 +1479,7 @@ size_t po2_multi_desc_bytes(void) { return sizeof(MultiDesc); }
 
 int po2_multi_desc_fill(void* host_table, int index, const void* w_master, void* qw_out, float* scale_out, void* packed,
                         size_t packed_bytes, int B, int C, int H, int W, int K, int R, int S, int stride, int pad,
-                        int groups, int bits, int fsr, int mode, int flavor, int compute) {
+                        int groups, int bits, int fsr, int mode, int flavor, int compute, double* sse_out) {
   if (!host_table || index < 0 || !w_master || !qw_out || !scale_out || !packed) return PO2_E_NULL;
   if (int e = check_quant_args(bits, fsr, mode, flavor)) return e;
   ConvGeom g;
@@ -1504,7 +1495,7 @@ int po2_multi_desc_fill(void* host_table, int index, const void* w_master, void*
   while (csize < 8 && (int64_t)csize * cap < wn) csize <<= 1;
   if ((int64_t)csize * cap < wn) return PO2_E_UNSUPPORTED;                        // does not fit one cluster
   MultiDesc d;
-  d.x = (const uint4*)w_master; d.y = (uint4*)qw_out; d.scale_out = scale_out; d.n = wn;
+  d.x = (const uint4*)w_master; d.y = (uint4*)qw_out; d.scale_out = scale_out; d.sse_out = sse_out; d.n = wn;
   d.bits = bits; d.fsr = fsr; d.mode = mode; d.flavor = flavor;
   d.pk.Bp = packed;
   d.pk.G = g.G; d.pk.C = C; d.pk.K = K; d.pk.taps = g.ntaps; d.pk.NT = g.NT; d.pk.ncg = C / g.G;
@@ -1558,13 +1549,11 @@ int po2_conv2d_wgrad(const void* g_out, const void* x, void* gw, int B, int C, i
   const size_t need = wgrad_partial_bytes(g, wg);
   if (!workspace || workspace_bytes < need) return PO2_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)K3_SMEM_BUDGET + 1024);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
+  static PerDeviceOnce wgrad_once;
+  if (cudaError_t e0 = wgrad_once.run([]() -> cudaError_t {
+        return cudaFuncSetAttribute(conv_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)K3_SMEM_BUDGET + 1024);
+      })) return (int)e0;
   const size_t smem = (size_t)wg.nst * wg.stage_bytes + WG_A_SPAN + 512;
   conv_wgrad_umma_kernel<<<dim3(wg.m_ctas, wg.tap_splits), K3_THREADS, smem, st>>>((const float*)x, (const float*)g_out,
                                                                                    (float*)workspace, g, wg);

@@ -634,8 +634,18 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_kernel(const uint4* __res
 __global__ void __launch_bounds__(FUSED_THREADS) multi_fused_kernel(const MultiDesc* __restrict__ descs, int csize) {
   const uint32_t t = blockIdx.x / (uint32_t)csize, lblock = blockIdx.x % (uint32_t)csize;
   const MultiDesc d = descs[t];
-  fused_body<PO2_F32, false, false>(d.x, d.y, nullptr, nullptr, nullptr, d.scale_out, d.n, d.bits, d.fsr, d.mode, d.flavor,
-                                    nullptr, 1, d.pk, (uint32_t)csize, lblock);
+  // The squared quantization error of every tensor comes out of the same pass (x and y are both in
+  // registers): this is what QuantizedConv2d.get_quantization_error / the models' error walkers
+  // (train.py:106) read, so they cost no launch of their own.  The CTAs of the cluster add their shares
+  // atomically; CTA 0 clears the slot first, ordered before the adds by the cluster barriers of the max
+  // exchange (csize > 1) or by program order (csize == 1: the same thread clears and adds).
+  if (d.sse_out && lblock == 0 && threadIdx.x == 0) { *d.sse_out = 0.0; __threadfence(); }
+  if (d.sse_out)
+    fused_body<PO2_F32, false, true>(d.x, d.y, nullptr, nullptr, d.sse_out, d.scale_out, d.n, d.bits, d.fsr, d.mode,
+                                     d.flavor, nullptr, 1, d.pk, (uint32_t)csize, lblock);
+  else
+    fused_body<PO2_F32, false, false>(d.x, d.y, nullptr, nullptr, nullptr, d.scale_out, d.n, d.bits, d.fsr, d.mode,
+                                      d.flavor, nullptr, 1, d.pk, (uint32_t)csize, lblock);
 }
 
 
@@ -715,8 +725,9 @@ __global__ void __launch_bounds__(256) ste_backward_kernel(const void* __restric
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-struct DevInfo { int sms; int fused_blocks_per_sm[3]; bool ok; };
-static DevInfo g_dev[64];
+struct DevInfo { int sms; int fused_blocks_per_sm[3]; };
+static DevInfo g_dev[PO2_MAX_DEVICES];
+static PerDeviceOnce g_dev_once;
 
 template <int DT> static int fused_occupancy() {
   int nb = 0;
@@ -728,19 +739,25 @@ template <int DT> static int fused_occupancy() {
 }
 
 static const DevInfo* dev_info() {
-  int d = 0;
-  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return nullptr;
-  DevInfo& I = g_dev[d];
-  if (!I.ok) {                                           // idempotent; a benign race re-computes
+  const int d = current_device();
+  if (d < 0) return nullptr;
+  const cudaError_t e = g_dev_once.run([&]() -> cudaError_t {
+    DevInfo& I = g_dev[d];
     int sms = 0;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d) != cudaSuccess) return nullptr;
+    const cudaError_t q = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d);
+    if (q != cudaSuccess) return q;
     I.sms = sms;
     I.fused_blocks_per_sm[0] = fused_occupancy<PO2_F32>();
     I.fused_blocks_per_sm[1] = fused_occupancy<PO2_BF16>();
     I.fused_blocks_per_sm[2] = fused_occupancy<PO2_F16>();
-    I.ok = true;
-  }
-  return &I;
+    return cudaSuccess;
+  });
+  return e == cudaSuccess ? &g_dev[d] : nullptr;
+}
+
+int device_sm_count() {
+  const DevInfo* I = dev_info();
+  return (I && I->sms > 0) ? I->sms : 148;
 }
 
 static inline int elem_bytes(int dtype) { return dtype == PO2_F32 ? 4 : 2; }

@@ -122,6 +122,13 @@ class BatchSharded(torch.nn.Module):
 
     def _on_grad(self, p) -> None:
         bi = self._bucket_of[id(p)]
+        if self._pending[bi] < 0:
+            # this bucket was already all-reduced for the current step: a second backward() (gradient
+            # accumulation) would add un-averaged local gradients on top of averaged ones and race with the
+            # all-reduce still running on the side stream -- ranks would silently diverge
+            raise RuntimeError("BatchSharded: backward() ran again before average_gradients(); call "
+                               "average_gradients() after every backward (gradient accumulation is not supported "
+                               "with overlap=True -- construct BatchSharded(..., overlap=False) for that)")
         if self._pending[bi] > 0:
             self._pending[bi] -= 1
             if self._pending[bi] == 0:
@@ -132,6 +139,10 @@ class BatchSharded(torch.nn.Module):
         returns how many gradient tensors this step exchanged."""
         if self.world <= 1:
             return sum(1 for p in self.module.parameters() if p.grad is not None)
+        from . import batchnorm
+        for ex in batchnorm._exchanges.values():             # a timed-out SyncBatchNorm exchange raises here
+            if ex is not None:
+                ex.check()
         if self._comm is None:
             grads = [p.grad for p in self.module.parameters() if p.grad is not None]
             if grads:

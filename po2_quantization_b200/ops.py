@@ -41,6 +41,29 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
 
 _workspaces = {}
 
+# ---- library paths taken instead of our kernels are never silent ------------------------------------
+_noted = set()
+
+
+def note_library_path(key: str, message: str) -> None:
+    """A call that leaves the sm_100a kernels for a stock torch/cuDNN path says so: a warning the first
+    time each distinct reason occurs, or a Po2Error when PO2_STRICT=1 (what the GPU test-suite and the
+    benchmarks run with, so that a silent library fallback cannot pass for the product path)."""
+    if os.environ.get("PO2_STRICT", "0") == "1":
+        raise _lib.Po2Error(f"PO2_STRICT=1: {message}")
+    if key not in _noted:
+        _noted.add(key)
+        import warnings
+        warnings.warn(f"po2_quantization_b200: {message}", RuntimeWarning, stacklevel=3)
+
+
+def release_workspaces() -> None:
+    """Drop the per-(device, stream) scratch buffers (they are re-created on demand).  Call after the
+    streams that used them are idle, e.g. between benchmark configurations."""
+    _workspaces.clear()
+    from . import batchnorm
+    batchnorm._bn_workspaces.clear()
+
 # number of kernels of libpo2b200.so launched through this module (bench.py's `gpu_launches`)
 LAUNCHES = 0
 
@@ -227,8 +250,11 @@ def conv2d_out(x, w, scale, out, stride, pad, groups, compute, w_format=_lib.W_F
     packed codes of such a tensor (w_format=W_CODES, wshape=(K, C/groups, R, S))."""
     global LAUNCHES
     lib = _lib.load()
+    check_conv_shapes(x.shape, w.shape if wshape is None else wshape, groups, pad)
     B, C, H, W_ = x.shape
     K, _, R, S = w.shape if wshape is None else wshape
+    if w_format == _lib.W_CODES and w.numel() < _code_bytes(K * (C // groups) * R * S, bits):
+        raise RuntimeError(f"po2 conv2d: {w.numel()} code bytes for a weight of shape {list(wshape)} at {bits} bits")
     need = lib.po2_conv2d_workspace(B, C, H, W_, K, R, S, stride, pad, groups, compute)
     ws = torch.empty(max(int(need), 16), dtype=torch.uint8, device=x.device)
     fp32_w_bytes = (K * (C // groups) * R * S * 4 + 255) // 256 * 256
@@ -237,6 +263,26 @@ def conv2d_out(x, w, scale, out, stride, pad, groups, compute, w_format=_lib.W_F
                                   out.data_ptr(), B, C, H, W_, K, R, S, stride, pad, groups, w_format,
                                   bits, fsr, compute, ws.data_ptr(), ws.numel(), _stream_ptr(x.device)),
                "po2_conv2d_fwd")
+
+
+def check_conv_shapes(xshape, wshape, groups: int, pad: int) -> None:
+    """The argument errors nn.Conv2d / the reference raise (a RuntimeError, same wording as ATen) --
+    the C ABI has no weight-channel argument, so a mismatch must be caught before the launch: the
+    kernels would index K*(C/groups)*R*S weights past the end of a smaller buffer."""
+    if len(xshape) != 4 or len(wshape) != 4:
+        raise RuntimeError(f"Expected 4D (batched) input and 4D weight to conv2d, but got input of size: {list(xshape)} "
+                           f"and weight of size: {list(wshape)}")
+    B, C, H, W_ = xshape
+    K, Cw, R, S = wshape
+    if groups < 1 or K % groups != 0:
+        raise RuntimeError(f"Given groups={groups}, expected weight to be divisible by {groups} at dimension 0, "
+                           f"but got weight of size {list(wshape)}")
+    if C != Cw * groups:
+        raise RuntimeError(f"Given groups={groups}, weight of size {list(wshape)}, expected input{list(xshape)} to have "
+                           f"{Cw * groups} channels, but got {C} channels instead")
+    if H + 2 * pad < R or W_ + 2 * pad < S:
+        raise RuntimeError(f"Calculated padded input size per channel: ({H + 2 * pad} x {W_ + 2 * pad}). Kernel size: "
+                           f"({R} x {S}). Kernel size can't be greater than actual input size")
 
 
 def _conv_out_shape(x, w, stride, pad):
@@ -254,6 +300,7 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor], stri
     _require_cuda(x, "po2::conv2d")
     if x.dtype != torch.float32 or w.dtype != torch.float32:
         raise TypeError("po2::conv2d: fp32 NCHW activations and fp32 weights only")
+    check_conv_shapes(x.shape, w.shape, groups, pad)
     x = x.contiguous()
     w = w.contiguous()
     out = torch.empty(_conv_out_shape(x, w, stride, pad), dtype=torch.float32, device=x.device)
@@ -283,8 +330,11 @@ def conv2d_dgrad_out(g, w, scale, gx, pad, compute: int = 0) -> bool:
     """gx = dL/dx of conv2d(x, w) (stride 1, dense) from g = dL/dout.  False if the shape is not taken."""
     global LAUNCHES
     lib = _lib.load()
+    check_conv_shapes(gx.shape, w.shape, 1, pad)
     B, C, H, W_ = gx.shape
     K, _, R, S = w.shape
+    if tuple(g.shape) != (B, K, H + 2 * pad - R + 1, W_ + 2 * pad - S + 1):
+        raise RuntimeError(f"po2 conv2d dgrad: grad_output {list(g.shape)} does not match input {list(gx.shape)} / weight {list(w.shape)}")
     need = lib.po2_conv2d_dgrad_workspace(B, C, H, W_, K, R, S, pad, compute)
     if need == 0:
         return False
@@ -315,8 +365,11 @@ def conv2d_wgrad_out(g, x, gw, pad, compute: int = 0) -> bool:
     """gw = dL/dW of conv2d(x, W) (stride 1, dense) from g = dL/dout.  False if the shape is not taken."""
     global LAUNCHES
     lib = _lib.load()
+    check_conv_shapes(x.shape, gw.shape, 1, pad)
     B, C, H, W_ = x.shape
     K, _, R, S = gw.shape
+    if tuple(g.shape) != (B, K, H + 2 * pad - R + 1, W_ + 2 * pad - S + 1):
+        raise RuntimeError(f"po2 conv2d wgrad: grad_output {list(g.shape)} does not match input {list(x.shape)} / weight {list(gw.shape)}")
     need = lib.po2_conv2d_wgrad_workspace(B, C, H, W_, K, R, S, 1, pad, 1, compute)
     if need == 0:
         return False
@@ -414,6 +467,7 @@ def qconv2d(x: torch.Tensor, weight: torch.Tensor, bits: int, fsr: int, plus: bo
     _require_cuda(x, "po2::qconv2d")
     if x.dtype != torch.float32 or weight.dtype != torch.float32:
         raise TypeError("po2::qconv2d: fp32 NCHW activations and fp32 weights only")
+    check_conv_shapes(x.shape, weight.shape, groups, pad)
     x = x.contiguous()
     w = weight.contiguous()
     lib = _lib.load()
@@ -476,6 +530,7 @@ def conv2d_pack(w: torch.Tensor, scale: Optional[torch.Tensor], xshape, stride: 
     run on the tensor-core kernel."""
     global LAUNCHES
     lib = _lib.load()
+    check_conv_shapes(xshape, w.shape, groups, pad)
     B, C, H, W_ = xshape
     K, _, R, S = w.shape
     nbytes = lib.po2_conv2d_pack_bytes(B, C, H, W_, K, R, S, stride, pad, groups, compute)
@@ -496,8 +551,15 @@ def conv2d_packed(x: torch.Tensor, packed: torch.Tensor, scale: Optional[torch.T
     """conv2d from a pre-packed weight operand (inference with static weights): one kernel launch."""
     global LAUNCHES
     _require_cuda(x, "po2::conv2d_packed")
+    if x.dim() != 4:
+        raise RuntimeError(f"Expected 4D (batched) input to conv2d, but got input of size: {list(x.shape)}")
     x = x.contiguous()
     B, C, H, W_ = x.shape
+    # the packed operand was laid out for ONE (input shape, weight shape): re-validate it against this input
+    need = int(_lib.load().po2_conv2d_pack_bytes(B, C, H, W_, K, R, S, stride, pad, groups, compute))
+    if need == 0 or packed.numel() != need:
+        raise RuntimeError(f"po2::conv2d_packed: the packed operand ({packed.numel()} bytes) was not built for input "
+                           f"{list(x.shape)} / weight [{K}, {C // max(groups, 1)}, {R}, {S}] (needs {need} bytes)")
     out = torch.empty((B, K, (H + 2 * pad - R) // stride + 1, (W_ + 2 * pad - S) // stride + 1),
                       dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):

@@ -23,7 +23,7 @@ from . import _lib, ops
 
 
 class _Slot:
-    __slots__ = ("key", "qw", "scale", "packed")
+    __slots__ = ("key", "qw", "scale", "packed", "sse")
 
 
 class _Table:
@@ -77,6 +77,7 @@ def prefetch_weights(modules: Iterable[torch.nn.Module]) -> int:
             slot.qw = torch.empty_like(w, memory_format=torch.contiguous_format)
             slot.scale = torch.empty((), dtype=torch.float32, device=w.device)
             slot.packed = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+            slot.sse = torch.zeros((), dtype=torch.float64, device=w.device)   # sum((Q(w)-w)^2), refreshed by every launch
             slot.key = None
             m.__dict__["_po2_prefetch"] = slot
         if slot.key != key:
@@ -100,9 +101,10 @@ def prefetch_weights(modules: Iterable[torch.nn.Module]) -> int:
                 rc = lib.po2_multi_desc_fill(host.data_ptr(), len(multi), m.weight.data_ptr(), slot.qw.data_ptr(),
                                              slot.scale.data_ptr(), slot.packed.data_ptr(), slot.packed.numel(), B, C, H,
                                              W_, K, R, S, m.stride[0], m.padding[0], m.groups, int(m.bits), 1, int(key[4]),
-                                             ops._flavor, compute)
+                                             ops._flavor, compute, slot.sse.data_ptr())
                 if rc == -10:
                     single.append(m)
+                    slot.sse = None                              # po2_quantize_pack has no fused error output
                     continue
                 if rc <= 0:
                     _lib.check(rc if rc < 0 else -6, "po2_multi_desc_fill")

@@ -30,16 +30,42 @@ class QuantizedConv2d(nn.Conv2d):
                         if k not in ("_po2_pack_cache", "_po2_prefetch", "_po2_prefetch_single", "_po2_prefetch_static")}
         tag = self.__dict__.get("_po2_ptq")
         if tag is not None and tag[0] == self.weight._version:
-            new.__dict__["_po2_ptq"] = (new.weight._version, new.__dict__["_po2_ptq"][1])
+            new.__dict__["_po2_ptq"] = (new.weight._version,) + tuple(new.__dict__["_po2_ptq"][1:])
         return new
 
-    # ---- which inputs the sm_100a conv kernels take (anything else goes to nn.Conv2d's own path)
+    # ---- which inputs the sm_100a conv kernels take.  Anything else goes to nn.Conv2d's own path
+    # (cuDNN) -- never silently: _why_not() names the reason and forward() reports it once per reason
+    # (ops.note_library_path; an error under PO2_STRICT=1).  Every QuantizedConv2d the reference's model
+    # files construct (bias=False, dilation 1, square stride/padding, fp32) is taken.
+    def _why_not(self, input):
+        if ops.get_conv_mode() == "cudnn":
+            return None                                       # the caller asked for cuDNN: not a fallback
+        if not input.is_cuda:
+            return "CPU input"
+        if input.dtype != torch.float32 or self.weight.dtype != torch.float32:
+            return f"dtype {input.dtype}/{self.weight.dtype} (fp32 NCHW only)"
+        if input.dim() != 4:
+            return f"{input.dim()}-D input (batched NCHW only)"
+        if self.bias is not None:
+            return "bias=True"
+        if self.dilation != (1, 1):
+            return f"dilation {self.dilation}"
+        if self.padding_mode != "zeros" or not isinstance(self.padding, tuple):
+            return f"padding {self.padding!r} / padding_mode {self.padding_mode!r}"
+        if self.stride[0] != self.stride[1] or self.padding[0] != self.padding[1]:
+            return f"non-square stride {self.stride} / padding {self.padding}"
+        return ""
+
     def _po2_conv_ok(self, input) -> bool:
-        return (ops.get_conv_mode() != "cudnn" and input.is_cuda and input.dtype == torch.float32
-                and input.dim() == 4 and self.bias is None and self.dilation == (1, 1)
-                and self.padding_mode == "zeros" and isinstance(self.padding, tuple)
-                and self.stride[0] == self.stride[1] and self.padding[0] == self.padding[1]
-                and self.weight.dtype == torch.float32)
+        return self._why_not(input) == ""
+
+    def _library_conv(self, input, weight, why):
+        if why:
+            ops.note_library_path("qconv:" + why, f"QuantizedConv2d runs nn.Conv2d's own convolution (cuDNN) for this "
+                                  f"layer: {why}")
+        if input.dim() == 4:
+            ops.check_conv_shapes(input.shape, weight.shape, self.groups, self.padding[0] if isinstance(self.padding, tuple) else 0)
+        return self._conv_forward(input, weight, self.bias)
 
     def _po2_conv(self, input, weight, scale):
         return ops.conv2d(input, weight, scale, self.stride[0], self.padding[0], self.groups,
@@ -64,10 +90,15 @@ class QuantizedConv2d(nn.Conv2d):
                 out, _qw, _scale = ops.qconv2d(input, self.weight, int(self.bits), 1, bool(plus), self.stride[0],
                                                self.padding[0], self.groups, ops.COMPUTE[ops.get_conv_mode()])
                 return out
+            # lin / lin+ (the conv of their result is nn.Conv2d's: those weights are not on a PO2 grid), or
+            # a PO2 layer whose configuration the kernels do not take
             quantized_weight = self.quantize_fn.apply(self.weight, self.bits)
-            return self._conv_forward(input, quantized_weight, self.bias)
+            return self._library_conv(input, quantized_weight, self._why_not(input) if plus is not None else None)
         tag = getattr(self, "_po2_ptq", None)
-        if tag is not None and tag[0] == self.weight._version and self._po2_conv_ok(input):
+        if tag is not None and tag[0] == self.weight._version:
+            why = self._why_not(input)
+            if why:
+                return self._library_conv(input, self.weight, why)
             # post-training-quantized weights (quantize_model): already on the grid +-scale*2^q
             mode = ops.get_conv_mode()
             if mode in ("tc", "tf32") and not (torch.is_grad_enabled() and (input.requires_grad or self.weight.requires_grad)):
@@ -84,12 +115,30 @@ class QuantizedConv2d(nn.Conv2d):
                     K, _, R, S = self.weight.shape
                     return ops.conv2d_packed(input, cache[1], tag[1], K, R, S, self.stride[0], self.padding[0], self.groups,
                                              ops.COMPUTE[mode])
+            if why is None:
+                return self._conv_forward(input, self.weight, self.bias)
             return self._po2_conv(input, self.weight, tag[1])
+        # no quantizer and no PTQ tag: a full-precision layer, i.e. plain nn.Conv2d (models/quantized_conv.py:38)
         return self._conv_forward(input, self.weight, self.bias)
 
     def get_quantization_error(self):
-        # models/quantized_conv.py:40-45
+        """models/quantized_conv.py:40-45: (sum((Q(w) - w)^2), numel); (0, numel) without a quantizer.
+
+        For PO2 / PO2+ on CUDA the sum is the fused fp64 output of the quantizer kernel itself: either the
+        value the multi-tensor prefetch already produced for the current weight version (no launch at
+        all -- what the models' per-epoch error walkers, train.py:106, then read for all layers), or one
+        launch of the single-tensor kernel.  The reference sums in fp32 with 12 ATen launches; the
+        value returned here is the fp64 sum rounded once to fp32 (a detached 0-dim tensor)."""
         if self.quantize_fn is not None:
+            plus = getattr(self.quantize_fn, "_PLUS", None)
+            w = self.weight
+            if plus is not None and w.is_cuda and w.dtype in ops._DT and w.numel() > 0:
+                slot = self.__dict__.get("_po2_prefetch")
+                if (slot and slot.sse is not None and slot.key is not None and slot.key[0] == w._version
+                        and slot.key[3] == int(self.bits) and slot.key[4] == bool(plus)):
+                    return slot.sse.to(torch.float32), w.numel()
+                sse = ops.quantize_full(w.detach(), int(self.bits), 1, bool(plus))[4]
+                return sse.to(torch.float32), w.numel()
             quantized_weight = self.quantize_fn.apply(self.weight, self.bits)
             return torch.sum((quantized_weight - self.weight) ** 2), self.weight.numel()
         return 0, self.weight.numel()

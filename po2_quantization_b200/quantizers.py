@@ -88,7 +88,14 @@ def _lin_forward(w: torch.Tensor, bits: int, num_iters: int, plus: bool) -> torc
         y = _lin_forward_cuda(w.detach(), bits, num_iters, plus)
         if y is not None:
             return y
-    # op-by-op form in the reference's order (CPU tensors, other dtypes, very large channels)
+        why = "a channel exceeds the kernel's shared-memory capacity or bits is outside 2..16"
+    else:
+        why = ("CPU tensor" if not w.is_cuda else f"dtype {w.dtype}" if w.dtype != torch.float32 else
+               f"{w.dim()}-D tensor" if w.dim() != 4 else "empty tensor" if w.numel() == 0 else "PO2_LIN != cuda")
+    # op-by-op ATen form in the reference's order (utils/quantizers.py:59-136) -- a library path, so it is
+    # reported (once per reason; an error under PO2_STRICT=1).  lin / lin+ are SURVEY section 8f "next" rows:
+    # unlike PO2 / PO2+ they keep this form for the inputs the kernel does not take.
+    ops.note_library_path("lin:" + why, f"lin/lin+ quantizer runs as stock ATen ops: {why}")
     hi = torch.amax(w, dim=(0, 2, 3))
     lo = torch.amin(w, dim=(0, 2, 3))
     step = (hi - lo) / (2 ** bits - 1)
@@ -152,10 +159,28 @@ def quantize_model(model: torch.nn.Module, quantizer: Optional[Callable[..., Non
                 if scale is not None and param is module.weight:
                     # non-persistent tag (state_dict stays {weight}): the weight is now on the grid
                     # +-scale*2^q, which lets forward() feed the tensor-core conv an exact operand
-                    module._po2_ptq = (param._version, scale)
+                    module._po2_ptq = (param._version, scale, int(bits), bool(quantizer._PLUS))
     if total is None:
         raise ZeroDivisionError("quantize_model: the model has no QuantizedConv2d parameters")
     return float((total / numel).item())
+
+
+def model_quantization_error(model: torch.nn.Module):
+    """(sum over all QuantizedConv2d layers of sum((Q(w) - w)^2), total numel) -- the quantity the
+    reference's per-model walkers accumulate layer by layer (models/resnet.py:214-224, train.py:106),
+    without their denominator quirks.  With `enable_weight_prefetch` every layer's
+    term is already on the device from the multi-tensor launch of the last forward; the terms are summed
+    in fp64 by ONE stack+sum instead of one add per layer."""
+    terms, numel = [], 0
+    for m in model.modules():
+        if isinstance(m, QuantizedConv2d):
+            e, n = m.get_quantization_error()
+            numel += n
+            if torch.is_tensor(e):
+                terms.append(e.double())
+    if not terms:
+        return 0, numel
+    return torch.stack(terms).sum(), numel
 
 
 quantizer_dict = {

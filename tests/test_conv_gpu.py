@@ -223,9 +223,15 @@ def test_module_qat_forward_backward_vs_oracle(plus):
         assert torch.allclose(m.weight.grad.cpu(), o.weight.grad, rtol=2e-3, atol=2e-3)
     finally:
         ops.set_wgrad_mode("tc")
+    # models/quantized_conv.py:40-45: (sum((Q(w) - w)^2), numel) against the oracle quantizer in fp64
     e1, n1 = m.get_quantization_error()
-    ref_e = torch.sum((PO2_PLUS if plus else PO2).forward(None, o.weight.detach()) - o.weight.detach()).item()
-    assert n1 == o.weight.numel() and np.isfinite(e1.item()) and np.isfinite(ref_e)
+    wd = o.weight.detach()
+    ref_e = torch.sum(((PO2_PLUS if plus else PO2).forward(None, wd, bits=4).double() - wd.double()) ** 2).item()
+    assert n1 == o.weight.numel()
+    assert abs(e1.item() - ref_e) <= 1e-6 * ref_e, (e1.item(), ref_e)
+    # no quantizer: (0, numel)
+    m_fp = P.QuantizedConv2d(32, 32, 3, quantize_fn=None).cuda()
+    assert m_fp.get_quantization_error() == (0, m_fp.weight.numel())
 
 
 def test_ptq_quantize_model_and_forward_resnet20_top1():

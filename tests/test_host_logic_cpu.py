@@ -132,3 +132,73 @@ def test_workloads_keep_state_dict_keys_with_fused_norms():
         assert all(sa[k].shape == sb[k].shape for k in sa)
         assert any(isinstance(m, P.FusedSyncBatchNorm) for m in a.modules())
         assert not any(isinstance(m, P.FusedSyncBatchNorm) for m in b.modules())
+
+
+def test_conv_shape_validation_raises_like_nn_conv2d():
+    """ops.check_conv_shapes: the RuntimeErrors nn.Conv2d / the reference raise for a wrong channel count,
+    indivisible groups or a kernel larger than the padded input (the C ABI has no
+    weight-channel argument, so the host must catch these before any launch)."""
+    from po2_quantization_b200 import ops
+    ops.check_conv_shapes((2, 16, 8, 8), (32, 16, 3, 3), 1, 1)
+    ops.check_conv_shapes((2, 16, 8, 8), (16, 1, 3, 3), 16, 1)
+    with pytest.raises(RuntimeError, match="expected input.* to have 16 channels, but got 24"):
+        ops.check_conv_shapes((2, 24, 8, 8), (32, 16, 3, 3), 1, 1)
+    with pytest.raises(RuntimeError, match="divisible"):
+        ops.check_conv_shapes((2, 16, 8, 8), (30, 4, 3, 3), 4, 1)
+    with pytest.raises(RuntimeError, match="Kernel size"):
+        ops.check_conv_shapes((2, 16, 1, 1), (32, 16, 3, 3), 1, 0)
+    with pytest.raises(RuntimeError, match="4D"):
+        ops.check_conv_shapes((16, 8, 8), (32, 16, 3, 3), 1, 1)
+    # the same errors as torch's own convolution
+    conv = torch.nn.Conv2d(16, 32, 3, padding=1, bias=False)
+    with pytest.raises(RuntimeError, match="to have 16 channels, but got 24"):
+        conv(torch.randn(2, 24, 8, 8))
+
+
+def test_library_paths_are_reported_and_strict_mode_raises(monkeypatch):
+    from po2_quantization_b200 import _lib, ops
+    ops._noted.discard("t:why")
+    with pytest.warns(RuntimeWarning, match="because"):
+        ops.note_library_path("t:why", "because")
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        ops.note_library_path("t:why", "because")            # second time: silent
+    monkeypatch.setenv("PO2_STRICT", "1")
+    with pytest.raises(_lib.Po2Error, match="because"):
+        ops.note_library_path("t:why", "because")
+
+
+def test_batch_sharded_rejects_a_second_backward_before_averaging():
+    """with overlap=True a bucket is reduced from the grad hooks; a second backward() before
+    average_gradients() must raise instead of silently mixing averaged and local gradients."""
+    from po2_quantization_b200.distributed import BatchSharded
+    m = BatchSharded(torch.nn.Linear(4, 2))
+    m._buckets = [list(m.module.parameters())]
+    m._bucket_of = {id(p): 0 for p in m._buckets[0]}
+    m._pending = [-1]                                         # state after the bucket's all-reduce was launched
+    with pytest.raises(RuntimeError, match="average_gradients"):
+        m._on_grad(m._buckets[0][0])
+
+
+def test_reference_file_loader_variants():
+    """workloads/reference_files.py: the reference's model files import on the drop-in shims and on
+    their own classes, side by side, without leaking `models` / `utils` into sys.modules."""
+    import sys
+    from workloads import reference_files as RF
+    if RF.find_reference() is None:
+        pytest.skip("no reference checkout (baseline/_ref or /root/reference)")
+    d, s = RF.load("dropin"), RF.load("stock")
+    assert d.QuantizedConv2d is P.QuantizedConv2d and s.QuantizedConv2d is not P.QuantizedConv2d
+    assert d.quantizers.quantizer_dict["po2+"] is P.PowerOfTwoPlusQuantizer
+    assert not any(k == "models" or k.startswith("models.") for k in sys.modules)
+    torch.manual_seed(8)
+    a = s.get_model("resnet20", 10, None, 4, (32, 32))
+    b = d.get_model("resnet20", 10, None, 4, (32, 32))
+    b.load_state_dict(a.state_dict(), strict=True)
+    x = torch.randn(2, 3, 32, 32)
+    a.eval(); b.eval()
+    with torch.no_grad():
+        assert torch.equal(a(x), b(x))
+    v = RF.mobilevit_224(s)
+    assert sum(1 for m in v.modules() if isinstance(m, s.QuantizedConv2d)) == 33

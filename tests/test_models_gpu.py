@@ -1,0 +1,324 @@
+"""Model-level GPU parity: (1) QAT convergence of the operand modes against the reference's own
+arithmetic over 50 optimizer steps, (2) the reference's OWN model files (baseline/_ref, staged from the
+unmodified checkout) running on the drop-in classes on the B200 against the same files on their stock
+torch path, (3) the argument errors nn.Conv2d raises.  Results that are worth keeping are also written
+to gpurun_out/ (copied to profiles/ by hand)."""
+import json
+import os
+
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+
+import po2_quantization_b200 as P  # noqa: E402
+from po2_quantization_b200 import ops  # noqa: E402
+
+OUT = os.path.join(os.environ.get("GRAFT_REPO_ROOT", os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "gpurun_out")
+
+
+def _dump(name, obj):
+    try:
+        os.makedirs(OUT, exist_ok=True)
+        json.dump(obj, open(os.path.join(OUT, name), "w"), indent=1)
+    except OSError:
+        pass
+
+
+def _learnable_batches(n_batches=4, batch=64, seed=0):
+    """a small fixed data set whose labels are a function of the images, so that the loss really falls"""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n_batches * batch, 3, 32, 32, generator=g)
+    proj = torch.randn(10, 3 * 8 * 8, generator=g)
+    y = (torch.nn.functional.avg_pool2d(x, 4).flatten(1) @ proj.t()).argmax(1)
+    return [(x[i * batch:(i + 1) * batch], y[i * batch:(i + 1) * batch]) for i in range(n_batches)]
+
+
+def _train_curve(model, batches, steps, lr=0.05):
+    opt = torch.optim.SGD(model.parameters(), lr=lr, momentum=0.9, weight_decay=1e-4)
+    crit = nn.CrossEntropyLoss()
+    losses = []
+    for i in range(steps):
+        x, y = batches[i % len(batches)]
+        opt.zero_grad()
+        loss = crit(model(x), y)
+        loss.backward()
+        opt.step()
+        losses.append(loss.detach())
+    return [float(v) for v in torch.stack(losses).cpu()]
+
+
+def _smooth(c, k=8):
+    return [sum(c[max(0, i - k + 1):i + 1]) / len(c[max(0, i - k + 1):i + 1]) for i in range(len(c))]
+
+
+def test_qat_loss_curves_bf16_tf32_fp32_track_the_reference():
+    """50 SGD steps of ResNet-20 PO2 4-bit QAT (train-mode BatchNorm, momentum 0.9) from identical
+    weights on identical data: the bf16-operand mode (default), the tf32-operand mode and the
+    fp32-accumulate mode of this library against the reference's arithmetic on the same GPU in true fp32
+    (stock ATen quantizer ops + cuDNN with allow_tf32=False) and in the reference's own default (cuDNN
+    TF32).  Training is chaotic, so curves are compared after smoothing: every mode must stay within a
+    band of the fp32 reference no wider than twice the band the reference's OWN TF32 default shows, and
+    must reach the same final loss level."""
+    from oracle.po2_oracle_torch import PO2, QuantizedConv2dOracle
+    from workloads import resnet_cifar
+    steps = 50
+    batches = [(x.cuda(), y.cuda()) for x, y in _learnable_batches()]
+    torch.manual_seed(8)
+    init = resnet_cifar(20, 10, PO2, 4, conv_cls=QuantizedConv2dOracle).state_dict()
+    curves = {}
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    try:
+        for name, tf32 in (("reference_fp32", False), ("reference_tf32_default", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            m = resnet_cifar(20, 10, PO2, 4, conv_cls=QuantizedConv2dOracle)
+            m.load_state_dict(init)
+            curves[name] = _train_curve(m.cuda().train(), batches, steps)
+        torch.backends.cudnn.allow_tf32 = False          # the stem conv of our models stays true fp32
+        for name, mode in (("po2_bf16_operands", "tc"), ("po2_tf32_operands", "tf32"), ("po2_fp32_accumulate", "fp32")):
+            ops.set_conv_mode(mode)
+            m = resnet_cifar(20, 10, P.PowerOfTwoQuantizer, 4)
+            m.load_state_dict(init)
+            curves[name] = _train_curve(m.cuda().train(), batches, steps)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old_tf32
+        ops.set_conv_mode("tc")
+    ref = _smooth(curves["reference_fp32"])
+    band = {k: max(abs(a - b) for a, b in zip(_smooth(v), ref)) for k, v in curves.items()}
+    final = {k: sum(v[-10:]) / 10 for k, v in curves.items()}
+    _dump("qat_loss_curves_resnet20.json", {"steps": steps, "curves": curves, "max_smoothed_gap_vs_reference_fp32": band,
+                                            "mean_loss_last_10_steps": final})
+    assert final["reference_fp32"] < 0.8 * curves["reference_fp32"][0], "the reference itself did not learn"
+    allowed = max(2.0 * band["reference_tf32_default"], 0.08 * curves["reference_fp32"][0])
+    for k in ("po2_bf16_operands", "po2_tf32_operands", "po2_fp32_accumulate"):
+        assert band[k] <= allowed, (k, band[k], allowed, band)
+        assert abs(final[k] - final["reference_fp32"]) <= 0.15 * curves["reference_fp32"][0], (k, final)
+        assert final[k] < 0.8 * curves[k][0], (k, "did not learn", final[k], curves[k][0])
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's own model files on the B200
+# ------------------------------------------------------------------------------------------------
+def _ref_ns():
+    from workloads import reference_files as RF
+    d, s = RF.load("dropin"), RF.load("stock")
+    if d is None or s is None:
+        pytest.skip("no reference checkout staged (baseline/_ref; run baseline/stage_reference.py in the build container)")
+    return RF, d, s
+
+
+@pytest.mark.parametrize("name,bits", [("resnet20", 4), ("resnet56", 4), ("mobilenet", 4), ("mobilevit", 4)])
+def test_reference_model_files_ptq_forward_on_gpu(name, bits):
+    """models/{resnet,mobilenet,mobile_vit}.py UNMODIFIED: built once on the drop-in classes (our kernels)
+    and once on the reference's own classes (stock torch), same weights; quantize_model + eval forward on
+    the GPU.  Quantized weights bit-equal, MSE equal, logits within the bf16 tolerance, and -- in
+    fp32-accumulate mode -- identical top-1 (north_star (c))."""
+    RF, d, s = _ref_ns()
+    torch.manual_seed(8)
+    ref = s.get_model(name, 10, None, bits, (32, 32))
+    mine = d.get_model(name, 10, None, bits, (32, 32))
+    mine.load_state_dict(ref.state_dict(), strict=True)
+    ref, mine = ref.cuda().eval(), mine.cuda().eval()
+    nq = sum(1 for m in mine.modules() if isinstance(m, P.QuantizedConv2d))
+    assert nq == {"resnet20": 20, "resnet56": 56, "mobilenet": 50, "mobilevit": 33}[name]
+    mse_ref = s.quantizers.quantize_model(ref, s.quantizers.PowerOfTwoPlusQuantizer, bits)
+    ops.set_log2_flavor("torch_cuda")                 # the reference ran on THIS GPU: compare under its log2 flavor
+    try:
+        mse = d.quantizers.quantize_model(mine, d.quantizers.PowerOfTwoPlusQuantizer, bits)
+    finally:
+        ops.set_log2_flavor("ieee")
+    assert abs(mse - mse_ref) <= 1e-5 * mse_ref
+    for (k, a), (_, b) in zip(mine.state_dict().items(), ref.state_dict().items()):
+        assert torch.equal(a, b), f"{k}: PTQ weights differ from the reference's on this GPU"
+    x = torch.randn(64, 3, 32, 32, generator=torch.Generator().manual_seed(0)).cuda()
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            ops.LAUNCHES = 0
+            out = mine(x)
+            assert ops.LAUNCHES >= nq, "the reference model file did not reach the po2 conv kernels"
+            want = ref(x)
+            rel = ((out.double() - want.double()).abs().max() / want.double().abs().max()).item()
+            assert rel < 1e-2, (name, rel)
+            ops.set_conv_mode("fp32")
+            try:
+                out32 = mine(x)
+            finally:
+                ops.set_conv_mode("tc")
+            rel32 = ((out32.double() - want.double()).abs().max() / want.double().abs().max()).item()
+            assert rel32 < 1e-4, (name, rel32)
+            assert torch.equal(out32.argmax(1), want.argmax(1)), "top-1 differs in fp32-accumulate mode"
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    err, numel = mine.get_quantization_error()        # quantize_fn=None after PTQ: (0, numel) per layer
+    assert err == 0 and numel > 0
+
+
+@pytest.mark.parametrize("name", ["resnet20", "mobilenet"])
+def test_reference_model_files_qat_step_on_gpu(name):
+    """One QAT training step (train.py:79-92) of the reference's own model file on the drop-in classes vs
+    the same file on the reference's classes, fp32-accumulate mode: loss and every weight gradient."""
+    RF, d, s = _ref_ns()
+    torch.manual_seed(8)
+    ref = s.get_model(name, 10, s.quantizers.PowerOfTwoQuantizer, 4, (32, 32))
+    mine = d.get_model(name, 10, P.PowerOfTwoQuantizer, 4, (32, 32))
+    mine.load_state_dict(ref.state_dict(), strict=True)
+    train_bn = name == "resnet20"                      # see test_qat_training_step_matches_oracle_model
+    ref, mine = ref.cuda().train(train_bn), mine.cuda().train(train_bn)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(32, 3, 32, 32, generator=g).cuda()
+    y = torch.randint(0, 10, (32,), generator=g).cuda()
+    crit = nn.CrossEntropyLoss()
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    ops.set_conv_mode("fp32")
+    ops.set_log2_flavor("torch_cuda")
+    try:
+        lr_ = crit(ref(x), y); lr_.backward()
+        lm = crit(mine(x), y); lm.backward()
+    finally:
+        ops.set_conv_mode("tc")
+        ops.set_log2_flavor("ieee")
+        torch.backends.cudnn.allow_tf32 = old
+    assert abs(lm.item() - lr_.item()) < 5e-3 * max(1.0, abs(lr_.item()))
+    pr = dict(ref.named_parameters())
+    gscale = max(v.grad.double().pow(2).mean().sqrt().item() for v in pr.values())
+    checked = 0
+    for k, p in mine.named_parameters():
+        assert p.grad is not None, k
+        gr = pr[k].grad.double()
+        if gr.pow(2).mean().sqrt().item() < 1e-7 * gscale or p.numel() < 64:
+            continue
+        rel = ((p.grad.double() - gr).pow(2).mean().sqrt() / gr.pow(2).mean().sqrt()).item()
+        assert rel < 3e-2, (k, rel)
+        checked += 1
+    assert checked >= 10
+    # the model-level error walker (train.py:106) on the drop-in classes == on the reference's
+    e1, n1 = mine.get_quantization_error()
+    e2, n2 = ref.get_quantization_error()
+    assert n1 == n2 and abs(float(e1) - float(e2)) <= 1e-5 * float(e2)
+
+
+def test_conv_argument_errors_match_nn_conv2d():
+    """A wrong channel count must raise like nn.Conv2d / the reference do (RuntimeError), never read out
+    of bounds: module forward (QAT, PTQ, prefetched), the ops, and the raw launchers."""
+    conv = P.QuantizedConv2d(16, 32, 3, quantize_fn=P.PowerOfTwoQuantizer, bits=4).cuda()
+    good, bad = torch.randn(2, 16, 8, 8, device="cuda"), torch.randn(2, 24, 8, 8, device="cuda")
+    conv(good)
+    with pytest.raises(RuntimeError, match="channels"):
+        conv(bad)
+    seq = nn.Sequential(P.QuantizedConv2d(16, 32, 3)).cuda()
+    P.quantize_model(seq, P.PowerOfTwoQuantizer, 4)
+    with torch.no_grad():
+        seq(good)
+        with pytest.raises(RuntimeError, match="channels"):
+            seq(bad)
+    w = torch.randn(32, 16, 3, 3, device="cuda")
+    qw, scale = torch.ops.po2.quantize_scaled(w, 4, 1, False)
+    with pytest.raises(RuntimeError, match="channels"):
+        torch.ops.po2.conv2d(bad, qw, scale, 1, 1, 1, 0)
+    with pytest.raises(RuntimeError, match="channels"):
+        torch.ops.po2.qconv2d(bad, w, 4, 1, False, 1, 1, 1, 0)
+    packed = ops.conv2d_pack(qw, scale, tuple(good.shape), 1, 1, 1, 0)
+    torch.ops.po2.conv2d_packed(good, packed, scale, 32, 3, 3, 1, 1, 1, 0)
+    with pytest.raises(RuntimeError, match="packed operand"):
+        torch.ops.po2.conv2d_packed(bad, packed, scale, 32, 3, 3, 1, 1, 1, 0)
+    with pytest.raises(RuntimeError, match="Kernel size"):
+        torch.ops.po2.conv2d(torch.randn(1, 16, 1, 1, device="cuda"), qw, scale, 1, 0, 1, 0)
+
+
+def test_library_fallbacks_are_loud(monkeypatch):
+    """configurations the kernels do not take run nn.Conv2d's own path WITH a warning (once per reason),
+    and raise under PO2_STRICT=1"""
+    conv = P.QuantizedConv2d(8, 8, 3, dilation=2, padding=2, quantize_fn=P.PowerOfTwoQuantizer, bits=4).cuda()
+    x = torch.randn(1, 8, 8, 8, device="cuda")
+    ops._noted.clear()
+    with pytest.warns(RuntimeWarning, match="dilation"):
+        conv(x)
+    monkeypatch.setenv("PO2_STRICT", "1")
+    with pytest.raises(P._lib.Po2Error, match="dilation"):
+        conv(x)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused error sums for all layers, packed-code checkpoints
+# ------------------------------------------------------------------------------------------------
+def test_quantization_error_comes_from_the_quantizer_pass():
+    """QuantizedConv2d.get_quantization_error (models/quantized_conv.py:40-45) and the model-level sum
+    (models/resnet.py:214-224, train.py:106): equal to sum((Q(w)-w)^2) from the numpy oracle to 1e-6, one
+    launch per layer without the prefetch and NO launch at all once the multi-tensor prefetch has run."""
+    import numpy as np
+    from oracle import po2_oracle as O
+    from workloads import resnet_cifar
+    torch.manual_seed(8)
+    model = resnet_cifar(20, 10, P.PowerOfTwoPlusQuantizer, 4).cuda().train()
+    convs = [m for m in model.modules() if isinstance(m, P.QuantizedConv2d)]
+    want = []
+    for m in convs:
+        w = m.weight.detach().cpu().numpy().ravel()
+        want.append(float(np.sum((O.po2_plus(w, 4).astype(np.float64) - w.astype(np.float64)) ** 2)))
+    ops.LAUNCHES = 0
+    got = [m.get_quantization_error() for m in convs]
+    assert ops.LAUNCHES == len(convs)                       # one fused launch each (the reference: 12 ATen launches each)
+    for (e, n), w_, m in zip(got, want, convs):
+        assert n == m.weight.numel() and abs(e.item() - w_) <= 1e-6 * w_, (e.item(), w_)
+    P.enable_weight_prefetch(model)
+    x = torch.randn(8, 3, 32, 32, device="cuda")
+    model(x); model(x)                                       # first forward records the shapes, second prefetches
+    ops.LAUNCHES = 0
+    tot, numel = P.model_quantization_error(model)
+    assert ops.LAUNCHES == 0, "the prefetched error sums were not used"
+    assert numel == sum(m.weight.numel() for m in convs)
+    assert abs(tot.item() - sum(want)) <= 1e-6 * sum(want)
+    # a weight update invalidates the cached value
+    with torch.no_grad():
+        convs[3].weight.mul_(1.5)
+    w = convs[3].weight.detach().cpu().numpy().ravel()
+    e, _ = convs[3].get_quantization_error()
+    ref = float(np.sum((O.po2_plus(w, 4).astype(np.float64) - w.astype(np.float64)) ** 2))
+    assert abs(e.item() - ref) <= 1e-6 * ref
+
+
+@pytest.mark.parametrize("bits,plus", [(4, True), (4, False), (8, True), (3, False)])
+def test_packed_checkpoint_round_trip_is_bit_exact(tmp_path, bits, plus):
+    """state_dict -> packed codes + scales -> state_dict: bit-identical for a PTQ model (exact zeros and
+    the DDP 'module.' prefix included); for a QAT model the unpacked weights are exactly Q(w)."""
+    from workloads import resnet_cifar
+    Q = P.PowerOfTwoPlusQuantizer if plus else P.PowerOfTwoQuantizer
+    torch.manual_seed(8)
+    model = resnet_cifar(20, 10, None, bits).cuda()
+    convs = [m for m in model.modules() if isinstance(m, P.QuantizedConv2d)]
+    with torch.no_grad():
+        convs[2].weight.view(-1)[::7] = 0.0                  # exact zeros have no code: they travel as a bitmask
+    P.quantize_model(model, Q, bits)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    path = str(tmp_path / "ptq.po2")
+    meta = P.save_packed_checkpoint(model, path)
+    assert meta["raw_fallbacks"] == []
+    ratio = meta["quantized_packed_bytes"] / meta["quantized_fp32_bytes"]
+    assert ratio < (0.14 if bits <= 4 else 0.27), ratio
+    back = P.load_packed_checkpoint(path)
+    assert list(back) == list(sd)
+    for k in sd:
+        assert back[k].dtype == sd[k].dtype and torch.equal(back[k].cpu(), sd[k].cpu()), k
+        if sd[k].dtype == torch.float32:
+            assert torch.equal(back[k].view(torch.int32).cpu(), sd[k].view(torch.int32).cpu()), k
+    fresh = resnet_cifar(20, 10, None, bits).cuda()
+    fresh.load_state_dict(back, strict=True)
+    # QAT model: master weights are NOT on the grid; the packed file holds what the forward convolves with
+    torch.manual_seed(9)
+    qat = resnet_cifar(20, 10, Q, bits).cuda()
+    packed = P.pack_state_dict(qat)
+    un = P.unpack_state_dict(packed)
+    for name, m in qat.named_modules():
+        if isinstance(m, P.QuantizedConv2d):
+            assert torch.equal(un[name + ".weight"], Q.forward(None, m.weight.detach(), bits=bits)), name
+    # DDP-style prefix survives
+    wrapped = torch.nn.Sequential()
+    wrapped.add_module("module", model)
+    back2 = P.unpack_state_dict(P.pack_state_dict(wrapped))
+    assert all(k.startswith("module.") for k in back2) and len(back2) == len(sd)
+    for k in sd:
+        assert torch.equal(back2["module." + k].cpu(), sd[k].cpu())

@@ -276,8 +276,8 @@ def test_stock_torch_cuda_disagreements(P, tmp_path):
 @pytest.mark.parametrize("plus", [False, True])
 @pytest.mark.parametrize("scale", [1.0, 1.337])
 def test_exhaustive_fp32_patterns_vs_stock_cuda(P, plus, scale):
-    """Every fp32 bit pattern with 0 <= |x| <= scale (about 1.07e9 of them, both quantizers, bits 4
-    and 8) against the reference run on this GPU (stock ATen CUDA ops), bitwise, under the
+    """Every fp32 bit pattern with 0 <= |x| <= scale (about 1.07e9 of them, both quantizers, bits 2..8
+    at scale 1, bits 4 and 8 at scale 1.337) against the reference run on this GPU (stock ATen CUDA ops), bitwise, under the
     torch_cuda boundary table.  The max is planted so that the tensor's scale is exactly `scale`."""
     from oracle.po2_oracle_torch import quantize_ref
     Q = P.PowerOfTwoPlusQuantizer if plus else P.PowerOfTwoQuantizer
@@ -292,7 +292,7 @@ def test_exhaustive_fp32_patterns_vs_stock_cuda(P, plus, scale):
             # alternate signs, plant the maximum at the end
             x = torch.where((bits_ & 1).bool(), -x, x)
             x = torch.cat([x, torch.tensor([scale], device="cuda")])
-            for nbits in (4, 8):
+            for nbits in ((2, 3, 4, 5, 6, 7, 8) if scale == 1.0 else (4, 8)):
                 ours = Q.forward(None, x, bits=nbits)
                 stock = quantize_ref(x, nbits, 1, plus)
                 bad = ours.view(torch.int32) != stock.view(torch.int32)
@@ -328,6 +328,91 @@ def test_ieee_vs_torch_cuda_flavor_difference_is_the_enumerated_boundaries(P):
     assert diffs[False] == []
     # cuda boundaries are 1 ulp below the cpu ones at k=-6..-4: exactly those three patterns flip
     assert sorted(diffs[True]) == [0x3C3FFFFE, 0x3CC00002, 0x3D3FFFFE], [hex(v) for v in diffs[True]]
+
+
+def _half_patterns(dt, scale_bits):
+    """all 2^16 bit patterns of a half type whose magnitude does not exceed `scale_bits` (both signs,
+    +-0, subnormals), the scale itself planted last so that max|x| is exactly it"""
+    u = np.arange(1 << 16, dtype=np.uint32)
+    keep = (u & 0x7FFF) <= scale_bits
+    return np.concatenate([u[keep], np.array([scale_bits], dtype=np.uint32)]).astype(np.uint16)
+
+
+@pytest.mark.parametrize("dt", ["bf16", "f16"])
+@pytest.mark.parametrize("plus", [False, True])
+def test_exhaustive_half_patterns_both_flavors(P, dt, plus):
+    """ALL 2^16 bit patterns of bf16 and fp16 as inputs (every intermediate of the
+    reference is rounded to the storage dtype, utils/quantizers.py:22-32 / 42-52), bits 2..8, both
+    quantizers, at several scales:
+      * flavor "ieee"       bitwise against the numpy oracle (== the reference on CPU),
+      * flavor "torch_cuda" bitwise against the reference's ops run on this GPU in the half dtype."""
+    from oracle.po2_oracle_torch import quantize_ref
+    Q = P.PowerOfTwoPlusQuantizer if plus else P.PowerOfTwoQuantizer
+    one = 0x3F80 if dt == "bf16" else 0x3C00
+    # 1.0, a non-power-of-two, the largest finite value, a tiny normal, a subnormal scale
+    scales = [one, one + 0x2B, (0x7F7F if dt == "bf16" else 0x7BFF), (0x0100 if dt == "bf16" else 0x0500), 0x0007]
+    for sb in scales:
+        xb = _half_patterns(dt, sb)
+        x = _to_dev(xb, dt)
+        vals = G.bits_to_f32(xb, dt)
+        for nbits in range(2, 9):
+            P.set_log2_flavor("ieee")
+            got = _bits(Q.forward(None, x, bits=nbits))
+            ref = G.f32_to_bits(O.quantize(vals, nbits, 1, plus, dtype=dt), dt)
+            _assert_same(got, ref, dt, f"ieee {dt} plus={plus} scale={sb:#x} bits={nbits}")
+            P.set_log2_flavor("torch_cuda")
+            try:
+                got_c = _bits(Q.forward(None, x, bits=nbits))
+            finally:
+                P.set_log2_flavor("ieee")
+            stock = _bits(quantize_ref(x, nbits, 1, plus))
+            _assert_same(got_c, stock, dt, f"torch_cuda {dt} plus={plus} scale={sb:#x} bits={nbits}")
+
+
+@pytest.mark.parametrize("plus", [False, True])
+def test_flavor_difference_all_bits_is_the_table_difference(P, plus):
+    """For every bit width 2..8 the two log2 flavors may differ ONLY between the boundaries where the
+    compiled tables differ (16 po2 and 44 po2+ boundaries of 150), and never below
+    the clamp: exhaustive over all fp32 magnitudes <= 1.  Together with the exhaustive torch_cuda check
+    above this pins the default (ieee) flavor at every bit width, not only at 4 bits."""
+    import json
+    import os
+    tdir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "po2_quantization_b200", "tables")
+    key = "f32|po2+" if plus else "f32|po2"
+    ta = json.load(open(os.path.join(tdir, "oracle.json")))["tables"][key]
+    tb = json.load(open(os.path.join(tdir, "torch_cuda.json")))["tables"][key]
+    Q = P.PowerOfTwoPlusQuantizer if plus else P.PowerOfTwoQuantizer
+    top = 0x3F800000
+    chunk = 1 << 27
+    ndiff = {b: 0 for b in range(2, 9)}
+    lo_pat = {b: None for b in range(2, 9)}
+    for start in range(0, top + 1, chunk):
+        n = min(chunk, top + 1 - start)
+        bits_ = torch.arange(start, start + n, device="cuda", dtype=torch.int64).to(torch.int32)
+        x = torch.cat([bits_.view(torch.float32), torch.ones(1, device="cuda")])
+        for nbits in range(2, 9):
+            P.set_log2_flavor("ieee")
+            a = Q.forward(None, x, bits=nbits)
+            P.set_log2_flavor("torch_cuda")
+            try:
+                b = Q.forward(None, x, bits=nbits)
+            finally:
+                P.set_log2_flavor("ieee")
+            d = (a.view(torch.int32) != b.view(torch.int32)).nonzero().flatten()
+            ndiff[nbits] += int(d.numel())
+            if d.numel():
+                v = int(x[d].view(torch.int32).min().item())
+                lo_pat[nbits] = v if lo_pat[nbits] is None else min(lo_pat[nbits], v)
+    # expected: sum over boundaries k in (qmin, 0] of |threshold_ieee(k) - threshold_cuda(k)| patterns
+    def thresholds(t):
+        # tables/*.json: bounds_f32bits[i] = smallest bit pattern of v with raw(v) >= kmin + i
+        return {t["kmin"] + i: int(v) for i, v in enumerate(t["bounds_f32bits"])}
+    A, B = thresholds(ta), thresholds(tb)
+    for nbits in range(2, 9):
+        qmin = 1 - 2 ** (nbits - 1)
+        expect = sum(abs(A[k] - B[k]) for k in A if qmin < k <= 0 and k in B)
+        assert ndiff[nbits] == expect, (nbits, ndiff[nbits], expect)
+    assert ndiff[2] == ndiff[3] == 0 and (ndiff[4] == (3 if plus else 0))
 
 
 def test_lin_quantizers_cuda_kernel_matches_reference_vectors():

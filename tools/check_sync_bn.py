@@ -110,6 +110,31 @@ def main():
     if rank == 0:
         print(json.dumps({"batch_sharded_grad_avg_max_rel_err": t.item(), "tensors": nred, "buckets": len(model._buckets)}), flush=True)
     ok = ok and t.item() < 1e-6
+    # sharded_quantize on the sm_100a kernels: every rank quantizes its shard of
+    # ONE tensor after a single all_reduce(MAX) of the scale; the result must equal the single-device
+    # quantizer on the whole tensor, bit for bit -- also when a NaN sits in another rank's shard
+    from po2_quantization_b200.distributed import sharded_quantize
+    bad = 0
+    for case, (n, plus, bits, dt) in enumerate([(1 << 20, False, 4, torch.float32), ((1 << 18) + 37, True, 4, torch.float32),
+                                                (1 << 19, True, 8, torch.bfloat16), (4099, False, 3, torch.float32)]):
+        for with_nan in (False, True):
+            g = torch.Generator().manual_seed(900 + case)
+            full = (torch.randn(n, generator=g) * 0.3).to(dt)
+            if with_nan:
+                full[5] = float("nan")
+            shard = torch.tensor_split(full, world)[rank].cuda()
+            y, scale = sharded_quantize(shard, bits=bits, plus=plus)
+            Q = P.PowerOfTwoPlusQuantizer if plus else P.PowerOfTwoQuantizer
+            want = torch.tensor_split(Q.forward(None, full.cuda(), bits=bits), world)[rank]
+            same = torch.equal(y.view(torch.int16 if dt != torch.float32 else torch.int32),
+                               want.view(torch.int16 if dt != torch.float32 else torch.int32)) or \
+                bool((torch.isnan(y) & torch.isnan(want)).all())
+            bad += 0 if same else 1
+    t = torch.tensor([bad], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        print(json.dumps({"sharded_quantize_cuda_backend_mismatching_cases": int(t.item()), "cases": 8, "world": world}), flush=True)
+    ok = ok and t.item() == 0
     dist.barrier()
     torch.cuda.synchronize()
     os._exit(0 if ok else 1)
