@@ -104,6 +104,11 @@ int po2_ste_backward(const void* g, void* gx, int64_t n, int dtype, int accumula
  * the precision of the reference's own cuDNN default), 1: fp32 CUDA cores everywhere. */
 size_t po2_conv2d_workspace(int B, int C, int H, int W, int K, int R, int S, int stride, int pad,
                             int groups, int compute);
+/* Which kernel po2_conv2d_fwd runs for a geometry (planning query, no launch): 0 direct fp32 CUDA cores,
+ * 1 depthwise, 2 tcgen05 implicit GEMM with the register-fed activation producer, 3 tcgen05 implicit
+ * GEMM fed by tensor-map TMA (tf32 operands straight from fp32 NCHW); negative: PO2_E_*. */
+int po2_conv2d_kernel_kind(int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups,
+                           int compute);
 int po2_conv2d_fwd(const void* x, const void* w, const float* scale, void* out, int B, int C,
                    int H, int W, int K, int R, int S, int stride, int pad, int groups,
                    int w_format, int bits, int fsr, int compute, void* workspace,

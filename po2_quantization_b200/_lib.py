@@ -31,6 +31,7 @@ SIGNATURES = {
     "po2_dequantize": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _vp]),
     "po2_ste_backward": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     "po2_conv2d_workspace": (_sz, [_i] * 11),
+    "po2_conv2d_kernel_kind": (_i, [_i] * 11),
     "po2_conv2d_fwd": (_i, [_vp, _vp, _vp, _vp] + [_i] * 14 + [_vp, _sz, _vp]),
     "po2_conv2d_pack_bytes": (_sz, [_i] * 11),
     "po2_conv2d_pack": (_i, [_vp, _vp, _vp, _sz] + [_i] * 14 + [_vp]),

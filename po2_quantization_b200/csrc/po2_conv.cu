@@ -14,6 +14,7 @@
 //   --  conv_direct_kernel    any dense/grouped shape in fp32 FMA (the "fp32-accumulate" parity path and
 //                            the fallback for shapes K3 does not take).
 #include <limits.h>
+#include <stdlib.h>
 
 #include "po2_common.cuh"
 
@@ -837,6 +838,16 @@ static bool plan_umma(ConvGeom& g, bool tf32) {
 
 static size_t umma_pack_bytes(const ConvGeom& g) { return (size_t)g.ntiles_n * g.b_slab_bytes; }
 
+}  // namespace po2
+#include "po2_conv_tma.cuh"   // K3T: the TMA-fed tf32 form (plan_tma / launch_tma)
+namespace po2 {
+
+// PO2_CONV_TMA=0 keeps every shape on the register-fed kernel (A/B measurements)
+static bool tma_enabled() {
+  static const bool on = [] { const char* e = getenv("PO2_CONV_TMA"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 // transpose: 0/1 = run pack_weights_kernel first (forward / data-gradient orientation); -1 = pack_buf
 // already holds the operand.  pdl: launch the conv with programmatic stream serialization -- ONLY
 // legal when the kernel directly in front of it in the stream is one of ours that was launched
@@ -855,6 +866,13 @@ static int launch_umma(const void* x, const void* w, const float* scale, void* o
           w_format == PO2_W_CODES ? nullptr : scale, Bp, g, bits, fsr, transpose);
       e = cudaGetLastError();
       if (e != cudaSuccess) return (int)e;
+    }
+    if (g.tf32 && tma_enabled()) {                        // K3T where the shape allows: activations by tensor-map TMA
+      TmaPlan tp;
+      if (plan_tma(g, tp)) {
+        const int rc = launch_tma(x, Bp, scale, out, g, tp, st, pdl);
+        if (rc != PO2_E_UNSUPPORTED) return rc;
+      }
     }
     static PerDeviceOnce attr_once;                       // the opt-in shared-memory size is a per-device attribute
     e = attr_once.run([]() -> cudaError_t {
@@ -1283,6 +1301,19 @@ size_t po2_conv2d_workspace(int B, int C, int H, int W, int K, int R, int S, int
   size_t bytes = (size_t)K * (C / groups) * R * S * sizeof(float);       // decoded fp32 weights (codes input)
   if (compute != 1 && umma_eligible(g) && plan_umma(g, compute == 2)) bytes += umma_pack_bytes(g) + 256;
   return (bytes + 255) / 256 * 256;
+}
+
+// which kernel po2_conv2d_fwd runs for this geometry: 0 direct fp32, 1 depthwise, 2 tcgen05 with the
+// register-fed activation producer, 3 tcgen05 with the tensor-map TMA producer (K3T); < 0: PO2_E_*
+int po2_conv2d_kernel_kind(int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups,
+                           int compute) {
+  ConvGeom g;
+  if (!fill_geom(g, B, C, H, W, K, R, S, stride, pad, groups)) return PO2_E_SHAPE;
+  if (compute != 1 && umma_eligible(g) && plan_umma(g, compute == 2)) {
+    TmaPlan tp;
+    return (g.tf32 && tma_enabled() && plan_tma(g, tp)) ? 3 : 2;
+  }
+  return (groups == C && groups == K) ? 1 : 0;
 }
 
 int po2_conv2d_fwd(const void* x, const void* w, const float* scale, void* out, int B, int C, int H,

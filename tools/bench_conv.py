@@ -69,12 +69,18 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--compute", type=int, default=0, help="0: bf16 operands, 2: tf32 operands (TMA-fed where eligible)")
+    ap.add_argument("--only", default=None, help="substring filter on the layer name")
     a = ap.parse_args()
+    from po2_quantization_b200 import _lib
+    lib = _lib.load()
     flush = torch.zeros(320 * 1024 * 1024 // 4, dtype=torch.int32, device="cuda")
     REPS = 10
     t_flush = graph_time(lambda: flush.add_(1), REPS)
     rows = []
     for name, C, H, W, K, k, stride, pad, groups, cnt in SHAPES:
+        if a.only and a.only not in name:
+            continue
         B = a.batch
         x = torch.randn(B, C, H, W, device="cuda")
         w = torch.randn(K, C // groups, k, k, device="cuda") * 0.1
@@ -83,8 +89,14 @@ def main():
         out = torch.empty(B, K, P, Q, device="cuda")
         flops = 2.0 * B * K * P * Q * (C // groups) * k * k
         bytes_io = 4.0 * (x.numel() + out.numel())
-        r = {"layer": name, "batch": B, "gflop": flops / 1e9, "io_mb": bytes_io / 1e6, "count_r56": cnt}
-        cands = {"po2_tc": lambda: ops.conv2d_out(x, y, scale, out, stride, pad, groups, 0)}
+        r = {"layer": name, "batch": B, "gflop": flops / 1e9, "io_mb": bytes_io / 1e6, "count_r56": cnt,
+             "compute": a.compute,
+             "kernel_kind": lib.po2_conv2d_kernel_kind(B, C, H, W, K, k, k, stride, pad, groups, a.compute)}
+        cands = {"po2_tc": lambda: ops.conv2d_out(x, y, scale, out, stride, pad, groups, a.compute)}
+        torch.backends.cudnn.allow_tf32 = False
+        ref = F.conv2d(x, y, None, stride, pad, 1, groups)
+        cands["po2_tc"]()
+        r["max_rel_err_vs_fp32"] = ((out - ref).abs().max() / ref.abs().max()).item()
         torch.backends.cudnn.allow_tf32 = True
         F.conv2d(x, y, None, stride, pad, 1, groups)
         cands["cudnn_tf32"] = lambda: F.conv2d(x, y, None, stride, pad, 1, groups)
