@@ -427,9 +427,10 @@ def step_variants(a, device, ms_main):
     from po2_quantization_b200 import ops
     res = {"main_ms": ms_main}
     prev = ops.get_conv_mode()
-    for name, mode, source in (("tf32_operands", "tf32", "workload"),
+    other = "tc" if prev == "tf32" else "tf32"
+    for name, mode, source in ((("bf16_operands" if other == "tc" else "tf32_operands"), other, "workload"),
                                ("reference_model_files", prev, "reference_files"),
-                               ("reference_model_files_tf32", "tf32", "reference_files")):
+                               ("reference_model_files_" + ("bf16" if other == "tc" else "tf32"), other, "reference_files")):
         try:
             ops.set_conv_mode(mode)
             h = StepHarness(a, 1, 0, device.index or 0, device, source)

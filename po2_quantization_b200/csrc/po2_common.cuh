@@ -111,6 +111,8 @@ struct PackArgs {
   void* Bp;                  // nullptr: off
   int G;                     // 8: bf16 operand, 4: tf32 (fp32) operand -- channels per 16-byte plane entry
   int C, K, taps, NT, ncg;   // ncg = C / G
+  int tapminor;              // 1 (3x3, TMA-fed conv): Bp[nt][r][c/G][s][n][G] -- the three filter columns of a row are
+                             // consecutive N rows, so one MMA covers them (N = 3 * NT)
   FastDiv div_ct, div_t, div_nt;   // by C*taps, taps, NT
 };
 

@@ -143,6 +143,7 @@ struct ConvGeom {
   int vec4, items_per_row;   // producer fast path: float4 loads along W
   int prod_groups;           // independent producer groups (stages in flight per CTA)
   int dual_issue;            // two MMA issuers alternate tiles (only when a tile is one stage)
+  int tapminor;              // weight operand layout Bp[nt][r][c/G][s][n][G] (the TMA-fed kernel, 3x3): see PackArgs
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -164,11 +165,19 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const uint8_t* 
   const float s = scale ? *scale : 1.0f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     // i = (((nt * taps + tap) * ncg + cg) * NT + n) * G + j, decoded with mul-hi divisions
+    // (tapminor: i = ((((nt * 3 + r) * ncg + cg) * 3 + s) * NT + n) * G + j, tap = 3 r + s)
     const int j = i & (G - 1);
     int t = i >> lgG;
     int q = fdiv(t, g.div_NT);  const int n = t - q * g.NT;  t = q;
-    q = fdiv(t, g.div_ncg);     const int cg = t - q * ncg;   t = q;
-    q = fdiv(t, g.div_taps);    const int tap = t - q * taps; const int nt = q;
+    int cg, tap, nt;
+    if (g.tapminor) {
+      const int s3 = t % 3; t /= 3;
+      q = fdiv(t, g.div_ncg); cg = t - q * ncg; t = q;
+      tap = (t % 3) * 3 + s3; nt = t / 3;
+    } else {
+      q = fdiv(t, g.div_ncg);     cg = t - q * ncg;   t = q;
+      q = fdiv(t, g.div_taps);    tap = t - q * taps; nt = q;
+    }
     const int c = cg * G + j;
     const int k = nt * g.NT + n;
     float v = 0.0f;
@@ -754,6 +763,8 @@ static size_t umma_smem_bytes(const ConvGeom& g) {
   return (size_t)g.b_slab_bytes + (size_t)g.nst * g.a_stage_bytes + (3 * K3_MAX_STAGES + 8) * 8 + 64;
 }
 
+static bool tma_takes(const ConvGeom& g);    // po2_conv_tma.cuh: the TMA-fed kernel runs this (planned) geometry
+
 // returns false if the shape does not fit the kernel's shared-memory plan
 static bool plan_umma(ConvGeom& g, bool tf32) {
   const bool k3 = (g.R == 3);
@@ -833,20 +844,21 @@ static bool plan_umma(ConvGeom& g, bool tf32) {
   g.vec4 = (g.stride == 1 && g.W % 4 == 0) ? 1 : 0;
   g.items_per_row = g.W / 4 + (g.pitch > g.W ? 1 : 0);
   g.div_ipr = make_fastdiv((uint32_t)(g.items_per_row > 0 ? g.items_per_row : 1));
+  g.tapminor = (g.ntaps == 9 && tma_takes(g)) ? 1 : 0;
   return true;
 }
 
 static size_t umma_pack_bytes(const ConvGeom& g) { return (size_t)g.ntiles_n * g.b_slab_bytes; }
-
-}  // namespace po2
-#include "po2_conv_tma.cuh"   // K3T: the TMA-fed tf32 form (plan_tma / launch_tma)
-namespace po2 {
 
 // PO2_CONV_TMA=0 keeps every shape on the register-fed kernel (A/B measurements)
 static bool tma_enabled() {
   static const bool on = [] { const char* e = getenv("PO2_CONV_TMA"); return !(e && e[0] == '0'); }();
   return on;
 }
+
+}  // namespace po2
+#include "po2_conv_tma.cuh"   // K3T: the TMA-fed tf32 form (plan_tma / launch_tma)
+namespace po2 {
 
 // transpose: 0/1 = run pack_weights_kernel first (forward / data-gradient orientation); -1 = pack_buf
 // already holds the operand.  pdl: launch the conv with programmatic stream serialization -- ONLY
@@ -867,11 +879,12 @@ static int launch_umma(const void* x, const void* w, const float* scale, void* o
       e = cudaGetLastError();
       if (e != cudaSuccess) return (int)e;
     }
-    if (g.tf32 && tma_enabled()) {                        // K3T where the shape allows: activations by tensor-map TMA
+    {                                                     // K3T where the shape allows: activations by tensor-map TMA
       TmaPlan tp;
-      if (plan_tma(g, tp)) {
-        const int rc = launch_tma(x, Bp, scale, out, g, tp, st, pdl);
-        if (rc != PO2_E_UNSUPPORTED) return rc;
+      if (g.tf32 && tma_enabled() && plan_tma(g, tp)) {
+        // (the operand may already be packed in K3T's layout: an x that cannot be described by a tensor map --
+        // misaligned -- is an error here, not a fallback)
+        return launch_tma(x, Bp, scale, out, g, tp, st, pdl);
       }
     }
     static PerDeviceOnce attr_once;                       // the opt-in shared-memory size is a per-device attribute
@@ -1461,7 +1474,7 @@ int po2_qconv2d_fwd(const void* x, const void* w_master, void* qw_out, float* sc
     if ((int64_t)B * C * H * W >= (1ll << 31) || (int64_t)B * K * g.P * g.Q >= (1ll << 31)) return PO2_E_SIZE;
     PackArgs pk;
     pk.Bp = reinterpret_cast<char*>(workspace) + wbytes;
-    pk.G = g.G; pk.C = C; pk.K = K; pk.taps = g.ntaps; pk.NT = g.NT; pk.ncg = C / g.G;
+    pk.G = g.G; pk.C = C; pk.K = K; pk.taps = g.ntaps; pk.NT = g.NT; pk.ncg = C / g.G; pk.tapminor = g.tapminor;
     pk.div_ct = make_fastdiv((uint32_t)(C * g.ntaps));
     pk.div_t = make_fastdiv((uint32_t)g.ntaps);
     pk.div_nt = make_fastdiv((uint32_t)g.NT);
@@ -1492,7 +1505,7 @@ int po2_quantize_pack(const void* w_master, void* qw_out, float* scale_out, void
   if (g.Cpad == C && g.ntiles_n * g.NT == K) {
     PackArgs pk;
     pk.Bp = packed;
-    pk.G = g.G; pk.C = C; pk.K = K; pk.taps = g.ntaps; pk.NT = g.NT; pk.ncg = C / g.G;
+    pk.G = g.G; pk.C = C; pk.K = K; pk.taps = g.ntaps; pk.NT = g.NT; pk.ncg = C / g.G; pk.tapminor = g.tapminor;
     pk.div_ct = make_fastdiv((uint32_t)(C * g.ntaps));
     pk.div_t = make_fastdiv((uint32_t)g.ntaps);
     pk.div_nt = make_fastdiv((uint32_t)g.NT);
@@ -1529,7 +1542,7 @@ int po2_multi_desc_fill(void* host_table, int index, const void* w_master, void*
   d.x = (const uint4*)w_master; d.y = (uint4*)qw_out; d.scale_out = scale_out; d.sse_out = sse_out; d.n = wn;
   d.bits = bits; d.fsr = fsr; d.mode = mode; d.flavor = flavor;
   d.pk.Bp = packed;
-  d.pk.G = g.G; d.pk.C = C; d.pk.K = K; d.pk.taps = g.ntaps; d.pk.NT = g.NT; d.pk.ncg = C / g.G;
+  d.pk.G = g.G; d.pk.C = C; d.pk.K = K; d.pk.taps = g.ntaps; d.pk.NT = g.NT; d.pk.ncg = C / g.G; d.pk.tapminor = g.tapminor;
   d.pk.div_ct = make_fastdiv((uint32_t)(C * g.ntaps));
   d.pk.div_t = make_fastdiv((uint32_t)g.ntaps);
   d.pk.div_nt = make_fastdiv((uint32_t)g.NT);

@@ -57,6 +57,7 @@ struct TmaPlan {
   int nitems_m, m_step;
   int NCGS, nchunk;          // 8-channel groups per pipeline stage, stages per tile
   int nst;
+  int cps;                   // CTAs per SM the plan was sized for (2 when two CTAs' shared memory and TMEM fit)
   int debug;                 // PO2_TMA_DEBUG bit mask (1: no TMA loads, 2: no MMAs, 4: no descriptor prefetch)
   int HW, Himg, Wimg;        // image geometry (ConvGeom's H/W are flattened for 1x1 layers)
   uint32_t stage_bytes, cg_bytes;                 // per stage / per channel group (modes 0-2)
@@ -68,6 +69,7 @@ struct TmaPlan {
 constexpr int KT_EPI_WARPS = 4;
 constexpr int KT_THREADS = 32 * (KT_EPI_WARPS + 2);
 constexpr uint32_t KT_SMEM_BUDGET = 222 * 1024;
+constexpr uint32_t KT_SMEM_BUDGET_2 = 110 * 1024;     // per CTA when two share an SM (228 KB - 1 KB reserved each)
 constexpr uint32_t KT_STAGE_TARGET = 32 * 1024;
 
 __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, int c4,
@@ -95,7 +97,7 @@ __device__ __forceinline__ uint32_t make_idesc_tma(uint32_t m, uint32_t n) {
 }
 
 template <int NTAPS>
-__global__ void __launch_bounds__(KT_THREADS, 1) conv_tma_kernel(const __grid_constant__ CUtensorMap tmx,
+__global__ void __launch_bounds__(KT_THREADS, 2) conv_tma_kernel(const __grid_constant__ CUtensorMap tmx,
                                                                  const uint8_t* __restrict__ Bp,
                                                                  const float* __restrict__ scale,
                                                                  float* __restrict__ out, ConvGeom g, TmaPlan tp) {
@@ -114,6 +116,11 @@ __global__ void __launch_bounds__(KT_THREADS, 1) conv_tma_kernel(const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tready + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef PO2_K3_TRACE
+  for (int i = tid; i < 8 * 64; i += KT_THREADS) k3_trace_smem[i] = 0;
+  __syncthreads();
+#endif
+  if (tid == 0) K3_TRACE(6, 0);
   const int nt = blockIdx.x % g.ntiles_n;
   const int m_first = blockIdx.x / g.ntiles_n;
   const int nitems = tp.nitems_m, m_step = tp.m_step, nst = tp.nst, nchunk = tp.nchunk;
@@ -122,15 +129,23 @@ __global__ void __launch_bounds__(KT_THREADS, 1) conv_tma_kernel(const __grid_co
   uint32_t ncols = 32;
   while (ncols < (uint32_t)tp.nacc * acc_cols) ncols <<= 1;
 
-  if (warp == KT_EPI_WARPS + 1 && lane == 0) {
-    if (!(tp.debug & 4)) tma_prefetch_desc(&tmx);
-    for (int i = 0; i < nst; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, KT_EPI_WARPS); }
-    mbar_init(bfull, 1);
-    mbar_init(tready, 1);
+  // Barrier initialisation is spread over the producer warp's lanes (one mbarrier.init each instead of ~18 in
+  // a row on one thread); the producer does not wait for the rest of the CTA: it arrives on named barrier 1
+  // and starts issuing TMA loads, the other warps sync on it.
+  if (warp == KT_EPI_WARPS + 1) {
+    if (lane == 0 && !(tp.debug & 4)) tma_prefetch_desc(&tmx);
+    if (lane < nst) mbar_init(full + lane, 1);
+    else if (lane < 2 * nst) mbar_init(empty + (lane - nst), 1);
+    else if (lane < 2 * nst + 2) mbar_init(tfull + (lane - 2 * nst), 1);
+    else if (lane < 2 * nst + 4) mbar_init(tempty + (lane - 2 * nst - 2), KT_EPI_WARPS);
+    else if (lane == 2 * nst + 4) mbar_init(bfull, 1);
+    else if (lane == 2 * nst + 5) mbar_init(tready, 1);
     fence_mbar_init();
+    __syncwarp();
+    asm volatile("bar.arrive 1, %0;" ::"n"(KT_THREADS) : "memory");
+  } else {
+    asm volatile("bar.sync 1, %0;" ::"n"(KT_THREADS) : "memory");
   }
-  __syncthreads();
   uint32_t tmem_base = 0;
   if (warp == KT_EPI_WARPS) {
     tmem_alloc(tmem_slot, ncols);
@@ -145,12 +160,15 @@ __global__ void __launch_bounds__(KT_THREADS, 1) conv_tma_kernel(const __grid_co
     tmem_base = *tmem_slot;
   }
 
+  if (tid == 0) K3_TRACE(6, 1);
   if (warp == KT_EPI_WARPS + 1) {
     // =========================== TMA producer (one lane) ===========================
     // x was complete before the kernel in front of this one started (see launch_umma: programmatic
     // launch only behind our own pack / quantize kernels), so no griddepcontrol.wait here.
     if (elect_one()) {
       uint32_t s = 0, sphase = 0;
+      int tr_it = 0;
+      (void)tr_it;
       for (int m = m_first; m < nitems; m += m_step) {
         int c0 = 0, c1 = 0, c3 = 0;                          // box coordinates of the tile
         if (tp.mode == 0) {                                  // (w, image, c % 8, h, c / 8)
@@ -168,6 +186,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) conv_tma_kernel(const __grid_co
         }
         for (int chunk = 0; chunk < nchunk; ++chunk) {
           mbar_wait(empty + s, sphase ^ 1);
+          K3_TRACE(2, 2 * tr_it);
           uint8_t* stage = sA + (size_t)s * tp.stage_bytes;
           const int cg0 = chunk * tp.NCGS;
           if (tp.debug & 1) { mbar_arrive(full + s); if (++s == (uint32_t)nst) { s = 0; sphase ^= 1; } continue; }
@@ -186,6 +205,8 @@ __global__ void __launch_bounds__(KT_THREADS, 1) conv_tma_kernel(const __grid_co
           } else {                                           // (pixel % 32, c % 8, run, image, c / 8)
             tma_load_5d(stage, &tmx, 0, 0, c0, c3, cg0, full + s);
           }
+          K3_TRACE(2, 2 * tr_it + 1);
+          ++tr_it;
           if (++s == (uint32_t)nst) { s = 0; sphase ^= 1; }
         }
       }
@@ -199,16 +220,17 @@ __global__ void __launch_bounds__(KT_THREADS, 1) conv_tma_kernel(const __grid_co
       bulk_g2s(sB, Bp + (size_t)nt * g.b_slab_bytes, g.b_slab_bytes, bfull);
     }
     mbar_wait(bfull, 0);
-    const uint32_t idesc = make_idesc_tma((uint32_t)tp.MT, (uint32_t)g.NT);
+    if (leader) K3_TRACE(3, 0);
+    const uint32_t idesc = make_idesc_tma((uint32_t)tp.MT, acc_cols);        // N = NT, or 3 * NT (3x3: [s][n])
     constexpr uint32_t atom16 = KT_ATOM >> 4;
     // A: MN-major, SWIZZLE_128B_BASE32B (layout type 1).  lo = start >> 4 | LBO >> 4 << 16 (LBO: next 32-pixel
     //    run along M = next atom);  hi = SBO >> 4 (next 4 channels along K = half an atom) | version 1 | layout
     const uint32_t a_hi = (uint32_t)(512 >> 4) | (1u << 14) | (1u << 29);
     const uint32_t a_lo_fixed = tp.a_lbo16 << 16;
     const uint32_t a_ks16 = tp.a_ks16, a_r16 = tp.a_r16;
-    (void)atom16;
-    // B: K-major, no swizzle (planes of 4 channels x NT rows x 16 bytes): LBO = plane, SBO = 8 rows
-    const uint32_t b_plane16 = (uint32_t)g.NT;
+    (void)atom16; (void)a_r16;
+    // B: K-major, no swizzle (planes of 4 channels x N rows x 16 bytes): LBO = plane, SBO = 8 rows
+    const uint32_t b_plane16 = acc_cols;
     const uint32_t b_hi = 8u | (1u << 14);
     const uint32_t b_lo_fixed = b_plane16 << 16;
     const uint32_t b0_16 = smem_u32(sB) >> 4, a0_16 = smem_u32(sA) >> 4;
@@ -219,27 +241,41 @@ __global__ void __launch_bounds__(KT_THREADS, 1) conv_tma_kernel(const __grid_co
     for (int m = m_first; m < nitems; m += m_step, ++tile) {
       const uint32_t acc = tile & accmask;
       const uint32_t d = tmem_base + acc * acc_cols;
+      if (leader) K3_TRACE(4, 3 * (int)tile);
       mbar_wait(tempty + acc, (acc ? aph1 : aph0) ^ 1);        // the epilogue has drained this accumulator
+      if (leader) K3_TRACE(4, 3 * (int)tile + 1);
       for (int chunk = 0; chunk < nchunk; ++chunk) {
         mbar_wait(full + s, sphase);
+        if (leader && chunk == 0) K3_TRACE(4, 3 * (int)tile + 2);
         tc_fence_after();
         if (leader) {
+          K3_TRACE(0, 2 * (int)(tile * nchunk + chunk));
           const uint32_t a_s16 = a0_16 + s * stage16;
           const int ksteps = min(NCGS, ncg8_total - chunk * NCGS);
           for (int ks = 0; ks < ksteps; ++ks) {
-            const uint32_t b_k16 = b0_16 + (uint32_t)((chunk * NCGS + ks) * 2) * b_plane16;
+            const uint32_t cg4 = (uint32_t)((chunk * NCGS + ks) * 2);     // first of the two 4-channel planes of this k-step
+            if (NTAPS == 9) {
+              // one MMA per filter row: its three filter columns are N rows [s][n] of the operand and land in
+              // the three accumulators Y_s = TMEM columns [s * NT, s * NT + NT)
 #pragma unroll
-            for (int tap = 0; tap < NTAPS; ++tap) {
-              // filter row = atom shift (or row-shifted copy); filter column = its own accumulator
-              const uint32_t a16 = a_s16 + (uint32_t)ks * a_ks16 + (uint32_t)(tap / 3) * a_r16;
+              for (int r = 0; r < 3; ++r) {
+                const uint32_t a16 = a_s16 + (uint32_t)ks * a_ks16 + (uint32_t)r * a_r16;
+                const uint32_t b16 = b0_16 + ((uint32_t)r * (uint32_t)ncg4 + cg4) * b_plane16;
+                const uint64_t ad = ((uint64_t)a_hi << 32) | (a_lo_fixed | (a16 & 0x3FFFu));
+                const uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo_fixed | (b16 & 0x3FFFu));
+                umma<true>(d, ad, bd, idesc, (uint32_t)((chunk | ks | r) != 0));
+              }
+            } else {
+              const uint32_t a16 = a_s16 + (uint32_t)ks * a_ks16;
+              const uint32_t b16 = b0_16 + cg4 * b_plane16;
               const uint64_t ad = ((uint64_t)a_hi << 32) | (a_lo_fixed | (a16 & 0x3FFFu));
-              const uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo_fixed | ((b_k16 + (uint32_t)(tap * ncg4) * b_plane16) & 0x3FFFu));
-              if (!(tp.debug & 2))
-                umma<true>(d + (uint32_t)((tap % 3) * g.NT), ad, bd, idesc, (uint32_t)((chunk | ks | (tap / 3)) != 0));
+              const uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo_fixed | (b16 & 0x3FFFu));
+              umma<true>(d, ad, bd, idesc, (uint32_t)((chunk | ks) != 0));
             }
           }
           umma_commit(empty + s);                              // stage reusable once these MMAs retire
           if (chunk == nchunk - 1) umma_commit(tfull + acc);   // accumulator complete
+          K3_TRACE(0, 2 * (int)(tile * nchunk + chunk) + 1);
         }
         __syncwarp();
         if (++s == (uint32_t)nst) { s = 0; sphase ^= 1; }
@@ -260,6 +296,8 @@ __global__ void __launch_bounds__(KT_THREADS, 1) conv_tma_kernel(const __grid_co
     const bool edge_l = qw == 0, edge_r = qw == tp.WB - 1;     // image-row borders inside the run (3x3 only)
     const uint32_t accmask = (uint32_t)tp.nacc - 1u;
     uint32_t acc = 0, aphase = 0;
+    int tr_item = 0;
+    (void)tr_item;
     for (int m = m_first; m < nitems; m += m_step) {
       bool valid = lane_ok;
       int obase = 0;
@@ -284,6 +322,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) conv_tma_kernel(const __grid_co
       }
       mbar_wait(tfull + acc, aphase);
       tc_fence_after();
+      if (warp == 0 && lane == 0) K3_TRACE(1, 2 * tr_item);
       const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * acc_cols;
       for (int cb = 0; cb < NT / 16; ++cb) {
         float v[16];
@@ -323,12 +362,20 @@ __global__ void __launch_bounds__(KT_THREADS, 1) conv_tma_kernel(const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + acc);
+      if (warp == 0 && lane == 0) K3_TRACE(1, 2 * tr_item + 1);
+      ++tr_item;
       acc = (acc + 1) & accmask;
       aphase ^= (acc == 0);
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) K3_TRACE(6, 2);
+#ifdef PO2_K3_TRACE
+  __syncthreads();
+  if (g_k3_trace && blockIdx.x < 4)
+    for (int i = tid; i < 8 * 64; i += KT_THREADS) g_k3_trace[blockIdx.x * 8 * 64 + i] = k3_trace_smem[i];
+#endif
   if (warp == KT_EPI_WARPS) tmem_dealloc(tmem_base, ncols);
 }
 
@@ -389,7 +436,7 @@ static bool plan_tma(const ConvGeom& g, TmaPlan& tp) {
   tp.MT = 128;
   if (count_items(128) * g.ntiles_n < sms && count_items(64) > count_items(128) && (tp.ntaps == 1 || tp.WB <= 16)) tp.MT = 64;
   const int accw = (tp.ntaps == 9 ? 3 : 1) * g.NT;
-  if (accw > 512) return false;
+  if (accw > 256) return false;                              // one MMA spans the accumulator row (N <= 256)
   tp.nacc = 2 * accw <= 512 ? 2 : 1;
   tp.APT = tp.MT / 32;
   tp.rows_st = tp.APT + (tp.mode == 0 ? 2 : 0);
@@ -424,10 +471,22 @@ static bool plan_tma(const ConvGeom& g, TmaPlan& tp) {
   }
   const size_t fixed = (size_t)g.b_slab_bytes + 1024 + (2 * K3_MAX_STAGES + 8) * 8 + 64;
   if (fixed + 2 * (size_t)tp.stage_bytes > KT_SMEM_BUDGET) return false;
-  int nst = (int)((KT_SMEM_BUDGET - fixed) / tp.stage_bytes);
+  // Two CTAs per SM when both fit (shared memory, 2 x TMEM columns <= 512) and there are tiles for them: the
+  // kernel is bound by the serial latency of its single-thread roles (mbarrier waits, MMA issue), which a
+  // second resident CTA hides.
+  uint32_t ncols = 32;
+  while (ncols < (uint32_t)(tp.nacc * accw)) ncols <<= 1;
+  size_t budget = KT_SMEM_BUDGET;
+  tp.cps = 1;
+  if (fixed + 3 * (size_t)tp.stage_bytes <= KT_SMEM_BUDGET_2 && 2 * ncols <= 512 && tp.nitems_m * g.ntiles_n > sms &&
+      !(getenv("PO2_TMA_CPS") && getenv("PO2_TMA_CPS")[0] == '1')) {
+    tp.cps = 2;
+    budget = KT_SMEM_BUDGET_2;
+  }
+  int nst = (int)((budget - fixed) / tp.stage_bytes);
   if (nst > K3_MAX_STAGES) nst = K3_MAX_STAGES;
   tp.nst = nst;
-  int per_n = sms / g.ntiles_n;
+  int per_n = tp.cps * sms / g.ntiles_n;
   if (per_n < 1) per_n = 1;
   tp.m_step = tp.nitems_m < per_n ? tp.nitems_m : per_n;
   tp.div_ncol = make_fastdiv((uint32_t)(tp.ncol > 0 ? tp.ncol : 1));
@@ -467,6 +526,11 @@ static bool encode_x_map(CUtensorMap* tm, const void* x, const ConvGeom& g, cons
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+static bool tma_takes(const ConvGeom& g) {
+  TmaPlan tp;
+  return g.tf32 && tma_enabled() && plan_tma(g, tp);
+}
+
 // the conv launch behind the packed operand (same contract as the register-fed launch in launch_umma)
 static int launch_tma(const void* x, const uint8_t* Bp, const float* scale, void* out, const ConvGeom& g, const TmaPlan& tp,
                       cudaStream_t st, bool pdl) {
@@ -477,6 +541,8 @@ static int launch_tma(const void* x, const uint8_t* Bp, const float* scale, void
     const int smax = (int)KT_SMEM_BUDGET + 1024;
     cudaError_t a = cudaFuncSetAttribute(conv_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
     if (a == cudaSuccess) a = cudaFuncSetAttribute(conv_tma_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+    if (a == cudaSuccess) a = cudaFuncSetAttribute(conv_tma_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (a == cudaSuccess) a = cudaFuncSetAttribute(conv_tma_kernel<9>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     return a;
   });
   if (e != cudaSuccess) return (int)e;

@@ -509,7 +509,9 @@ __device__ __forceinline__ void pack_vec(const PackArgs& pk, const uint4& o, int
     const float yv = __uint_as_float(ob[j]);
     const float r = (s == 1.0f) ? yv : __fdiv_rn(yv, s);
     const int cg = pk.G == 8 ? (c >> 3) : (c >> 2), cj = c & (pk.G - 1);
-    const size_t idx = ((((size_t)nt * pk.taps + tap) * pk.ncg + cg) * pk.NT + n) * pk.G + cj;
+    const size_t idx = pk.tapminor
+        ? (((((size_t)nt * 3 + tap / 3) * pk.ncg + cg) * 3 + tap % 3) * pk.NT + n) * pk.G + cj
+        : ((((size_t)nt * pk.taps + tap) * pk.ncg + cg) * pk.NT + n) * pk.G + cj;
     if (pk.G == 8) reinterpret_cast<__nv_bfloat16*>(pk.Bp)[idx] = __float2bfloat16_rn(r);
     else reinterpret_cast<float*>(pk.Bp)[idx] = r;
   }

@@ -68,12 +68,14 @@ def release_workspaces() -> None:
 LAUNCHES = 0
 
 
-# "tc": tcgen05 tensor cores with bf16 operands where the shape allows (default); "tf32": the same
-# kernel with tf32 operands (activations keep 10 mantissa bits, the precision of the reference's own
-# cuDNN default); "fp32": CUDA-core fp32 FMA everywhere (the fp32-accumulate parity mode); "cudnn":
-# leave the convolution to F.conv2d.
+# "tf32" (default): tcgen05 tensor cores with tf32 operands -- the arithmetic of the reference's own cuDNN
+# default on a GPU (activations keep 10 mantissa bits, PO2 weights exact); the stride-1 dense layers run on
+# the TMA-fed kernel (csrc/po2_conv_tma.cuh: fp32 NCHW tiles staged by tensor-map TMA, no conversion pass).
+# "tc": the register-fed kernel with bf16 operands (activations rounded to 8 mantissa bits; opt-in).
+# "fp32": CUDA-core fp32 FMA everywhere (the fp32-accumulate parity mode); "cudnn": leave the convolution
+# to F.conv2d.
 COMPUTE = {"tc": 0, "fp32": 1, "tf32": 2}
-_conv_mode = os.environ.get("PO2_CONV", "tc")
+_conv_mode = os.environ.get("PO2_CONV", "tf32")
 
 
 def set_conv_mode(mode: str) -> None:
@@ -395,9 +397,11 @@ def _conv_backward(g, x, w, scale, stride, pad, groups, compute, need_x, need_w)
             cand = torch.empty_like(x)
             if conv2d_dgrad_out(g, w, scale, cand, pad, compute):
                 gx = cand
-        if need_w and ours and _wgrad_mode == "tc" and compute == 0:
+        if need_w and ours and _wgrad_mode == "tc":
             cand = torch.empty_like(w)
-            if conv2d_wgrad_out(g, x.contiguous(), cand, pad, compute):
+            # the weight gradient is a leaf of the backward pass (its rounding does not propagate into other
+            # layers' gradients, unlike the data gradient), so the tf32 mode shares the bf16-operand kernel
+            if conv2d_wgrad_out(g, x.contiguous(), cand, pad, 0):
                 gw = cand
     if (need_x and gx is None) or (need_w and gw is None):
         gx2, gw2, _ = torch.ops.aten.convolution_backward(

@@ -93,6 +93,9 @@ def main():
              "compute": a.compute,
              "kernel_kind": lib.po2_conv2d_kernel_kind(B, C, H, W, K, k, k, stride, pad, groups, a.compute)}
         cands = {"po2_tc": lambda: ops.conv2d_out(x, y, scale, out, stride, pad, groups, a.compute)}
+        packed = ops.conv2d_pack(y, scale, x.shape, stride, pad, groups, a.compute)
+        if packed is not None:     # static weights (PTQ) / multi-tensor prefetch (QAT): the conv kernel alone
+            cands["po2_packed"] = lambda: torch.ops.po2.conv2d_packed(x, packed, scale, K, k, k, stride, pad, groups, a.compute)
         torch.backends.cudnn.allow_tf32 = False
         ref = F.conv2d(x, y, None, stride, pad, 1, groups)
         cands["po2_tc"]()
@@ -110,10 +113,13 @@ def main():
         r["io_GBs_po2_tc_cold"] = bytes_io / r["us_po2_tc_cold"] / 1e3
         r["io_GBs_cudnn_cold"] = bytes_io / r["us_cudnn_tf32_cold"] / 1e3
         rows.append(r)
-        print(json.dumps({k_: (round(v, 2) if isinstance(v, float) else v) for k_, v in r.items()}), flush=True)
+        r["max_rel_err_vs_fp32"] = ((out.double() - ref.double()).abs().max() / ref.double().abs().max()).item()
+        print(json.dumps({k_: (round(v, 5 if "err" in k_ else 2) if isinstance(v, float) else v) for k_, v in r.items()}), flush=True)
     tot = lambda key: sum(r[key] * r["count_r56"] for r in rows)
+    tot = lambda key: sum(r.get(key, 0.0) * r["count_r56"] for r in rows)
     summ = {"resnet56_forward_qconv_us": {k_: round(tot(k_), 1) for k_ in
-            ("us_po2_tc_cold", "us_po2_tc_warm", "us_cudnn_tf32_cold", "us_cudnn_tf32_warm")}}
+            ("us_po2_tc_cold", "us_po2_tc_warm", "us_po2_packed_cold", "us_po2_packed_warm", "us_cudnn_tf32_cold",
+             "us_cudnn_tf32_warm")}}
     print(json.dumps(summ))
     if a.out:
         json.dump({"rows": rows, **summ}, open(a.out, "w"), indent=1)
