@@ -214,6 +214,14 @@ int po2_bn_apply(const void* x, const void* residual, void* y, const float* stat
                  float* stats_dense, const float* gamma, const float* beta, float* running_mean,
                  float* running_var, long long* num_batches_tracked, float momentum, float eps, int act,
                  int use_running, float* save_mean, float* save_invstd, int B, int C, int HW, void* stream);
+/* The backward of FusedSyncBatchNorm as ONE launch (one rank; tensors that fit the CTAs' registers, the same
+ * condition as po2_bn_fwd_fused): per-channel sums of the activation-masked gradient, dgamma / dbeta, dx and
+ * the masked gradient of the residual branch (dres, may be NULL) -- models/resnet.py:55-71 under autograd.
+ * Returns PO2_E_UNSUPPORTED when the pair po2_bn_bwd_reduce + po2_bn_bwd_apply has to be used. */
+int po2_bn_bwd_fused(const void* dy, const void* x, const void* y, const float* save_mean, const float* save_invstd,
+                     const float* gamma, float* dgamma, float* dbeta, void* dx, void* dres, int act, int B, int C, int HW,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
 /* po2_bn_stats + po2_bn_apply in ONE launch for tensors whose per-channel slice fits the registers of
  * the CTAs working on it (the CIFAR-scale layers): x is read once, the CTAs of a channel meet at a
  * barrier in the workspace, statistics are combined (through the mailboxes when world > 1) and y is

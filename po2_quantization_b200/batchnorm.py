@@ -7,6 +7,7 @@ block so that ``relu(bn(x) + shortcut)`` is one streaming pass forward and one b
 
     forward :  bn_stats  -> [all_gather of 2C+1 statistics when world_size > 1] -> bn_apply
     backward:  bn_bwd_reduce -> [all_reduce of 2C sums]                         -> bn_bwd_apply
+               (one rank, small tensors: ONE launch, po2_bn_bwd_fused)
 
 The collective sits exactly where torch's SyncBatchNorm has it (same algebra: per-rank mean / M2 /
 count combined with the parallel-variance formula; gradient of the affine parameters from local
@@ -200,6 +201,25 @@ def bn_fwd_fused_out(x, residual, y, weight, bias, running_mean, running_var, nu
     return True
 
 
+def bn_bwd_fused_out(dy, x, y, save_mean, save_invstd, weight, dgamma, dbeta, dx, dres, relu) -> bool:
+    """sums + apply of the backward in one launch (one rank, tensors that fit the registers of their CTAs);
+    False if the shape is not taken"""
+    if os.environ.get("PO2_BN_FUSED", "1") != "1" or os.environ.get("PO2_BN_FUSED_BWD", "1") != "1":
+        return False
+    B, C = x.shape[0], x.shape[1]
+    HW = x.numel() // (B * C)
+    ws = _bn_workspace(x.device, C)
+    rc = _lib.load().po2_bn_bwd_fused(
+        dy.data_ptr(), x.data_ptr(), _ptr(y), save_mean.data_ptr(), save_invstd.data_ptr(), _ptr(weight),
+        _ptr(dgamma), _ptr(dbeta), dx.data_ptr(), _ptr(dres), int(relu), B, C, HW, ws.data_ptr(), ws.numel(),
+        ops._stream_ptr(x.device))
+    if rc == -10:
+        return False
+    _lib.check(rc, "po2_bn_bwd_fused")
+    ops.LAUNCHES += 1
+    return True
+
+
 def bn_bwd_reduce_out(dy, x, y, save_mean, save_invstd, sums, dgamma, dbeta, relu, exch=None) -> None:
     B, C = x.shape[0], x.shape[1]
     HW = x.numel() // (B * C)
@@ -276,18 +296,21 @@ class _BatchNormTrain(torch.autograd.Function):
         need_x, need_res, need_w, need_b = ctx.needs_input_grad[:4]
         exch = ctx.exch if ctx.world > 1 else None
         with torch.cuda.device(x.device):
-            sums = torch.empty(2 * C, dtype=torch.float32, device=x.device)
             dgamma = torch.empty(C, dtype=torch.float32, device=x.device) if weight is not None else None
             dbeta = torch.empty(C, dtype=torch.float32, device=x.device) if weight is not None else None
-            bn_bwd_reduce_out(dy, x, y, save_mean, save_invstd, sums, dgamma, dbeta, ctx.relu, exch)
-            if ctx.world > 1 and exch is None:
-                dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=ctx.group)
             dx = torch.empty_like(x)
             dres = None
             if ctx.has_res and need_res:
                 dres = torch.empty_like(x) if ctx.relu else dy       # without the ReLU the branch gets dy itself
-            bn_bwd_apply_out(dy, x, y, save_mean, save_invstd, weight, sums, stats, dx,
-                             dres if ctx.relu else None, ctx.relu, exch)
+            # one rank, small tensor: sums + apply as ONE launch (dy / x / y read once)
+            if not (ctx.world == 1 and bn_bwd_fused_out(dy, x, y, save_mean, save_invstd, weight, dgamma, dbeta, dx,
+                                                        dres if ctx.relu else None, ctx.relu)):
+                sums = torch.empty(2 * C, dtype=torch.float32, device=x.device)
+                bn_bwd_reduce_out(dy, x, y, save_mean, save_invstd, sums, dgamma, dbeta, ctx.relu, exch)
+                if ctx.world > 1 and exch is None:
+                    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=ctx.group)
+                bn_bwd_apply_out(dy, x, y, save_mean, save_invstd, weight, sums, stats, dx,
+                                 dres if ctx.relu else None, ctx.relu, exch)
         return (dx if need_x else None, dres, dgamma if need_w else None, dbeta if need_b else None,
                 None, None, None, None, None, None, None, None, None)
 

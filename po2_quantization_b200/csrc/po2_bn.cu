@@ -708,6 +708,96 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_fwd_fused_kernel(const float
   }
 }
 
+
+// ---- fused backward for tensors that fit in registers (one rank) -------------------------------------------
+// Sums and apply in ONE launch, the mirror image of bn_fwd_fused_kernel: CTA (s, c) loads its slabs of
+// dy (masked by the activation's open interval on y), and x once into registers, the S CTAs of a channel
+// meet at the per-channel barrier, every CTA combines the channel's sums and writes dx (and the masked
+// gradient of the residual branch) from its registers.  dy / x / y are read once instead of twice.
+__global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_fused_kernel(const float* __restrict__ dy,
+                                                                     const float* __restrict__ x,
+                                                                     const float* __restrict__ y,
+                                                                     const float* __restrict__ mean,
+                                                                     const float* __restrict__ invstd,
+                                                                     const float* __restrict__ gamma,
+                                                                     float* __restrict__ dgamma,
+                                                                     float* __restrict__ dbeta,
+                                                                     float* __restrict__ dx,
+                                                                     float* __restrict__ dres, int act, BnGeom g,
+                                                                     BnWorkspace ws) {
+  __shared__ double sm[BN_THREADS / 32][2];
+  __shared__ int s_ok;
+  const int s = blockIdx.x, c = blockIdx.y, C = g.C, L = g.L;
+  const int nslab = (g.B - s + g.S - 1) / g.S;
+  const int n = nslab * L;
+  const float mu = __ldg(mean + c);
+  // ---- phase 1: masked gradient and x into registers, local sums
+  float4 vg[BN_FUSED_R], vx[BN_FUSED_R];
+  int off[BN_FUSED_R];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int u = 0; u < BN_FUSED_R; ++u) {
+    const int i = threadIdx.x + u * BN_THREADS;
+    vg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    vx[u] = make_float4(mu, mu, mu, mu);
+    off[u] = 0;
+    if (i < n) {
+      const int k = fdiv(i, g.div_l);
+      off[u] = ((s + k * g.S) * C + c) * L + (i - k * L);
+      vg[u] = __ldg(reinterpret_cast<const float4*>(dy) + off[u]);
+      vx[u] = __ldg(reinterpret_cast<const float4*>(x) + off[u]);
+      if (act) {
+        const float4 vy = __ldg(reinterpret_cast<const float4*>(y) + off[u]);
+        vg[u].x = bn_act_open(vy.x, act) ? vg[u].x : 0.f; vg[u].y = bn_act_open(vy.y, act) ? vg[u].y : 0.f;
+        vg[u].z = bn_act_open(vy.z, act) ? vg[u].z : 0.f; vg[u].w = bn_act_open(vy.w, act) ? vg[u].w : 0.f;
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < BN_FUSED_R; ++u) {
+    s1 += (vg[u].x + vg[u].y) + (vg[u].z + vg[u].w);
+    s2 = fmaf(vg[u].x, vx[u].x - mu, s2); s2 = fmaf(vg[u].y, vx[u].y - mu, s2);
+    s2 = fmaf(vg[u].z, vx[u].z - mu, s2); s2 = fmaf(vg[u].w, vx[u].w - mu, s2);
+  }
+  double a = (double)s1, b = (double)s2;
+  block_sum2(a, b, sm);
+  if (threadIdx.x == 0) ws.partial[c * BN_MAX_SPLIT + s] = make_double2(a, b);
+  const bool barrier_ok = channel_barrier(ws, c, g.S, nullptr, &s_ok);
+  // ---- phase 2: the channel's sums (every CTA of the channel computes the same numbers)
+  double pa = 0.0, pb = 0.0;
+  if ((int)threadIdx.x < g.S) {
+    const double2 p = __ldcg(ws.partial + c * BN_MAX_SPLIT + threadIdx.x);
+    pa = p.x; pb = p.y;
+  }
+  block_sum2(pa, pb, sm);                                   // valid in warp 0: broadcast through shared memory
+  __shared__ double s_tot[2];
+  if (threadIdx.x == 0) { s_tot[0] = pa; s_tot[1] = pb; }
+  __syncthreads();
+  pa = s_tot[0]; pb = s_tot[1];
+  const double is = (double)__ldg(invstd + c), M = (double)g.B * (double)g.HW;
+  const float sg = (float)pa, sgx = (float)pb;              // the values the two-kernel form passes through `sums`
+  if (s == 0 && threadIdx.x == 0) {
+    if (dbeta) dbeta[c] = sg;
+    if (dgamma) dgamma[c] = (float)(pb * is);
+  }
+  const float ga = gamma ? __ldg(gamma + c) : 1.0f;
+  float p_y = (float)((double)sg / M), p_z = (float)(is * is * (double)sgx / M);
+  const float p_w = (float)((double)ga * is);
+  if (!barrier_ok) p_y = __uint_as_float(0x7FC00000u);      // incomplete sums must not pass for a result
+  // ---- phase 3: dx from the registers
+#pragma unroll
+  for (int u = 0; u < BN_FUSED_R; ++u) {
+    const int i = threadIdx.x + u * BN_THREADS;
+    if (i < n) {
+      float4 o;
+      o.x = (vg[u].x - p_y - (vx[u].x - mu) * p_z) * p_w; o.y = (vg[u].y - p_y - (vx[u].y - mu) * p_z) * p_w;
+      o.z = (vg[u].z - p_y - (vx[u].z - mu) * p_z) * p_w; o.w = (vg[u].w - p_y - (vx[u].w - mu) * p_z) * p_w;
+      reinterpret_cast<float4*>(dx)[off[u]] = o;
+      if (dres) reinterpret_cast<float4*>(dres)[off[u]] = vg[u];
+    }
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------
 static int bn_sms() { return device_sm_count(); }        // per device (po2_common.cuh)
 
@@ -871,6 +961,41 @@ int po2_bn_fwd_fused(const void* x, const void* residual, void* y, const float* 
   void* args[] = {&xf, &rf, &yf, &gamma, &beta, &running_mean, &running_var, &num_batches_tracked, &momentum, &eps, &act,
                   &save_mean, &save_invstd, &stats_dense, &g, &wsv, &pr};
   const cudaError_t e = cudaLaunchCooperativeKernel((const void*)bn_fwd_fused_kernel, dim3(g.S, C), dim3(BN_THREADS), args, 0,
+                                                    (cudaStream_t)stream);
+  if (e == cudaErrorCooperativeLaunchTooLarge) {
+    (void)cudaGetLastError();
+    return PO2_E_UNSUPPORTED;
+  }
+  return (int)e;
+}
+
+// Backward of the same layer as ONE launch (one rank, tensors that fit the CTAs' registers): sums + apply.
+// PO2_E_UNSUPPORTED: take po2_bn_bwd_reduce + po2_bn_bwd_apply.
+int po2_bn_bwd_fused(const void* dy, const void* x, const void* y, const float* save_mean, const float* save_invstd,
+                     const float* gamma, float* dgamma, float* dbeta, void* dx, void* dres, int act, int B, int C, int HW,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  if (!dy || !x || !save_mean || !save_invstd || !dx || !workspace) return PO2_E_NULL;
+  if (act < 0 || act > 2) return PO2_E_MODE;               // SiLU (3) has no backward here
+  if (act != 0 && !y) return PO2_E_NULL;
+  if (workspace_bytes < po2_bn_workspace_bytes(C)) return PO2_E_WORKSPACE;
+  if (!aligned16(workspace)) return PO2_E_ALIGN;
+  BnGeom g;
+  const int v = bn_geom(g, B, C, HW, aligned16(dy) && aligned16(x) && aligned16(y) && aligned16(dx) && aligned16(dres));
+  if (v < 0) return v;
+  if (v == 0) return PO2_E_UNSUPPORTED;                                   // 128-bit path only
+  const int64_t per_cta = (int64_t)BN_FUSED_R * BN_THREADS;
+  int64_t need_s = ((int64_t)B * g.L + per_cta - 1) / per_cta;
+  for (int attempt = 0; attempt < 2; ++attempt, ++need_s) {
+    if (need_s > BN_MAX_SPLIT || need_s > B || need_s * C > 2 * (int64_t)bn_sms()) return PO2_E_UNSUPPORTED;
+    if ((int64_t)((B + need_s - 1) / need_s) * g.L <= per_cta) break;     // slabs are dealt round-robin: largest share fits
+    if (attempt == 1) return PO2_E_UNSUPPORTED;
+  }
+  g.S = (int)need_s;
+  BnWorkspace wsv = bn_ws(workspace, C);
+  const float *df = (const float*)dy, *xf = (const float*)x, *yf = (const float*)y;
+  float *dxf = (float*)dx, *drf = (float*)dres;
+  void* args[] = {&df, &xf, &yf, &save_mean, &save_invstd, &gamma, &dgamma, &dbeta, &dxf, &drf, &act, &g, &wsv};
+  const cudaError_t e = cudaLaunchCooperativeKernel((const void*)bn_bwd_fused_kernel, dim3(g.S, C), dim3(BN_THREADS), args, 0,
                                                     (cudaStream_t)stream);
   if (e == cudaErrorCooperativeLaunchTooLarge) {
     (void)cudaGetLastError();

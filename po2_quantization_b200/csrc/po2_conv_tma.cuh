@@ -58,6 +58,7 @@ struct TmaPlan {
   int NCGS, nchunk;          // 8-channel groups per pipeline stage, stages per tile
   int nst;
   int cps;                   // CTAs per SM the plan was sized for (2 when two CTAs' shared memory and TMEM fit)
+  int pdl;                   // launched with programmatic stream serialization behind the weight-pack kernel
   int debug;                 // PO2_TMA_DEBUG bit mask (1: no TMA loads, 2: no MMAs, 4: no descriptor prefetch)
   int HW, Himg, Wimg;        // image geometry (ConvGeom's H/W are flattened for 1x1 layers)
   uint32_t stage_bytes, cg_bytes;                 // per stage / per channel group (modes 0-2)
@@ -148,7 +149,20 @@ __global__ void __launch_bounds__(KT_THREADS, 2) conv_tma_kernel(const __grid_co
   }
   uint32_t tmem_base = 0;
   if (warp == KT_EPI_WARPS) {
+    // The weight slab is the longest single transfer of a CTA: it goes out before the TMEM allocation --
+    // unless this grid was launched programmatically behind the kernel that packs the slab, in which case
+    // the allocation overlaps that kernel and the copy waits for its completion.
+    if (!tp.pdl && lane == 0) {
+      mbar_expect_tx(bfull, g.b_slab_bytes);
+      bulk_g2s(sB, Bp + (size_t)nt * g.b_slab_bytes, g.b_slab_bytes, bfull);
+    }
+    __syncwarp();
     tmem_alloc(tmem_slot, ncols);
+    if (tp.pdl && lane == 0) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");       // the weight-pack kernel has completed and flushed
+      mbar_expect_tx(bfull, g.b_slab_bytes);
+      bulk_g2s(sB, Bp + (size_t)nt * g.b_slab_bytes, g.b_slab_bytes, bfull);
+    }
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(tready);
@@ -214,11 +228,6 @@ __global__ void __launch_bounds__(KT_THREADS, 2) conv_tma_kernel(const __grid_co
   } else if (warp == KT_EPI_WARPS) {
     // =========================== MMA issuer ===========================
     const bool leader = elect_one();
-    if (leader) {
-      asm volatile("griddepcontrol.wait;" ::: "memory");       // the weight-pack kernel has completed and flushed
-      mbar_expect_tx(bfull, g.b_slab_bytes);
-      bulk_g2s(sB, Bp + (size_t)nt * g.b_slab_bytes, g.b_slab_bytes, bfull);
-    }
     mbar_wait(bfull, 0);
     if (leader) K3_TRACE(3, 0);
     const uint32_t idesc = make_idesc_tma((uint32_t)tp.MT, acc_cols);        // N = NT, or 3 * NT (3x3: [s][n])
@@ -532,8 +541,10 @@ static bool tma_takes(const ConvGeom& g) {
 }
 
 // the conv launch behind the packed operand (same contract as the register-fed launch in launch_umma)
-static int launch_tma(const void* x, const uint8_t* Bp, const float* scale, void* out, const ConvGeom& g, const TmaPlan& tp,
+static int launch_tma(const void* x, const uint8_t* Bp, const float* scale, void* out, const ConvGeom& g, const TmaPlan& tp_in,
                       cudaStream_t st, bool pdl) {
+  TmaPlan tp = tp_in;
+  tp.pdl = pdl ? 1 : 0;
   CUtensorMap tm;
   if (!encode_x_map(&tm, x, g, tp)) return PO2_E_UNSUPPORTED;
   static PerDeviceOnce attr_once;
