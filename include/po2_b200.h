@@ -161,6 +161,17 @@ int po2_multi_desc_fill(void* host_table, int index, const void* w, void* qw_out
                         int groups, int bits, int fsr, int mode, int flavor, int compute, double* sse_out);
 int po2_quantize_pack_multi(const void* device_table, int ntensors, int cluster_size, void* stream);
 
+/* The data-gradient operand packed ahead of time: po2_multi_desc_fill_dgrad amends entry `index` of a
+ * MultiDesc table so that the multi-tensor quantizer launch of the FORWARD pass also emits the operand of
+ * the layer's data-gradient conv (in/out channels swapped, taps rotated; po2_conv2d_dgrad_pack_bytes bytes,
+ * 0 = shape not taken); po2_conv2d_dgrad_packed then computes gx = dL/dx in one launch (autograd of
+ * models/quantized_conv.py:36 for the stride-1 dense layers). */
+size_t po2_conv2d_dgrad_pack_bytes(int B, int C, int H, int W, int K, int R, int S, int pad, int compute);
+int po2_multi_desc_fill_dgrad(void* host_table, int index, void* packed_dgrad, size_t packed_bytes, int B, int C, int H,
+                              int W, int K, int R, int S, int stride, int pad, int groups, int compute);
+int po2_conv2d_dgrad_packed(const void* g, const void* packed, const float* scale, void* gx, int B, int C, int H,
+                            int W, int K, int R, int S, int pad, int compute, void* stream);
+
 /* Data gradient of the same conv (SURVEY.md section 8f "next" #2, first half): gx = dL/dx given g = dL/dout,
  * for the stride-1 dense shapes (3x3 pad 1, 1x1 pad 0), on the tensor-core kernel with the
  * channel-transposed, 180-degree-rotated PO2 weights (exact in bf16; g is rounded to bf16).

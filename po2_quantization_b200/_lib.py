@@ -41,6 +41,9 @@ SIGNATURES = {
     "po2_multi_desc_bytes": (_sz, []),
     "po2_multi_desc_fill": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _sz] + [_i] * 15 + [_vp]),
     "po2_quantize_pack_multi": (_i, [_vp, _i, _i, _vp]),
+    "po2_conv2d_dgrad_pack_bytes": (_sz, [_i] * 9),
+    "po2_multi_desc_fill_dgrad": (_i, [_vp, _i, _vp, _sz] + [_i] * 11),
+    "po2_conv2d_dgrad_packed": (_i, [_vp] * 4 + [_i] * 9 + [_vp]),
     "po2_conv2d_dgrad_workspace": (_sz, [_i] * 9),
     "po2_conv2d_dgrad": (_i, [_vp, _vp, _vp, _vp] + [_i] * 14 + [_vp, _sz, _vp]),
     "po2_conv2d_wgrad_workspace": (_sz, [_i] * 11),

@@ -114,6 +114,11 @@ struct PackArgs {
   int tapminor;              // 1 (3x3, TMA-fed conv): Bp[nt][r][c/G][s][n][G] -- the three filter columns of a row are
                              // consecutive N rows, so one MMA covers them (N = 3 * NT)
   FastDiv div_ct, div_t, div_nt;   // by C*taps, taps, NT
+  // second operand of the same weight: the DATA-GRADIENT conv's (in = K, out = C channels, taps rotated by 180
+  // degrees), so that backward needs no pack launch.  Bp2 == nullptr: off.
+  void* Bp2;
+  int NT2, ncg2, tapminor2;        // ncg2 = K / G
+  FastDiv div_nt2;
 };
 
 // quantize w (fp32, n = K*C*taps elements) into y + scale AND the packed operand, one launch

@@ -1472,7 +1472,7 @@ int po2_qconv2d_fwd(const void* x, const void* w_master, void* qw_out, float* sc
     const size_t wbytes = ((size_t)wn * sizeof(float) + 255) / 256 * 256;
     if (!workspace || workspace_bytes < need) return PO2_E_WORKSPACE;
     if ((int64_t)B * C * H * W >= (1ll << 31) || (int64_t)B * K * g.P * g.Q >= (1ll << 31)) return PO2_E_SIZE;
-    PackArgs pk;
+    PackArgs pk = {};
     pk.Bp = reinterpret_cast<char*>(workspace) + wbytes;
     pk.G = g.G; pk.C = C; pk.K = K; pk.taps = g.ntaps; pk.NT = g.NT; pk.ncg = C / g.G; pk.tapminor = g.tapminor;
     pk.div_ct = make_fastdiv((uint32_t)(C * g.ntaps));
@@ -1503,7 +1503,7 @@ int po2_quantize_pack(const void* w_master, void* qw_out, float* scale_out, void
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t wn = (int64_t)K * (C / groups) * R * S;
   if (g.Cpad == C && g.ntiles_n * g.NT == K) {
-    PackArgs pk;
+    PackArgs pk = {};
     pk.Bp = packed;
     pk.G = g.G; pk.C = C; pk.K = K; pk.taps = g.ntaps; pk.NT = g.NT; pk.ncg = C / g.G; pk.tapminor = g.tapminor;
     pk.div_ct = make_fastdiv((uint32_t)(C * g.ntaps));
@@ -1538,7 +1538,7 @@ int po2_multi_desc_fill(void* host_table, int index, const void* w_master, void*
   int csize = 1;
   while (csize < 8 && (int64_t)csize * cap < wn) csize <<= 1;
   if ((int64_t)csize * cap < wn) return PO2_E_UNSUPPORTED;                        // does not fit one cluster
-  MultiDesc d;
+  MultiDesc d = {};
   d.x = (const uint4*)w_master; d.y = (uint4*)qw_out; d.scale_out = scale_out; d.sse_out = sse_out; d.n = wn;
   d.bits = bits; d.fsr = fsr; d.mode = mode; d.flavor = flavor;
   d.pk.Bp = packed;
@@ -1552,6 +1552,50 @@ int po2_multi_desc_fill(void* host_table, int index, const void* w_master, void*
 
 int po2_quantize_pack_multi(const void* device_table, int ntensors, int cluster_size, void* stream) {
   return multi_fused_launch((const MultiDesc*)device_table, ntensors, cluster_size, (cudaStream_t)stream);
+}
+
+// ---- the data-gradient operand packed ahead of time (by the multi-tensor quantizer of the forward pass) ----
+// geometry of the data-gradient conv of a stride-1 dense layer: in = K channels, out = C channels
+static bool dgrad_geom(ConvGeom& g, int B, int C, int H, int W, int K, int R, int S, int pad, int compute) {
+  if (compute == 1) return false;
+  if (!((R == 3 && S == 3 && pad == 1) || (R == 1 && S == 1 && pad == 0))) return false;
+  if (!fill_geom(g, B, K, H, W, C, R, S, 1, pad, 1)) return false;
+  if ((int64_t)B * C * H * W >= (1ll << 31) || (int64_t)B * K * H * W >= (1ll << 31)) return false;
+  return plan_umma(g, compute == 2);
+}
+
+size_t po2_conv2d_dgrad_pack_bytes(int B, int C, int H, int W, int K, int R, int S, int pad, int compute) {
+  ConvGeom g;
+  if (!dgrad_geom(g, B, C, H, W, K, R, S, pad, compute)) return 0;
+  if (!(g.Cpad == K && g.ntiles_n * g.NT == C)) return 0;                 // the fused emitter writes no padding
+  return (umma_pack_bytes(g) + 255) / 256 * 256;
+}
+
+// amend entry `index` of a MultiDesc table (after po2_multi_desc_fill): also emit the data-gradient operand
+int po2_multi_desc_fill_dgrad(void* host_table, int index, void* packed_dgrad, size_t packed_bytes, int B, int C, int H,
+                              int W, int K, int R, int S, int stride, int pad, int groups, int compute) {
+  if (!host_table || index < 0 || !packed_dgrad) return PO2_E_NULL;
+  if (stride != 1 || groups != 1) return PO2_E_UNSUPPORTED;
+  ConvGeom g;
+  if (!dgrad_geom(g, B, C, H, W, K, R, S, pad, compute)) return PO2_E_UNSUPPORTED;
+  if (!(g.Cpad == K && g.ntiles_n * g.NT == C)) return PO2_E_UNSUPPORTED;
+  if (packed_bytes < umma_pack_bytes(g)) return PO2_E_WORKSPACE;
+  MultiDesc& d = reinterpret_cast<MultiDesc*>(host_table)[index];
+  if (d.pk.G != g.G || d.pk.taps != g.ntaps) return PO2_E_SHAPE;
+  d.pk.Bp2 = packed_dgrad;
+  d.pk.NT2 = g.NT; d.pk.ncg2 = K / g.G; d.pk.tapminor2 = g.tapminor;
+  d.pk.div_nt2 = make_fastdiv((uint32_t)g.NT);
+  return 0;
+}
+
+// gx = dL/dx from g = dL/dout and the pre-packed data-gradient operand: one launch
+int po2_conv2d_dgrad_packed(const void* g_out, const void* packed, const float* scale, void* gx, int B, int C, int H,
+                            int W, int K, int R, int S, int pad, int compute, void* stream) {
+  if (!g_out || !packed || !gx) return PO2_E_NULL;
+  ConvGeom g;
+  if (!dgrad_geom(g, B, C, H, W, K, R, S, pad, compute)) return PO2_E_UNSUPPORTED;
+  return launch_umma(g_out, nullptr, scale, gx, g, PO2_W_F32_PO2, 4, 1, -1, const_cast<void*>(packed), (cudaStream_t)stream,
+                     /*pdl=*/false);
 }
 
 size_t po2_conv2d_dgrad_workspace(int B, int C, int H, int W, int K, int R, int S, int pad, int compute) {

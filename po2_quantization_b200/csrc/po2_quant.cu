@@ -514,6 +514,18 @@ __device__ __forceinline__ void pack_vec(const PackArgs& pk, const uint4& o, int
         : ((((size_t)nt * pk.taps + tap) * pk.ncg + cg) * pk.NT + n) * pk.G + cj;
     if (pk.G == 8) reinterpret_cast<__nv_bfloat16*>(pk.Bp)[idx] = __float2bfloat16_rn(r);
     else reinterpret_cast<float*>(pk.Bp)[idx] = r;
+    if (pk.Bp2) {
+      // data-gradient operand: out channel = c, in channel = k, tap rotated (csrc/po2_conv.cu, transpose)
+      const int tap2 = pk.taps - 1 - tap;
+      const int nt2 = fdiv(c, pk.div_nt2);
+      const int n2 = c - nt2 * pk.NT2;
+      const int cg2 = pk.G == 8 ? (k >> 3) : (k >> 2), cj2 = k & (pk.G - 1);
+      const size_t idx2 = pk.tapminor2
+          ? (((((size_t)nt2 * 3 + tap2 / 3) * pk.ncg2 + cg2) * 3 + tap2 % 3) * pk.NT2 + n2) * pk.G + cj2
+          : ((((size_t)nt2 * pk.taps + tap2) * pk.ncg2 + cg2) * pk.NT2 + n2) * pk.G + cj2;
+      if (pk.G == 8) reinterpret_cast<__nv_bfloat16*>(pk.Bp2)[idx2] = __float2bfloat16_rn(r);
+      else reinterpret_cast<float*>(pk.Bp2)[idx2] = r;
+    }
   }
 }
 

@@ -385,7 +385,18 @@ def conv2d_wgrad_out(g, x, gw, pad, compute: int = 0) -> bool:
     return True
 
 
-def _conv_backward(g, x, w, scale, stride, pad, groups, compute, need_x, need_w):
+def conv2d_dgrad_packed_out(g, packed, scale, gx, wshape, pad, compute) -> None:
+    """gx = dL/dx from the data-gradient operand the forward's multi-tensor quantizer already packed: one launch"""
+    global LAUNCHES
+    B, C, H, W_ = gx.shape
+    K, _, R, S = wshape
+    LAUNCHES += 1
+    _lib.check(_lib.load().po2_conv2d_dgrad_packed(g.data_ptr(), packed.data_ptr(), scale.data_ptr(), gx.data_ptr(),
+                                                   B, C, H, W_, K, R, S, pad, compute, _stream_ptr(g.device)),
+               "po2_conv2d_dgrad_packed")
+
+
+def _conv_backward(g, x, w, scale, stride, pad, groups, compute, need_x, need_w, packed_d=None):
     """(gx, gw) of conv2d(x, w): the stride-1 dense layers on the tcgen05 kernels (data gradient:
     forward kernel with transposed weights; weight gradient: conv_wgrad_umma_kernel), everything else
     through aten.convolution_backward."""
@@ -395,7 +406,10 @@ def _conv_backward(g, x, w, scale, stride, pad, groups, compute, need_x, need_w)
     with torch.cuda.device(x.device):
         if need_x and ours and _dgrad_mode == "tc" and scale is not None:
             cand = torch.empty_like(x)
-            if conv2d_dgrad_out(g, w, scale, cand, pad, compute):
+            if packed_d is not None:
+                conv2d_dgrad_packed_out(g, packed_d, scale, cand, w.shape, pad, compute)
+                gx = cand
+            elif conv2d_dgrad_out(g, w, scale, cand, pad, compute):
                 gx = cand
         if need_w and ours and _wgrad_mode == "tc":
             cand = torch.empty_like(w)

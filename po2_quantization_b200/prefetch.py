@@ -23,7 +23,7 @@ from . import _lib, ops
 
 
 class _Slot:
-    __slots__ = ("key", "qw", "scale", "packed", "sse")
+    __slots__ = ("key", "qw", "scale", "packed", "sse", "packed_d")
 
 
 class _Table:
@@ -78,6 +78,11 @@ def prefetch_weights(modules: Iterable[torch.nn.Module]) -> int:
             slot.scale = torch.empty((), dtype=torch.float32, device=w.device)
             slot.packed = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
             slot.sse = torch.zeros((), dtype=torch.float64, device=w.device)   # sum((Q(w)-w)^2), refreshed by every launch
+            # the data-gradient conv's operand (stride-1 dense layers), emitted by the same launch
+            nd = 0
+            if m.stride[0] == 1 and m.groups == 1 and ops._dgrad_mode == "tc":
+                nd = int(lib.po2_conv2d_dgrad_pack_bytes(B, C, H, W_, K, R, S, m.padding[0], compute))
+            slot.packed_d = torch.empty(nd, dtype=torch.uint8, device=w.device) if nd else None
             slot.key = None
             m.__dict__["_po2_prefetch"] = slot
         if slot.key != key:
@@ -105,9 +110,18 @@ def prefetch_weights(modules: Iterable[torch.nn.Module]) -> int:
                 if rc == -10:
                     single.append(m)
                     slot.sse = None                              # po2_quantize_pack has no fused error output
+                    slot.packed_d = None
                     continue
                 if rc <= 0:
                     _lib.check(rc if rc < 0 else -6, "po2_multi_desc_fill")
+                if slot.packed_d is not None:
+                    rd = lib.po2_multi_desc_fill_dgrad(host.data_ptr(), len(multi), slot.packed_d.data_ptr(),
+                                                       slot.packed_d.numel(), B, C, H, W_, K, R, S, m.stride[0],
+                                                       m.padding[0], m.groups, compute)
+                    if rd == -10:
+                        slot.packed_d = None
+                    else:
+                        _lib.check(rd, "po2_multi_desc_fill_dgrad")
                 csize = max(csize, rc)
                 multi.append(m)
             tab = _Table()
@@ -140,10 +154,11 @@ class _QConvPrefetched(torch.autograd.Function):
     """conv2d(x, Q(weight)) from a prefetched (qw, scale, packed) triple; straight-through gradient"""
 
     @staticmethod
-    def forward(ctx, x, weight, qw, scale, packed, stride, pad, groups, compute):
+    def forward(ctx, x, weight, qw, scale, packed, stride, pad, groups, compute, packed_d):
         K, _, R, S = qw.shape
         out = ops.conv2d_packed(x, packed, scale, K, R, S, stride, pad, groups, compute)
         ctx.save_for_backward(x, qw, scale)
+        ctx.packed_d = packed_d          # valid until the next prefetch launch, i.e. through this step's backward
         ctx.cfg = (stride, pad, groups, compute)
         return out
 
@@ -152,8 +167,8 @@ class _QConvPrefetched(torch.autograd.Function):
         x, qw, scale = ctx.saved_tensors
         stride, pad, groups, compute = ctx.cfg
         gx, gw = ops._conv_backward(g, x, qw, scale, stride, pad, groups, compute, ctx.needs_input_grad[0],
-                                    ctx.needs_input_grad[1])
-        return gx, gw, None, None, None, None, None, None, None
+                                    ctx.needs_input_grad[1], packed_d=ctx.packed_d)
+        return gx, gw, None, None, None, None, None, None, None, None
 
 
 def try_prefetched_forward(m, x, mode):
@@ -162,7 +177,7 @@ def try_prefetched_forward(m, x, mode):
     if not slot or slot.key != _layer_key(m, x.shape, mode):
         return None
     return _QConvPrefetched.apply(x, m.weight, slot.qw, slot.scale, slot.packed, m.stride[0], m.padding[0], m.groups,
-                                  ops.COMPUTE[mode])
+                                  ops.COMPUTE[mode], getattr(slot, "packed_d", None))
 
 
 def enable_weight_prefetch(model: torch.nn.Module) -> torch.nn.Module:
