@@ -189,6 +189,10 @@ int po2_conv2d_dgrad(const void* g, const void* w, const float* scale, void* gx,
  * deterministic).  PO2_E_UNSUPPORTED for anything else (the caller keeps aten.convolution_backward). */
 size_t po2_conv2d_wgrad_workspace(int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups,
                                   int compute);
+/* planning query: 0 = shape not taken (the caller keeps aten.convolution_backward), 1 = tcgen05 kernel with
+ * bf16 operands, 2 = the TMA-fed tf32 kernel (compute == 2, dense stride-1 3x3 with W in {4,8,16,32} / 1x1) */
+int po2_conv2d_wgrad_kernel_kind(int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups,
+                                 int compute);
 int po2_conv2d_wgrad(const void* g, const void* x, void* gw, int B, int C, int H, int W, int K, int R, int S,
                      int stride, int pad, int groups, int compute, void* workspace, size_t workspace_bytes,
                      void* stream);

@@ -47,6 +47,7 @@ SIGNATURES = {
     "po2_conv2d_dgrad_workspace": (_sz, [_i] * 9),
     "po2_conv2d_dgrad": (_i, [_vp, _vp, _vp, _vp] + [_i] * 14 + [_vp, _sz, _vp]),
     "po2_conv2d_wgrad_workspace": (_sz, [_i] * 11),
+    "po2_conv2d_wgrad_kernel_kind": (_i, [_i] * 11),
     "po2_conv2d_wgrad": (_i, [_vp, _vp, _vp] + [_i] * 11 + [_vp, _sz, _vp]),
     "po2_lin_max_channel_elems": (_i, []),
     "po2_lin_quantize": (_i, [_vp, _vp] + [_i] * 7 + [_vp]),

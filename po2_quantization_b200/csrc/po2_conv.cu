@@ -1295,6 +1295,7 @@ static size_t wgrad_partial_bytes(const ConvGeom& g, const WgGeom& wg) {
 }
 
 }  // namespace po2
+#include "po2_wgrad_tma.cuh"   // K5T: the TMA-fed tf32 weight gradient
 
 using namespace po2;
 
@@ -1619,21 +1620,50 @@ static bool wgrad_plan(ConvGeom& g, WgGeom& wg, int B, int C, int H, int W, int 
   return plan_wgrad(g, wg);
 }
 
+// compute == 2 (tf32 operands): the TMA-fed kernel K5T where the shape allows, else the bf16-operand kernel
+// (the weight gradient is a leaf of the backward pass: its rounding does not propagate into other gradients)
+static bool wgrad_tma_plan(WgTmaPlan& wp, int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups,
+                           int compute) {
+  if (compute != 2 || stride != 1 || groups != 1 || !tma_enabled()) return false;
+  static const bool off = [] { const char* e = getenv("PO2_WGRAD_TMA"); return e && e[0] == '0'; }();
+  return !off && plan_wgrad_tma(wp, B, C, H, W, K, R, S, pad);
+}
+
 size_t po2_conv2d_wgrad_workspace(int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups,
                                   int compute) {
+  WgTmaPlan wp;
+  if (wgrad_tma_plan(wp, B, C, H, W, K, R, S, stride, pad, groups, compute))
+    return (wgrad_tma_partial_bytes(wp) + 255) / 256 * 256;
   ConvGeom g;
   WgGeom wg;
-  if (!wgrad_plan(g, wg, B, C, H, W, K, R, S, stride, pad, groups, compute)) return 0;
+  if (!wgrad_plan(g, wg, B, C, H, W, K, R, S, stride, pad, groups, compute == 2 ? 0 : compute)) return 0;
   return (wgrad_partial_bytes(g, wg) + 255) / 256 * 256;
+}
+
+// 0: not taken (aten), 1: bf16-operand tcgen05 kernel (K5), 2: TMA-fed tf32 kernel (K5T)
+int po2_conv2d_wgrad_kernel_kind(int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups,
+                                 int compute) {
+  WgTmaPlan wp;
+  if (wgrad_tma_plan(wp, B, C, H, W, K, R, S, stride, pad, groups, compute)) return 2;
+  ConvGeom g;
+  WgGeom wg;
+  return wgrad_plan(g, wg, B, C, H, W, K, R, S, stride, pad, groups, compute == 2 ? 0 : compute) ? 1 : 0;
 }
 
 int po2_conv2d_wgrad(const void* g_out, const void* x, void* gw, int B, int C, int H, int W, int K, int R, int S,
                      int stride, int pad, int groups, int compute, void* workspace, size_t workspace_bytes,
                      void* stream) {
   if (!g_out || !x || !gw) return PO2_E_NULL;
+  {
+    WgTmaPlan wp;
+    if (wgrad_tma_plan(wp, B, C, H, W, K, R, S, stride, pad, groups, compute)) {
+      if (!workspace || workspace_bytes < wgrad_tma_partial_bytes(wp)) return PO2_E_WORKSPACE;
+      return launch_wgrad_tma(g_out, x, gw, workspace, wp, (cudaStream_t)stream);
+    }
+  }
   ConvGeom g;
   WgGeom wg;
-  if (!wgrad_plan(g, wg, B, C, H, W, K, R, S, stride, pad, groups, compute)) return PO2_E_UNSUPPORTED;
+  if (!wgrad_plan(g, wg, B, C, H, W, K, R, S, stride, pad, groups, compute == 2 ? 0 : compute)) return PO2_E_UNSUPPORTED;
   const size_t need = wgrad_partial_bytes(g, wg);
   if (!workspace || workspace_bytes < need) return PO2_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;

@@ -179,10 +179,13 @@ __global__ void __launch_bounds__(KT_THREADS, 2) conv_tma_kernel(const __grid_co
     // =========================== TMA producer (one lane) ===========================
     // x was complete before the kernel in front of this one started (see launch_umma: programmatic
     // launch only behind our own pack / quantize kernels), so no griddepcontrol.wait here.
-    if (elect_one()) {
+    // (mode 4 issues 3 * APT boxes per stage: they are spread over the lanes of the warp -- a TMA issue costs a
+    // thread ~150 cycles -- lane i owns box i; the other modes have one box per stage, issued by lane 0)
+    {
       uint32_t s = 0, sphase = 0;
       int tr_it = 0;
       (void)tr_it;
+      const int nbox = tp.mode == 4 ? 3 * tp.APT : 1;
       for (int m = m_first; m < nitems; m += m_step) {
         int c0 = 0, c1 = 0, c3 = 0;                          // box coordinates of the tile
         if (tp.mode == 0) {                                  // (w, image, c % 8, h, c / 8)
@@ -199,27 +202,29 @@ __global__ void __launch_bounds__(KT_THREADS, 2) conv_tma_kernel(const __grid_co
           c3 = m * tp.IPT;
         }
         for (int chunk = 0; chunk < nchunk; ++chunk) {
-          mbar_wait(empty + s, sphase ^ 1);
-          K3_TRACE(2, 2 * tr_it);
+          if (lane == 0) {
+            mbar_wait(empty + s, sphase ^ 1);
+            K3_TRACE(2, 2 * tr_it);
+            if (tp.debug & 1) mbar_arrive(full + s);
+            else mbar_expect_tx(full + s, tp.stage_bytes);
+          }
+          __syncwarp();
           uint8_t* stage = sA + (size_t)s * tp.stage_bytes;
           const int cg0 = chunk * tp.NCGS;
-          if (tp.debug & 1) { mbar_arrive(full + s); if (++s == (uint32_t)nst) { s = 0; sphase ^= 1; } continue; }
-          mbar_expect_tx(full + s, tp.stage_bytes);
-          if (tp.mode == 0) {
-            tma_load_5d(stage, &tmx, c0, c1, 0, c3, cg0, full + s);
-          } else if (tp.mode == 4) {                         // (flat pixel, c % 8, c / 8, image, -): one box per run
-            const uint32_t run_bytes = (uint32_t)tp.NCGS * KT_ATOM;
-            for (int r = 0; r < 3; ++r)
-              for (int j = 0; j < tp.APT; ++j) {
-                const int n = tp.tiles_per_img > 0 ? c3 : c3 + (j >> tp.lgAH);
-                const int run = tp.tiles_per_img > 0 ? c0 + j : (j & (tp.AH - 1));
-                tma_load_5d(stage + (size_t)(r * tp.APT + j) * run_bytes, &tmx, (r - 1) * tp.Wimg + 32 * run, 0, cg0, n, 0,
-                            full + s);
-              }
-          } else {                                           // (pixel % 32, c % 8, run, image, c / 8)
-            tma_load_5d(stage, &tmx, 0, 0, c0, c3, cg0, full + s);
+          if (lane < nbox && !(tp.debug & 1)) {
+            if (tp.mode == 0) {
+              tma_load_5d(stage, &tmx, c0, c1, 0, c3, cg0, full + s);
+            } else if (tp.mode == 4) {                       // (flat pixel, c % 8, c / 8, image, -): one box per run
+              const uint32_t run_bytes = (uint32_t)tp.NCGS * KT_ATOM;
+              const int r = lane / tp.APT, j = lane - r * tp.APT;
+              const int n = tp.tiles_per_img > 0 ? c3 : c3 + (j >> tp.lgAH);
+              const int run = tp.tiles_per_img > 0 ? c0 + j : (j & (tp.AH - 1));
+              tma_load_5d(stage + (size_t)lane * run_bytes, &tmx, (r - 1) * tp.Wimg + 32 * run, 0, cg0, n, 0, full + s);
+            } else {                                         // (pixel % 32, c % 8, run, image, c / 8)
+              tma_load_5d(stage, &tmx, 0, 0, c0, c3, cg0, full + s);
+            }
           }
-          K3_TRACE(2, 2 * tr_it + 1);
+          if (lane == 0) K3_TRACE(2, 2 * tr_it + 1);
           ++tr_it;
           if (++s == (uint32_t)nst) { s = 0; sphase ^= 1; }
         }

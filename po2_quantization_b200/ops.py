@@ -413,9 +413,10 @@ def _conv_backward(g, x, w, scale, stride, pad, groups, compute, need_x, need_w,
                 gx = cand
         if need_w and ours and _wgrad_mode == "tc":
             cand = torch.empty_like(w)
-            # the weight gradient is a leaf of the backward pass (its rounding does not propagate into other
-            # layers' gradients, unlike the data gradient), so the tf32 mode shares the bf16-operand kernel
-            if conv2d_wgrad_out(g, x.contiguous(), cand, pad, 0):
+            # tf32 mode: the TMA-fed tf32 kernel where the shape allows; elsewhere the library takes the
+            # bf16-operand kernel (the weight gradient is a leaf of the backward pass: its rounding does not
+            # propagate into other layers' gradients, unlike the data gradient)
+            if conv2d_wgrad_out(g, x.contiguous(), cand, pad, compute):
                 gw = cand
     if (need_x and gx is None) or (need_w and gw is None):
         gx2, gw2, _ = torch.ops.aten.convolution_backward(

@@ -175,7 +175,7 @@ def test_conv_wgrad_tensor_core_path(case):
     x = torch.randn(B, C, H, W, device="cuda", generator=g0)
     gout = torch.randn(B, K, H, W, device="cuda", generator=g0)
     gw = torch.full((K, C, k, k), float("nan"), device="cuda")
-    assert ops.conv2d_wgrad_out(gout, x, gw, pad)
+    assert ops.conv2d_wgrad_out(gout, x, gw, pad, 0)
     ref = torch.nn.grad.conv2d_weight(x.double(), (K, C, k, k), gout.double(), stride=1, padding=pad)
     assert _rel(gw, ref) < TOL_TC, (name, _rel(gw, ref))
     rms = ((gw.double() - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
@@ -186,6 +186,39 @@ def test_conv_wgrad_tensor_core_path(case):
     # operands that are exact in bf16 make the result exact up to fp32 accumulation order
     xb, gb = x.bfloat16().float(), gout.bfloat16().float()
     assert ops.conv2d_wgrad_out(gb, xb, gw2, pad)
+    ref_b = torch.nn.grad.conv2d_weight(xb.double(), (K, C, k, k), gb.double(), stride=1, padding=pad)
+    assert _rel(gw2, ref_b) < 1e-5, (name, _rel(gw2, ref_b))
+
+
+WGRAD_TMA_CASES = [RESNET[0], RESNET[3], RESNET[6], MOBILENET[1],
+                   ("wg 8->8 3x3 @32 B=3", 3, 8, 32, 32, 8, 3, 1, 1, 1), ("wg 16->24 3x3 @8 B=6", 6, 16, 8, 8, 24, 3, 1, 1, 1),
+                   ("wg 24->40 3x3 @4x4", 9, 24, 4, 4, 40, 3, 1, 1, 1), ("wg 64->128 3x3 @8 (M = 128)", 8, 64, 8, 8, 128, 3, 1, 1, 1),
+                   ("wg 40->72 1x1 @6x6", 3, 40, 6, 6, 72, 1, 1, 0, 1), ("wg 32->128 1x1 @56", 4, 32, 56, 56, 128, 1, 1, 0, 1),
+                   ("wg 16->16 3x3 @16x32 (H != W)", 5, 16, 16, 32, 16, 3, 1, 1, 1)]
+
+
+@pytest.mark.parametrize("case", WGRAD_TMA_CASES, ids=lambda c: c[0])
+def test_conv_wgrad_tma_tf32_path(case):
+    """K5T (csrc/po2_wgrad_tma.cuh): go and x staged by tensor-map TMA straight from fp32 NCHW, tf32 operands (the
+    low 13 mantissa bits are ignored by the tensor core, as in the reference's own cuDNN TF32 kernels), the
+    two column-shifted copies of x derived inside shared memory.  Against fp64: rel 2e-3; deterministic;
+    exact up to accumulation order when the operands are tf32-exact."""
+    from po2_quantization_b200 import ops, _lib
+    name, B, C, H, W, K, k, stride, pad, groups = case
+    assert _lib.load().po2_conv2d_wgrad_kernel_kind(B, C, H, W, K, k, k, stride, pad, groups, 2) == 2, name
+    g0 = torch.Generator(device="cuda").manual_seed(B + C + K)
+    x = torch.randn(B, C, H, W, device="cuda", generator=g0)
+    gout = torch.randn(B, K, H, W, device="cuda", generator=g0)
+    gw = torch.full((K, C, k, k), float("nan"), device="cuda")
+    assert ops.conv2d_wgrad_out(gout, x, gw, pad, 2)
+    ref = torch.nn.grad.conv2d_weight(x.double(), (K, C, k, k), gout.double(), stride=1, padding=pad)
+    assert _rel(gw, ref) < TOL_TF32, (name, _rel(gw, ref))
+    gw2 = torch.empty_like(gw)
+    assert ops.conv2d_wgrad_out(gout, x, gw2, pad, 2)
+    assert torch.equal(gw, gw2), "wgrad must be deterministic"
+    trunc = lambda t: (t.view(torch.int32) & ~0x1FFF).view(torch.float32)       # tf32-exact operands
+    xb, gb = trunc(x.clone()), trunc(gout.clone())
+    assert ops.conv2d_wgrad_out(gb, xb, gw2, pad, 2)
     ref_b = torch.nn.grad.conv2d_weight(xb.double(), (K, C, k, k), gb.double(), stride=1, padding=pad)
     assert _rel(gw2, ref_b) < 1e-5, (name, _rel(gw2, ref_b))
 

@@ -14,7 +14,7 @@ B = int(sys.argv[8]) if len(sys.argv) > 8 else 128
 lib_path = os.path.join(ROOT, "gpurun_out", "libpo2b200_trace.so")
 os.makedirs(os.path.dirname(lib_path), exist_ok=True)
 WGRAD = len(sys.argv) > 9 and sys.argv[9] == "wgrad"
-COMPUTE = 2 if (len(sys.argv) > 9 and sys.argv[9] == "tf32") else 0
+COMPUTE = 2 if (len(sys.argv) > 9 and sys.argv[9] == "tf32") or (len(sys.argv) > 10 and sys.argv[10] == "tf32") else 0
 src = [os.path.join(ROOT, "po2_quantization_b200", "csrc", f) for f in ("po2_quant.cu", "po2_conv.cu", "po2_bn.cu", "po2_lin.cu")]
 subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-shared",
                        "-Xcompiler", "-fPIC", "-DPO2_K3_TRACE", *os.environ.get("PO2_TRACE_DEFS", "").split(), "-I", os.path.join(ROOT, "include"), "-o", lib_path, *src])
@@ -32,7 +32,7 @@ gw = torch.empty_like(w)
 
 def run():
     if WGRAD:
-        assert ops.conv2d_wgrad_out(out, x, gw, pad)
+        assert ops.conv2d_wgrad_out(out, x, gw, pad, COMPUTE)
     else:
         ops.conv2d_out(x, y, scale, out, stride, pad, 1, COMPUTE)
 
