@@ -743,7 +743,7 @@ def conv_forward_roofline(device, batch):
     every conv).  These layers have 36-144 flop/B at the fp32 NCHW module boundary, so the binding
     roof is HBM: algorithmic bytes = 4*(B*C*H*W + B*K*P*Q)."""
     import torch.nn.functional as F
-    from po2_quantization_b200 import ops
+    from po2_quantization_b200 import _lib, ops
     pk = peaks()
     flush = torch.zeros(320 * 1024 * 1024 // 4, dtype=torch.int32, device=device)
     compute = ops.COMPUTE.get(ops.get_conv_mode(), 0)
@@ -775,7 +775,15 @@ def conv_forward_roofline(device, batch):
         y, _, scale, _, _ = torch.ops.po2.quantize_full(w, 4, 1, False)
         out = torch.empty(batch, K, HW, HW, device=device)
 
+        # the launch the timed step performs: the conv kernel alone, its weight operand packed by the
+        # step's multi-tensor quantizer launch (prefetch.py); `us_with_pack` = the un-prefetched QAT forward
+        packed = ops.conv2d_pack(y, scale, x.shape, 1, 1, 1, compute)
+
         def ours():
+            flush.add_(1)
+            torch.ops.po2.conv2d_packed(x, packed, scale, K, 3, 3, 1, 1, 1, compute)
+
+        def ours_with_pack():
             flush.add_(1)
             ops.conv2d_out(x, y, scale, out, 1, 1, 1, compute)
 
@@ -783,28 +791,38 @@ def conv_forward_roofline(device, batch):
             flush.add_(1)
             F.conv2d(x, y, None, 1, 1)
         us = (graph_ms(ours) - t_flush) * 1e3
+        us_p = (graph_ms(ours_with_pack) - t_flush) * 1e3
         us_c = (graph_ms(cudnn) - t_flush) * 1e3
         flop = 2.0 * batch * K * HW * HW * C * 9
         byts = 4.0 * (x.numel() + out.numel())
-        rows.append({"layer": name, "count_in_resnet56": count, "us": us, "us_cudnn_tf32": us_c,
+        kind = _lib.load().po2_conv2d_kernel_kind(batch, C, HW, HW, K, 3, 3, 1, 1, 1, compute)
+        rows.append({"layer": name, "count_in_resnet56": count, "us": us, "us_with_pack": us_p, "us_cudnn_tf32": us_c,
+                     "kernel": {3: "conv_tma_kernel<9>", 2: "conv_umma_kernel<9>"}.get(kind, str(kind)),
                      "TFLOPs": flop / us / 1e6, "io_GBs": byts / us / 1e3, "frac_hbm": byts / us / 1e3 / pk["hbm_gbs"]})
         tot_us += us * count; tot_cudnn += us_c * count; tot_flop += flop * count; tot_bytes += byts * count
     del flush
     torch.cuda.empty_cache()
-    return {"bound": "hbm", "kernel": "po2::conv_umma_kernel<9> (+pack_weights_kernel)", "unit": "GB/s",
+    tma = compute == 2
+    return {"bound": "hbm",
+            "kernel": "po2::conv_tma_kernel<9> (tensor-map TMA producer, tcgen05 tf32)" if tma else "po2::conv_umma_kernel<9>",
+            "unit": "GB/s",
             "achieved": tot_bytes / tot_us / 1e3, "peak": pk["hbm_gbs"], "frac": tot_bytes / tot_us / 1e3 / pk["hbm_gbs"],
-            "traffic": 8.43e6, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the 16->16 @32x32 layer under "
-            "`ncu --set full` (profiles/r01_ncu_conv_umma_resnet56_16to16_3x3_at32_b128.csv): 8.43 MB read = the fp32 input exactly "
-            "once, 0 B written back during the kernel (the 8.39 MB output is still dirty in the 126 MB L2 when the kernel "
-            "ends); algorithmic bytes of that layer = 16.78 MB",
+            "traffic": 8.427e6 if tma else 8.43e6,
+            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the 16->16 @32x32 layer under `ncu --set full` "
+            "(profiles/r02_ncu_conv_tma_resnet56_16to16_3x3_at32_b128.csv): 8.427 MB read = the fp32 input exactly once (the "
+            "halo rows of neighbouring tiles come out of L2), 0 B written back during the kernel (the 8.39 MB output is still "
+            "dirty in the 126 MB L2 when the kernel ends); algorithmic bytes of that layer = 16.78 MB",
             "peak_source": pk["source"],
             "TFLOPs": tot_flop / tot_us / 1e6, "frac_of_bf16_peak": tot_flop / tot_us / 1e6 / pk["bf16_tflops"],
             "resnet56_3x3_forward_us": tot_us, "resnet56_3x3_forward_us_cudnn_tf32": tot_cudnn,
             "images_per_s_forward_qconv_only": batch / (tot_us * 1e-6), "layers": rows,
             "conv_operands": operand_label(ops.get_conv_mode()),
-            "note": "the dominant kernel of the timed step (largest share of the launch list in profiles/); "
-                    "52 stride-1 3x3 quantized convs of ResNet-56 at batch %d, cold L2, CUDA-graph timed; algorithmic "
-                    "bytes per launch = 4*(B*C*H*W + B*K*P*Q)" % batch}
+            "note": "the kernel family with the most launches and the largest share of the timed step (forward + data "
+                    "gradient: 104 of 327 launches, profiles/r02_launches_*.csv); 52 stride-1 3x3 quantized convs of "
+                    "ResNet-56 at batch %d, cold L2 (a 320 MB buffer is rewritten before every launch), CUDA-graph timed, the "
+                    "launch the step performs (weight operand pre-packed by the step's multi-tensor quantizer launch); "
+                    "algorithmic bytes per launch = 4*(B*C*H*W + B*K*P*Q).  These layers move 4-17 MB per launch: at the "
+                    "measured HBM peak that is 0.6-2.6 us, of the order of a kernel launch itself" % batch}
 
 
 # ------------------------------------------------------------------------------------------------
