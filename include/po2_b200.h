@@ -181,6 +181,19 @@ int po2_conv2d_dgrad(const void* g, const void* w, const float* scale, void* gx,
                      int W, int K, int R, int S, int stride, int pad, int groups, int w_format,
                      int bits, int fsr, int compute, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Backward of the layer kinds the tensor-core kernels do not take directly (csrc/po2_conv_bwd.cu):
+ * po2_dilate2: g (planes, P, Q) -> g_up (planes, 2P, 2Q) with g_up[2p][2q] = g[p][q], zero elsewhere -- both
+ * gradients of a STRIDE-2 dense conv are the stride-1 gradients (po2_conv2d_dgrad / po2_conv2d_wgrad) taken with
+ * g_up (models/resnet.py:25-50, the four stride-2 layers of ResNet-20/56).
+ * Depthwise 3x3 pad 1 (models/mobilenet.py:64-74): the data gradient and the deterministic weight gradient;
+ * `g` is the output gradient at the INPUT resolution (stride 2: zero-inserted with po2_dilate2); the
+ * workspace's first 16 KB (tickets) must be zero before the first call and are left zero. */
+int po2_dilate2(const void* g, void* g_up, int planes, int P, int Q, void* stream);
+int po2_conv2d_depthwise_dgrad(const void* g, const void* w, void* gx, int B, int C, int H, int W, void* stream);
+size_t po2_conv2d_depthwise_wgrad_workspace(int C);
+int po2_conv2d_depthwise_wgrad(const void* g, const void* x, void* gw, int B, int C, int H, int W, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
 /* Weight gradient of the same conv (SURVEY.md section 8f "next" #2, second half): gw (K, C, R, S) = dL/dW
  * given g = dL/dout (B, K, P, Q) and the forward input x (B, C, H, W).  QuantizedConv2d's quantizer is
  * a straight-through estimator (utils/quantizers.py:34-36), so this is the gradient of the fp32

@@ -46,6 +46,10 @@ SIGNATURES = {
     "po2_conv2d_dgrad_packed": (_i, [_vp] * 4 + [_i] * 9 + [_vp]),
     "po2_conv2d_dgrad_workspace": (_sz, [_i] * 9),
     "po2_conv2d_dgrad": (_i, [_vp, _vp, _vp, _vp] + [_i] * 14 + [_vp, _sz, _vp]),
+    "po2_dilate2": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "po2_conv2d_depthwise_dgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "po2_conv2d_depthwise_wgrad_workspace": (_sz, [_i]),
+    "po2_conv2d_depthwise_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "po2_conv2d_wgrad_workspace": (_sz, [_i] * 11),
     "po2_conv2d_wgrad_kernel_kind": (_i, [_i] * 11),
     "po2_conv2d_wgrad": (_i, [_vp, _vp, _vp] + [_i] * 11 + [_vp, _sz, _vp]),

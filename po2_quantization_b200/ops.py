@@ -61,6 +61,7 @@ def release_workspaces() -> None:
     """Drop the per-(device, stream) scratch buffers (they are re-created on demand).  Call after the
     streams that used them are idle, e.g. between benchmark configurations."""
     _workspaces.clear()
+    _dw_workspaces.clear()
     from . import batchnorm
     batchnorm._bn_workspaces.clear()
 
@@ -396,29 +397,86 @@ def conv2d_dgrad_packed_out(g, packed, scale, gx, wshape, pad, compute) -> None:
                "po2_conv2d_dgrad_packed")
 
 
+def dilate2_out(g, g_up) -> None:
+    """g_up[2p][2q] = g[p][q], zero elsewhere (the output gradient of a stride-2 conv at the input resolution)"""
+    global LAUNCHES
+    B, K, P, Q = g.shape
+    LAUNCHES += 1
+    _lib.check(_lib.load().po2_dilate2(g.data_ptr(), g_up.data_ptr(), B * K, P, Q, _stream_ptr(g.device)), "po2_dilate2")
+
+
+_dw_workspaces = {}
+
+
+def _depthwise_backward(g_full, x, w, need_x, need_w):
+    """(gx, gw) of a depthwise 3x3 pad-1 conv from the output gradient at the input resolution"""
+    global LAUNCHES
+    lib = _lib.load()
+    B, C, H, W_ = x.shape
+    gx = gw = None
+    if need_x:
+        gx = torch.empty_like(x)
+        LAUNCHES += 1
+        _lib.check(lib.po2_conv2d_depthwise_dgrad(g_full.data_ptr(), w.data_ptr(), gx.data_ptr(), B, C, H, W_,
+                                                  _stream_ptr(x.device)), "po2_conv2d_depthwise_dgrad")
+    if need_w:
+        key = (x.device.index, torch.cuda.current_stream(x.device).cuda_stream)
+        ws = _dw_workspaces.get(key)
+        need = int(lib.po2_conv2d_depthwise_wgrad_workspace(4096))
+        if ws is None:
+            ws = _dw_workspaces[key] = torch.zeros(need, dtype=torch.uint8, device=x.device)
+        gw = torch.empty_like(w)
+        LAUNCHES += 1
+        _lib.check(lib.po2_conv2d_depthwise_wgrad(g_full.data_ptr(), x.data_ptr(), gw.data_ptr(), B, C, H, W_,
+                                                  ws.data_ptr(), ws.numel(), _stream_ptr(x.device)),
+                   "po2_conv2d_depthwise_wgrad")
+    return gx, gw
+
+
 def _conv_backward(g, x, w, scale, stride, pad, groups, compute, need_x, need_w, packed_d=None):
-    """(gx, gw) of conv2d(x, w): the stride-1 dense layers on the tcgen05 kernels (data gradient:
-    forward kernel with transposed weights; weight gradient: conv_wgrad_umma_kernel), everything else
-    through aten.convolution_backward."""
+    """(gx, gw) of conv2d(x, w) on our kernels: dense layers on the tcgen05 kernels (data gradient: the forward
+    kernel with transposed weights; weight gradient: K5T / K5) -- stride-2 layers through the zero-inserted
+    output gradient, which turns both into stride-1 problems -- and depthwise 3x3 layers on the CUDA-core
+    kernels of csrc/po2_conv_bwd.cu.  Whatever is left goes through aten.convolution_backward, loudly."""
     g = g.contiguous()
     gx = gw = None
-    ours = compute != 1 and stride == 1 and groups == 1 and g.dtype == torch.float32 and x.dtype == torch.float32
+    B, C, H, W_ = x.shape
+    K, _, R, S = w.shape
+    fp32 = g.dtype == torch.float32 and x.dtype == torch.float32 and w.dtype == torch.float32
+    ours = compute != 1 and groups == 1 and fp32 and stride in (1, 2)
+    depthwise = (fp32 and _dgrad_mode == "tc" and groups == C == K and R == 3 and S == 3 and pad == 1 and stride in (1, 2)
+                 and C <= 4096)
+    s2_ok = stride == 2 and H % 2 == 0 and W_ % 2 == 0 and ((R == 3 and pad == 1) or (R == 1 and pad == 0)) and \
+        g.shape[2] * 2 == H and g.shape[3] * 2 == W_ and g.shape[3] % 2 == 0
     with torch.cuda.device(x.device):
-        if need_x and ours and _dgrad_mode == "tc" and scale is not None:
-            cand = torch.empty_like(x)
-            if packed_d is not None:
-                conv2d_dgrad_packed_out(g, packed_d, scale, cand, w.shape, pad, compute)
-                gx = cand
-            elif conv2d_dgrad_out(g, w, scale, cand, pad, compute):
-                gx = cand
-        if need_w and ours and _wgrad_mode == "tc":
-            cand = torch.empty_like(w)
-            # tf32 mode: the TMA-fed tf32 kernel where the shape allows; elsewhere the library takes the
-            # bf16-operand kernel (the weight gradient is a leaf of the backward pass: its rounding does not
-            # propagate into other layers' gradients, unlike the data gradient)
-            if conv2d_wgrad_out(g, x.contiguous(), cand, pad, compute):
-                gw = cand
+        g_s1 = g
+        if stride == 2 and (ours or depthwise) and s2_ok and (need_x or need_w):
+            g_s1 = torch.empty(B, K, H, W_, dtype=torch.float32, device=g.device)
+            dilate2_out(g, g_s1)
+        elif stride == 2:
+            ours = depthwise = False
+        if depthwise:
+            gx, gw = _depthwise_backward(g_s1, x.contiguous(), w.contiguous(), need_x, need_w)
+        else:
+            if need_x and ours and _dgrad_mode == "tc" and scale is not None:
+                cand = torch.empty_like(x)
+                if packed_d is not None and stride == 1:
+                    conv2d_dgrad_packed_out(g_s1, packed_d, scale, cand, w.shape, pad, compute)
+                    gx = cand
+                elif conv2d_dgrad_out(g_s1, w, scale, cand, pad, compute):
+                    gx = cand
+            if need_w and ours and _wgrad_mode == "tc":
+                cand = torch.empty_like(w)
+                # tf32 mode: the TMA-fed tf32 kernel where the shape allows; elsewhere the library takes the
+                # bf16-operand kernel (the weight gradient is a leaf of the backward pass: its rounding does not
+                # propagate into other layers' gradients, unlike the data gradient)
+                if conv2d_wgrad_out(g_s1, x.contiguous(), cand, pad, compute):
+                    gw = cand
     if (need_x and gx is None) or (need_w and gw is None):
+        if x.is_cuda and _conv_mode != "cudnn":
+            note_library_path("conv_backward_aten",
+                              f"convolution backward of input {list(x.shape)} / weight {list(w.shape)} stride {stride} groups "
+                              f"{groups} runs on aten.convolution_backward (cuDNN): shape not taken by the po2 kernels")
         gx2, gw2, _ = torch.ops.aten.convolution_backward(
             g, x, w, None, [stride, stride], [pad, pad], [1, 1], False, [0, 0], groups,
             [need_x and gx is None, need_w and gw is None, False])

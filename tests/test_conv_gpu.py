@@ -223,6 +223,36 @@ def test_conv_wgrad_tma_tf32_path(case):
     assert _rel(gw2, ref_b) < 1e-5, (name, _rel(gw2, ref_b))
 
 
+BWD_CASES = [RESNET[1], RESNET[2], RESNET[4], RESNET[5], MOBILENET[9], MOBILENET[10],
+             ("dw_144_s2_at8", 16, 144, 8, 8, 144, 3, 2, 1, 144), ("dw_24_s1_odd", 3, 24, 7, 9, 24, 3, 1, 1, 24)]
+
+
+@pytest.mark.parametrize("case", BWD_CASES, ids=[c[0] for c in BWD_CASES])
+def test_conv_backward_stride2_and_depthwise_leave_aten(case):
+    """Autograd of models/quantized_conv.py:36 for the stride-2 layers of models/resnet.py (zero-inserted output
+    gradient -> the stride-1 tcgen05 kernels) and the depthwise layers of models/mobilenet.py (CUDA-core kernels
+    of csrc/po2_conv_bwd.cu): gradients against fp64 autograd of F.conv2d, and no aten.convolution_backward."""
+    from po2_quantization_b200 import ops
+    name, B, C, H, W, K, k, stride, pad, groups = case
+    x, y, codes, scale = _make(case)
+    x.requires_grad_(True)
+    w = y.clone().requires_grad_(True)
+    ops._noted.discard("conv_backward_aten")
+    out = torch.ops.po2.conv2d(x, w, scale, stride, pad, groups, 2)
+    g = torch.randn(out.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(7))
+    out.backward(g)
+    assert "conv_backward_aten" not in ops._noted, "the backward fell back to aten.convolution_backward"
+    xd, wd = x.detach().double().requires_grad_(True), y.double().requires_grad_(True)
+    F.conv2d(xd, wd, None, stride, pad, 1, groups).backward(g.double())
+    tol = TOL_FP32 * 10 if groups > 1 else TOL_TF32
+    assert _rel(x.grad, xd.grad) < tol, (name, _rel(x.grad, xd.grad))
+    assert _rel(w.grad, wd.grad) < tol, (name, _rel(w.grad, wd.grad))
+    x.grad = None
+    w2 = y.clone().requires_grad_(True)
+    torch.ops.po2.conv2d(x, w2, scale, stride, pad, groups, 2).backward(g)
+    assert torch.equal(w.grad, w2.grad), "the weight gradient must be deterministic"
+
+
 @pytest.mark.parametrize("plus", [False, True])
 def test_module_qat_forward_backward_vs_oracle(plus):
     """QuantizedConv2d (QAT mode) against the oracle module on CPU: forward within the bf16
