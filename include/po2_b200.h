@@ -106,7 +106,8 @@ size_t po2_conv2d_workspace(int B, int C, int H, int W, int K, int R, int S, int
                             int groups, int compute);
 /* Which kernel po2_conv2d_fwd runs for a geometry (planning query, no launch): 0 direct fp32 CUDA cores,
  * 1 depthwise, 2 tcgen05 implicit GEMM with the register-fed activation producer, 3 tcgen05 implicit
- * GEMM fed by tensor-map TMA (tf32 operands straight from fp32 NCHW); negative: PO2_E_*. */
+ * GEMM fed by tensor-map TMA (tf32 operands straight from fp32 NCHW), 4 fp32 CUDA-core GEMM split over a
+ * thread-block cluster (1x1 stride-1 layers on feature maps of <= 16 pixels); negative: PO2_E_*. */
 int po2_conv2d_kernel_kind(int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups,
                            int compute);
 int po2_conv2d_fwd(const void* x, const void* w, const float* scale, void* out, int B, int C,
@@ -126,6 +127,18 @@ int po2_conv2d_pack(const void* w, const float* scale, void* packed, size_t pack
 int po2_conv2d_fwd_packed(const void* x, const void* packed, const float* scale, void* out, int B, int C,
                           int H, int W, int K, int R, int S, int stride, int pad, int groups, int compute,
                           void* stream);
+
+/* Inference with eval-mode BatchNorm folded into the conv (models/resnet.py:55-71, models/mobilenet.py:29-31 in
+ * eval()): out = act(conv(x, W) * ep_a[k] + ep_b[k] + residual), ep_a[k] = gamma / sqrt(running_var + eps),
+ * ep_b[k] = beta - running_mean * ep_a[k]; residual (same shape as out) may be NULL; act: 0 none, 1 ReLU, 2 ReLU6,
+ * 3 SiLU.  Same arguments as po2_conv2d_fwd / po2_conv2d_fwd_packed otherwise. */
+int po2_conv2d_fwd_ep(const void* x, const void* w, const float* scale, void* out, int B, int C, int H, int W, int K,
+                      int R, int S, int stride, int pad, int groups, int w_format, int bits, int fsr, int compute,
+                      void* workspace, size_t workspace_bytes, const float* ep_a, const float* ep_b,
+                      const void* residual, int act, void* stream);
+int po2_conv2d_fwd_packed_ep(const void* x, const void* packed, const float* scale, void* out, int B, int C, int H,
+                             int W, int K, int R, int S, int stride, int pad, int groups, int compute,
+                             const float* ep_a, const float* ep_b, const void* residual, int act, void* stream);
 
 /* QuantizedConv2d.forward in QAT mode as one call -- models/quantized_conv.py:34-36: quantize the fp32
  * master weight w (K, C/groups, R, S) with PO2 (mode 0) / PO2+ (mode 1), then convolve.  qw_out receives

@@ -137,6 +137,33 @@ int multi_fused_capacity();
 int multi_fused_launch(const MultiDesc* descs_dev, int ntensors, int csize, cudaStream_t st);
 int check_quant_args(int bits, int fsr, int mode, int flavor);
 
+// ---- optional conv epilogue: eval-mode BatchNorm folded into the conv (per-out-channel affine), the residual add
+// and the activation of the block -- y = act(conv * a[k] + b[k] + res) -- models/resnet.py:55-71 at inference.
+// a == nullptr: plain conv.  act: 0 none, 1 ReLU, 2 ReLU6, 3 SiLU (the codes of the BatchNorm kernels).
+struct ConvEpilogue {
+  const float* a;
+  const float* b;
+  const float* res;      // same shape as the output, or nullptr
+  int act;
+};
+__device__ __forceinline__ float conv_act(float v, int act) {
+  if (act == 1) return fmaxf(v, 0.f);
+  if (act == 2) return fminf(fmaxf(v, 0.f), 6.f);
+  if (act == 3) return v / (1.f + __expf(-v));
+  return v;
+}
+// v: conv result of out channel k; idx: its offset in the output tensor
+__device__ __forceinline__ float conv_epilogue(float v, const ConvEpilogue& ep, int k, size_t idx) {
+  v = fmaf(v, __ldg(ep.a + k), __ldg(ep.b + k));
+  if (ep.res) v += __ldg(ep.res + idx);
+  return conv_act(v, ep.act);
+}
+
+// csrc/po2_conv_bwd.cu: fp32 cluster split-K GEMM for 1x1 convs on feature maps of <= 16 pixels
+bool pw_small_takes(int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups);
+int launch_pw_small(const float* x, const float* w, float* out, int B, int C, int HW, int K, const ConvEpilogue& ep,
+                    cudaStream_t st);
+
 // ---- per-device one-time host state ---------------------------------------------------------------
 // Kernel attributes (cudaFuncSetAttribute) and the SM count belong to a DEVICE, not to the process:
 // a process that drives several GPUs must set them once per device, and two host threads may race

@@ -257,7 +257,7 @@ template <int NTAPS, bool TF32>
 __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* __restrict__ x,
                                                                   const uint8_t* __restrict__ Bp,
                                                                   const float* __restrict__ scale,
-                                                                  float* __restrict__ out, ConvGeom g) {
+                                                                  float* __restrict__ out, ConvGeom g, ConvEpilogue ep) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sB = smem;
   uint8_t* sA = smem + g.b_slab_bytes;
@@ -416,7 +416,12 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
         if (valid) {
           float* po = out + obase + cb * 16 * PQ;
           const int kleft = K - (kbase + cb * 16);
-          if (kleft >= 16) {
+          if (ep.a) {                                            // folded BatchNorm (+ residual) (+ activation)
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < kleft)
+                po[j * PQ] = conv_epilogue(__uint_as_float(r[j]) * sc, ep, kbase + cb * 16 + j, (size_t)(obase + (cb * 16 + j) * PQ));
+          } else if (kleft >= 16) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) po[j * PQ] = __uint_as_float(r[j]) * sc;
           } else {
@@ -607,7 +612,7 @@ struct DwGeom {
 template <int STRIDE>
 __global__ void __launch_bounds__(256) conv_depthwise_vec_kernel(const float* __restrict__ x,
                                                                  const float* __restrict__ w,
-                                                                 float* __restrict__ out, DwGeom g) {
+                                                                 float* __restrict__ out, DwGeom g, ConvEpilogue ep) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.total; i += gridDim.x * blockDim.x) {
     int t = fdiv(i, g.div_q4);
     const int q0 = (i - t * g.Q4) * 4;
@@ -644,7 +649,12 @@ __global__ void __launch_bounds__(256) conv_depthwise_vec_kernel(const float* __
 #pragma unroll
         for (int s2 = 0; s2 < 3; ++s2) acc[o] = fmaf(in[o * STRIDE + s2], wk[r * 3 + s2], acc[o]);
     }
-    *reinterpret_cast<float4*>(out + ((size_t)plane * g.P + p) * g.Q + q0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    const size_t o = ((size_t)plane * g.P + p) * g.Q + q0;
+    if (ep.a) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[e] = conv_epilogue(acc[e], ep, c, o + e);
+    }
+    *reinterpret_cast<float4*>(out + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
   }
 }
 
@@ -652,7 +662,7 @@ __global__ void __launch_bounds__(256) conv_depthwise_vec_kernel(const float* __
 __global__ void __launch_bounds__(256) conv_depthwise_kernel(const float* __restrict__ x,
                                                              const float* __restrict__ w,
                                                              float* __restrict__ out, ConvGeom g,
-                                                             FastDiv div_q, FastDiv div_p, FastDiv div_c) {
+                                                             FastDiv div_q, FastDiv div_p, FastDiv div_c, ConvEpilogue ep) {
   const int total = g.B * g.C * g.P * g.Q;                 // < 2^31 (checked on the host)
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     int t = fdiv(i, div_q);
@@ -672,7 +682,7 @@ __global__ void __launch_bounds__(256) conv_depthwise_kernel(const float* __rest
         acc = fmaf(__ldg(px + ih * g.W + iw), __ldg(pw + r * g.S + s), acc);
       }
     }
-    out[i] = acc;
+    out[i] = ep.a ? conv_epilogue(acc, ep, c, (size_t)i) : acc;
   }
 }
 
@@ -682,7 +692,7 @@ __global__ void __launch_bounds__(256) conv_depthwise_kernel(const float* __rest
 constexpr int DK = 8;
 __global__ void __launch_bounds__(128) conv_direct_kernel(const float* __restrict__ x,
                                                           const float* __restrict__ w,
-                                                          float* __restrict__ out, ConvGeom g) {
+                                                          float* __restrict__ out, ConvGeom g, ConvEpilogue ep) {
   extern __shared__ float sw[];                             // [DK][Cg*R*S] weights of this k block
   const int Cg = g.C / g.groups, Kg = g.K / g.groups;
   const int kblocks_g = (Kg + DK - 1) / DK;
@@ -720,8 +730,10 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const float* __restric
         }
       }
     }
-    for (int kk = 0; kk < DK && k0 + kk < kend; ++kk)
-      out[(((int64_t)n * g.K + k0 + kk) * g.P + p) * g.Q + q] = acc[kk];
+    for (int kk = 0; kk < DK && k0 + kk < kend; ++kk) {
+      const size_t o = (size_t)((((int64_t)n * g.K + k0 + kk) * g.P + p) * g.Q + q);
+      out[o] = ep.a ? conv_epilogue(acc[kk], ep, k0 + kk, o) : acc[kk];
+    }
   }
 }
 
@@ -753,10 +765,15 @@ static bool fill_geom(ConvGeom& g, int B, int C, int H, int W, int K, int R, int
 }
 
 // K3 takes: dense, square 3x3 pad 1 or 1x1 pad 0, stride 1 or 2
-static bool umma_eligible(const ConvGeom& g) {
+static bool umma_shape_ok(const ConvGeom& g) {
   if (g.groups != 1 || (g.stride != 1 && g.stride != 2)) return false;
   if (!((g.R == 3 && g.S == 3 && g.pad == 1) || (g.R == 1 && g.S == 1 && g.pad == 0))) return false;
   return true;
+}
+// the FORWARD runs on K3 / K3T: shapes they take, minus the pointwise layers on tiny feature maps, which go to
+// the fp32 cluster GEMM of csrc/po2_conv_bwd.cu (no packed operand)
+static bool umma_eligible(const ConvGeom& g) {
+  return umma_shape_ok(g) && !pw_small_takes(g.B, g.C, g.H, g.W, g.K, g.R, g.S, g.stride, g.pad, g.groups);
 }
 
 static size_t umma_smem_bytes(const ConvGeom& g) {
@@ -866,7 +883,8 @@ namespace po2 {
 // with a full dependency (pack_weights_kernel, fused_kernel): the conv's producers read x without a
 // griddepcontrol.wait, which is safe only if x's producer finished before that kernel started.
 static int launch_umma(const void* x, const void* w, const float* scale, void* out, ConvGeom& g, int w_format,
-                       int bits, int fsr, int transpose, void* pack_buf, cudaStream_t st, bool pdl = true) {
+                       int bits, int fsr, int transpose, void* pack_buf, cudaStream_t st, bool pdl = true,
+                       const ConvEpilogue& ep = ConvEpilogue{nullptr, nullptr, nullptr, 0}) {
   {
     uint8_t* Bp = reinterpret_cast<uint8_t*>(pack_buf);
     cudaError_t e = cudaSuccess;
@@ -884,7 +902,7 @@ static int launch_umma(const void* x, const void* w, const float* scale, void* o
       if (g.tf32 && tma_enabled() && plan_tma(g, tp)) {
         // (the operand may already be packed in K3T's layout: an x that cannot be described by a tensor map --
         // misaligned -- is an error here, not a fallback)
-        return launch_tma(x, Bp, scale, out, g, tp, st, pdl);
+        return launch_tma(x, Bp, scale, out, g, tp, st, pdl, ep);
       }
     }
     static PerDeviceOnce attr_once;                       // the opt-in shared-memory size is a per-device attribute
@@ -911,11 +929,11 @@ static int launch_umma(const void* x, const void* w, const float* scale, void* o
     const uint8_t* bpc = Bp;
     float* of = (float*)out;
     if (g.tf32) {
-      if (g.ntaps == 1) e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, true>, xf, bpc, scale, of, g);
-      else e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<9, true>, xf, bpc, scale, of, g);
+      if (g.ntaps == 1) e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, true>, xf, bpc, scale, of, g, ep);
+      else e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<9, true>, xf, bpc, scale, of, g, ep);
     } else {
-      if (g.ntaps == 1) e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, false>, xf, bpc, scale, of, g);
-      else e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<9, false>, xf, bpc, scale, of, g);
+      if (g.ntaps == 1) e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<1, false>, xf, bpc, scale, of, g, ep);
+      else e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<9, false>, xf, bpc, scale, of, g, ep);
     }
     return (int)e;
   }
@@ -1318,7 +1336,8 @@ size_t po2_conv2d_workspace(int B, int C, int H, int W, int K, int R, int S, int
 }
 
 // which kernel po2_conv2d_fwd runs for this geometry: 0 direct fp32, 1 depthwise, 2 tcgen05 with the
-// register-fed activation producer, 3 tcgen05 with the tensor-map TMA producer (K3T); < 0: PO2_E_*
+// register-fed activation producer, 3 tcgen05 with the tensor-map TMA producer (K3T), 4 fp32 cluster GEMM for
+// pointwise layers on <= 16-pixel feature maps; < 0: PO2_E_*
 int po2_conv2d_kernel_kind(int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups,
                            int compute) {
   ConvGeom g;
@@ -1327,14 +1346,34 @@ int po2_conv2d_kernel_kind(int B, int C, int H, int W, int K, int R, int S, int 
     TmaPlan tp;
     return (g.tf32 && tma_enabled() && plan_tma(g, tp)) ? 3 : 2;
   }
+  if (pw_small_takes(B, C, H, W, K, R, S, stride, pad, groups)) return 4;
   return (groups == C && groups == K) ? 1 : 0;
+}
+
+static int check_epilogue(const float* ep_a, const float* ep_b, int act) {
+  if (act < 0 || act > 3) return PO2_E_MODE;
+  if (!ep_a != !ep_b) return PO2_E_NULL;
+  return 0;
 }
 
 int po2_conv2d_fwd(const void* x, const void* w, const float* scale, void* out, int B, int C, int H,
                    int W, int K, int R, int S, int stride, int pad, int groups, int w_format,
                    int bits, int fsr, int compute, void* workspace, size_t workspace_bytes,
                    void* stream) {
+  return po2_conv2d_fwd_ep(x, w, scale, out, B, C, H, W, K, R, S, stride, pad, groups, w_format, bits, fsr, compute, workspace,
+                           workspace_bytes, nullptr, nullptr, nullptr, 0, stream);
+}
+
+// the same conv with a per-out-channel affine (eval-mode BatchNorm folded in), residual add and activation in
+// its epilogue: out = act(conv(x, W) * ep_a[k] + ep_b[k] + residual)
+int po2_conv2d_fwd_ep(const void* x, const void* w, const float* scale, void* out, int B, int C, int H,
+                      int W, int K, int R, int S, int stride, int pad, int groups, int w_format,
+                      int bits, int fsr, int compute, void* workspace, size_t workspace_bytes,
+                      const float* ep_a, const float* ep_b, const void* residual, int act, void* stream) {
   if (!x || !w || !out) return PO2_E_NULL;
+  if (int e = check_epilogue(ep_a, ep_b, act)) return e;
+  if (!ep_a && (residual || act)) return PO2_E_NULL;
+  const ConvEpilogue ep{ep_a, ep_b, (const float*)residual, act};
   ConvGeom g;
   if (!fill_geom(g, B, C, H, W, K, R, S, stride, pad, groups)) return PO2_E_SHAPE;
   if (w_format != PO2_W_F32_PO2 && w_format != PO2_W_CODES) return PO2_E_UNSUPPORTED;
@@ -1347,7 +1386,7 @@ int po2_conv2d_fwd(const void* x, const void* w, const float* scale, void* out, 
 
   if (compute != 1 && umma_eligible(g) && plan_umma(g, compute == 2)) {
     if (!workspace || workspace_bytes < need) return PO2_E_WORKSPACE;
-    return launch_umma(x, w, scale, out, g, w_format, bits, fsr, 0, reinterpret_cast<char*>(workspace) + wbytes, st);
+    return launch_umma(x, w, scale, out, g, w_format, bits, fsr, 0, reinterpret_cast<char*>(workspace) + wbytes, st, true, ep);
   }
   // CUDA-core paths work on fp32 weights
   const float* wf = (const float*)w;
@@ -1359,6 +1398,8 @@ int po2_conv2d_fwd(const void* x, const void* w, const float* scale, void* out, 
     if (e != cudaSuccess) return (int)e;
     wf = (const float*)workspace;
   }
+  if (pw_small_takes(B, C, H, W, K, R, S, stride, pad, groups))
+    return launch_pw_small((const float*)x, wf, (float*)out, B, C, H * W, K, ep, st);
   if (groups == C && groups == K) {
     const int64_t total = (int64_t)B * C * g.P * g.Q;
     // vector kernel: 3x3 pad 1, stride 1 or 2, rows and outputs in whole 16-byte groups
@@ -1369,13 +1410,13 @@ int po2_conv2d_fwd(const void* x, const void* w, const float* scale, void* out, 
       d.total = (int)(total / 4);
       d.div_q4 = make_fastdiv((uint32_t)d.Q4); d.div_p = make_fastdiv((uint32_t)g.P); d.div_c = make_fastdiv((uint32_t)C);
       const int blocks = (int)((d.total + 255) / 256 < sm_count() * 16 ? (d.total + 255) / 256 : sm_count() * 16);
-      if (stride == 1) conv_depthwise_vec_kernel<1><<<blocks, 256, 0, st>>>((const float*)x, wf, (float*)out, d);
-      else conv_depthwise_vec_kernel<2><<<blocks, 256, 0, st>>>((const float*)x, wf, (float*)out, d);
+      if (stride == 1) conv_depthwise_vec_kernel<1><<<blocks, 256, 0, st>>>((const float*)x, wf, (float*)out, d, ep);
+      else conv_depthwise_vec_kernel<2><<<blocks, 256, 0, st>>>((const float*)x, wf, (float*)out, d, ep);
       return (int)cudaGetLastError();
     }
     const int blocks = (int)((total + 255) / 256 < (int64_t)sm_count() * 16 ? (total + 255) / 256 : (int64_t)sm_count() * 16);
     conv_depthwise_kernel<<<blocks, 256, 0, st>>>((const float*)x, wf, (float*)out, g, make_fastdiv((uint32_t)g.Q),
-                                                  make_fastdiv((uint32_t)g.P), make_fastdiv((uint32_t)C));
+                                                  make_fastdiv((uint32_t)g.P), make_fastdiv((uint32_t)C), ep);
     return (int)cudaGetLastError();
   }
   const int Cg = C / groups, Kg = K / groups;
@@ -1390,7 +1431,7 @@ int po2_conv2d_fwd(const void* x, const void* w, const float* scale, void* out, 
   int bx = (int)((npix + 127) / 128);
   const int cap = sm_count() * 16 / (kblocks < 16 ? kblocks : 16) + 1;
   if (bx > cap) bx = cap;
-  conv_direct_kernel<<<dim3(bx, kblocks), 128, smem, st>>>((const float*)x, wf, (float*)out, g);
+  conv_direct_kernel<<<dim3(bx, kblocks), 128, smem, st>>>((const float*)x, wf, (float*)out, g, ep);
   return (int)cudaGetLastError();
 }
 
@@ -1444,13 +1485,23 @@ int po2_conv2d_pack(const void* w, const float* scale, void* packed, size_t pack
 
 int po2_conv2d_fwd_packed(const void* x, const void* packed, const float* scale, void* out, int B, int C, int H,
                           int W, int K, int R, int S, int stride, int pad, int groups, int compute, void* stream) {
+  return po2_conv2d_fwd_packed_ep(x, packed, scale, out, B, C, H, W, K, R, S, stride, pad, groups, compute, nullptr, nullptr,
+                                  nullptr, 0, stream);
+}
+
+int po2_conv2d_fwd_packed_ep(const void* x, const void* packed, const float* scale, void* out, int B, int C, int H,
+                             int W, int K, int R, int S, int stride, int pad, int groups, int compute,
+                             const float* ep_a, const float* ep_b, const void* residual, int act, void* stream) {
   if (!x || !packed || !out) return PO2_E_NULL;
+  if (int e = check_epilogue(ep_a, ep_b, act)) return e;
+  if (!ep_a && (residual || act)) return PO2_E_NULL;
+  const ConvEpilogue ep{ep_a, ep_b, (const float*)residual, act};
   ConvGeom g;
   if (!fill_geom(g, B, C, H, W, K, R, S, stride, pad, groups)) return PO2_E_SHAPE;
   if (compute == 1 || !umma_eligible(g) || !plan_umma(g, compute == 2)) return PO2_E_UNSUPPORTED;
   if ((int64_t)B * C * H * W >= (1ll << 31) || (int64_t)B * K * g.P * g.Q >= (1ll << 31)) return PO2_E_SIZE;
   return launch_umma(x, nullptr, scale, out, g, PO2_W_F32_PO2, 4, 1, -1, const_cast<void*>(packed), (cudaStream_t)stream,
-                     /*pdl=*/false);
+                     /*pdl=*/false, ep);
 }
 
 // QuantizedConv2d.forward in QAT mode as ONE call (models/quantized_conv.py:34-36): quantize the fp32
@@ -1616,7 +1667,7 @@ static bool wgrad_plan(ConvGeom& g, WgGeom& wg, int B, int C, int H, int W, int 
   if (!((R == 3 && S == 3 && pad == 1) || (R == 1 && S == 1 && pad == 0))) return false;
   if (!fill_geom(g, B, C, H, W, K, R, S, stride, pad, groups)) return false;
   if ((int64_t)B * C * H * W >= (1ll << 31) || (int64_t)B * K * g.P * g.Q >= (1ll << 31)) return false;
-  if (!umma_eligible(g) || !plan_umma(g, false)) return false;
+  if (!umma_shape_ok(g) || !plan_umma(g, false)) return false;
   return plan_wgrad(g, wg);
 }
 

@@ -9,6 +9,8 @@
 //   * depthwise 3x3 pad 1 (groups == C == K): data gradient = the depthwise forward kernel's arithmetic with
 //     the filter rotated by 180 degrees (on g, or on g_up for stride 2); weight gradient = nine per-channel
 //     inner products over the batch, a two-stage fixed-order reduction (deterministic).
+#include <stdlib.h>
+
 #include "po2_common.cuh"
 
 namespace po2 {
@@ -178,3 +180,179 @@ int po2_conv2d_depthwise_wgrad(const void* g, const void* x, void* gw, int B, in
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Pointwise (1x1, stride 1) convs on tiny feature maps -- MobileNetV2's 4x4 / 2x2 / 1x1 stages
+// (models/mobilenet.py:106-116: 576->160, 160->960, 960->160, 960->320 at 1x1 ...): out[m][k] = sum_c x[m][c] w[k][c]
+// with m = (image, pixel), a GEMM with M = B*HW <= a few thousand rows and up to 960 channels on either side.
+// The tcgen05 kernels have nothing to pipeline there (one 128-pixel tile, all the time in weight traffic and
+// fixed costs: 41 us for 960->320 against cuDNN's 6).  This is a plain fp32 CUDA-core GEMM (exact fp32 FMA,
+// i.e. the precision of the fp32-accumulate mode): 32 x 64 output tiles, the channel dimension split over
+// a thread-block CLUSTER of up to 8 CTAs whose partial tiles are added through distributed shared memory
+// in rank order (deterministic, no global scratch).
+// ------------------------------------------------------------------------------------------------
+namespace po2 {
+
+constexpr int PW_TM = 32, PW_TN = 64, PW_TK = 16, PW_THREADS = 128;
+
+struct PwGeom {
+  int M, C, K, HW, KS;      // KS: cluster size along the channel split
+  FastDiv div_hw;
+};
+
+__device__ __forceinline__ uint32_t pw_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void pw_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float pw_ld_remote(const float* local, uint32_t rank) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(local), ra;
+  float v;
+  asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra));
+  return v;
+}
+
+__global__ void __launch_bounds__(PW_THREADS) conv_pw_small_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                   float* __restrict__ out, PwGeom g, ConvEpilogue ep) {
+  __shared__ __align__(16) float As[PW_TK][PW_TM + 4];
+  __shared__ __align__(16) float Bs[PW_TK][PW_TN + 4];
+  __shared__ float red[PW_TM][PW_TN + 1];                  // this CTA's partial tile, read by cluster rank 0
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int m0 = blockIdx.x * PW_TM, k0 = blockIdx.y * PW_TN;
+  const int rank = g.KS > 1 ? (int)pw_cluster_rank() : 0;
+  const int M = g.M, C = g.C, K = g.K, HW = g.HW;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  // loader roles: A element (c = tid / 8, m = (tid % 8) * 4 .. +3); B rows k = tid / 2, channels (tid % 2) * 8 .. +7
+  const int ac = tid >> 3, am = (tid & 7) * 4;
+  const int bk = tid >> 1, bc = (tid & 1) * 8;
+  const bool cvec = (C & 3) == 0;
+  float av[4], bv[8];
+  auto load_chunk = [&](int c0) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int m = m0 + am + e, c = c0 + ac;
+      float v = 0.f;
+      if (m < M && c < C) {
+        const int n = fdiv(m, g.div_hw);
+        v = __ldg(x + ((size_t)n * C + c) * HW + (m - n * HW));
+      }
+      av[e] = v;
+    }
+    const int k = k0 + bk, cb = c0 + bc;
+    if (cvec && k < K && cb + 8 <= C) {
+      const float4 lo = __ldg(reinterpret_cast<const float4*>(w + (size_t)k * C + cb));
+      const float4 hi = __ldg(reinterpret_cast<const float4*>(w + (size_t)k * C + cb) + 1);
+      bv[0] = lo.x; bv[1] = lo.y; bv[2] = lo.z; bv[3] = lo.w; bv[4] = hi.x; bv[5] = hi.y; bv[6] = hi.z; bv[7] = hi.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) bv[e] = (k < K && cb + e < C) ? __ldg(w + (size_t)k * C + cb + e) : 0.f;
+    }
+  };
+  const int cstep = g.KS * PW_TK;
+  int c0 = rank * PW_TK;
+  if (c0 < C) load_chunk(c0);
+  for (; c0 < C; c0 += cstep) {
+    __syncthreads();                                        // the previous chunk has been consumed
+    *reinterpret_cast<float4*>(&As[ac][am]) = make_float4(av[0], av[1], av[2], av[3]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) Bs[bc + e][bk] = bv[e];
+    __syncthreads();
+    if (c0 + cstep < C) load_chunk(c0 + cstep);             // the next chunk's loads fly during this chunk's FMAs
+#pragma unroll
+    for (int c = 0; c < PW_TK; ++c) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[c][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[c][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+  }
+  if (g.KS > 1) {
+    // Partial tiles of the cluster: every rank publishes its tile in its own shared memory; rank r then owns the
+    // tile rows r, r + KS, ... and adds the KS partials of each of its outputs in rank order through distributed
+    // shared memory (deterministic; the reduction is spread over the whole cluster instead of queued on one CTA).
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red[ty * 4 + i][tx * 4 + j] = acc[i][j];
+    pw_cluster_sync();
+    for (int row = rank; row < PW_TM; row += g.KS) {
+      const int m = m0 + row;
+      if (m >= M) break;
+      const int n = fdiv(m, g.div_hw), hw = m - n * HW;
+      if (tid < PW_TN) {
+        const int k = k0 + tid;
+        float t[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t[r] = r < g.KS ? pw_ld_remote(&red[row][tid], (uint32_t)r) : 0.f;
+        float v = t[0];
+#pragma unroll
+        for (int r = 1; r < 8; ++r) v += t[r];
+        if (k < K) {
+          const size_t o = ((size_t)n * K + k) * HW + hw;
+          out[o] = ep.a ? conv_epilogue(v, ep, k, o) : v;
+        }
+      }
+    }
+    pw_cluster_sync();                                      // nobody leaves while its shared memory is still being read
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    const int n = fdiv(m, g.div_hw), hw = m - n * HW;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx * 4 + j;
+      if (k >= K) continue;
+      const size_t o = ((size_t)n * K + k) * HW + hw;
+      out[o] = ep.a ? conv_epilogue(acc[i][j], ep, k, o) : acc[i][j];
+    }
+  }
+}
+
+// 1x1 stride-1 dense layers whose feature map is too small for the TMA-fed kernel's 32-pixel runs
+bool pw_small_takes(int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups) {
+  static const bool off = [] { const char* e = getenv("PO2_PW_SMALL"); return e && e[0] == '0'; }();
+  if (off || R != 1 || S != 1 || stride != 1 || pad != 0 || groups != 1) return false;
+  const int64_t HW = (int64_t)H * W;
+  return HW <= 16 && (int64_t)B * HW <= 16384;
+}
+
+int launch_pw_small(const float* x, const float* w, float* out, int B, int C, int HW, int K, const ConvEpilogue& ep,
+                    cudaStream_t st) {
+  PwGeom g;
+  g.M = B * HW; g.C = C; g.K = K; g.HW = HW;
+  g.div_hw = make_fastdiv((uint32_t)HW);
+  const int tiles = ((g.M + PW_TM - 1) / PW_TM) * ((K + PW_TN - 1) / PW_TN);
+  int KS = (device_sm_count() + tiles - 1) / tiles;         // fill the SMs; every CTA keeps at least two channel chunks
+  const int max_ks = C / (2 * PW_TK);
+  if (KS > max_ks) KS = max_ks;
+  if (KS > 8) KS = 8;
+  { const char* e = getenv("PO2_PW_KS"); if (e && atoi(e) > 0 && KS > atoi(e)) KS = atoi(e); }
+  if (KS < 1) KS = 1;
+  g.KS = KS;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((g.M + PW_TM - 1) / PW_TM), (unsigned)((K + PW_TN - 1) / PW_TN), (unsigned)KS);
+  cfg.blockDim = dim3(PW_THREADS);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = (unsigned)KS;
+  cfg.attrs = attr;
+  cfg.numAttrs = KS > 1 ? 1 : 0;
+  return (int)cudaLaunchKernelEx(&cfg, conv_pw_small_kernel, x, w, out, g, ep);
+}
+
+}  // namespace po2

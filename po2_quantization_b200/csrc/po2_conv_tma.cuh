@@ -101,7 +101,8 @@ template <int NTAPS>
 __global__ void __launch_bounds__(KT_THREADS, 2) conv_tma_kernel(const __grid_constant__ CUtensorMap tmx,
                                                                  const uint8_t* __restrict__ Bp,
                                                                  const float* __restrict__ scale,
-                                                                 float* __restrict__ out, ConvGeom g, TmaPlan tp) {
+                                                                 float* __restrict__ out, ConvGeom g, TmaPlan tp,
+                                                                 ConvEpilogue ep) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
   uint8_t* sB = smem;
@@ -363,6 +364,11 @@ __global__ void __launch_bounds__(KT_THREADS, 2) conv_tma_kernel(const __grid_co
         if (valid) {
           float* po = out + obase + cb * 16 * HW;
           const int kleft = K - (kbase + cb * 16);
+          if (ep.a) {                                          // folded BatchNorm (+ residual) (+ activation)
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < kleft) v[j] = conv_epilogue(v[j], ep, kbase + cb * 16 + j, (size_t)(obase + (cb * 16 + j) * HW));
+          }
           if (kleft >= 16) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) po[j * HW] = v[j];
@@ -547,7 +553,7 @@ static bool tma_takes(const ConvGeom& g) {
 
 // the conv launch behind the packed operand (same contract as the register-fed launch in launch_umma)
 static int launch_tma(const void* x, const uint8_t* Bp, const float* scale, void* out, const ConvGeom& g, const TmaPlan& tp_in,
-                      cudaStream_t st, bool pdl) {
+                      cudaStream_t st, bool pdl, const ConvEpilogue& ep) {
   TmaPlan tp = tp_in;
   tp.pdl = pdl ? 1 : 0;
   CUtensorMap tm;
@@ -573,8 +579,8 @@ static int launch_tma(const void* x, const uint8_t* Bp, const float* scale, void
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
   float* of = (float*)out;
-  if (tp.ntaps == 1) e = cudaLaunchKernelEx(&cfg, conv_tma_kernel<1>, tm, Bp, scale, of, g, tp);
-  else e = cudaLaunchKernelEx(&cfg, conv_tma_kernel<9>, tm, Bp, scale, of, g, tp);
+  if (tp.ntaps == 1) e = cudaLaunchKernelEx(&cfg, conv_tma_kernel<1>, tm, Bp, scale, of, g, tp, ep);
+  else e = cudaLaunchKernelEx(&cfg, conv_tma_kernel<9>, tm, Bp, scale, of, g, tp, ep);
   return (int)e;
 }
 

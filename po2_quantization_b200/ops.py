@@ -653,3 +653,85 @@ def conv2d_packed(x: torch.Tensor, packed: torch.Tensor, scale: Optional[torch.T
 def _(x, packed, scale, K, R, S, stride, pad, groups, compute):
     B, C, H, W_ = x.shape
     return x.new_empty((B, K, (H + 2 * pad - R) // stride + 1, (W_ + 2 * pad - S) // stride + 1))
+
+
+# ------------------------------------------------------------------------------------------------
+# inference with eval-mode BatchNorm (+ residual add) (+ activation) folded into the conv's epilogue
+# ------------------------------------------------------------------------------------------------
+def _ep_check(out_shape, K, ep_a, ep_b, residual):
+    if ep_a.numel() != K or ep_b.numel() != K or ep_a.dtype != torch.float32 or ep_b.dtype != torch.float32:
+        raise RuntimeError(f"po2 conv epilogue: scale/shift must be fp32 vectors of {K} out channels")
+    if residual is not None and (tuple(residual.shape) != tuple(out_shape) or residual.dtype != torch.float32):
+        raise RuntimeError(f"po2 conv epilogue: residual {list(residual.shape)} does not match the output {list(out_shape)}")
+
+
+@torch.library.custom_op("po2::conv2d_packed_ep", mutates_args=(), device_types="cuda")
+def conv2d_packed_ep(x: torch.Tensor, packed: torch.Tensor, scale: Optional[torch.Tensor], K: int, R: int, S: int,
+                     stride: int, pad: int, groups: int, compute: int, ep_a: torch.Tensor, ep_b: torch.Tensor,
+                     residual: Optional[torch.Tensor], act: int) -> torch.Tensor:
+    """act(conv2d(x, W) * ep_a[k] + ep_b[k] + residual) from a pre-packed weight operand: one launch (inference)."""
+    global LAUNCHES
+    _require_cuda(x, "po2::conv2d_packed_ep")
+    x = x.contiguous()
+    B, C, H, W_ = x.shape
+    need = int(_lib.load().po2_conv2d_pack_bytes(B, C, H, W_, K, R, S, stride, pad, groups, compute))
+    if need == 0 or packed.numel() != need:
+        raise RuntimeError(f"po2::conv2d_packed_ep: the packed operand ({packed.numel()} bytes) was not built for input "
+                           f"{list(x.shape)} / weight [{K}, {C // max(groups, 1)}, {R}, {S}] (needs {need} bytes)")
+    out = torch.empty((B, K, (H + 2 * pad - R) // stride + 1, (W_ + 2 * pad - S) // stride + 1),
+                      dtype=torch.float32, device=x.device)
+    _ep_check(out.shape, K, ep_a, ep_b, residual)
+    if residual is not None:
+        residual = residual.contiguous()
+    with torch.cuda.device(x.device):
+        LAUNCHES += 1
+        _lib.check(_lib.load().po2_conv2d_fwd_packed_ep(
+            x.data_ptr(), packed.data_ptr(), scale.data_ptr() if scale is not None else None, out.data_ptr(),
+            B, C, H, W_, K, R, S, stride, pad, groups, compute, ep_a.data_ptr(), ep_b.data_ptr(),
+            residual.data_ptr() if residual is not None else None, int(act), _stream_ptr(x.device)),
+            "po2_conv2d_fwd_packed_ep")
+    return out
+
+
+@conv2d_packed_ep.register_fake
+def _(x, packed, scale, K, R, S, stride, pad, groups, compute, ep_a, ep_b, residual, act):
+    B, C, H, W_ = x.shape
+    return x.new_empty((B, K, (H + 2 * pad - R) // stride + 1, (W_ + 2 * pad - S) // stride + 1))
+
+
+@torch.library.custom_op("po2::conv2d_ep", mutates_args=(), device_types="cuda")
+def conv2d_ep(x: torch.Tensor, w: torch.Tensor, scale: Optional[torch.Tensor], stride: int, pad: int, groups: int,
+              compute: int, ep_a: torch.Tensor, ep_b: torch.Tensor, residual: Optional[torch.Tensor],
+              act: int) -> torch.Tensor:
+    """act(conv2d(x, w) * ep_a[k] + ep_b[k] + residual) for any layer kind (depthwise, direct, tensor-core with an
+    inline pack): inference only."""
+    global LAUNCHES
+    _require_cuda(x, "po2::conv2d_ep")
+    if x.dtype != torch.float32 or w.dtype != torch.float32:
+        raise TypeError("po2::conv2d_ep: fp32 NCHW activations and fp32 weights only")
+    check_conv_shapes(x.shape, w.shape, groups, pad)
+    x = x.contiguous()
+    w = w.contiguous()
+    lib = _lib.load()
+    B, C, H, W_ = x.shape
+    K, _, R, S = w.shape
+    out = torch.empty(_conv_out_shape(x, w, stride, pad), dtype=torch.float32, device=x.device)
+    _ep_check(out.shape, K, ep_a, ep_b, residual)
+    if residual is not None:
+        residual = residual.contiguous()
+    with torch.cuda.device(x.device):
+        need = lib.po2_conv2d_workspace(B, C, H, W_, K, R, S, stride, pad, groups, compute)
+        ws = torch.empty(max(int(need), 16), dtype=torch.uint8, device=x.device)
+        fp32_w_bytes = (K * (C // groups) * R * S * 4 + 255) // 256 * 256
+        LAUNCHES += 2 if need > fp32_w_bytes else 1
+        _lib.check(lib.po2_conv2d_fwd_ep(x.data_ptr(), w.data_ptr(), scale.data_ptr() if scale is not None else None,
+                                         out.data_ptr(), B, C, H, W_, K, R, S, stride, pad, groups, _lib.W_F32_PO2, 4, 1,
+                                         compute, ws.data_ptr(), ws.numel(), ep_a.data_ptr(), ep_b.data_ptr(),
+                                         residual.data_ptr() if residual is not None else None, int(act),
+                                         _stream_ptr(x.device)), "po2_conv2d_fwd_ep")
+    return out
+
+
+@conv2d_ep.register_fake
+def _(x, w, scale, stride, pad, groups, compute, ep_a, ep_b, residual, act):
+    return x.new_empty(_conv_out_shape(x, w, stride, pad))

@@ -121,6 +121,46 @@ class QuantizedConv2d(nn.Conv2d):
         # no quantizer and no PTQ tag: a full-precision layer, i.e. plain nn.Conv2d (models/quantized_conv.py:38)
         return self._conv_forward(input, self.weight, self.bias)
 
+    def forward_folded(self, input, ep_a, ep_b, residual=None, act=0):
+        """Inference forward with a per-out-channel affine (an eval-mode BatchNorm folded in), the residual add
+        and the activation in the conv kernel's epilogue: act(conv(input) * ep_a + ep_b + residual).  Returns
+        None when this layer / call cannot take the folded path (the caller then runs conv and norm separately):
+        autograd active, a configuration the kernels do not take, a QAT layer without a prefetched operand."""
+        if torch.is_grad_enabled() and (input.requires_grad or self.weight.requires_grad):
+            return None
+        mode = ops.get_conv_mode()
+        if mode == "cudnn" or self._why_not(input) != "":
+            return None
+        compute = ops.COMPUTE[mode]
+        K, _, R, S = self.weight.shape
+        if self.quantize_fn is not None:
+            plus = getattr(self.quantize_fn, "_PLUS", None)
+            if plus is None or mode not in ("tc", "tf32"):
+                return None
+            from . import prefetch
+            slot = self.__dict__.get("_po2_prefetch")
+            if not slot or slot.key != prefetch._layer_key(self, input.shape, mode):
+                self.__dict__["_po2_xshape"] = tuple(input.shape)
+                return None
+            return ops.conv2d_packed_ep(input, slot.packed, slot.scale, K, R, S, self.stride[0], self.padding[0], self.groups,
+                                        compute, ep_a, ep_b, residual, int(act))
+        tag = getattr(self, "_po2_ptq", None)
+        if tag is None or tag[0] != self.weight._version:
+            return None                                          # a full-precision layer: plain nn.Conv2d
+        if mode in ("tc", "tf32"):
+            key = (tag[0], tuple(input.shape), input.device, mode)
+            cache = self.__dict__.get("_po2_pack_cache")
+            if cache is None or cache[0] != key:
+                packed = ops.conv2d_pack(self.weight.detach(), tag[1], tuple(input.shape), self.stride[0],
+                                         self.padding[0], self.groups, compute)
+                cache = (key, packed)
+                self.__dict__["_po2_pack_cache"] = cache
+            if cache[1] is not None:
+                return ops.conv2d_packed_ep(input, cache[1], tag[1], K, R, S, self.stride[0], self.padding[0], self.groups,
+                                            compute, ep_a, ep_b, residual, int(act))
+        return ops.conv2d_ep(input, self.weight.detach(), tag[1], self.stride[0], self.padding[0], self.groups, compute,
+                             ep_a, ep_b, residual, int(act))
+
     def get_quantization_error(self):
         """models/quantized_conv.py:40-45: (sum((Q(w) - w)^2), numel); (0, numel) without a quantizer.
 

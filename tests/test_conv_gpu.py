@@ -680,3 +680,33 @@ def test_weight_prefetch_equals_inline_quantization():
     torch.backends.cudnn.deterministic = False
     for (n, pa), pb in zip(a.named_parameters(), b.parameters()):
         assert torch.equal(pa, pb), n
+
+
+EP_CASES = [RESNET[0], RESNET[1], RESNET[2], RESNET[3], RESNET[6], MOBILENET[1], MOBILENET[4], MOBILENET[7], MOBILENET[9],
+            MOBILENET[10], MOBILENET[12], ODD[1], ODD[3], ODD[5]]
+
+
+@pytest.mark.parametrize("act", [0, 1, 2, 3], ids=["none", "relu", "relu6", "silu"])
+@pytest.mark.parametrize("case", EP_CASES, ids=[c[0] for c in EP_CASES])
+def test_conv_epilogue_affine_residual_activation(case, act):
+    """Inference epilogue (eval-mode BatchNorm folded into the conv, models/resnet.py:55-71): every kernel kind
+    computes act(conv * a[k] + b[k] + residual) -- against fp64, with the conv's own operand tolerance."""
+    from po2_quantization_b200 import ops
+    name, B, C, H, W, K, k, stride, pad, groups = case
+    x, y, codes, scale = _make(case)
+    g0 = torch.Generator(device="cuda").manual_seed(K + act)
+    a = torch.rand(K, device="cuda", generator=g0) + 0.5
+    b = torch.randn(K, device="cuda", generator=g0)
+    conv = _ref(x, y, stride, pad, groups)
+    res = torch.randn(conv.shape, device="cuda", generator=g0) if act != 2 else None
+    ref = conv * a.double().view(1, -1, 1, 1) + b.double().view(1, -1, 1, 1)
+    if res is not None:
+        ref = ref + res.double()
+    ref = [lambda t: t, torch.relu, lambda t: t.clamp(0, 6), F.silu][act](ref)
+    out = torch.ops.po2.conv2d_ep(x, y, scale, stride, pad, groups, 2, a, b, res, act)
+    tol = TOL_FP32 * 10 if groups > 1 or k == 5 else TOL_TF32
+    assert _rel(out, ref) < tol, (name, _rel(out, ref))
+    packed = ops.conv2d_pack(y, scale, x.shape, stride, pad, groups, 2)
+    if packed is not None:
+        out2 = torch.ops.po2.conv2d_packed_ep(x, packed, scale, K, k, k, stride, pad, groups, 2, a, b, res, act)
+        assert torch.equal(out, out2), name

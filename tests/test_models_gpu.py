@@ -322,3 +322,49 @@ def test_packed_checkpoint_round_trip_is_bit_exact(tmp_path, bits, plus):
     assert all(k.startswith("module.") for k in back2) and len(back2) == len(sd)
     for k in sd:
         assert torch.equal(back2["module." + k].cpu(), sd[k].cpu())
+
+
+@pytest.mark.parametrize("family", ["resnet20", "mobilenet", "mobilevit"])
+def test_folded_batchnorm_inference_matches_separate_kernels(family, monkeypatch):
+    """PTQ inference with the eval-mode norms (+ residual add, + activation) folded into the conv epilogues
+    (po2_quantization_b200/fold.py) against the same model running conv and norm as separate kernels: same
+    logits up to fp32 rounding of the affine, same top-1; and far fewer launches."""
+    import po2_quantization_b200 as P
+    from po2_quantization_b200 import ops
+    from workloads.mobilenet_cifar import mobilenet_v2_cifar
+    from workloads.mobilevit import mobilevit_xs
+    from workloads.resnet_cifar import resnet_cifar
+    torch.manual_seed(3)
+    if family == "resnet20":
+        m, x = resnet_cifar(20, 10, None, 4), torch.randn(64, 3, 32, 32, device="cuda")
+    elif family == "mobilenet":
+        m, x = mobilenet_v2_cifar(10, None, 4), torch.randn(64, 3, 32, 32, device="cuda")
+    else:
+        m, x = mobilevit_xs((64, 64), 10, (2, 2), None, 8), torch.randn(8, 3, 64, 64, device="cuda")
+    m = m.cuda()
+    with torch.no_grad():                                   # non-trivial running statistics and affine parameters
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm):
+                mod.running_mean.normal_(0, 0.2); mod.running_var.uniform_(0.5, 1.5)
+                mod.weight.uniform_(0.7, 1.3); mod.bias.normal_(0, 0.1)
+    P.quantize_model(m, P.PowerOfTwoPlusQuantizer, 8 if family == "mobilevit" else 4)
+    m.eval()
+    with torch.no_grad():
+        monkeypatch.setenv("PO2_FOLD_BN", "0")
+        ref = m(x)
+        n0 = ops.LAUNCHES
+        m(x)
+        separate = ops.LAUNCHES - n0
+        monkeypatch.setenv("PO2_FOLD_BN", "1")
+        folded_pairs = P.fold_conv_bn(m)
+        out = m(x)
+        n0 = ops.LAUNCHES
+        m(x)
+        folded = ops.LAUNCHES - n0
+    assert family == "resnet20" or folded_pairs > 0
+    assert folded < separate, (folded, separate)
+    rel = ((out - ref).abs().max() / ref.abs().max()).item()
+    assert rel < 2e-4, rel
+    margin = ref.topk(2, dim=1).values
+    decisive = (margin[:, 0] - margin[:, 1]) > 1e-3 * ref.abs().max()
+    assert torch.equal(out.argmax(1)[decisive], ref.argmax(1)[decisive])

@@ -38,6 +38,14 @@ SHAPES = [  # name, C, H, W, K, k, stride, pad, groups, count in ResNet-56 (0 = 
 ]
 
 
+MOBILENET_PW = [  # the 33 pointwise layers of MobileNetV2-CIFAR (C, HW side, K, count)
+    (32, 16, 16, 1), (16, 16, 96, 1), (96, 8, 24, 1), (24, 8, 144, 2), (144, 8, 24, 1), (144, 4, 32, 1), (32, 4, 192, 3),
+    (192, 4, 32, 2), (192, 2, 64, 1), (64, 2, 384, 4), (384, 2, 64, 3), (384, 2, 96, 1), (96, 2, 576, 3), (576, 2, 96, 2),
+    (576, 1, 160, 1), (160, 1, 960, 3), (960, 1, 160, 2), (960, 1, 320, 1)]
+MOBILENET_DW = [(32, 16, 1, 1), (96, 16, 2, 1), (144, 8, 1, 1), (144, 8, 2, 1), (192, 4, 1, 2), (192, 4, 2, 1), (384, 2, 1, 4),
+                (576, 2, 1, 2), (576, 2, 2, 1), (960, 1, 1, 3)]
+
+
 def graph_time(body, reps, iters=5):
     """median ms of one replay of a graph that runs `body` `reps` times"""
     s = torch.cuda.Stream()
@@ -71,6 +79,7 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--compute", type=int, default=0, help="0: bf16 operands, 2: tf32 operands (TMA-fed where eligible)")
     ap.add_argument("--only", default=None, help="substring filter on the layer name")
+    ap.add_argument("--set", default="default", help="default | mobilenet (all 33 pointwise + 17 depthwise layers)")
     a = ap.parse_args()
     from po2_quantization_b200 import _lib
     lib = _lib.load()
@@ -78,7 +87,11 @@ def main():
     REPS = 10
     t_flush = graph_time(lambda: flush.add_(1), REPS)
     rows = []
-    for name, C, H, W, K, k, stride, pad, groups, cnt in SHAPES:
+    shapes = SHAPES
+    if a.set == "mobilenet":
+        shapes = [(f"mbv2 pw {C}->{K} @{hw}", C, hw, hw, K, 1, 1, 0, 1, n) for C, hw, K, n in MOBILENET_PW] + \
+                 [(f"mbv2 dw {C} s{st} @{hw}", C, hw, hw, C, 3, st, 1, C, n) for C, hw, st, n in MOBILENET_DW]
+    for name, C, H, W, K, k, stride, pad, groups, cnt in shapes:
         if a.only and a.only not in name:
             continue
         B = a.batch

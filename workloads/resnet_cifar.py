@@ -11,6 +11,15 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+def conv_bn_act(conv, bn, x, residual=None, relu=False):
+    """relu(bn(conv(x)) + residual).  With this repo's classes at inference (eval mode, no autograd) the norm,
+    the add and the ReLU are folded into the conv kernel's epilogue: one launch (po2_quantization_b200/fold.py)."""
+    if getattr(bn, "fused_residual_relu", False) and not bn.training and not torch.is_grad_enabled():
+        from po2_quantization_b200 import conv_bn_act as folded
+        return folded(conv, bn, x, residual, relu)
+    return bn_act(bn, conv(x), residual, relu)
+
+
 def bn_act(bn, x, residual=None, relu=False):
     """relu(bn(x) + residual): one call on a FusedSyncBatchNorm, the three stock ops otherwise."""
     if getattr(bn, "fused_residual_relu", False):
@@ -35,9 +44,9 @@ class _Block(nn.Module):
                 norm_cls(c_out))
 
     def forward(self, x):
-        y = bn_act(self.bn1, self.conv1(x), relu=True)
-        sc = x if self.downsample is None else self.downsample(x)
-        return bn_act(self.bn2, self.conv2(y), residual=sc, relu=True)
+        y = conv_bn_act(self.conv1, self.bn1, x, relu=True)
+        sc = x if self.downsample is None else conv_bn_act(self.downsample[0], self.downsample[1], x)
+        return conv_bn_act(self.conv2, self.bn2, y, residual=sc, relu=True)
 
 
 class ResNetCifar(nn.Module):
