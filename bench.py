@@ -584,6 +584,8 @@ def other_configs(device):
                 m.load_state_dict(ref.state_dict(), strict=True)       # same weights in all arms
             m = m.to(device).eval()
             mse = P.quantize_model(m, P.PowerOfTwoPlusQuantizer, bits)
+            # inference: eval-mode norms (+ residual add, + activation) folded into the conv epilogues
+            r["folded_conv_bn_pairs"] = P.fold_conv_bn(m)
             x = torch.randn(B, 3, *img, generator=torch.Generator().manual_seed(0)).to(device)
             ops.LAUNCHES = 0
             ms, top1, out = _graph_forward_ms(m, x)
@@ -594,7 +596,7 @@ def other_configs(device):
             try:
                 ms_c, _, _ = _graph_forward_ms(m, x)
             finally:
-                ops.set_conv_mode("tc")
+                ops.set_conv_mode(ops.DEFAULT_CONV_MODE)
             r.update({"ours_with_cudnn_convs_ms": ms_c, "speedup_vs_own_cudnn_convs": ms_c / ms})
             if dropin is not None and refname != "mobilevit224":
                 # the reference's own model file on the drop-in classes (stock norms/activations)

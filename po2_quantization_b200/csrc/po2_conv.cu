@@ -401,6 +401,16 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
     const float sc = scale ? *reinterpret_cast<const volatile float*>(scale) : 1.0f;
     const int K = g.K, NT = g.NT, m_step = g.m_step, nitems = g.nitems_m;
     const int kbase = nt * NT;
+    // folded BatchNorm: this CTA's NT scale / shift values staged in shared memory once
+    __shared__ float s_ep[2][256];
+    if (ep.a) {
+      for (int i = tid; i < NT; i += 32 * K3_EPI_WARPS) {
+        const bool ok = kbase + i < K;
+        s_ep[0][i] = ok ? __ldg(ep.a + kbase + i) : 0.f;
+        s_ep[1][i] = ok ? __ldg(ep.b + kbase + i) : 0.f;
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(32 * K3_EPI_WARPS) : "memory");
+    }
     uint32_t item = 0, acc = 0, aphase = 0;
     for (int m = m_first; m < nitems; m += m_step, ++item) {
       int img = 0, a = 0, b = 0;
@@ -417,10 +427,19 @@ __global__ void __launch_bounds__(K3_THREADS, 1) conv_umma_kernel(const float* _
           float* po = out + obase + cb * 16 * PQ;
           const int kleft = K - (kbase + cb * 16);
           if (ep.a) {                                            // folded BatchNorm (+ residual) (+ activation)
+            float rs[16];
+            if (ep.res) {
+              const float* pr = ep.res + obase + cb * 16 * PQ;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) rs[j] = j < kleft ? __ldg(pr + j * PQ) : 0.f;
+            }
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (j < kleft)
-                po[j * PQ] = conv_epilogue(__uint_as_float(r[j]) * sc, ep, kbase + cb * 16 + j, (size_t)(obase + (cb * 16 + j) * PQ));
+              if (j < kleft) {
+                float t = fmaf(__uint_as_float(r[j]) * sc, s_ep[0][cb * 16 + j], s_ep[1][cb * 16 + j]);
+                if (ep.res) t += rs[j];
+                po[j * PQ] = conv_act(t, ep.act);
+              }
           } else if (kleft >= 16) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) po[j * PQ] = __uint_as_float(r[j]) * sc;

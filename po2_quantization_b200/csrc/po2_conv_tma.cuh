@@ -309,6 +309,17 @@ __global__ void __launch_bounds__(KT_THREADS, 2) conv_tma_kernel(const __grid_co
     const int atom = pix >> 5, q = pix & 31;                  // 32-pixel run inside the tile, position in the run
     const int qw = q & (tp.WB - 1);                            // pixel inside its image row
     const bool edge_l = qw == 0, edge_r = qw == tp.WB - 1;     // image-row borders inside the run (3x3 only)
+    // folded BatchNorm: this CTA's NT scale / shift values are staged in shared memory once (the epilogue is on
+    // the critical path: 2 x 16 broadcast global loads per thread and tile were measured to double the kernel)
+    __shared__ float s_ep[2][256];
+    if (ep.a) {
+      for (int i = tid; i < NT; i += 32 * KT_EPI_WARPS) {
+        const bool ok = kbase + i < K;
+        s_ep[0][i] = ok ? __ldg(ep.a + kbase + i) : 0.f;
+        s_ep[1][i] = ok ? __ldg(ep.b + kbase + i) : 0.f;
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(32 * KT_EPI_WARPS) : "memory");
+    }
     const uint32_t accmask = (uint32_t)tp.nacc - 1u;
     uint32_t acc = 0, aphase = 0;
     int tr_item = 0;
@@ -365,9 +376,18 @@ __global__ void __launch_bounds__(KT_THREADS, 2) conv_tma_kernel(const __grid_co
           float* po = out + obase + cb * 16 * HW;
           const int kleft = K - (kbase + cb * 16);
           if (ep.a) {                                          // folded BatchNorm (+ residual) (+ activation)
+            float rs[16];
+            if (ep.res) {
+              const float* pr = ep.res + obase + cb * 16 * HW;
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j < kleft) v[j] = conv_epilogue(v[j], ep, kbase + cb * 16 + j, (size_t)(obase + (cb * 16 + j) * HW));
+              for (int j = 0; j < 16; ++j) rs[j] = j < kleft ? __ldg(pr + j * HW) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float t = fmaf(v[j], s_ep[0][cb * 16 + j], s_ep[1][cb * 16 + j]);
+              if (ep.res) t += rs[j];
+              v[j] = conv_act(t, ep.act);
+            }
           }
           if (kleft >= 16) {
 #pragma unroll

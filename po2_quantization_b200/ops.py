@@ -76,7 +76,8 @@ LAUNCHES = 0
 # "fp32": CUDA-core fp32 FMA everywhere (the fp32-accumulate parity mode); "cudnn": leave the convolution
 # to F.conv2d.
 COMPUTE = {"tc": 0, "fp32": 1, "tf32": 2}
-_conv_mode = os.environ.get("PO2_CONV", "tf32")
+DEFAULT_CONV_MODE = os.environ.get("PO2_CONV", "tf32")      # the mode of a fresh process (tests restore it)
+_conv_mode = DEFAULT_CONV_MODE
 
 
 def set_conv_mode(mode: str) -> None:

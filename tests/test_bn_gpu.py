@@ -240,7 +240,7 @@ def test_resnet20_train_step_with_fused_norm_equals_stock_norm():
             if "running" in n:
                 assert _rel(va, vb) < 1e-4, n
     finally:
-        ops.set_conv_mode("tc")
+        ops.set_conv_mode(ops.DEFAULT_CONV_MODE)
         ops.set_dgrad_mode("tc")
         torch.backends.cudnn.allow_tf32 = old
 
@@ -300,5 +300,5 @@ def test_mobilenet_and_mobilevit_fused_norm_state_dict_and_forward():
                 ya, yb = a(x), b(x)
             assert _rel(ya, yb.double()) < 1e-3, _rel(ya, yb.double())
     finally:
-        ops.set_conv_mode("tc")
+        ops.set_conv_mode(ops.DEFAULT_CONV_MODE)
         torch.backends.cudnn.allow_tf32 = old_tf32

@@ -335,7 +335,7 @@ def test_ptq_quantize_model_and_forward_resnet20_top1():
         try:
             logits32 = mcopy(x.cuda()).cpu()
         finally:
-            ops.set_conv_mode("tc")
+            ops.set_conv_mode(ops.DEFAULT_CONV_MODE)
         assert _rel(logits32, ref.double()) < 1e-4
         assert torch.equal(logits32.argmax(1), ref.argmax(1)), "top-1 differs in fp32-accumulate mode"
     # a second deepcopy keeps the tag; an in-place weight update invalidates it
@@ -373,7 +373,7 @@ def test_ptq_forward_mobilenetv2_matches_oracle():
         try:
             logits32 = model(x.cuda()).cpu()
         finally:
-            ops.set_conv_mode("tc")
+            ops.set_conv_mode(ops.DEFAULT_CONV_MODE)
         assert _rel(logits32, ref.double()) < 1e-4
 
 
@@ -593,7 +593,7 @@ def test_qat_training_step_matches_oracle_model(family):
                 checked += 1
             assert checked >= 10, checked
     finally:
-        ops.set_conv_mode("tc")
+        ops.set_conv_mode(ops.DEFAULT_CONV_MODE)
         ops.set_dgrad_mode("tc")
         torch.backends.cudnn.allow_tf32 = old_tf32
 
@@ -629,7 +629,7 @@ def test_tf32_mode_end_to_end_module_paths():
         r2 = _ref(x.detach(), seq[0].weight.detach(), 1, 0, 1)
         assert torch.equal(a, b) and _rel(a, r2) < TOL_TF32
     finally:
-        ops.set_conv_mode("tc")
+        ops.set_conv_mode(ops.DEFAULT_CONV_MODE)
 
 
 def test_weight_prefetch_equals_inline_quantization():

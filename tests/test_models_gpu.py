@@ -83,7 +83,7 @@ def test_qat_loss_curves_bf16_tf32_fp32_track_the_reference():
             curves[name] = _train_curve(m.cuda().train(), batches, steps)
     finally:
         torch.backends.cudnn.allow_tf32 = old_tf32
-        ops.set_conv_mode("tc")
+        ops.set_conv_mode(ops.DEFAULT_CONV_MODE)
     ref = _smooth(curves["reference_fp32"])
     band = {k: max(abs(a - b) for a, b in zip(_smooth(v), ref)) for k, v in curves.items()}
     final = {k: sum(v[-10:]) / 10 for k, v in curves.items()}
@@ -146,7 +146,7 @@ def test_reference_model_files_ptq_forward_on_gpu(name, bits):
             try:
                 out32 = mine(x)
             finally:
-                ops.set_conv_mode("tc")
+                ops.set_conv_mode(ops.DEFAULT_CONV_MODE)
             rel32 = ((out32.double() - want.double()).abs().max() / want.double().abs().max()).item()
             assert rel32 < 1e-4, (name, rel32)
             assert torch.equal(out32.argmax(1), want.argmax(1)), "top-1 differs in fp32-accumulate mode"
@@ -179,7 +179,7 @@ def test_reference_model_files_qat_step_on_gpu(name):
         lr_ = crit(ref(x), y); lr_.backward()
         lm = crit(mine(x), y); lm.backward()
     finally:
-        ops.set_conv_mode("tc")
+        ops.set_conv_mode(ops.DEFAULT_CONV_MODE)
         ops.set_log2_flavor("ieee")
         torch.backends.cudnn.allow_tf32 = old
     assert abs(lm.item() - lr_.item()) < 5e-3 * max(1.0, abs(lr_.item()))

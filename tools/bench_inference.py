@@ -64,7 +64,7 @@ def main():
             ms = graph_ms(lambda: m(x))
             r[f"ms_{mode}"] = ms
             r[f"images_per_s_{mode}"] = B / ms * 1e3
-        ops.set_conv_mode("tc")
+        ops.set_conv_mode(ops.DEFAULT_CONV_MODE)
         r["speedup_vs_cudnn_convs"] = r["ms_cudnn"] / r["ms_tc"]
         rows.append(r)
         print(json.dumps(r), flush=True)
