@@ -46,7 +46,11 @@ def _foldable(conv, bn, x) -> bool:
 def conv_bn_act(conv, bn, x: torch.Tensor, residual: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
     """act(bn(conv(x)) + residual).  One launch at inference where the layer allows; the separate calls otherwise."""
     act = 1 if relu else ACT[getattr(bn, "act", None)]
-    if _foldable(conv, bn, x) and os.environ.get("PO2_FOLD_BN", "1") == "1":
+    # (SiLU on very large outputs stays a separate pass: measured on MobileViT 224x224 at batch 256, the conv
+    # kernels' four epilogue warps per CTA fall behind HBM when they also evaluate exp() per element --
+    # 23.6 ms folded against 22.5 ms with the norm kernels -- while the small maps gain)
+    big_silu = act == 3 and x.shape[0] * conv.out_channels * x.shape[2] * x.shape[3] // (conv.stride[0] ** 2) > (1 << 24)
+    if _foldable(conv, bn, x) and not big_silu and os.environ.get("PO2_FOLD_BN", "1") == "1":
         a, b = _affine(bn)
         out = conv.forward_folded(x, a, b, residual, act)
         if out is not None:
