@@ -219,6 +219,14 @@ size_t po2_conv2d_wgrad_workspace(int B, int C, int H, int W, int K, int R, int 
  * bf16 operands, 2 = the TMA-fed tf32 kernel (compute == 2, dense stride-1 3x3 with W in {4,8,16,32} / 1x1) */
 int po2_conv2d_wgrad_kernel_kind(int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups,
                                  int compute);
+/* po2_conv2d_wgrad_z: the same as po2_conv2d_wgrad with `zeroed_tickets` = 8 bytes of device memory that are zero
+ * before the first call (left zero by the kernels; not to be shared by calls that may run concurrently): the TMA-fed
+ * kernel then adds its per-CTA partial sums itself, in the same fixed order, after a grid barrier (cooperative
+ * launch) -- one launch instead of two.  Measured slower than the two launches on the ResNet shapes; the library
+ * takes this path only with PO2_WGRAD_FUSED_REDUCE=1 in the environment. */
+int po2_conv2d_wgrad_z(const void* g, const void* x, void* gw, int B, int C, int H, int W, int K, int R, int S,
+                       int stride, int pad, int groups, int compute, void* workspace, size_t workspace_bytes,
+                       void* zeroed_tickets, void* stream);
 int po2_conv2d_wgrad(const void* g, const void* x, void* gw, int B, int C, int H, int W, int K, int R, int S,
                      int stride, int pad, int groups, int compute, void* workspace, size_t workspace_bytes,
                      void* stream);

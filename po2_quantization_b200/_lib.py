@@ -54,6 +54,7 @@ SIGNATURES = {
     "po2_conv2d_depthwise_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "po2_conv2d_wgrad_workspace": (_sz, [_i] * 11),
     "po2_conv2d_wgrad_kernel_kind": (_i, [_i] * 11),
+    "po2_conv2d_wgrad_z": (_i, [_vp, _vp, _vp] + [_i] * 11 + [_vp, _sz, _vp, _vp]),
     "po2_conv2d_wgrad": (_i, [_vp, _vp, _vp] + [_i] * 11 + [_vp, _sz, _vp]),
     "po2_lin_max_channel_elems": (_i, []),
     "po2_lin_quantize": (_i, [_vp, _vp] + [_i] * 7 + [_vp]),

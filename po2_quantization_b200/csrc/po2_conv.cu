@@ -1723,12 +1723,28 @@ int po2_conv2d_wgrad_kernel_kind(int B, int C, int H, int W, int K, int R, int S
 int po2_conv2d_wgrad(const void* g_out, const void* x, void* gw, int B, int C, int H, int W, int K, int R, int S,
                      int stride, int pad, int groups, int compute, void* workspace, size_t workspace_bytes,
                      void* stream) {
+  return po2_conv2d_wgrad_z(g_out, x, gw, B, C, H, W, K, R, S, stride, pad, groups, compute, workspace, workspace_bytes,
+                            nullptr, stream);
+}
+
+// the same with `zeroed_tickets`: 8 bytes of device memory that are zero before the first call (the kernels leave
+// them zero) and are not shared by calls that may run concurrently.  With them the TMA-fed kernel reduces its
+// partial sums itself (one launch instead of two); NULL: two launches.
+int po2_conv2d_wgrad_z(const void* g_out, const void* x, void* gw, int B, int C, int H, int W, int K, int R, int S,
+                       int stride, int pad, int groups, int compute, void* workspace, size_t workspace_bytes,
+                       void* zeroed_tickets, void* stream) {
   if (!g_out || !x || !gw) return PO2_E_NULL;
   {
     WgTmaPlan wp;
     if (wgrad_tma_plan(wp, B, C, H, W, K, R, S, stride, pad, groups, compute)) {
       if (!workspace || workspace_bytes < wgrad_tma_partial_bytes(wp)) return PO2_E_WORKSPACE;
-      return launch_wgrad_tma(g_out, x, gw, workspace, wp, (cudaStream_t)stream);
+      // measured (profiles/README.md, r02): the in-kernel reduction is SLOWER than the second launch -- 21.5 / 22.3 /
+      // 22.5 us against 20.0 / 15.4 / 13.2 us per ResNet-56 layer class, 3.33 against 3.00 ms per step: a
+      // cooperative launch plus a grid barrier cost more than the launch they save, and 148 CTAs have far less
+      // load parallelism for the partials than the 1152-CTA reduce kernel.  Opt-in only (PO2_WGRAD_FUSED_REDUCE=1).
+      static const bool fuse = [] { const char* e = getenv("PO2_WGRAD_FUSED_REDUCE"); return e && e[0] == '1'; }();
+      return launch_wgrad_tma(g_out, x, gw, workspace, wp, (cudaStream_t)stream,
+                              fuse ? (unsigned int*)zeroed_tickets : nullptr);
     }
   }
   ConvGeom g;

@@ -58,6 +58,12 @@ constexpr int WT_THREADS = 32 * 6;
 constexpr uint32_t WT_SMEM_BUDGET = 220 * 1024;
 constexpr uint32_t WT_STAGE_TARGET = 104 * 1024;   // default; PO2_WT_STAGE_KB overrides (tuning)
 
+__device__ __forceinline__ unsigned long long global_ns_wt() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // instruction descriptor: D = f32, A = B = tf32, both K-major, M, N
 __device__ __forceinline__ uint32_t make_idesc_wt(uint32_t m, uint32_t n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
@@ -65,7 +71,8 @@ __device__ __forceinline__ uint32_t make_idesc_wt(uint32_t m, uint32_t n) {
 
 __global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmg,
                                                                        const __grid_constant__ CUtensorMap tmx,
-                                                                       float* __restrict__ partial, WgTmaPlan wp) {
+                                                                       float* __restrict__ partial, WgTmaPlan wp,
+                                                                       float* __restrict__ gw, unsigned int* tickets) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
   uint8_t* sS = smem + (((smem_base + 1023u) & ~1023u) - smem_base);          // stages: 1 KB aligned swizzle atoms
@@ -315,6 +322,67 @@ __global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_tma_kernel(const __g
     tc_fence_before();
   }
   tc_fence_before();
+  if (gw) {
+    // ---- fused fixed-order reduction of the partials (instead of a second launch): a grid barrier (the grid
+    // is launched cooperatively: every CTA is resident), then CTA i adds the m_ctas partials of its slice of
+    // the [tap][k][c] outputs in partial order -- the same sums in the same order as conv_wgrad_reduce_kernel.
+    __threadfence();
+    __syncthreads();
+    const unsigned int nctas = gridDim.x * gridDim.y;
+    if (tid == 0) {
+      atomicAdd(tickets, 1u);
+      const unsigned long long t0 = global_ns_wt();
+      while (*reinterpret_cast<volatile unsigned int*>(tickets) < nctas) {
+        if (global_ns_wt() - t0 > 2000000000ull) break;          // never hang the GPU (the result is then incomplete)
+        __nanosleep(32);
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    const int n = wp.ntaps * wp.C * wp.K, P = wp.m_ctas;
+    const int cta = (int)(blockIdx.y * gridDim.x + blockIdx.x);
+    const int per = (n + (int)nctas - 1) / (int)nctas;
+    const int o0 = cta * per;
+    const int cnt = max(0, min(per, n - o0));
+    int L = 1;
+    while (L < 32 && 2 * L * cnt <= WT_THREADS) L <<= 1;           // lanes per output (cnt * L <= threads), or 1
+    float* scratch = reinterpret_cast<float*>(sS);                 // the stages are idle now
+    for (int base = 0; base < cnt * L; base += WT_THREADS) {
+      const int idx = base + tid;
+      const bool live = idx < cnt * L;
+      const int o = o0 + (live ? idx / L : 0), l = live ? idx % L : 0;
+      float acc = 0.f;
+      if (live) {
+        const float* src = partial + o;
+        int p = l;
+        for (; p + 3 * L < P; p += 4 * L) {                        // four independent loads per round, fixed order
+          const float v0 = __ldcg(src + (size_t)p * n), v1 = __ldcg(src + (size_t)(p + L) * n);
+          const float v2 = __ldcg(src + (size_t)(p + 2 * L) * n), v3 = __ldcg(src + (size_t)(p + 3 * L) * n);
+          acc += v0; acc += v1; acc += v2; acc += v3;
+        }
+        for (; p < P; p += L) acc += __ldcg(src + (size_t)p * n);
+      }
+      if (L > 1) {
+        scratch[tid] = acc;
+        __syncthreads();
+        if (live && l == 0) {
+          float t = 0.f;
+          for (int q = 0; q < L; ++q) t += scratch[tid + q];
+          acc = t;
+        }
+        __syncthreads();
+      }
+      if (live && l == 0) {
+        const int c = o % wp.C, tk = o / wp.C, k = tk % wp.K, tap = tk / wp.K;
+        gw[((size_t)k * wp.C + c) * wp.ntaps + tap] = acc;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {                                                // self-resetting: the last CTA to leave clears both counters
+      const unsigned int d = atomicAdd(tickets + 1, 1u);
+      if (d == nctas - 1) { tickets[0] = 0u; tickets[1] = 0u; __threadfence(); }
+    }
+  }
   __syncthreads();
   if (tid == 0) K3_TRACE(6, 2);
 #ifdef PO2_K3_TRACE
@@ -424,8 +492,10 @@ static size_t wgrad_tma_partial_bytes(const WgTmaPlan& wp) {
   return (size_t)wp.m_ctas * wp.ntaps * wp.C * wp.K * sizeof(float);
 }
 
+// tickets != nullptr: 8 zero bytes (left zero) -> the partials are reduced inside the main kernel, launched
+// cooperatively; nullptr: conv_wgrad_reduce_kernel as a second (programmatic dependent) launch
 static int launch_wgrad_tma(const void* g_out, const void* x, void* gw, void* workspace, const WgTmaPlan& wp,
-                            cudaStream_t st) {
+                            cudaStream_t st, unsigned int* tickets = nullptr) {
   CUtensorMap tmg, tmx;
   const int runs = wp.merged ? wp.APT : 0;
   if (!encode_flat_map(&tmg, g_out, wp.B, wp.K, wp.HW, wp.KG, runs) ||
@@ -437,7 +507,19 @@ static int launch_wgrad_tma(const void* g_out, const void* x, void* gw, void* wo
                                     (int)WT_SMEM_BUDGET + 1024);
       })) return (int)e0;
   const size_t smem = 1024 + (size_t)wp.nst * wp.stage_bytes + 8192 + (3 * K3_MAX_STAGES + 8) * 8 + 64;
-  conv_wgrad_tma_kernel<<<dim3(wp.m_ctas, wp.rsplit), WT_THREADS, smem, st>>>(tmg, tmx, (float*)workspace, wp);
+  float* partial = (float*)workspace;
+  float* gwf = (float*)gw;
+  if (tickets) {
+    WgTmaPlan wpv = wp;
+    void* args[] = {&tmg, &tmx, &partial, &wpv, &gwf, &tickets};
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void*)conv_wgrad_tma_kernel, dim3(wp.m_ctas, wp.rsplit),
+                                                      dim3(WT_THREADS), args, smem, st);
+    if (e != cudaErrorCooperativeLaunchTooLarge) return (int)e;
+    (void)cudaGetLastError();                                     // not co-resident on this device: two launches
+  }
+  float* nogw = nullptr;
+  unsigned int* notk = nullptr;
+  conv_wgrad_tma_kernel<<<dim3(wp.m_ctas, wp.rsplit), WT_THREADS, smem, st>>>(tmg, tmx, partial, wp, nogw, notk);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   const int n = wp.ntaps * wp.C * wp.K;

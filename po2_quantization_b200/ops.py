@@ -62,6 +62,7 @@ def release_workspaces() -> None:
     streams that used them are idle, e.g. between benchmark configurations."""
     _workspaces.clear()
     _dw_workspaces.clear()
+    _wgrad_tickets.clear()
     from . import batchnorm
     batchnorm._bn_workspaces.clear()
 
@@ -378,12 +379,19 @@ def conv2d_wgrad_out(g, x, gw, pad, compute: int = 0) -> bool:
     if need == 0:
         return False
     ws = torch.empty(int(need), dtype=torch.uint8, device=g.device)
-    rc = lib.po2_conv2d_wgrad(g.data_ptr(), x.data_ptr(), gw.data_ptr(), B, C, H, W_, K, R, S, 1, pad, 1, compute,
-                              ws.data_ptr(), ws.numel(), _stream_ptr(g.device))
+    # 8 zeroed bytes per (device, stream): the grid barrier of the TMA-fed kernel's fused partial-sum reduction
+    key = (g.device.index, torch.cuda.current_stream(g.device).cuda_stream)
+    tk = _wgrad_tickets.get(key)
+    if tk is None:
+        tk = _wgrad_tickets[key] = torch.zeros(64, dtype=torch.uint8, device=g.device)
+    rc = lib.po2_conv2d_wgrad_z(g.data_ptr(), x.data_ptr(), gw.data_ptr(), B, C, H, W_, K, R, S, 1, pad, 1, compute,
+                                ws.data_ptr(), ws.numel(), tk.data_ptr(), _stream_ptr(g.device))
     if rc == -10:                      # PO2_E_UNSUPPORTED
         return False
     _lib.check(rc, "po2_conv2d_wgrad")
-    LAUNCHES += 2
+    fused = lib.po2_conv2d_wgrad_kernel_kind(B, C, H, W_, K, R, S, 1, pad, 1, compute) == 2 and \
+        os.environ.get("PO2_WGRAD_FUSED_REDUCE", "0") == "1"
+    LAUNCHES += 1 if fused else 2
     return True
 
 
@@ -407,6 +415,7 @@ def dilate2_out(g, g_up) -> None:
 
 
 _dw_workspaces = {}
+_wgrad_tickets = {}
 
 
 def _depthwise_backward(g_full, x, w, need_x, need_w):
