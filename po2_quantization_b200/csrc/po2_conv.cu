@@ -1739,9 +1739,10 @@ int po2_conv2d_wgrad_z(const void* g_out, const void* x, void* gw, int B, int C,
     if (wgrad_tma_plan(wp, B, C, H, W, K, R, S, stride, pad, groups, compute)) {
       if (!workspace || workspace_bytes < wgrad_tma_partial_bytes(wp)) return PO2_E_WORKSPACE;
       // measured (profiles/README.md, r02): the in-kernel reduction is SLOWER than the second launch -- 21.5 / 22.3 /
-      // 22.5 us against 20.0 / 15.4 / 13.2 us per ResNet-56 layer class, 3.33 against 3.00 ms per step: a
-      // cooperative launch plus a grid barrier cost more than the launch they save, and 148 CTAs have far less
-      // load parallelism for the partials than the 1152-CTA reduce kernel.  Opt-in only (PO2_WGRAD_FUSED_REDUCE=1).
+      // 22.5 us against 20.0 / 15.4 / 13.2 us per ResNet-56 layer class, 3.33 against 3.00 ms per step: the grid
+      // barrier costs more than the launch it saves, and 148 CTAs have far less load parallelism for the partials
+      // than the 1152-CTA reduce kernel (the cooperative launch itself is free: the fused BatchNorm kernels run the
+      // same with a plain launch).  Opt-in only (PO2_WGRAD_FUSED_REDUCE=1).
       static const bool fuse = [] { const char* e = getenv("PO2_WGRAD_FUSED_REDUCE"); return e && e[0] == '1'; }();
       return launch_wgrad_tma(g_out, x, gw, workspace, wp, (cudaStream_t)stream,
                               fuse ? (unsigned int*)zeroed_tickets : nullptr);
