@@ -140,6 +140,20 @@ int po2_conv2d_fwd_packed_ep(const void* x, const void* packed, const float* sca
                              int W, int K, int R, int S, int stride, int pad, int groups, int compute,
                              const float* ep_a, const float* ep_b, const void* residual, int act, void* stream);
 
+/* Training: the batch statistics of the BatchNorm behind a conv come out of the conv's own epilogue
+ * (models/resnet.py:55-71 in train(): bn(conv(x))).  po2_conv2d_fwd_packed_stats = po2_conv2d_fwd_packed that also adds,
+ * per out channel, the sum and the sum of squares of its output into `sums` (fp64 atomics; layout [sum (K) | sum of
+ * squares (K) | 8-byte ticket slot], zero before the first call); po2_bn_apply_sums is the one-launch train-mode
+ * forward of the norm for ONE rank that consumes them and zeroes them again.  PO2_E_UNSUPPORTED from the conv:
+ * run it plainly and let the norm compute its statistics. */
+int po2_conv2d_fwd_packed_stats(const void* x, const void* packed, const float* scale, void* out, int B, int C, int H,
+                                int W, int K, int R, int S, int stride, int pad, int groups, int compute, void* sums,
+                                void* stream);
+int po2_bn_apply_sums(const void* x, const void* residual, void* y, void* sums, float* stats_dense, const float* gamma,
+                      const float* beta, float* running_mean, float* running_var, long long* num_batches_tracked,
+                      float momentum, float eps, int act, float* save_mean, float* save_invstd, int B, int C, int HW,
+                      void* stream);
+
 /* QuantizedConv2d.forward in QAT mode as one call -- models/quantized_conv.py:34-36: quantize the fp32
  * master weight w (K, C/groups, R, S) with PO2 (mode 0) / PO2+ (mode 1), then convolve.  qw_out receives
  * the quantized weight (what quantize_fn.apply returns), scale_out its scale.  Where the shape allows,

@@ -35,6 +35,8 @@ SIGNATURES = {
     "po2_conv2d_fwd": (_i, [_vp, _vp, _vp, _vp] + [_i] * 14 + [_vp, _sz, _vp]),
     "po2_conv2d_fwd_ep": (_i, [_vp, _vp, _vp, _vp] + [_i] * 14 + [_vp, _sz, _vp, _vp, _vp, _i, _vp]),
     "po2_conv2d_fwd_packed_ep": (_i, [_vp] * 4 + [_i] * 11 + [_vp, _vp, _vp, _i, _vp]),
+    "po2_conv2d_fwd_packed_stats": (_i, [_vp] * 4 + [_i] * 11 + [_vp, _vp]),
+    "po2_bn_apply_sums": (_i, [_vp] * 10 + [_c.c_float, _c.c_float, _i, _vp, _vp, _i, _i, _i, _vp]),
     "po2_conv2d_pack_bytes": (_sz, [_i] * 11),
     "po2_conv2d_pack": (_i, [_vp, _vp, _vp, _sz] + [_i] * 14 + [_vp]),
     "po2_conv2d_fwd_packed": (_i, [_vp] * 4 + [_i] * 11 + [_vp]),

@@ -903,7 +903,8 @@ namespace po2 {
 // griddepcontrol.wait, which is safe only if x's producer finished before that kernel started.
 static int launch_umma(const void* x, const void* w, const float* scale, void* out, ConvGeom& g, int w_format,
                        int bits, int fsr, int transpose, void* pack_buf, cudaStream_t st, bool pdl = true,
-                       const ConvEpilogue& ep = ConvEpilogue{nullptr, nullptr, nullptr, 0}) {
+                       const ConvEpilogue& ep = ConvEpilogue{nullptr, nullptr, nullptr, 0, nullptr}) {
+  if (ep.sums && !g.tf32) return PO2_E_UNSUPPORTED;         // only the TMA-fed kernel accumulates statistics
   {
     uint8_t* Bp = reinterpret_cast<uint8_t*>(pack_buf);
     cudaError_t e = cudaSuccess;
@@ -918,11 +919,12 @@ static int launch_umma(const void* x, const void* w, const float* scale, void* o
     }
     {                                                     // K3T where the shape allows: activations by tensor-map TMA
       TmaPlan tp;
-      if (g.tf32 && tma_enabled() && plan_tma(g, tp)) {
+      if (g.tf32 && tma_enabled() && plan_tma(g, tp, ep.sums != nullptr)) {
         // (the operand may already be packed in K3T's layout: an x that cannot be described by a tensor map --
         // misaligned -- is an error here, not a fallback)
         return launch_tma(x, Bp, scale, out, g, tp, st, pdl, ep);
       }
+      if (ep.sums) return PO2_E_UNSUPPORTED;
     }
     static PerDeviceOnce attr_once;                       // the opt-in shared-memory size is a per-device attribute
     e = attr_once.run([]() -> cudaError_t {
@@ -1519,6 +1521,26 @@ int po2_conv2d_fwd_packed_ep(const void* x, const void* packed, const float* sca
   if (!fill_geom(g, B, C, H, W, K, R, S, stride, pad, groups)) return PO2_E_SHAPE;
   if (compute == 1 || !umma_eligible(g) || !plan_umma(g, compute == 2)) return PO2_E_UNSUPPORTED;
   if ((int64_t)B * C * H * W >= (1ll << 31) || (int64_t)B * K * g.P * g.Q >= (1ll << 31)) return PO2_E_SIZE;
+  return launch_umma(x, nullptr, scale, out, g, PO2_W_F32_PO2, 4, 1, -1, const_cast<void*>(packed), (cudaStream_t)stream,
+                     /*pdl=*/false, ep);
+}
+
+// Training forward from a pre-packed operand that also accumulates the batch statistics of the BatchNorm behind
+// the conv: sums[k] += sum of out[:, k], sums[K + k] += sum of out[:, k]^2 (fp64 atomics from the epilogue of the
+// TMA-fed kernel).  PO2_E_UNSUPPORTED: the geometry does not run on that kernel (or its N tile is wider than 32
+// channels) -- the caller then runs the conv plainly and the norm computes its own statistics.
+int po2_conv2d_fwd_packed_stats(const void* x, const void* packed, const float* scale, void* out, int B, int C, int H,
+                                int W, int K, int R, int S, int stride, int pad, int groups, int compute, void* sums,
+                                void* stream) {
+  if (!x || !packed || !out || !sums) return PO2_E_NULL;
+  if (reinterpret_cast<uintptr_t>(sums) & 7) return PO2_E_ALIGN;
+  ConvGeom g;
+  if (!fill_geom(g, B, C, H, W, K, R, S, stride, pad, groups)) return PO2_E_SHAPE;
+  if (compute != 2 || !umma_eligible(g) || !plan_umma(g, true)) return PO2_E_UNSUPPORTED;
+  TmaPlan tp;
+  if (!tma_enabled() || !plan_tma(g, tp) || g.NT > 32) return PO2_E_UNSUPPORTED;
+  if ((int64_t)B * C * H * W >= (1ll << 31) || (int64_t)B * K * g.P * g.Q >= (1ll << 31)) return PO2_E_SIZE;
+  const ConvEpilogue ep{nullptr, nullptr, nullptr, 0, reinterpret_cast<double*>(sums)};
   return launch_umma(x, nullptr, scale, out, g, PO2_W_F32_PO2, 4, 1, -1, const_cast<void*>(packed), (cudaStream_t)stream,
                      /*pdl=*/false, ep);
 }

@@ -97,8 +97,10 @@ __device__ __forceinline__ uint32_t make_idesc_tma(uint32_t m, uint32_t n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
-template <int NTAPS>
-__global__ void __launch_bounds__(KT_THREADS, 2) conv_tma_kernel(const __grid_constant__ CUtensorMap tmx,
+// STATS: the epilogue also accumulates per-out-channel sum / sum of squares (64 more registers per thread: that
+// variant is built for one CTA per SM)
+template <int NTAPS, bool STATS>
+__global__ void __launch_bounds__(KT_THREADS, STATS ? 1 : 2) conv_tma_kernel(const __grid_constant__ CUtensorMap tmx,
                                                                  const uint8_t* __restrict__ Bp,
                                                                  const float* __restrict__ scale,
                                                                  float* __restrict__ out, ConvGeom g, TmaPlan tp,
@@ -320,6 +322,13 @@ __global__ void __launch_bounds__(KT_THREADS, 2) conv_tma_kernel(const __grid_co
       }
       asm volatile("bar.sync 2, %0;" ::"n"(32 * KT_EPI_WARPS) : "memory");
     }
+    // batch statistics for the norm behind this conv: every thread sums its pixels' values per out channel over
+    // all tiles of the CTA (registers: 2 * NT <= 64), reduced once at the end
+    // (NT <= 32: two column blocks, in separately named arrays so that they stay in registers)
+    float st_s0[16], st_q0[16], st_s1[16], st_q1[16];
+    constexpr bool stats = STATS;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { st_s0[j] = 0.f; st_q0[j] = 0.f; st_s1[j] = 0.f; st_q1[j] = 0.f; }
     const uint32_t accmask = (uint32_t)tp.nacc - 1u;
     uint32_t acc = 0, aphase = 0;
     int tr_item = 0;
@@ -372,6 +381,15 @@ __global__ void __launch_bounds__(KT_THREADS, 2) conv_tma_kernel(const __grid_co
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * sc;
         }
+        if (stats && valid) {
+          if (cb == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { st_s0[j] += v[j]; st_q0[j] = fmaf(v[j], v[j], st_q0[j]); }
+          } else if (cb == 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { st_s1[j] += v[j]; st_q1[j] = fmaf(v[j], v[j], st_q1[j]); }
+          }
+        }
         if (valid) {
           float* po = out + obase + cb * 16 * HW;
           const int kleft = K - (kbase + cb * 16);
@@ -406,6 +424,29 @@ __global__ void __launch_bounds__(KT_THREADS, 2) conv_tma_kernel(const __grid_co
       ++tr_item;
       acc = (acc + 1) & accmask;
       aphase ^= (acc == 0);
+    }
+    if (stats) {
+      // lanes -> warp (fp64 from here on) -> the four epilogue warps through shared memory -> one fp64 atomic per
+      // (channel, CTA) and statistic.  Rounding: fp32 only inside a thread's own <= a-dozen values.
+      __shared__ double s_st[KT_EPI_WARPS][2][32];
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          double a = (double)(b == 0 ? st_s0[j] : st_s1[j]), q2 = (double)(b == 0 ? st_q0[j] : st_q1[j]);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
+            q2 += __shfl_xor_sync(0xFFFFFFFFu, q2, o);
+          }
+          if (lane == 0) { s_st[warp][0][b * 16 + j] = a; s_st[warp][1][b * 16 + j] = q2; }
+        }
+      asm volatile("bar.sync 2, %0;" ::"n"(32 * KT_EPI_WARPS) : "memory");
+      if (tid < 2 * NT && NT <= 32) {
+        const int which = tid / NT, ch = tid - which * NT;
+        const double t = s_st[0][which][ch] + s_st[1][which][ch] + s_st[2][which][ch] + s_st[3][which][ch];
+        if (kbase + ch < K) atomicAdd(ep.sums + which * K + kbase + ch, t);
+      }
     }
   }
   tc_fence_before();
@@ -443,7 +484,7 @@ static size_t tma_smem_bytes(const ConvGeom& g, const TmaPlan& tp) {
 
 // g: through plan_umma(g, tf32 = true) (supplies the weight-operand plan NT / ntiles_n / Cpad / slab bytes,
 // so that every existing pack path feeds this kernel unchanged).  False: shape stays on the register-fed kernel.
-static bool plan_tma(const ConvGeom& g, TmaPlan& tp) {
+static bool plan_tma(const ConvGeom& g, TmaPlan& tp, bool one_cta_per_sm = false) {
   if (!g.tf32 || g.groups != 1 || g.stride != 1) return false;
   if (!((g.R == 3 && g.S == 3 && g.pad == 1) || (g.R == 1 && g.S == 1 && g.pad == 0))) return false;
   if (g.C % 8 || g.Cpad != g.C) return false;
@@ -518,7 +559,7 @@ static bool plan_tma(const ConvGeom& g, TmaPlan& tp) {
   while (ncols < (uint32_t)(tp.nacc * accw)) ncols <<= 1;
   size_t budget = KT_SMEM_BUDGET;
   tp.cps = 1;
-  if (fixed + 3 * (size_t)tp.stage_bytes <= KT_SMEM_BUDGET_2 && 2 * ncols <= 512 && tp.nitems_m * g.ntiles_n > sms &&
+  if (!one_cta_per_sm && fixed + 3 * (size_t)tp.stage_bytes <= KT_SMEM_BUDGET_2 && 2 * ncols <= 512 && tp.nitems_m * g.ntiles_n > sms &&
       !(getenv("PO2_TMA_CPS") && getenv("PO2_TMA_CPS")[0] == '1')) {
     tp.cps = 2;
     budget = KT_SMEM_BUDGET_2;
@@ -581,10 +622,13 @@ static int launch_tma(const void* x, const uint8_t* Bp, const float* scale, void
   static PerDeviceOnce attr_once;
   cudaError_t e = attr_once.run([]() -> cudaError_t {
     const int smax = (int)KT_SMEM_BUDGET + 1024;
-    cudaError_t a = cudaFuncSetAttribute(conv_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
-    if (a == cudaSuccess) a = cudaFuncSetAttribute(conv_tma_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
-    if (a == cudaSuccess) a = cudaFuncSetAttribute(conv_tma_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    if (a == cudaSuccess) a = cudaFuncSetAttribute(conv_tma_kernel<9>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaError_t a = cudaSuccess;
+    const void* kerns[4] = {(const void*)conv_tma_kernel<1, false>, (const void*)conv_tma_kernel<9, false>,
+                            (const void*)conv_tma_kernel<1, true>, (const void*)conv_tma_kernel<9, true>};
+    for (int i = 0; i < 4 && a == cudaSuccess; ++i) {
+      a = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+      if (a == cudaSuccess) a = cudaFuncSetAttribute(kerns[i], cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    }
     return a;
   });
   if (e != cudaSuccess) return (int)e;
@@ -599,8 +643,13 @@ static int launch_tma(const void* x, const uint8_t* Bp, const float* scale, void
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
   float* of = (float*)out;
-  if (tp.ntaps == 1) e = cudaLaunchKernelEx(&cfg, conv_tma_kernel<1>, tm, Bp, scale, of, g, tp, ep);
-  else e = cudaLaunchKernelEx(&cfg, conv_tma_kernel<9>, tm, Bp, scale, of, g, tp, ep);
+  if (ep.sums) {                     // the variant that also accumulates the following norm's batch statistics
+    if (tp.ntaps == 1) e = cudaLaunchKernelEx(&cfg, conv_tma_kernel<1, true>, tm, Bp, scale, of, g, tp, ep);
+    else e = cudaLaunchKernelEx(&cfg, conv_tma_kernel<9, true>, tm, Bp, scale, of, g, tp, ep);
+  } else {
+    if (tp.ntaps == 1) e = cudaLaunchKernelEx(&cfg, conv_tma_kernel<1, false>, tm, Bp, scale, of, g, tp, ep);
+    else e = cudaLaunchKernelEx(&cfg, conv_tma_kernel<9, false>, tm, Bp, scale, of, g, tp, ep);
+  }
   return (int)e;
 }
 

@@ -55,6 +55,17 @@ def conv_bn_act(conv, bn, x: torch.Tensor, residual: Optional[torch.Tensor] = No
         out = conv.forward_folded(x, a, b, residual, act)
         if out is not None:
             return out
+    if (isinstance(bn, FusedSyncBatchNorm) and isinstance(conv, QuantizedConv2d) and bn.training and x.is_cuda
+            and x.dtype == torch.float32 and bn.momentum is not None and os.environ.get("PO2_CONV_STATS", "0") == "1"
+            and not (torch.distributed.is_available() and torch.distributed.is_initialized()
+                     and torch.distributed.get_world_size() > 1)):
+        # training on one rank, opt-in (PO2_CONV_STATS=1): the conv's epilogue accumulates the norm's batch
+        # statistics (no statistics pass over the conv output).  Measured on the ResNet-56 step: 2.998 vs 3.013 ms --
+        # the one-launch norm kernel already reads x once, so little is left to save -- and the fp64 atomics make the
+        # summation order, hence the last bit of the statistics, run-dependent; off by default for reproducibility.
+        stats = {"sums": bn.conv_sums(x.device), "ok": False}
+        y = conv.forward_with_stats(x, stats)
+        return bn(y, residual, relu, stats["sums"] if stats["ok"] else None)
     y = conv(x)
     if getattr(bn, "fused_residual_relu", False):
         return bn(y, residual, relu)

@@ -154,9 +154,23 @@ class _QConvPrefetched(torch.autograd.Function):
     """conv2d(x, Q(weight)) from a prefetched (qw, scale, packed) triple; straight-through gradient"""
 
     @staticmethod
-    def forward(ctx, x, weight, qw, scale, packed, stride, pad, groups, compute, packed_d):
+    def forward(ctx, x, weight, qw, scale, packed, stride, pad, groups, compute, packed_d, stats=None):
         K, _, R, S = qw.shape
-        out = ops.conv2d_packed(x, packed, scale, K, R, S, stride, pad, groups, compute)
+        out = None
+        if stats is not None:
+            # the BatchNorm behind this conv asked for its batch statistics: the conv's epilogue accumulates the
+            # per-channel sums into stats["sums"] (stats["ok"] tells the norm whether that happened)
+            xc = x.contiguous()
+            B, C, H, W_ = xc.shape
+            cand = torch.empty((B, K, (H + 2 * pad - R) // stride + 1, (W_ + 2 * pad - S) // stride + 1),
+                               dtype=torch.float32, device=x.device)
+            with torch.cuda.device(x.device):
+                stats["ok"] = ops.conv2d_packed_stats_out(xc, packed, scale, cand, K, R, S, stride, pad, groups, compute,
+                                                          stats["sums"])
+            if stats["ok"]:
+                out = cand
+        if out is None:
+            out = ops.conv2d_packed(x, packed, scale, K, R, S, stride, pad, groups, compute)
         ctx.save_for_backward(x, qw, scale)
         ctx.packed_d = packed_d          # valid until the next prefetch launch, i.e. through this step's backward
         ctx.cfg = (stride, pad, groups, compute)
@@ -168,16 +182,17 @@ class _QConvPrefetched(torch.autograd.Function):
         stride, pad, groups, compute = ctx.cfg
         gx, gw = ops._conv_backward(g, x, qw, scale, stride, pad, groups, compute, ctx.needs_input_grad[0],
                                     ctx.needs_input_grad[1], packed_d=ctx.packed_d)
-        return gx, gw, None, None, None, None, None, None, None, None
+        return gx, gw, None, None, None, None, None, None, None, None, None
 
 
-def try_prefetched_forward(m, x, mode):
-    """The layer's forward from its prefetched operand, or None if there is no valid one."""
+def try_prefetched_forward(m, x, mode, stats=None):
+    """The layer's forward from its prefetched operand, or None if there is no valid one.  stats: {"sums": fp64
+    tensor} of the norm behind the layer; on return stats["ok"] says whether the conv accumulated them."""
     slot = m.__dict__.get("_po2_prefetch")
     if not slot or slot.key != _layer_key(m, x.shape, mode):
         return None
     return _QConvPrefetched.apply(x, m.weight, slot.qw, slot.scale, slot.packed, m.stride[0], m.padding[0], m.groups,
-                                  ops.COMPUTE[mode], getattr(slot, "packed_d", None))
+                                  ops.COMPUTE[mode], getattr(slot, "packed_d", None), stats)
 
 
 def enable_weight_prefetch(model: torch.nn.Module) -> torch.nn.Module:

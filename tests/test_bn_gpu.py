@@ -302,3 +302,47 @@ def test_mobilenet_and_mobilevit_fused_norm_state_dict_and_forward():
     finally:
         ops.set_conv_mode(ops.DEFAULT_CONV_MODE)
         torch.backends.cudnn.allow_tf32 = old_tf32
+
+
+@pytest.mark.parametrize("shape", [(128, 16, 32, 32), (128, 32, 16, 16), (128, 64, 8, 8), (6, 24, 8, 8)], ids=lambda s: "x".join(map(str, s)))
+def test_batch_statistics_from_the_conv_epilogue(shape, monkeypatch):
+    """Training on one rank: QuantizedConv2d's TMA-fed kernel accumulates the per-channel sum / sum of squares of its
+    output (fp64 atomics) and FusedSyncBatchNorm normalises from them in one launch (conv_bn_act).  Against the same
+    layers with the norm computing its own statistics: output, running statistics and all gradients."""
+    import copy
+    import po2_quantization_b200 as P
+    from po2_quantization_b200 import ops
+    monkeypatch.setenv("PO2_CONV_STATS", "1")          # opt-in (fp64 atomics: summation order is run-dependent)
+    B, C, H, W = shape
+    torch.manual_seed(C)
+    conv = P.QuantizedConv2d(C, C, 3, quantize_fn=P.PowerOfTwoQuantizer, bits=4).cuda()
+    bn = P.FusedSyncBatchNorm(C).cuda().train()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.2)
+    conv2, bn2 = copy.deepcopy(conv), copy.deepcopy(bn)
+    P.enable_weight_prefetch(conv)                    # the statistics ride on the prefetched single-launch forward
+    P.enable_weight_prefetch(conv2)
+    x = torch.randn(B, C, H, W, device="cuda") * 1.3 + 0.4
+    res = torch.randn(B, C, H, W, device="cuda")
+    go = torch.randn(B, C, H, W, device="cuda")
+    outs = []
+    for cv, b, use in ((conv, bn, True), (conv2, bn2, False)):
+        for it in range(2):                            # first call records the input shape, second runs prefetched
+            xi = x.clone().requires_grad_(True)
+            cv(xi)
+        cv.weight.grad = None
+        xi = x.clone().requires_grad_(True)
+        n0 = ops.LAUNCHES
+        if use:
+            y = P.conv_bn_act(cv, b, xi, res, True)
+        else:
+            y = b(cv(xi), res, True)
+        launches = ops.LAUNCHES - n0
+        y.backward(go)
+        outs.append((y.detach(), xi.grad, cv.weight.grad, b.weight.grad, b.bias.grad, b.running_mean.clone(), b.running_var.clone(), launches))
+    a, r = outs
+    assert a[7] <= r[7], (a[7], r[7])
+    for u, v, name in zip(a[:7], r[:7], ("y", "dx", "dw", "dgamma", "dbeta", "running_mean", "running_var")):
+        err = ((u - v).abs().max() / v.abs().max().clamp_min(1e-12)).item()
+        assert err < 2e-4, (name, err)
+    assert float(bn.conv_sums(x.device).abs().sum()) == 0.0   # consumed and zeroed for the next forward
