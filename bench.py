@@ -129,7 +129,8 @@ def build_training(device, world, local_rank, source="workload"):
         else:
             # same arithmetic, coalesced NCCL all-reduce(AVG) per bucket (distributed.BatchSharded)
             from po2_quantization_b200.distributed import BatchSharded
-            model = BatchSharded(model)
+            model = BatchSharded(model, overlap=os.environ.get("PO2_GRAD_OVERLAP", "0") == "1",
+                                 buckets=int(os.environ.get("PO2_GRAD_BUCKETS", "4")))
     # reference train.py:51-56: SGD momentum 0.9, wd 1e-4, lr 0.1 * world
     opt = torch.optim.SGD(model.parameters(), lr=0.1 * world, momentum=0.9, weight_decay=1e-4)
     crit = nn.CrossEntropyLoss()
@@ -139,7 +140,9 @@ def build_training(device, world, local_rank, source="workload"):
 def _parallelism_note():
     from po2_quantization_b200 import batchnorm
     grads = ("torch DDP buckets" if os.environ.get("PO2_DDP", "0") == "1"
-             else "coalesced NCCL all-reduce(AVG) of the gradients in 4 buckets, issued from grad hooks under backward")
+             else ("coalesced NCCL all-reduce(AVG) of the gradients in buckets, issued from grad hooks under backward"
+                   if os.environ.get("PO2_GRAD_OVERLAP", "0") == "1"
+                   else "one coalesced NCCL all-reduce(AVG) of all gradients behind backward"))
     ex = [e for e in batchnorm._exchanges.values()]
     mode = os.environ.get("PO2_BN_EXCHANGE", "peer")
     bn = ("SyncBatchNorm statistics exchanged inside the BN kernels over NVLink peer stores" if any(e is not None for e in ex)

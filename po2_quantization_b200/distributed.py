@@ -63,9 +63,15 @@ class BatchSharded(torch.nn.Module):
     in backward order; a group's all-reduce is issued from a post-accumulate-grad hook as soon as its
     last gradient exists, on a side stream, so it runs under the rest of the backward pass (also inside
     a CUDA-graph capture, where the side stream becomes a parallel branch).  ``average_gradients()``
-    after ``backward()`` reduces whatever is left and joins the side stream."""
+    after ``backward()`` reduces whatever is left and joins the side stream.
 
-    def __init__(self, module: torch.nn.Module, group: Optional[dist.ProcessGroup] = None, overlap: bool = True,
+    ``overlap`` defaults to False since round 2: measured on the ResNet-56 step (3.4 MB of gradients), ONE coalesced
+    all-reduce behind backward beats the overlapped buckets -- 3.65 vs 3.80 ms per step at 2 GPUs, 3.80 vs 4.04 ms at
+    8 -- because the NCCL kernels running under backward take SMs from kernels that are sized one or two CTAs per
+    SM (persistent tcgen05 convs, cooperative norm kernels), which costs more than the exposed tail of a 3.4 MB
+    all-reduce over NVLink.  Models with far larger gradients may prefer ``overlap=True``."""
+
+    def __init__(self, module: torch.nn.Module, group: Optional[dist.ProcessGroup] = None, overlap: bool = False,
                  buckets: int = 4):
         super().__init__()
         self.module = module

@@ -89,7 +89,7 @@ def main():
                               torch.nn.Flatten(), torch.nn.Linear(8 * 8 * 8, 10)).cuda()
     import copy
     ref = copy.deepcopy(net)                              # un-wrapped replica: its gradients stay local
-    model = BatchSharded(net, buckets=3)
+    model = BatchSharded(net, overlap=True, buckets=3)    # the overlapped form is the harder one to get right
     ref.load_state_dict(net.state_dict())                 # rank 0's parameters, as broadcast by the wrapper
     xb = torch.randn(4, 3, 8, 8, device="cuda")
     worst = 0.0
