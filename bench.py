@@ -111,6 +111,15 @@ def build_training(device, world, local_rank, source="workload"):
         if ns is None:
             return None
         model = ns.get_model("resnet56", 10, P.PowerOfTwoQuantizer, 4, (32, 32)).to(device).train()
+    elif source == "reference_files_fused_norm":
+        # the reference's own models/resnet.py, unmodified, plus ONE added line in the training script:
+        # po2_quantization_b200.fuse_batchnorm(model) -- its nn.SyncBatchNorm modules run on this library's norm kernels
+        from workloads import reference_files as RF
+        ns = RF.load("dropin")
+        if ns is None:
+            return None
+        model = ns.get_model("resnet56", 10, P.PowerOfTwoQuantizer, 4, (32, 32)).to(device).train()
+        P.fuse_batchnorm(model)
     elif source == "workload_stock_norm":
         from workloads import resnet_cifar
         model = resnet_cifar(56, 10, P.PowerOfTwoQuantizer, 4, norm_cls=nn.SyncBatchNorm).to(device).train()
@@ -388,7 +397,8 @@ def _run_ours_on_stream(a, ops, world, rank, local_rank, device):
             weight_quantization=("one multi-tensor launch per step (prefetch)" if os.environ.get("PO2_PREFETCH", "1") == "1"
                                  else "one launch per layer"),
             model_source="workloads/resnet_cifar.py (layer graph of models/resnet.py; FusedSyncBatchNorm); the reference's "
-                         "own models/resnet.py is timed in extra.step_variants.reference_model_files",
+                         "own models/resnet.py, unmodified, is timed in extra.step_variants.reference_model_files (torch norms) and "
+                         "reference_model_files_plus_fuse_batchnorm (one added line: po2_quantization_b200.fuse_batchnorm(model))",
             top1_identity="asserted bit-for-bit in fp32-accumulate mode; bf16/tf32 operand modes are checked on decisive "
                           "margins (tests/test_conv_gpu.py::test_ptq_quantize_model_and_forward_resnet20_top1)",
             bn_exchange_timeouts=timeouts),
@@ -433,6 +443,7 @@ def step_variants(a, device, ms_main):
     other = "tc" if prev == "tf32" else "tf32"
     for name, mode, source in ((("bf16_operands" if other == "tc" else "tf32_operands"), other, "workload"),
                                ("reference_model_files", prev, "reference_files"),
+                               ("reference_model_files_plus_fuse_batchnorm", prev, "reference_files_fused_norm"),
                                ("reference_model_files_" + ("bf16" if other == "tc" else "tf32"), other, "reference_files")):
         try:
             ops.set_conv_mode(mode)
@@ -441,8 +452,9 @@ def step_variants(a, device, ms_main):
                 h = StepHarness(a, 1, 0, device.index or 0, device, "workload_stock_norm")
                 src = "workloads/resnet_cifar.py with stock nn.SyncBatchNorm (baseline/_ref not staged)"
             else:
-                src = "models/resnet.py of the reference, unmodified (baseline/_ref)" if source == "reference_files" \
-                    else "workloads/resnet_cifar.py"
+                src = {"reference_files": "models/resnet.py of the reference, unmodified (baseline/_ref)",
+                       "reference_files_fused_norm": "models/resnet.py of the reference, unmodified (baseline/_ref), plus one "
+                       "line in the training script: po2_quantization_b200.fuse_batchnorm(model)"}.get(source, "workloads/resnet_cifar.py")
             h.capture()
             ms = h.time_resident(min(a.steps, 10), 3) / min(a.steps, 10)
             res[name] = {"ms_per_step": ms, "images_per_s": a.batch / ms * 1e3, "conv_operands": operand_label(mode),

@@ -101,3 +101,32 @@ def fold_conv_bn(model: nn.Module) -> int:
                 seq._modules[k1] = nn.Identity()
                 n += 1
     return n
+
+
+_ACT_OF = {nn.ReLU: "relu", nn.ReLU6: "relu6", nn.SiLU: "silu"}
+
+
+def fuse_batchnorm(model: nn.Module, fuse_activations: bool = True) -> int:
+    """Put the ``nn.SyncBatchNorm`` modules of an UNMODIFIED model (the reference's ``models/resnet.py``,
+    ``models/mobilenet.py``, ``models/mobile_vit.py`` construct them directly) on this library's norm kernels, in
+    place and after construction: one added line in ``train.py`` / ``test.py`` --
+    ``po2_quantization_b200.fuse_batchnorm(model)`` -- instead of an edit of the model files.  Every
+    ``nn.SyncBatchNorm`` instance becomes a ``FusedSyncBatchNorm`` (same parameters, buffers and ``state_dict`` keys:
+    only the class changes); with ``fuse_activations`` an ``nn.ReLU`` / ``nn.ReLU6`` / ``nn.SiLU`` that directly follows
+    a norm inside an ``nn.Sequential`` moves into the norm kernel (its slot becomes ``nn.Identity``).  Activations and
+    residual adds that a model applies in its own ``forward`` (``F.relu(self.bn1(...))``) stay torch ops.  Returns the
+    number of converted norms."""
+    n = 0
+    for m in model.modules():
+        if type(m) is nn.SyncBatchNorm:
+            m.__class__ = FusedSyncBatchNorm
+            m.act = None
+            n += 1
+    if fuse_activations:
+        for seq in [m for m in model.modules() if isinstance(m, nn.Sequential)]:
+            items = list(seq._modules.items())
+            for (k0, m0), (k1, m1) in zip(items, items[1:]):
+                if isinstance(m0, FusedSyncBatchNorm) and getattr(m0, "act", None) is None and type(m1) in _ACT_OF:
+                    m0.act = _ACT_OF[type(m1)]
+                    seq._modules[k1] = nn.Identity()
+    return n

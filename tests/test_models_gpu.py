@@ -368,3 +368,40 @@ def test_folded_batchnorm_inference_matches_separate_kernels(family, monkeypatch
     margin = ref.topk(2, dim=1).values
     decisive = (margin[:, 0] - margin[:, 1]) > 1e-3 * ref.abs().max()
     assert torch.equal(out.argmax(1)[decisive], ref.argmax(1)[decisive])
+
+
+def test_fuse_batchnorm_on_the_reference_model_files():
+    """The reference's own models/resnet.py + ONE line (fuse_batchnorm): same state_dict keys, same training step
+    (loss and gradients against the unconverted model, whose norms are torch's), norms on this library's kernels."""
+    import copy
+    import po2_quantization_b200 as P
+    from po2_quantization_b200 import ops
+    from workloads import reference_files as RF
+    ns = RF.load("dropin")
+    if ns is None:
+        pytest.skip("no reference checkout (baseline/_ref)")
+    torch.manual_seed(5)
+    a = ns.get_model("resnet20", 10, P.PowerOfTwoQuantizer, 4, (32, 32)).cuda().train()
+    b = copy.deepcopy(a)
+    keys = list(b.state_dict().keys())
+    n = P.fuse_batchnorm(b)
+    assert n == 19 + 2 and list(b.state_dict().keys()) == keys
+    assert all(type(m) is P.FusedSyncBatchNorm for m in b.modules() if isinstance(m, torch.nn.SyncBatchNorm))
+    x = torch.randn(32, 3, 32, 32, device="cuda")
+    yl = torch.randint(0, 10, (32,), device="cuda")
+    la = torch.nn.functional.cross_entropy(a(x), yl); la.backward()
+    n0 = ops.LAUNCHES
+    lb = torch.nn.functional.cross_entropy(b(x), yl); lb.backward()
+    assert ops.LAUNCHES - n0 > 19 * 4                      # convs AND norms launched from libpo2b200.so
+    assert abs(la.item() - lb.item()) < 1e-3 * abs(la.item())
+    for (ka, pa), (kb, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert ka == kb
+        cos = torch.nn.functional.cosine_similarity(pa.grad.flatten(), pb.grad.flatten(), dim=0).item()
+        assert cos > 0.98, (ka, cos)
+    for (ka, ba), (kb, bb) in zip(a.named_buffers(), b.named_buffers()):
+        assert torch.allclose(ba.float(), bb.float(), rtol=1e-4, atol=1e-5), ka
+    # MobileNetV2 / MobileViT: the activation behind a norm inside an nn.Sequential moves into the norm
+    m = ns.get_model("mobilenet", 10, P.PowerOfTwoPlusQuantizer, 4, (32, 32)).cuda()
+    P.fuse_batchnorm(m)
+    assert sum(1 for mod in m.modules() if isinstance(mod, P.FusedSyncBatchNorm) and mod.act == "relu6") >= 30
+    assert not any(isinstance(mod, torch.nn.ReLU6) for mod in m.modules())
