@@ -622,6 +622,12 @@ def other_configs(device):
                 P.quantize_model(md, P.PowerOfTwoPlusQuantizer, bits)
                 ms_d, top1_d, _ = _graph_forward_ms(md, x)
                 r.update({"reference_model_file_on_dropin_ms": ms_d, "reference_model_file_on_dropin_images_per_s": B / ms_d * 1e3})
+                # ... plus two added lines in the evaluation script: fuse_batchnorm(model); fold_conv_bn(model)
+                P.fuse_batchnorm(md)
+                P.fold_conv_bn(md)
+                ms_f, top1_f, _ = _graph_forward_ms(md, x)
+                r.update({"reference_model_file_on_dropin_plus_fuse_and_fold_ms": ms_f,
+                          "reference_model_file_plus_fuse_and_fold_top1_agreement": float((top1_f == top1_d).float().mean().item())})
                 del md
             if ref is not None:
                 ref = ref.to(device).eval()
