@@ -202,3 +202,59 @@ def test_reference_file_loader_variants():
         assert torch.equal(a(x), b(x))
     v = RF.mobilevit_224(s)
     assert sum(1 for m in v.modules() if isinstance(m, s.QuantizedConv2d)) == 33
+
+
+def test_fuse_batchnorm_and_fold_conv_bn_rewrite_the_module_tree():
+    """fold.py on CPU: fuse_batchnorm re-classes nn.SyncBatchNorm instances in place (same state_dict keys) and moves
+    an activation behind a norm in an nn.Sequential into the norm; fold_conv_bn pairs conv + norm for inference; the
+    functional conv_bn_act falls back to the separate calls for CPU tensors and gives the same numbers."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    seq = nn.Sequential(P.QuantizedConv2d(4, 8, 3), nn.SyncBatchNorm(8), nn.ReLU6(inplace=True),
+                        P.QuantizedConv2d(8, 8, 1, padding=0), nn.SyncBatchNorm(8))
+    keys = list(seq.state_dict().keys())
+    assert P.fuse_batchnorm(seq) == 2
+    assert list(seq.state_dict().keys()) == keys
+    assert type(seq[1]) is P.FusedSyncBatchNorm and seq[1].act == "relu6" and isinstance(seq[2], nn.Identity)
+    assert type(seq[4]) is P.FusedSyncBatchNorm and seq[4].act is None
+    seq.eval()
+    with torch.no_grad():
+        seq[1].running_mean.normal_(); seq[1].running_var.uniform_(0.5, 2.0)
+        x = torch.randn(2, 4, 6, 6)
+        ref = seq(x)
+        assert P.fold_conv_bn(seq) == 2
+        assert isinstance(seq[0], P.FoldedConvBN) and isinstance(seq[1], nn.Identity)
+        assert torch.allclose(seq(x), ref, atol=1e-6)
+        # functional form, CPU tensors: conv, norm, add, ReLU as separate torch ops
+        conv, bn = P.QuantizedConv2d(4, 4, 3), P.FusedSyncBatchNorm(4).eval()
+        r = torch.randn(2, 4, 6, 6)
+        out = P.conv_bn_act(conv, bn, x, r, True)
+        assert torch.allclose(out, F.relu(bn(conv(x)) + r), atol=1e-6)
+
+
+def test_argument_errors_and_planning_queries_of_the_round_2_entry_points():
+    import ctypes
+    from po2_quantization_b200 import _lib
+    lib = _lib.load()
+    one = ctypes.c_void_p(4096)
+    conv = (8, 16, 32, 32, 16, 3, 3)
+    # planning queries answer on the host (no GPU): kernel kinds, pack sizes
+    assert lib.po2_conv2d_kernel_kind(128, 960, 1, 1, 320, 1, 1, 1, 0, 1, 2) == 4          # small-map pointwise GEMM
+    assert lib.po2_conv2d_kernel_kind(128, 96, 16, 16, 96, 3, 3, 2, 1, 96, 2) == 1          # depthwise
+    assert lib.po2_conv2d_kernel_kind(*conv, 2, 1, 1, 2) == 2                               # stride 2: register-fed tcgen05
+    assert lib.po2_conv2d_kernel_kind(*conv, 1, 1, 1, 1) == 0                               # fp32 mode: direct
+    assert lib.po2_conv2d_wgrad_kernel_kind(*conv, 2, 1, 1, 2) == 0                          # stride 2 goes through po2_dilate2
+    assert lib.po2_conv2d_pack_bytes(128, 960, 1, 1, 320, 1, 1, 1, 0, 1, 2) == 0             # no packed operand for kind 4
+    assert lib.po2_conv2d_depthwise_wgrad_workspace(96) > 4096 * 4
+    # argument errors come back as PO2_E_* before any launch
+    assert lib.po2_conv2d_fwd_ep(one, one, one, one, *conv, 1, 1, 1, 0, 4, 1, 2, one, 1 << 20, one, one, None, 7, None) == -9
+    assert lib.po2_conv2d_fwd_ep(one, one, one, one, *conv, 1, 1, 1, 0, 4, 1, 2, one, 1 << 20, one, None, None, 0, None) == -3
+    assert lib.po2_conv2d_fwd_packed_ep(one, one, one, one, *conv, 1, 1, 1, 2, None, None, one, 0, None) == -3   # residual without affine
+    assert lib.po2_dilate2(one, one, 4, 8, 7, None) == -10                                    # odd width
+    assert lib.po2_dilate2(None, one, 4, 8, 8, None) == -3
+    assert lib.po2_conv2d_depthwise_dgrad(one, None, one, 2, 8, 4, 4, None) == -3
+    assert lib.po2_conv2d_depthwise_wgrad(one, one, one, 2, 8, 4, 4, one, 16, None) == -8
+    assert lib.po2_bn_bwd_fused(one, one, one, one, one, one, None, None, one, None, 3, 8, 16, 64, one, 1 << 20, None) == -9
+    assert lib.po2_bn_apply_sums(one, None, one, None, one, None, None, None, None, None, 0.1, 1e-5, 0, None, None, 8, 16, 64, None) == -3
+    assert lib.po2_conv2d_fwd_packed_stats(one, one, one, one, *conv, 2, 1, 1, 2, one, None) == -10          # stride 2: not the TMA-fed kernel
+    assert lib.po2_conv2d_dgrad_packed(one, None, one, one, *conv, 1, 2, None) == -3
