@@ -1,7 +1,7 @@
 """Run the backward / norm kernels of one ResNet-56 layer shape a few times (for ncu captures).
     python tools/run_step_kernels_once.py [C H W K] [batch]
-Launches: conv_wgrad_umma_kernel + conv_wgrad_reduce_kernel, bn_reduce_kernel<0>, bn_apply_kernel,
-bn_reduce_kernel<2>, bn_bwd_apply_kernel on a (batch, C, H, W) activation."""
+Launches: conv_wgrad_tma_kernel + conv_wgrad_reduce_kernel, bn_fwd_fused_kernel, bn_bwd_fused_kernel (one rank)
+on a (batch, C, H, W) activation."""
 import os
 import sys
 
@@ -19,7 +19,7 @@ gw = torch.empty(K, C, 3, 3, device="cuda")
 bn = P.FusedSyncBatchNorm(C).cuda().train()
 res = torch.randn_like(x)
 for _ in range(3):
-    assert ops.conv2d_wgrad_out(go, x, gw, 1)
+    assert ops.conv2d_wgrad_out(go, x, gw, 1, 2)          # tf32 mode: conv_wgrad_tma_kernel (K5T)
     xi = x.detach().requires_grad_(True)
     y = bn(xi, res, True)
     y.backward(torch.ones_like(y))
