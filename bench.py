@@ -130,6 +130,10 @@ def build_training(device, world, local_rank, source="workload"):
         # quantize all 56 weights in ONE multi-tensor launch at the start of each forward instead of one
         # by one in front of each conv (po2_quantization_b200/prefetch.py); same arithmetic, same results
         P.enable_weight_prefetch(model)
+    # weight-gradient kernels on a side stream, joined at the end of backward (ops.set_wgrad_overlap): safe here
+    # because the step zeroes gradients to None and nothing hooks them; torch DDP's reducer hooks would read them
+    P.ops.set_wgrad_overlap(os.environ.get("PO2_WGRAD_STREAM", "1") == "1" and os.environ.get("PO2_DDP", "0") != "1"
+                            and os.environ.get("PO2_GRAD_OVERLAP", "0") != "1")
     if world > 1:
         if os.environ.get("PO2_DDP", "0") == "1":
             # torch's DistributedDataParallel, as the reference wraps its model (train.py:153-155)
@@ -306,7 +310,8 @@ def run_ours(a):
     # Everything (model/DDP construction, warm-up, capture, replay, timing events) runs on ONE side
     # stream: CUDA-graph capture is illegal on the legacy default stream, and DDP's AccumulateGrad
     # hooks must be created on the stream the captured step later runs on.
-    side = torch.cuda.Stream(device)
+    # high priority: where the step forks (weight gradients on ops' side stream) the main branch's CTAs go first
+    side = torch.cuda.Stream(device, priority=int(os.environ.get("PO2_MAIN_PRIORITY", "-1")))
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
         _run_ours_on_stream(a, ops, world, rank, local_rank, device)
@@ -346,6 +351,54 @@ def _run_ours_on_stream(a, ops, world, rank, local_rank, device):
                 for k, c, t in rows:
                     f.write(f"{t / 5:10.1f} us/step {c // 5:5d} x  {100 * t / tot:5.1f}%  {k[:110]}\n")
             print(json.dumps({"torch_profile": a.torch_profile, "device_us_per_step": tot / 5}))
+        return
+
+    if a.graph_timeline:
+        # device timeline of graph replays from torch.profiler (CUPTI): per-stream busy time, idle gaps on the
+        # main branch, per-kernel totals inside the captured step (where the side branch overlaps the main one)
+        from torch.profiler import ProfilerActivity, profile
+        h.capture()
+        for _ in range(5):
+            h.run()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                h.run()
+            torch.cuda.synchronize()
+        if rank == 0:
+            evs = [e for e in prof.events() if e.device_type.name == "CUDA" and e.time_range.end > e.time_range.start]
+            evs.sort(key=lambda e: e.time_range.start)
+            rows = [{"name": e.name[:90], "t0": e.time_range.start, "t1": e.time_range.end} for e in evs]
+            t_first, t_last = rows[0]["t0"], max(r["t1"] for r in rows)
+            # union of busy intervals
+            busy, cur0, cur1 = 0.0, None, None
+            for r in rows:
+                if cur1 is None or r["t0"] > cur1:
+                    if cur1 is not None:
+                        busy += cur1 - cur0
+                    cur0, cur1 = r["t0"], r["t1"]
+                else:
+                    cur1 = max(cur1, r["t1"])
+            busy += cur1 - cur0
+            per = {}
+            for r in rows:
+                k = r["name"].split("(")[0]
+                d = per.setdefault(k, [0, 0.0])
+                d[0] += 1
+                d[1] += r["t1"] - r["t0"]
+            top = sorted(per.items(), key=lambda kv: -kv[1][1])
+            with open(a.graph_timeline, "w") as f:
+                f.write(f"# 3 graph replays, world={world}: span {(t_last - t_first) / 3:.1f} us/step, device busy (union) "
+                        f"{busy / 3:.1f} us/step, sum of kernel durations {sum(v[1] for v in per.values()) / 3:.1f} us/step\n")
+                for k, (c, t) in top:
+                    f.write(f"{t / 3:10.1f} us/step {c // 3:5d} x {t / c:8.2f} us each  {k}\n")
+                f.write("# timeline of the second replay (start us, duration us, name)\n")
+                n = len(rows) // 3
+                base = rows[n]["t0"]
+                for r in rows[n:2 * n]:
+                    f.write(f"{r['t0'] - base:10.2f} {r['t1'] - r['t0']:8.2f} {r['name']}\n")
+            print(json.dumps({"graph_timeline": a.graph_timeline, "span_us_per_step": (t_last - t_first) / 3,
+                              "busy_us_per_step": busy / 3}))
         return
 
     if a.profile_step:
@@ -931,6 +984,7 @@ def main():
     ap.add_argument("--parts", default="roofline,variants,oracle,configs,sweep",
                     help="N=1 only: which of the untimed side measurements to run (comma separated)")
     ap.add_argument("--torch-profile", default=None, help="write a torch.profiler kernel table of eager steps and exit")
+    ap.add_argument("--graph-timeline", default=None, help="write the device timeline of graph replays (torch.profiler) and exit")
     ap.add_argument("--profile-step", action="store_true", help="run one eager step inside cudaProfilerStart/Stop and exit")
     a = ap.parse_args()
     if a.impl == "reference":

@@ -417,6 +417,72 @@ def dilate2_out(g, g_up) -> None:
 _dw_workspaces = {}
 _wgrad_tickets = {}
 
+# ---- weight gradients on a second stream --------------------------------------------------------------------
+# The weight gradient of a layer is a leaf of the backward pass: nothing before the optimizer reads it.  With the
+# overlap on, K5T / K5 (+ their reduce kernel) are launched on a per-device side stream that forks from the
+# backward stream where the layer's output gradient exists, and the backward stream goes on to the data gradient
+# and the norm kernels of the layers below; one join is queued on the autograd engine for the end of the backward
+# pass.  Inside a CUDA-graph capture the side stream is a parallel branch of the graph.
+_wgrad_overlap = os.environ.get("PO2_WGRAD_STREAM", "0") == "1"
+_side_streams = {}
+_side_pending = {}
+_side_task = -1
+_wgrad_trace = None                # tests: list that receives the data_ptr of every deferred gradient
+
+
+def set_wgrad_overlap(on: bool) -> None:
+    """Run the weight-gradient kernels of prefetched QuantizedConv2d layers on a side stream (joined at the end of
+    backward()).  Only for training loops in which nothing reads a conv weight's gradient before backward()
+    returns: the gradient tensor is handed to autograd while its kernel may still be running, which is safe when
+    autograd installs it as ``weight.grad`` by reference (``zero_grad(set_to_none=True)``, no tensor hooks, no
+    DistributedDataParallel reducer hooks); a layer whose weight already has a ``.grad`` is not deferred."""
+    global _wgrad_overlap
+    _wgrad_overlap = bool(on)
+
+
+def get_wgrad_overlap() -> bool:
+    return _wgrad_overlap
+
+
+def join_weight_gradients() -> None:
+    """Make the current stream (and the stream backward ran on) wait for the side stream's weight gradients.
+    Queued automatically for the end of every backward pass that deferred one."""
+    for side, main in list(_side_pending.values()):
+        cur = torch.cuda.current_stream(side.device)
+        cur.wait_stream(side)
+        if main != cur:
+            main.wait_stream(side)
+    _side_pending.clear()
+
+
+def _wgrad_on_side_stream(g, x, gw, pad, compute, ready=None) -> bool:
+    """ready: event on the backward stream after which g exists (default: everything queued so far)"""
+    global _side_task
+    dev = x.device
+    side = _side_streams.get(dev.index)
+    if side is None:
+        side = _side_streams[dev.index] = torch.cuda.Stream(dev)     # lowest priority: the main branch goes first
+    main = torch.cuda.current_stream(dev)
+    if ready is not None:
+        side.wait_event(ready)
+    else:
+        side.wait_stream(main)
+    with torch.cuda.stream(side):          # workspace and tickets belong to the side stream
+        ok = conv2d_wgrad_out(g, x, gw, pad, compute)
+    if not ok:
+        return False
+    # g and x are released by autograd on the backward stream while the side stream may still read them
+    g.record_stream(side)
+    x.record_stream(side)
+    _side_pending[dev.index] = (side, main)
+    task = torch._C._current_graph_task_id()
+    if task != _side_task or task < 0:
+        _side_task = task
+        torch.autograd.Variable._execution_engine.queue_callback(join_weight_gradients)
+    if _wgrad_trace is not None:
+        _wgrad_trace.append(gw.data_ptr())
+    return True
+
 
 def _depthwise_backward(g_full, x, w, need_x, need_w):
     """(gx, gw) of a depthwise 3x3 pad-1 conv from the output gradient at the input resolution"""
@@ -443,7 +509,7 @@ def _depthwise_backward(g_full, x, w, need_x, need_w):
     return gx, gw
 
 
-def _conv_backward(g, x, w, scale, stride, pad, groups, compute, need_x, need_w, packed_d=None):
+def _conv_backward(g, x, w, scale, stride, pad, groups, compute, need_x, need_w, packed_d=None, defer_w=False):
     """(gx, gw) of conv2d(x, w) on our kernels: dense layers on the tcgen05 kernels (data gradient: the forward
     kernel with transposed weights; weight gradient: K5T / K5) -- stride-2 layers through the zero-inserted
     output gradient, which turns both into stride-1 problems -- and depthwise 3x3 layers on the CUDA-core
@@ -468,6 +534,13 @@ def _conv_backward(g, x, w, scale, stride, pad, groups, compute, need_x, need_w,
         if depthwise:
             gx, gw = _depthwise_backward(g_s1, x.contiguous(), w.contiguous(), need_x, need_w)
         else:
+            defer_w = defer_w and _wgrad_overlap and need_w and ours and _wgrad_mode == "tc" and \
+                torch._C._current_graph_task_id() >= 0
+            ready = None
+            if defer_w:
+                # the side stream forks HERE (output gradient complete), not behind this layer's data gradient
+                ready = torch.cuda.Event()
+                ready.record(torch.cuda.current_stream(x.device))
             if need_x and ours and _dgrad_mode == "tc" and scale is not None:
                 cand = torch.empty_like(x)
                 if packed_d is not None and stride == 1:
@@ -480,7 +553,11 @@ def _conv_backward(g, x, w, scale, stride, pad, groups, compute, need_x, need_w,
                 # tf32 mode: the TMA-fed tf32 kernel where the shape allows; elsewhere the library takes the
                 # bf16-operand kernel (the weight gradient is a leaf of the backward pass: its rounding does not
                 # propagate into other layers' gradients, unlike the data gradient)
-                if conv2d_wgrad_out(g_s1, x.contiguous(), cand, pad, compute):
+                xc = x.contiguous()
+                if defer_w:
+                    if _wgrad_on_side_stream(g_s1, xc, cand, pad, compute, ready):
+                        gw = cand
+                elif conv2d_wgrad_out(g_s1, xc, cand, pad, compute):
                     gw = cand
     if (need_x and gx is None) or (need_w and gw is None):
         if x.is_cuda and _conv_mode != "cudnn":

@@ -173,6 +173,7 @@ class _QConvPrefetched(torch.autograd.Function):
             out = ops.conv2d_packed(x, packed, scale, K, R, S, stride, pad, groups, compute)
         ctx.save_for_backward(x, qw, scale)
         ctx.packed_d = packed_d          # valid until the next prefetch launch, i.e. through this step's backward
+        ctx.weight = weight              # the parameter: backward defers the weight gradient only if it has no .grad
         ctx.cfg = (stride, pad, groups, compute)
         return out
 
@@ -180,8 +181,13 @@ class _QConvPrefetched(torch.autograd.Function):
     def backward(ctx, g):
         x, qw, scale = ctx.saved_tensors
         stride, pad, groups, compute = ctx.cfg
+        wp = ctx.weight
+        # ops.set_wgrad_overlap: the weight gradient may run on the side stream when autograd will install it as
+        # wp.grad by reference (leaf without a gradient yet, no hooks that would read it during backward)
+        defer = (wp.is_leaf and wp.grad is None and not wp._backward_hooks
+                 and not getattr(wp, "_post_accumulate_grad_hooks", None))
         gx, gw = ops._conv_backward(g, x, qw, scale, stride, pad, groups, compute, ctx.needs_input_grad[0],
-                                    ctx.needs_input_grad[1], packed_d=ctx.packed_d)
+                                    ctx.needs_input_grad[1], packed_d=ctx.packed_d, defer_w=defer)
         return gx, gw, None, None, None, None, None, None, None, None, None
 
 

@@ -405,3 +405,80 @@ def test_fuse_batchnorm_on_the_reference_model_files():
     P.fuse_batchnorm(m)
     assert sum(1 for mod in m.modules() if isinstance(mod, P.FusedSyncBatchNorm) and mod.act == "relu6") >= 30
     assert not any(isinstance(mod, torch.nn.ReLU6) for mod in m.modules())
+
+
+def test_weight_gradients_on_the_side_stream_are_the_same_gradients():
+    """ops.set_wgrad_overlap: K5T / K5 run on a side stream that forks from backward and is joined at its end.
+    The gradients must be bit-identical to the in-order ones (deterministic kernels), autograd must have installed
+    the deferred tensors as .grad by reference (a clone would read them before their kernel ran), a weight that
+    already holds a .grad must not be deferred, and the whole step must survive a CUDA-graph capture."""
+    from workloads import resnet_cifar
+    torch.manual_seed(3)
+    dev = torch.device("cuda:0")
+    model = resnet_cifar(20, 10, P.PowerOfTwoQuantizer, 4).to(dev).train()
+    P.enable_weight_prefetch(model)
+    x = torch.randn(64, 3, 32, 32, device=dev)
+    y = torch.randint(0, 10, (64,), device=dev)
+    crit = nn.CrossEntropyLoss()
+    qconvs = [m for m in model.modules() if isinstance(m, P.QuantizedConv2d)]
+
+    def grads(overlap, accumulate=False):
+        ops.set_wgrad_overlap(overlap)
+        ops._wgrad_trace = []
+        try:
+            model.zero_grad(set_to_none=True)
+            crit(model(x), y).backward()
+            first = list(ops._wgrad_trace)
+            if accumulate:
+                ops._wgrad_trace = []
+                crit(model(x), y).backward()          # .grad exists now: nothing may be deferred
+                assert ops._wgrad_trace == []
+            torch.cuda.synchronize()
+            return [p.grad.clone() for p in model.parameters()], first
+        finally:
+            ops._wgrad_trace = None
+            ops.set_wgrad_overlap(False)
+
+    want, none_deferred = grads(False)
+    assert none_deferred == []
+    again, _ = grads(False)
+    # the plain stem conv's weight gradient is cuDNN's (atomics): compare what is reproducible in order
+    stable = [torch.equal(a, b) for a, b in zip(want, again)]
+    assert sum(stable) >= len(stable) - 1
+    got, deferred = grads(True)
+    assert len(deferred) >= len(qconvs) - 2, (len(deferred), len(qconvs))
+    ptrs = {m.weight.grad.data_ptr() for m in qconvs}
+    assert set(deferred) <= ptrs                      # installed by reference, not cloned
+    for ok, a, b in zip(stable, want, got):
+        assert torch.equal(a, b) if ok else torch.allclose(a, b, rtol=1e-4, atol=1e-6)
+    twice, _ = grads(True, accumulate=True)
+    once2, _ = grads(False, accumulate=True)
+    for ok, a, b in zip(stable, once2, twice):
+        assert torch.equal(a, b) if ok else torch.allclose(a, b, rtol=1e-4, atol=1e-6)
+
+    # the same step inside a CUDA graph: the side stream becomes a parallel branch and is joined before the end
+    opt = torch.optim.SGD(model.parameters(), lr=0.0)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    ops.set_wgrad_overlap(True)
+    try:
+        with torch.cuda.stream(s):
+            def step():
+                opt.zero_grad(set_to_none=True)
+                crit(model(x), y).backward()
+                opt.step()
+            for _ in range(3):
+                step()
+            s.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                step()
+            for _ in range(3):
+                g.replay()
+            s.synchronize()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        for ok, a, p in zip(stable, want, model.parameters()):
+            assert torch.equal(a, p.grad) if ok else torch.allclose(a, p.grad, rtol=1e-4, atol=1e-6)
+    finally:
+        ops.set_wgrad_overlap(False)
