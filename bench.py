@@ -145,7 +145,9 @@ def build_training(device, world, local_rank, source="workload"):
             model = BatchSharded(model, overlap=os.environ.get("PO2_GRAD_OVERLAP", "0") == "1",
                                  buckets=int(os.environ.get("PO2_GRAD_BUCKETS", "4")))
     # reference train.py:51-56: SGD momentum 0.9, wd 1e-4, lr 0.1 * world
-    opt = torch.optim.SGD(model.parameters(), lr=0.1 * world, momentum=0.9, weight_decay=1e-4)
+    # po2_quantization_b200.optim.SGD: torch.optim.SGD whose step() is one launch per 96 tensors (same roundings)
+    sgd = torch.optim.SGD if os.environ.get("PO2_SGD", "ours") == "torch" else P.optim.SGD
+    opt = sgd(model.parameters(), lr=0.1 * world, momentum=0.9, weight_decay=1e-4)
     crit = nn.CrossEntropyLoss()
     return model, opt, crit
 

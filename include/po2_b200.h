@@ -265,8 +265,10 @@ int po2_lin_quantize(const void* w, void* y, int K, int C, int RS, int bits, int
  *   torch.batch_norm_gather_stats_with_counts does), or use_running != 0: the running statistics
  *   (eval mode).  In train mode also updates running_mean / running_var (unbiased variance,
  *   `momentum`) and num_batches_tracked when given, and writes save_mean / save_invstd for backward.
- * po2_bn_bwd_reduce: sums[0..C) = sum g, sums[C..2C) = sum g*(x-mean) with g = dy (act 0) or
- *   dy*(y>0) (act 1); dgamma = sums[C+c]*invstd, dbeta = sums[c] (local sums, as SyncBatchNorm).
+ * po2_bn_bwd_reduce: sums[0..C) = sum g, sums[C..2C) = sum g*(x-mean) with g = dy (act 0),
+ *   dy*(y>0) (act 1), dy*(0<y<6) (act 2) or dy*silu'(z), z = (x-mean)*gamma*invstd + beta (act 3: SiLU behind the
+ *   norm, models/mobile_vit.py:16-22; z is recomputed from x, so gamma / beta are needed and y is not);
+ *   dgamma = sums[C+c]*invstd, dbeta = sums[c] (local sums, as SyncBatchNorm).
  * po2_bn_bwd_apply: dx = (g - sum_g/M - (x-mean)*invstd^2*sum_gx/M) * gamma*invstd, M = total count
  *   over the R stats entries; `sums` all-reduced over ranks by the caller.  dres (optional): g, the
  *   gradient of the residual branch behind the ReLU. */
@@ -282,8 +284,8 @@ int po2_bn_apply(const void* x, const void* residual, void* y, const float* stat
  * the masked gradient of the residual branch (dres, may be NULL) -- models/resnet.py:55-71 under autograd.
  * Returns PO2_E_UNSUPPORTED when the pair po2_bn_bwd_reduce + po2_bn_bwd_apply has to be used. */
 int po2_bn_bwd_fused(const void* dy, const void* x, const void* y, const float* save_mean, const float* save_invstd,
-                     const float* gamma, float* dgamma, float* dbeta, void* dx, void* dres, int act, int B, int C, int HW,
-                     void* workspace, size_t workspace_bytes, void* stream);
+                     const float* gamma, const float* beta, float* dgamma, float* dbeta, void* dx, void* dres, int act,
+                     int B, int C, int HW, void* workspace, size_t workspace_bytes, void* stream);
 
 /* po2_bn_stats + po2_bn_apply in ONE launch for tensors whose per-channel slice fits the registers of
  * the CTAs working on it (the CIFAR-scale layers): x is read once, the CTAs of a channel meet at a
@@ -296,11 +298,12 @@ int po2_bn_fwd_fused(const void* x, const void* residual, void* y, const float* 
                      int HW, void* workspace, size_t workspace_bytes, void* const* peers, int rank, int world,
                      void* stream);
 int po2_bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* save_mean, const float* save_invstd,
-                      float* sums, float* dgamma, float* dbeta, int act, int B, int C, int HW, void* workspace,
-                      size_t workspace_bytes, void* const* peers, int rank, int world, void* stream);
+                      const float* gamma, const float* beta, float* sums, float* dgamma, float* dbeta, int act, int B, int C,
+                      int HW, void* workspace, size_t workspace_bytes, void* const* peers, int rank, int world,
+                      void* stream);
 int po2_bn_bwd_apply(const void* dy, const void* x, const void* y, const float* save_mean, const float* save_invstd,
-                     const float* gamma, const float* sums, const float* stats, int R, void* mailbox, void* dx,
-                     void* dres, int act, int B, int C, int HW, void* stream);
+                     const float* gamma, const float* beta, const float* sums, const float* stats, int R, void* mailbox,
+                     void* dx, void* dres, int act, int B, int C, int HW, void* stream);
 
 /* Peer exchange (one NVLink domain, <= 8 ranks): SyncBatchNorm's two collectives done by the kernels
  * themselves.  Every rank allocates one zero-initialised mailbox of po2_bn_mailbox_bytes() in memory
@@ -313,6 +316,15 @@ int po2_bn_bwd_apply(const void* dy, const void* x, const void* y, const float* 
  * po2_bn_apply copies the gathered statistics to stats_dense[R][2C+1] for the backward call).
  * All ranks must issue the same sequence of exchanges (the rule of any collective). */
 size_t po2_bn_mailbox_bytes(void);
+
+/* ---- the QAT step's parameter update (train.py:54-56 optim.SGD(lr, momentum, weight_decay), :92 optimizer.step()) ----
+ * All parameters in one launch per po2_sgd_max_tensors_per_launch() tensors, torch.optim.SGD's arithmetic rounding by
+ * rounding (dampening 0, no Nesterov): g = fma(wd, p, grad); buf = rn(rn(buf*momentum) + g) (first_step: buf = g);
+ * p = fma(-lr, buf, p).  params / grads / bufs / numels: HOST arrays of `ntensors` device pointers (fp32,
+ * contiguous) and element counts; bufs may be NULL when momentum == 0. */
+int po2_sgd_step(void* const* params, const void* const* grads, void* const* bufs, const long long* numels, int ntensors,
+                 float lr, float momentum, float weight_decay, int first_step, void* stream);
+int po2_sgd_max_tensors_per_launch(void);
 
 #ifdef __cplusplus
 }

@@ -51,6 +51,8 @@ SIGNATURES = {
     "po2_conv2d_dgrad_workspace": (_sz, [_i] * 9),
     "po2_conv2d_dgrad": (_i, [_vp, _vp, _vp, _vp] + [_i] * 14 + [_vp, _sz, _vp]),
     "po2_dilate2": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "po2_sgd_step": (_i, [_vp, _vp, _vp, _vp, _i, _c.c_float, _c.c_float, _c.c_float, _i, _vp]),
+    "po2_sgd_max_tensors_per_launch": (_i, []),
     "po2_conv2d_depthwise_dgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "po2_conv2d_depthwise_wgrad_workspace": (_sz, [_i]),
     "po2_conv2d_depthwise_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
@@ -66,9 +68,9 @@ SIGNATURES = {
     "po2_bn_apply": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c.c_float, _c.c_float,
                           _i, _i, _vp, _vp, _i, _i, _i, _vp]),
     "po2_bn_fwd_fused": (_i, [_vp] * 8 + [_c.c_float, _c.c_float, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp, _i, _i, _vp]),
-    "po2_bn_bwd_fused": (_i, [_vp] * 10 + [_i] * 4 + [_vp, _sz, _vp]),
-    "po2_bn_bwd_reduce": (_i, [_vp] * 8 + [_i] * 4 + [_vp, _sz, _vp, _i, _i, _vp]),
-    "po2_bn_bwd_apply": (_i, [_vp] * 8 + [_i, _vp, _vp, _vp] + [_i] * 4 + [_vp]),
+    "po2_bn_bwd_fused": (_i, [_vp] * 11 + [_i] * 4 + [_vp, _sz, _vp]),
+    "po2_bn_bwd_reduce": (_i, [_vp] * 10 + [_i] * 4 + [_vp, _sz, _vp, _i, _i, _vp]),
+    "po2_bn_bwd_apply": (_i, [_vp] * 9 + [_i, _vp, _vp, _vp] + [_i] * 4 + [_vp]),
 }
 
 _lock = threading.Lock()

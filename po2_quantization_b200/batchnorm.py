@@ -213,7 +213,7 @@ def bn_apply_sums_out(x, residual, y, sums, stats_dense, weight, bias, running_m
         _ptr(save_mean), _ptr(save_invstd), B, C, HW, ops._stream_ptr(x.device)), "po2_bn_apply_sums")
 
 
-def bn_bwd_fused_out(dy, x, y, save_mean, save_invstd, weight, dgamma, dbeta, dx, dres, relu) -> bool:
+def bn_bwd_fused_out(dy, x, y, save_mean, save_invstd, weight, dgamma, dbeta, dx, dres, relu, bias=None) -> bool:
     """sums + apply of the backward in one launch (one rank, tensors that fit the registers of their CTAs);
     False if the shape is not taken"""
     if os.environ.get("PO2_BN_FUSED", "1") != "1" or os.environ.get("PO2_BN_FUSED_BWD", "1") != "1":
@@ -222,7 +222,7 @@ def bn_bwd_fused_out(dy, x, y, save_mean, save_invstd, weight, dgamma, dbeta, dx
     HW = x.numel() // (B * C)
     ws = _bn_workspace(x.device, C)
     rc = _lib.load().po2_bn_bwd_fused(
-        dy.data_ptr(), x.data_ptr(), _ptr(y), save_mean.data_ptr(), save_invstd.data_ptr(), _ptr(weight),
+        dy.data_ptr(), x.data_ptr(), _ptr(y), save_mean.data_ptr(), save_invstd.data_ptr(), _ptr(weight), _ptr(bias),
         _ptr(dgamma), _ptr(dbeta), dx.data_ptr(), _ptr(dres), int(relu), B, C, HW, ws.data_ptr(), ws.numel(),
         ops._stream_ptr(x.device))
     if rc == -10:
@@ -232,24 +232,25 @@ def bn_bwd_fused_out(dy, x, y, save_mean, save_invstd, weight, dgamma, dbeta, dx
     return True
 
 
-def bn_bwd_reduce_out(dy, x, y, save_mean, save_invstd, sums, dgamma, dbeta, relu, exch=None) -> None:
+def bn_bwd_reduce_out(dy, x, y, save_mean, save_invstd, sums, dgamma, dbeta, relu, exch=None, weight=None,
+                      bias=None) -> None:
     B, C = x.shape[0], x.shape[1]
     HW = x.numel() // (B * C)
     ws = _bn_workspace(x.device, C)
     ops.LAUNCHES += 1
     _lib.check(_lib.load().po2_bn_bwd_reduce(
-        dy.data_ptr(), x.data_ptr(), _ptr(y), save_mean.data_ptr(), save_invstd.data_ptr(), sums.data_ptr(),
-        _ptr(dgamma), _ptr(dbeta), int(relu), B, C, HW, ws.data_ptr(), ws.numel(), *_peer_args(exch),
+        dy.data_ptr(), x.data_ptr(), _ptr(y), save_mean.data_ptr(), save_invstd.data_ptr(), _ptr(weight), _ptr(bias),
+        sums.data_ptr(), _ptr(dgamma), _ptr(dbeta), int(relu), B, C, HW, ws.data_ptr(), ws.numel(), *_peer_args(exch),
         ops._stream_ptr(x.device)), "po2_bn_bwd_reduce")
 
 
-def bn_bwd_apply_out(dy, x, y, save_mean, save_invstd, weight, sums, stats, dx, dres, relu, exch=None) -> None:
+def bn_bwd_apply_out(dy, x, y, save_mean, save_invstd, weight, sums, stats, dx, dres, relu, exch=None, bias=None) -> None:
     B, C = x.shape[0], x.shape[1]
     HW = x.numel() // (B * C)
     R = stats.numel() // (2 * C + 1)
     ops.LAUNCHES += 1
     _lib.check(_lib.load().po2_bn_bwd_apply(
-        dy.data_ptr(), x.data_ptr(), _ptr(y), save_mean.data_ptr(), save_invstd.data_ptr(), _ptr(weight),
+        dy.data_ptr(), x.data_ptr(), _ptr(y), save_mean.data_ptr(), save_invstd.data_ptr(), _ptr(weight), _ptr(bias),
         _ptr(sums), stats.data_ptr(), R, exch.mailbox if exch is not None else None, dx.data_ptr(), _ptr(dres),
         int(relu), B, C, HW, ops._stream_ptr(x.device)), "po2_bn_bwd_apply")
 
@@ -303,12 +304,14 @@ class _BatchNormTrain(torch.autograd.Function):
                 bn_apply_out(x, residual, y, stats, weight, bias, running_mean, running_var, num_batches_tracked,
                              momentum, eps, relu, False, save_mean, save_invstd)
         ctx.relu, ctx.has_res, ctx.group, ctx.world, ctx.exch = int(relu), residual is not None, group, world, exch
-        ctx.save_for_backward(x, y if relu else None, weight, save_mean, save_invstd, stats)
+        # ReLU / ReLU6 mask on y; SiLU (3) recomputes its argument from x, gamma and beta instead
+        ctx.save_for_backward(x, y if relu in (1, 2, True) else None, weight, save_mean, save_invstd, stats,
+                              bias if int(relu) == 3 else None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y, weight, save_mean, save_invstd, stats = ctx.saved_tensors
+        x, y, weight, save_mean, save_invstd, stats, bias = ctx.saved_tensors
         dy = dy.contiguous()
         C = x.shape[1]
         need_x, need_res, need_w, need_b = ctx.needs_input_grad[:4]
@@ -322,13 +325,13 @@ class _BatchNormTrain(torch.autograd.Function):
                 dres = torch.empty_like(x) if ctx.relu else dy       # without the ReLU the branch gets dy itself
             # one rank, small tensor: sums + apply as ONE launch (dy / x / y read once)
             if not (ctx.world == 1 and bn_bwd_fused_out(dy, x, y, save_mean, save_invstd, weight, dgamma, dbeta, dx,
-                                                        dres if ctx.relu else None, ctx.relu)):
+                                                        dres if ctx.relu else None, ctx.relu, bias)):
                 sums = torch.empty(2 * C, dtype=torch.float32, device=x.device)
-                bn_bwd_reduce_out(dy, x, y, save_mean, save_invstd, sums, dgamma, dbeta, ctx.relu, exch)
+                bn_bwd_reduce_out(dy, x, y, save_mean, save_invstd, sums, dgamma, dbeta, ctx.relu, exch, weight, bias)
                 if ctx.world > 1 and exch is None:
                     dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=ctx.group)
                 bn_bwd_apply_out(dy, x, y, save_mean, save_invstd, weight, sums, stats, dx,
-                                 dres if ctx.relu else None, ctx.relu, exch)
+                                 dres if ctx.relu else None, ctx.relu, exch, bias)
         return (dx if need_x else None, dres, dgamma if need_w else None, dbeta if need_b else None,
                 None, None, None, None, None, None, None, None, None, None)
 
@@ -347,8 +350,8 @@ class FusedSyncBatchNorm(nn.SyncBatchNorm):
     ``act`` ("relu", "relu6", "silu" or None) is the activation the model applies right after this norm
     -- given at construction so that an ``nn.Sequential(conv, FusedSyncBatchNorm(c, act="relu6"),
     nn.Identity())`` keeps the reference's ``state_dict`` keys -- or per call with ``relu=True``.
-    SiLU is fused in the forward-only (no-grad) path; under autograd it is applied by ``F.silu`` behind
-    the norm kernel."""
+    SiLU runs inside the kernels forward and backward (its backward recomputes the activation's argument from x,
+    gamma and beta); only SiLU behind a residual add under autograd is applied by ``F.silu`` after the norm kernel."""
 
     fused_residual_relu = True
 
@@ -388,13 +391,14 @@ class FusedSyncBatchNorm(nn.SyncBatchNorm):
                         if n % 64 == 0:                              # about once per ResNet-56 step
                             exch.check()
             track = self.training and self.track_running_stats
-            kact = act if act != 3 else 0                            # SiLU has no fused backward
+            # SiLU's backward is in the kernels for the plain conv-norm-SiLU case; behind a residual add it stays F.silu
+            kact = act if (act != 3 or residual is None) else 0
             out = _BatchNormTrain.apply(
                 input, residual, self.weight, self.bias, self.running_mean if track else None,
                 self.running_var if track else None, self.num_batches_tracked if track else None,
                 self.momentum if self.momentum is not None else 0.0, self.eps, kact, group, world, exch,
                 sums if world == 1 else None)
-            return F.silu(out) if act == 3 else out
+            return F.silu(out) if kact != act else out
         if fast and not use_batch_stats and not (torch.is_grad_enabled() and (
                 input.requires_grad or (residual is not None and residual.requires_grad) or
                 (self.weight is not None and self.weight.requires_grad))):

@@ -12,7 +12,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libpo2b200.so")
-SOURCES = ["po2_quant.cu", "po2_conv.cu", "po2_conv_bwd.cu", "po2_bn.cu", "po2_lin.cu"]
+SOURCES = ["po2_quant.cu", "po2_conv.cu", "po2_conv_bwd.cu", "po2_bn.cu", "po2_lin.cu", "po2_sgd.cu"]
 HEADERS = ["po2_common.cuh", "po2_conv_tma.cuh", "po2_wgrad_tma.cuh", "po2_boundaries.inc", os.path.join(ROOT, "include", "po2_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

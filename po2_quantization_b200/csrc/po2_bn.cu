@@ -12,7 +12,7 @@
 //   bn_reduce_kernel<1|2>  per-channel sum(g), sum(g*(x-mean)), g = dy masked by the activation
 //   bn_bwd_apply_kernel    dx (and the masked gradient for the residual branch)
 //   bn_fwd_fused_kernel    the first two in ONE launch for tensors that fit in registers (one rank)
-//   act: none / ReLU / ReLU6 (forward + backward), SiLU (forward only)
+//   act: none / ReLU / ReLU6 / SiLU (forward + backward; SiLU's backward only without a residual branch)
 //
 // The split between the two halves of each direction is where SyncBatchNorm's collective goes
 // (all_gather of the 2C+1 statistics forward, all_reduce of the 2C sums backward) -- done by the
@@ -195,7 +195,7 @@ __device__ __forceinline__ bool publish_partial(double a, double b, const BnWork
 }
 
 // activations behind the norm: 0 none, 1 ReLU, 2 ReLU6 (hardtanh(0, 6): gradient passes for 0 < y < 6),
-// 3 SiLU (forward only)
+// 3 SiLU (backward: bn_silu_slope, z recomputed from x)
 __device__ __forceinline__ float bn_act(float v, int act) {
   if (act == 1) return fmaxf(v, 0.f);
   if (act == 2) return fminf(fmaxf(v, 0.f), 6.f);
@@ -203,6 +203,13 @@ __device__ __forceinline__ float bn_act(float v, int act) {
   return v;
 }
 __device__ __forceinline__ bool bn_act_open(float y, int act) { return y > 0.f && (act != 2 || y < 6.f); }
+// SiLU behind the norm (no residual branch): d silu(z) / dz at z = (x - mean) * a + b, a = gamma * invstd, b = beta --
+// the forward's own expression for z (bn_apply_kernel), sigmoid from the same __expf
+__device__ __forceinline__ float bn_silu_slope(float x, float mu, float a, float b) {
+  const float z = fmaf(x - mu, a, b);
+  const float sg = 1.f / (1.f + __expf(-z));
+  return sg * fmaf(z, 1.f - sg, 1.f);
+}
 
 // MODE 0: forward statistics (p = x - shift, q = p);  1: backward sums (p = dy, q = x - mean);
 // MODE 2: backward sums behind a ReLU (p = y > 0 ? dy : 0).
@@ -215,7 +222,9 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const float* __re
                                                                float* __restrict__ out,      // MODE 0: stat[2C+1]; else sums[2C]
                                                                float* __restrict__ dgamma,
                                                                float* __restrict__ dbeta, BnGeom g,
-                                                               BnWorkspace ws, BnPeers peers, int act) {
+                                                               BnWorkspace ws, BnPeers peers, int act,
+                                                               const float* __restrict__ gamma = nullptr,
+                                                               const float* __restrict__ beta = nullptr) {
   // the consuming kernel (apply / backward apply, launched with programmatic stream serialization) may
   // be scheduled as soon as every CTA of this grid is running; it waits for this grid's completion
   // (griddepcontrol.wait) before it reads anything this grid writes
@@ -229,6 +238,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const float* __re
   const int nslab = (g.B - s + g.S - 1) / g.S;                 // slabs b = s, s+S, ...
   const int n = nslab * L;
   const float shift = MODE == 0 ? __ldg(x + (size_t)c * g.HW) : __ldg(mean + c);
+  const bool silu = MODE == 2 && act == 3;
+  const float za = silu ? (gamma ? __ldg(gamma + c) : 1.f) * __ldg(invstd + c) : 0.f, zb = silu && beta ? __ldg(beta + c) : 0.f;
   // tag of the exchange this grid produces; read before any CTA can have advanced it (the advance
   // needs every CTA's ticket, taken below), visible to the CTA after the first barrier in block_sum2
   if (threadIdx.x == 0 && peers.world > 1)
@@ -247,7 +258,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const float* __re
           const size_t off = ((size_t)(s + k * g.S) * C + c) * L + (i - k * L);
           vx[u] = __ldg(reinterpret_cast<const float4*>(x) + off);
           if (MODE != 0) vd[u] = __ldg(reinterpret_cast<const float4*>(dy) + off);
-          if (MODE == 2) vy[u] = __ldg(reinterpret_cast<const float4*>(y) + off);
+          if (MODE == 2 && !silu) vy[u] = __ldg(reinterpret_cast<const float4*>(y) + off);
         }
       }
 #pragma unroll
@@ -260,7 +271,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const float* __re
           const float q = xs[e] - shift;
           if (MODE == 0) { s1 += q; s2 = fmaf(q, q, s2); }
           else {
-            const float p = (MODE == 2 && !bn_act_open(ys[e], act)) ? 0.f : ds[e];
+            float p = ds[e];
+            if (MODE == 2) p = silu ? p * bn_silu_slope(xs[e], shift, za, zb) : (bn_act_open(ys[e], act) ? p : 0.f);
             s1 += p; s2 = fmaf(p, q, s2);
           }
         }
@@ -272,11 +284,12 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const float* __re
         if (i < n) {
           const int k = fdiv(i, g.div_l);
           const size_t off = ((size_t)(s + k * g.S) * C + c) * L + (i - k * L);
-          const float q = __ldg(x + off) - shift;
+          const float xv = __ldg(x + off);
+          const float q = xv - shift;
           if (MODE == 0) { s1 += q; s2 = fmaf(q, q, s2); }
           else {
             float p = __ldg(dy + off);
-            if (MODE == 2 && !bn_act_open(__ldg(y + off), act)) p = 0.f;
+            if (MODE == 2) p = silu ? p * bn_silu_slope(xv, shift, za, zb) : (bn_act_open(__ldg(y + off), act) ? p : 0.f);
             s1 += p; s2 = fmaf(p, q, s2);
           }
         }
@@ -496,9 +509,11 @@ __global__ void __launch_bounds__(BN_THREADS, 4) bn_bwd_apply_kernel(const float
                                                                   const float* __restrict__ stats, int R,
                                                                   BnMailbox* mailbox,
                                                                   float* __restrict__ dx,
-                                                                  float* __restrict__ dres, int act, BnGeom g) {
+                                                                  float* __restrict__ dres, int act, BnGeom g,
+                                                                  const float* __restrict__ beta) {
   extern __shared__ float4 prm[];
   const int C = g.C;
+  float* prb = reinterpret_cast<float*>(prm + C);                 // beta per channel (SiLU: z is recomputed from x)
   asm volatile("griddepcontrol.wait;" ::: "memory");            // sums / mailbox epoch come from the reduce kernel
   double M = 0.0;
   for (int r = 0; r < R; ++r) M += (double)stats[(size_t)r * (2 * C + 1) + 2 * C];
@@ -516,9 +531,11 @@ __global__ void __launch_bounds__(BN_THREADS, 4) bn_bwd_apply_kernel(const float
       sg = (double)a; sgx = (double)b;
     } else { sg = (double)sums[c]; sgx = (double)sums[C + c]; }
     prm[c] = make_float4(mean[c], (float)(sg / M), (float)(is * is * sgx / M), (float)((double)ga * is));
+    prb[c] = beta ? beta[c] : 0.f;
   }
   __syncthreads();
-  const bool relu = act != 0;                                  // masked by the activation's open interval
+  const bool silu = act == 3;
+  const bool relu = act != 0 && !silu;                         // masked by the activation's open interval
   for (int i0 = blockIdx.x * (BN_UNROLL * BN_THREADS) + threadIdx.x; i0 < g.total;
        i0 += gridDim.x * (BN_UNROLL * BN_THREADS)) {
     if (VEC) {
@@ -543,6 +560,10 @@ __global__ void __launch_bounds__(BN_THREADS, 4) bn_bwd_apply_kernel(const float
           if (relu) {
             gr.x = bn_act_open(vy[u].x, act) ? gr.x : 0.f; gr.y = bn_act_open(vy[u].y, act) ? gr.y : 0.f;
             gr.z = bn_act_open(vy[u].z, act) ? gr.z : 0.f; gr.w = bn_act_open(vy[u].w, act) ? gr.w : 0.f;
+          } else if (silu) {
+            const float zb = prb[c];                               // p.w = gamma * invstd
+            gr.x *= bn_silu_slope(vx[u].x, p.x, p.w, zb); gr.y *= bn_silu_slope(vx[u].y, p.x, p.w, zb);
+            gr.z *= bn_silu_slope(vx[u].z, p.x, p.w, zb); gr.w *= bn_silu_slope(vx[u].w, p.x, p.w, zb);
           }
           float4 o;
           o.x = (gr.x - p.y - (vx[u].x - p.x) * p.z) * p.w; o.y = (gr.y - p.y - (vx[u].y - p.x) * p.z) * p.w;
@@ -561,6 +582,7 @@ __global__ void __launch_bounds__(BN_THREADS, 4) bn_bwd_apply_kernel(const float
           const float4 p = prm[c];
           float gr = __ldg(dy + i);
           if (relu && !bn_act_open(__ldg(y + i), act)) gr = 0.f;
+          if (silu) gr *= bn_silu_slope(__ldg(x + i), p.x, p.w, prb[c]);
           dx[i] = (gr - p.y - (__ldg(x + i) - p.x) * p.z) * p.w;
           if (dres) dres[i] = gr;
         }
@@ -763,7 +785,7 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_fused_kernel(const float
                                                                      float* __restrict__ dbeta,
                                                                      float* __restrict__ dx,
                                                                      float* __restrict__ dres, int act, BnGeom g,
-                                                                     BnWorkspace ws) {
+                                                                     BnWorkspace ws, const float* __restrict__ beta) {
   __shared__ double sm[BN_THREADS / 32][2];
   __shared__ int s_ok;
   const int s = blockIdx.x, c = blockIdx.y, C = g.C, L = g.L;
@@ -785,7 +807,11 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_fused_kernel(const float
       off[u] = ((s + k * g.S) * C + c) * L + (i - k * L);
       vg[u] = __ldg(reinterpret_cast<const float4*>(dy) + off[u]);
       vx[u] = __ldg(reinterpret_cast<const float4*>(x) + off[u]);
-      if (act) {
+      if (act == 3) {
+        const float za = (gamma ? __ldg(gamma + c) : 1.f) * __ldg(invstd + c), zb = beta ? __ldg(beta + c) : 0.f;
+        vg[u].x *= bn_silu_slope(vx[u].x, mu, za, zb); vg[u].y *= bn_silu_slope(vx[u].y, mu, za, zb);
+        vg[u].z *= bn_silu_slope(vx[u].z, mu, za, zb); vg[u].w *= bn_silu_slope(vx[u].w, mu, za, zb);
+      } else if (act) {
         const float4 vy = __ldg(reinterpret_cast<const float4*>(y) + off[u]);
         vg[u].x = bn_act_open(vy.x, act) ? vg[u].x : 0.f; vg[u].y = bn_act_open(vy.y, act) ? vg[u].y : 0.f;
         vg[u].z = bn_act_open(vy.z, act) ? vg[u].z : 0.f; vg[u].w = bn_act_open(vy.w, act) ? vg[u].w : 0.f;
@@ -1044,11 +1070,11 @@ int po2_bn_fwd_fused(const void* x, const void* residual, void* y, const float* 
 // Backward of the same layer as ONE launch (one rank, tensors that fit the CTAs' registers): sums + apply.
 // PO2_E_UNSUPPORTED: take po2_bn_bwd_reduce + po2_bn_bwd_apply.
 int po2_bn_bwd_fused(const void* dy, const void* x, const void* y, const float* save_mean, const float* save_invstd,
-                     const float* gamma, float* dgamma, float* dbeta, void* dx, void* dres, int act, int B, int C, int HW,
-                     void* workspace, size_t workspace_bytes, void* stream) {
+                     const float* gamma, const float* beta, float* dgamma, float* dbeta, void* dx, void* dres, int act,
+                     int B, int C, int HW, void* workspace, size_t workspace_bytes, void* stream) {
   if (!dy || !x || !save_mean || !save_invstd || !dx || !workspace) return PO2_E_NULL;
-  if (act < 0 || act > 2) return PO2_E_MODE;               // SiLU (3) has no backward here
-  if (act != 0 && !y) return PO2_E_NULL;
+  if (act < 0 || act > 3 || (act == 3 && dres)) return PO2_E_MODE;      // SiLU: only without a residual branch
+  if ((act == 1 || act == 2) && !y) return PO2_E_NULL;
   if (workspace_bytes < po2_bn_workspace_bytes(C)) return PO2_E_WORKSPACE;
   if (!aligned16(workspace)) return PO2_E_ALIGN;
   BnGeom g;
@@ -1066,7 +1092,7 @@ int po2_bn_bwd_fused(const void* dy, const void* x, const void* y, const float* 
   BnWorkspace wsv = bn_ws(workspace, C);
   const float *df = (const float*)dy, *xf = (const float*)x, *yf = (const float*)y;
   float *dxf = (float*)dx, *drf = (float*)dres;
-  void* args[] = {&df, &xf, &yf, &save_mean, &save_invstd, &gamma, &dgamma, &dbeta, &dxf, &drf, &act, &g, &wsv};
+  void* args[] = {&df, &xf, &yf, &save_mean, &save_invstd, &gamma, &dgamma, &dbeta, &dxf, &drf, &act, &g, &wsv, &beta};
   const cudaError_t e = cudaLaunchCooperativeKernel((const void*)bn_bwd_fused_kernel, dim3(g.S, C), dim3(BN_THREADS), args, 0,
                                                     (cudaStream_t)stream);
   if (e == cudaErrorCooperativeLaunchTooLarge) {
@@ -1077,11 +1103,12 @@ int po2_bn_bwd_fused(const void* dy, const void* x, const void* y, const float* 
 }
 
 int po2_bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* save_mean, const float* save_invstd,
-                      float* sums, float* dgamma, float* dbeta, int act, int B, int C, int HW, void* workspace,
-                      size_t workspace_bytes, void* const* peers, int rank, int world, void* stream) {
+                      const float* gamma, const float* beta, float* sums, float* dgamma, float* dbeta, int act, int B, int C,
+                      int HW, void* workspace, size_t workspace_bytes, void* const* peers, int rank, int world,
+                      void* stream) {
   if (!dy || !x || !save_mean || !save_invstd || !sums || !workspace) return PO2_E_NULL;
-  if (act < 0 || act > 2) return PO2_E_MODE;               // SiLU (3) has no backward here
-  if (act != 0 && !y) return PO2_E_NULL;
+  if (act < 0 || act > 3) return PO2_E_MODE;
+  if ((act == 1 || act == 2) && !y) return PO2_E_NULL;
   if (workspace_bytes < po2_bn_workspace_bytes(C)) return PO2_E_WORKSPACE;
   if (!aligned16(workspace)) return PO2_E_ALIGN;
   BnGeom g;
@@ -1095,8 +1122,8 @@ int po2_bn_bwd_reduce(const void* dy, const void* x, const void* y, const float*
   cudaStream_t st = (cudaStream_t)stream;
   const float *xf = (const float*)x, *df = (const float*)dy, *yf = (const float*)y;
   if (act != 0) {
-    if (v) bn_reduce_kernel<true, 2><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr, act);
-    else bn_reduce_kernel<false, 2><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr, act);
+    if (v) bn_reduce_kernel<true, 2><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr, act, gamma, beta);
+    else bn_reduce_kernel<false, 2><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr, act, gamma, beta);
   } else {
     if (v) bn_reduce_kernel<true, 1><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr, act);
     else bn_reduce_kernel<false, 1><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr, act);
@@ -1105,16 +1132,16 @@ int po2_bn_bwd_reduce(const void* dy, const void* x, const void* y, const float*
 }
 
 int po2_bn_bwd_apply(const void* dy, const void* x, const void* y, const float* save_mean, const float* save_invstd,
-                     const float* gamma, const float* sums, const float* stats, int R, void* mailbox, void* dx,
-                     void* dres, int act, int B, int C, int HW, void* stream) {
+                     const float* gamma, const float* beta, const float* sums, const float* stats, int R, void* mailbox,
+                     void* dx, void* dres, int act, int B, int C, int HW, void* stream) {
   if (!dy || !x || !save_mean || !save_invstd || (!sums && !mailbox) || !stats || !dx || R < 1) return PO2_E_NULL;
   if (R > BN_MAX_RANKS && mailbox) return PO2_E_SIZE;
-  if (act < 0 || act > 2) return PO2_E_MODE;               // SiLU (3) has no backward here
-  if (act != 0 && !y) return PO2_E_NULL;
+  if (act < 0 || act > 3 || (act == 3 && dres)) return PO2_E_MODE;      // SiLU: only without a residual branch
+  if ((act == 1 || act == 2) && !y) return PO2_E_NULL;
   BnGeom g;
   const int v = bn_geom(g, B, C, HW, aligned16(dy) && aligned16(x) && aligned16(y) && aligned16(dx) && aligned16(dres));
   if (v < 0) return v;
-  const size_t smem = (size_t)C * sizeof(float4);
+  const size_t smem = (size_t)C * (sizeof(float4) + sizeof(float));
   cudaStream_t st = (cudaStream_t)stream;
   auto kern = v ? bn_bwd_apply_kernel<true> : bn_bwd_apply_kernel<false>;
   if (smem > 48 * 1024) {
@@ -1132,7 +1159,7 @@ int po2_bn_bwd_apply(const void* dy, const void* x, const void* y, const float* 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return (int)cudaLaunchKernelEx(&cfg, kern, (const float*)dy, (const float*)x, (const float*)y, save_mean, save_invstd,
-                                 gamma, sums, stats, R, (BnMailbox*)mailbox, (float*)dx, (float*)dres, act, g);
+                                 gamma, sums, stats, R, (BnMailbox*)mailbox, (float*)dx, (float*)dres, act, g, beta);
 }
 
 }  // extern "C"

@@ -276,6 +276,49 @@ def test_activation_variants_match_torch(act, shape):
     assert _rel(ye, ref) < TOL
 
 
+@pytest.mark.parametrize("fused", ["1", "0"], ids=["one_launch", "reduce_apply"])
+@pytest.mark.parametrize("shape", [(16, 32, 16, 16), (8, 24, 6, 6), (16, 96, 3, 3)], ids=lambda s: "x".join(map(str, s)))
+def test_silu_backward_runs_in_the_norm_kernels(shape, fused, monkeypatch):
+    """conv-norm-SiLU (models/mobile_vit.py:16-22) under autograd: the SiLU slope is applied inside the backward
+    kernels (one-launch and reduce + apply forms, 128-bit and scalar paths), no separate F.silu pass; dx, dgamma and
+    dbeta against fp64 autograd.  Behind a residual add the activation stays a separate F.silu."""
+    import po2_quantization_b200 as P
+    from po2_quantization_b200 import ops
+    monkeypatch.setenv("PO2_BN_FUSED", fused)
+    g = torch.Generator(device="cuda").manual_seed(sum(shape) + 5)
+    x = (torch.randn(shape, device="cuda", generator=g) * 1.5 - 0.3).requires_grad_(True)
+    go = torch.randn(shape, device="cuda", generator=g)
+    bn = P.FusedSyncBatchNorm(shape[1], act="silu").cuda().train()
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(shape[1], device="cuda", generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(shape[1], device="cuda", generator=g) * 0.5)
+    before = ops.LAUNCHES
+    y = bn(x)
+    y.backward(go)
+    torch.cuda.synchronize()
+    one_launch = fused == "1" and (shape[2] * shape[3]) % 4 == 0          # the one-launch forms are 128-bit only
+    assert ops.LAUNCHES - before == (2 if one_launch else 4)
+    xd = x.detach().double().cpu().requires_grad_(True)
+    wd = bn.weight.detach().double().cpu().requires_grad_(True)
+    bd = bn.bias.detach().double().cpu().requires_grad_(True)
+    yr = F.silu(F.batch_norm(xd, None, None, wd, bd, True, 0.0, bn.eps))
+    yr.backward(go.double().cpu())
+    assert _rel(y, yr) < TOL
+    assert _rel(x.grad, xd.grad) < 1e-4
+    assert _rel(bn.weight.grad, wd.grad) < 1e-4
+    assert _rel(bn.bias.grad, bd.grad) < 1e-4
+    # SiLU behind a residual add: norm + add in the kernel, F.silu behind it, same numbers
+    x2 = x.detach().clone().requires_grad_(True)
+    r2 = torch.randn(shape, device="cuda", generator=g).requires_grad_(True)
+    bn.zero_grad()
+    bn(x2, residual=r2).backward(go)
+    xd2 = x.detach().double().cpu().requires_grad_(True)
+    rd2 = r2.detach().double().cpu().requires_grad_(True)
+    F.silu(F.batch_norm(xd2, None, None, wd.detach(), bd.detach(), True, 0.0, bn.eps) + rd2).backward(go.double().cpu())
+    assert _rel(x2.grad, xd2.grad) < 1e-4
+    assert _rel(r2.grad, rd2.grad) < 1e-4
+
+
 def test_mobilenet_and_mobilevit_fused_norm_state_dict_and_forward():
     """The fused-norm variants of the MobileNetV2 / MobileViT workloads keep the stock state_dict keys
     and compute the same eval-mode forward."""

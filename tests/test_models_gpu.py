@@ -482,3 +482,52 @@ def test_weight_gradients_on_the_side_stream_are_the_same_gradients():
             assert torch.equal(a, p.grad) if ok else torch.allclose(a, p.grad, rtol=1e-4, atol=1e-6)
     finally:
         ops.set_wgrad_overlap(False)
+
+
+@pytest.mark.parametrize("momentum,wd", [(0.9, 1e-4), (0.0, 1e-4), (0.9, 0.0), (0.0, 0.0)])
+def test_multi_tensor_sgd_is_torch_sgd_bit_for_bit(momentum, wd):
+    """optim.SGD.step() = po2_sgd_step (one launch per 96 tensors) against torch.optim.SGD (train.py:54-56) over four
+    steps: parameters and momentum buffers bit-identical, state_dict interchangeable; ragged sizes, > 96 tensors,
+    a tensor larger than one CTA's chunk, an unaligned view-free odd size, and a parameter without a gradient."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(11)
+    sizes = [1, 3, 16, 17, 64, 2304, 4095, 4096, 4097, 36864, 70001] + [5 + 7 * i for i in range(100)]
+    base = [torch.randn(n, generator=g) for n in sizes]
+    a = [torch.nn.Parameter(t.clone().to(dev)) for t in base] + [torch.nn.Parameter(torch.ones(4, device=dev))]
+    b = [torch.nn.Parameter(t.clone().to(dev)) for t in base] + [torch.nn.Parameter(torch.ones(4, device=dev))]
+    oa = P.optim.SGD(a, lr=0.1, momentum=momentum, weight_decay=wd)
+    ob = torch.optim.SGD(b, lr=0.1, momentum=momentum, weight_decay=wd)
+    before = ops.LAUNCHES
+    for step in range(4):
+        for pa, pb in zip(a[:-1], b[:-1]):
+            gr = torch.randn(pa.shape, generator=g).to(dev) * (10.0 ** (step - 2))
+            pa.grad = gr.clone()
+            pb.grad = gr.clone()
+        oa.step()
+        ob.step()
+        if step == 1:                                    # a scheduler changed the rate
+            for o in (oa, ob):
+                o.param_groups[0]["lr"] = 0.037
+    torch.cuda.synchronize()
+    assert ops.LAUNCHES - before == 4 * 2                # 111 tensors: two launches per step
+    for pa, pb in zip(a, b):
+        assert torch.equal(pa, pb)
+        if momentum:
+            sa, sb = oa.state[pa].get("momentum_buffer"), ob.state[pb].get("momentum_buffer")
+            assert (sa is None) == (sb is None)
+            if sa is not None:
+                assert torch.equal(sa, sb)
+    # the state dicts are interchangeable
+    ob.load_state_dict(oa.state_dict())
+    oa.load_state_dict(ob.state_dict())
+    # what the kernel does not take goes to torch's own step: Nesterov here
+    c = [torch.nn.Parameter(base[5].clone().to(dev))]
+    d = [torch.nn.Parameter(base[5].clone().to(dev))]
+    oc = P.optim.SGD(c, lr=0.1, momentum=0.9, nesterov=True)
+    od = torch.optim.SGD(d, lr=0.1, momentum=0.9, nesterov=True)
+    for _ in range(2):
+        c[0].grad = torch.ones_like(c[0])
+        d[0].grad = torch.ones_like(d[0])
+        oc.step()
+        od.step()
+    assert torch.equal(c[0], d[0])

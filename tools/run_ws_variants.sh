@@ -9,6 +9,7 @@ except Exception as e:
     print("$name", "failed", e)
 PY
 }
-run off PO2_WGRAD_STREAM=0
-run on_prio0 PO2_MAIN_PRIORITY=0
-run on_prio1 PO2_MAIN_PRIORITY=-1
+run on X=1
+run on_bwd2k PO2_BN_FUSED_BWD=0
+run on_bn2k PO2_BN_FUSED=0
+run off_bn2k PO2_BN_FUSED=0 PO2_WGRAD_STREAM=0
