@@ -317,6 +317,23 @@ int po2_bn_bwd_apply(const void* dy, const void* x, const void* y, const float* 
  * All ranks must issue the same sequence of exchanges (the rule of any collective). */
 size_t po2_bn_mailbox_bytes(void);
 
+/* ---- conv + train-mode BatchNorm (+ residual add) (+ activation) in ONE launch --------------------------------
+ * models/resnet.py:55-71 in train(): y = act(bn(conv2d(x, Q(w))) + residual) with batch statistics, from the packed
+ * operand (po2_conv2d_pack / the multi-tensor quantizer).  The TMA-fed kernel keeps every tile's accumulator in TMEM,
+ * sums the conv output per channel, meets at a grid barrier (cooperative launch), adds the per-CTA partial sums in CTA
+ * order (deterministic) and normalises straight out of TMEM: the norm kernel's launch, its read of the conv output
+ * and its statistics pass disappear.  conv_out: the conv result (po2_bn_bwd_* read it); save_mean / save_invstd /
+ * stats_dense[2K+1] / running statistics as po2_bn_apply writes them (one rank).  workspace:
+ * po2_conv2d_bn_workspace(...) bytes (0: shape not taken), zeroed ONCE by the caller and then reused call after call
+ * on the same stream.  PO2_E_UNSUPPORTED: run the conv and the norm separately. */
+size_t po2_conv2d_bn_workspace(int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups, int compute);
+int po2_conv2d_bn_fwd_packed(const void* x, const void* packed, const float* scale, void* conv_out, void* y,
+                             const void* residual, const float* gamma, const float* beta, float* running_mean,
+                             float* running_var, long long* num_batches_tracked, float momentum, float eps, int act,
+                             float* save_mean, float* save_invstd, float* stats_dense, int B, int C, int H, int W, int K,
+                             int R, int S, int stride, int pad, int groups, int compute, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
 /* ---- the QAT step's parameter update (train.py:54-56 optim.SGD(lr, momentum, weight_decay), :92 optimizer.step()) ----
  * All parameters in one launch per po2_sgd_max_tensors_per_launch() tensors, torch.optim.SGD's arithmetic rounding by
  * rounding (dampening 0, no Nesterov): g = fma(wd, p, grad); buf = rn(rn(buf*momentum) + g) (first_step: buf = g);

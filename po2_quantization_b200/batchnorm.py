@@ -312,28 +312,35 @@ class _BatchNormTrain(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, y, weight, save_mean, save_invstd, stats, bias = ctx.saved_tensors
-        dy = dy.contiguous()
-        C = x.shape[1]
         need_x, need_res, need_w, need_b = ctx.needs_input_grad[:4]
-        exch = ctx.exch if ctx.world > 1 else None
-        with torch.cuda.device(x.device):
-            dgamma = torch.empty(C, dtype=torch.float32, device=x.device) if weight is not None else None
-            dbeta = torch.empty(C, dtype=torch.float32, device=x.device) if weight is not None else None
-            dx = torch.empty_like(x)
-            dres = None
-            if ctx.has_res and need_res:
-                dres = torch.empty_like(x) if ctx.relu else dy       # without the ReLU the branch gets dy itself
-            # one rank, small tensor: sums + apply as ONE launch (dy / x / y read once)
-            if not (ctx.world == 1 and bn_bwd_fused_out(dy, x, y, save_mean, save_invstd, weight, dgamma, dbeta, dx,
-                                                        dres if ctx.relu else None, ctx.relu, bias)):
-                sums = torch.empty(2 * C, dtype=torch.float32, device=x.device)
-                bn_bwd_reduce_out(dy, x, y, save_mean, save_invstd, sums, dgamma, dbeta, ctx.relu, exch, weight, bias)
-                if ctx.world > 1 and exch is None:
-                    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=ctx.group)
-                bn_bwd_apply_out(dy, x, y, save_mean, save_invstd, weight, sums, stats, dx,
-                                 dres if ctx.relu else None, ctx.relu, exch, bias)
+        dx, dres, dgamma, dbeta = bn_backward(dy, x, y, weight, bias, save_mean, save_invstd, stats, ctx.relu,
+                                              ctx.has_res and need_res, ctx.world, ctx.exch, ctx.group)
         return (dx if need_x else None, dres, dgamma if need_w else None, dbeta if need_b else None,
                 None, None, None, None, None, None, None, None, None, None)
+
+
+def bn_backward(dy, x, y, weight, bias, save_mean, save_invstd, stats, act, want_res, world=1, exch=None, group=None):
+    """(dx, dres, dgamma, dbeta) of act(bn(x) + residual) in train mode from the tensors the forward saved"""
+    dy = dy.contiguous()
+    C = x.shape[1]
+    exch = exch if world > 1 else None
+    with torch.cuda.device(x.device):
+        dgamma = torch.empty(C, dtype=torch.float32, device=x.device) if weight is not None else None
+        dbeta = torch.empty(C, dtype=torch.float32, device=x.device) if weight is not None else None
+        dx = torch.empty_like(x)
+        dres = None
+        if want_res:
+            dres = torch.empty_like(x) if act else dy                # without the ReLU the branch gets dy itself
+        # one rank, small tensor: sums + apply as ONE launch (dy / x / y read once)
+        if not (world == 1 and bn_bwd_fused_out(dy, x, y, save_mean, save_invstd, weight, dgamma, dbeta, dx,
+                                                dres if act else None, act, bias)):
+            sums = torch.empty(2 * C, dtype=torch.float32, device=x.device)
+            bn_bwd_reduce_out(dy, x, y, save_mean, save_invstd, sums, dgamma, dbeta, act, exch, weight, bias)
+            if world > 1 and exch is None:
+                dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+            bn_bwd_apply_out(dy, x, y, save_mean, save_invstd, weight, sums, stats, dx,
+                             dres if act else None, act, exch, bias)
+    return dx, dres, dgamma, dbeta
 
 
 def _kernel_ok(x: torch.Tensor) -> bool:

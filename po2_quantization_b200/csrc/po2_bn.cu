@@ -211,6 +211,21 @@ __device__ __forceinline__ float bn_silu_slope(float x, float mu, float a, float
   return sg * fmaf(z, 1.f - sg, 1.f);
 }
 
+#ifdef PO2_BN_TRACE
+// debug-only phase stamps of the one-launch kernels (tools/trace_bn.py builds a separate library with -DPO2_BN_TRACE)
+__device__ unsigned long long* g_bn_trace = nullptr;
+#define BN_STAMP(i)                                                                                   \
+  do {                                                                                                \
+    if (g_bn_trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {                       \
+      unsigned long long t_;                                                                          \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                          \
+      g_bn_trace[i] = t_;                                                                             \
+    }                                                                                                 \
+  } while (0)
+#else
+#define BN_STAMP(i) do {} while (0)
+#endif
+
 // MODE 0: forward statistics (p = x - shift, q = p);  1: backward sums (p = dy, q = x - mean);
 // MODE 2: backward sums behind a ReLU (p = y > 0 ? dy : 0).
 template <bool VEC, int MODE>
@@ -623,13 +638,13 @@ __device__ __forceinline__ bool channel_barrier(const BnWorkspace& ws, int c, in
 
 // thread 0 of a CTA: turn the channel's shifted sums into (mean, gamma*invstd, beta), with the peer
 // exchange when there are several ranks; CTA s == 0 of the channel also writes the per-channel outputs
+// what thread 0 of a CTA keeps of the channel's statistics for the bookkeeping stores behind the apply phase
+struct BnChannelStats { double mean, var, n_tot, m2; float invstd; };
+
 __device__ __noinline__ float4 fused_channel_finish(double pa, double pb, float shift, int s, int c, const BnGeom& g,
                                                     const BnPeers& peers, BnMailbox* me, uint32_t tag, int R,
-                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                    float* running_mean, float* running_var,
-                                                    long long* num_batches_tracked, float momentum, float eps,
-                                                    float* __restrict__ save_mean, float* __restrict__ save_invstd,
-                                                    float* __restrict__ stats_dense) {
+                                                    float ga, float be, float eps, float* __restrict__ stats_dense,
+                                                    BnChannelStats& cs) {
   const int C = g.C;
   float4 prm_out;
     const double cnt = (double)g.B * (double)g.HW;
@@ -661,26 +676,34 @@ __device__ __noinline__ float4 fused_channel_finish(double pa, double pb, float 
           if (c == 0) stats_dense[(size_t)r * (2 * C + 1) + 2 * C] = g3[2][r];
         }
       }
-    } else if (s == 0 && stats_dense) {
-      stats_dense[c] = (float)mean;
-      stats_dense[C + c] = (float)m2;
-      if (c == 0) stats_dense[2 * C] = (float)cnt;
     }
     const double var = m2 / n_tot;
     const float invstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float ga = gamma ? gamma[c] : 1.0f, be = beta ? beta[c] : 0.0f;
     prm_out = make_float4((float)mean, ga * invstd, be, 0.f);
-    if (s == 0) {
-      if (save_mean) save_mean[c] = (float)mean;
-      if (save_invstd) save_invstd[c] = invstd;
-      if (running_mean && !mailbox_failed(me)) {           // a timed-out exchange must not reach the running statistics
-        const double unbiased = var * n_tot / fmax(n_tot - 1.0, 1.0);
-        running_mean[c] = (float)((1.0 - (double)momentum) * (double)running_mean[c] + (double)momentum * mean);
-        running_var[c] = (float)((1.0 - (double)momentum) * (double)running_var[c] + (double)momentum * unbiased);
-      }
-      if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
-    }
+    cs.mean = mean; cs.var = var; cs.n_tot = n_tot; cs.m2 = m2; cs.invstd = invstd;
   return prm_out;
+}
+
+// the stores nobody inside the kernel waits for (CTA (0, c), thread 0, behind the apply phase): saved statistics for
+// the backward pass, the running statistics (their old values were loaded at the start of the kernel)
+__device__ __forceinline__ void fused_channel_book(const BnChannelStats& cs, int c, int C, bool single_rank, BnMailbox* me,
+                                                   float* running_mean, float* running_var, float rm_old, float rv_old,
+                                                   long long* num_batches_tracked, long long nbt_old, float momentum,
+                                                   float* __restrict__ save_mean, float* __restrict__ save_invstd,
+                                                   float* __restrict__ stats_dense, double cnt_local) {
+  if (single_rank && stats_dense) {
+    stats_dense[c] = (float)cs.mean;
+    stats_dense[C + c] = (float)cs.m2;
+    if (c == 0) stats_dense[2 * C] = (float)cnt_local;
+  }
+  if (save_mean) save_mean[c] = (float)cs.mean;
+  if (save_invstd) save_invstd[c] = cs.invstd;
+  if (running_mean && !mailbox_failed(me)) {               // a timed-out exchange must not reach the running statistics
+    const double unbiased = cs.var * cs.n_tot / fmax(cs.n_tot - 1.0, 1.0);
+    running_mean[c] = (float)((1.0 - (double)momentum) * (double)rm_old + (double)momentum * cs.mean);
+    running_var[c] = (float)((1.0 - (double)momentum) * (double)rv_old + (double)momentum * unbiased);
+  }
+  if (c == 0 && num_batches_tracked) *num_batches_tracked = nbt_old + 1;
 }
 
 __global__ void __launch_bounds__(BN_THREADS, 2) bn_fwd_fused_kernel(const float* __restrict__ x,
@@ -703,7 +726,23 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_fwd_fused_kernel(const float
   const int R = peers.world > 1 ? peers.world : 1;
   BnMailbox* me = peers.world > 1 ? peers.box[peers.rank] : nullptr;
   const uint32_t tag = me ? *reinterpret_cast<volatile uint32_t*>(&me->epoch) + 1 : 0;   // read before anyone advances it
+  BN_STAMP(0);
   const float shift = __ldg(x + (size_t)c * g.HW);
+  // thread 0 needs these after the channel barrier: their loads go out now, under phase 1 (behind the barrier
+  // they were three serialised round trips of the whole CTA's critical path: measured 2.7 us of 8.9)
+  float ga = 1.0f, be = 0.0f, rm_old = 0.f, rv_old = 0.f;
+  long long nbt_old = 0;
+  if (threadIdx.x == 0) {
+    // (volatile asm: the compiler must not sink these loads to their uses behind the barrier)
+    if (gamma) asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(ga) : "l"(gamma + c));
+    if (beta) asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(be) : "l"(beta + c));
+    if (s == 0 && running_mean) {
+      asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(rm_old) : "l"(running_mean + c));
+      asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(rv_old) : "l"(running_var + c));
+    }
+    if (s == 0 && c == 0 && num_batches_tracked)
+      asm volatile("ld.global.cg.s64 %0, [%1];" : "=l"(nbt_old) : "l"(num_batches_tracked));
+  }
   // ---- phase 1: load into registers, shifted sums
   float4 v[BN_FUSED_R];
   int off[BN_FUSED_R];                                   // in 128-bit units (< 2^29, checked on the host)
@@ -725,10 +764,13 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_fwd_fused_kernel(const float
     s1 += (q0 + q1) + (q2 + q3);
     s2 = fmaf(q0, q0, s2); s2 = fmaf(q1, q1, s2); s2 = fmaf(q2, q2, s2); s2 = fmaf(q3, q3, s2);
   }
+  BN_STAMP(1);
   double a = (double)s1, b = (double)s2;
   block_sum2(a, b, sm);
   if (threadIdx.x == 0) ws.partial[c * BN_MAX_SPLIT + s] = make_double2(a, b);
+  BN_STAMP(2);
   const bool barrier_ok = channel_barrier(ws, c, g.S, me, &s_ok);
+  BN_STAMP(3);
   // ---- phase 2: this channel's statistics (every CTA of the channel computes the same numbers)
   double pa = 0.0, pb = 0.0;
   if ((int)threadIdx.x < g.S) {
@@ -736,13 +778,20 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_fwd_fused_kernel(const float
     pa = p.x; pb = p.y;
   }
   block_sum2(pa, pb, sm);
-  if (threadIdx.x == 0)
-    s_prm = fused_channel_finish(pa, pb, shift, s, c, g, peers, me, tag, R, gamma, beta, running_mean, running_var,
-                                 num_batches_tracked, momentum, eps, save_mean, save_invstd, stats_dense);
+  __shared__ BnChannelStats cs;                           // thread 0 only
+  if (threadIdx.x == 0) s_prm = fused_channel_finish(pa, pb, shift, s, c, g, peers, me, tag, R, ga, be, eps, stats_dense, cs);
   __syncthreads();
+  BN_STAMP(4);
   // ---- phase 3: normalise the registers
   float4 p = s_prm;
   if (!barrier_ok) p.z = __uint_as_float(0x7FC00000u);     // incomplete statistics must not pass for a result
+  // the residual branch: all loads in flight before the first use (one round trip instead of eight)
+  float4 rr[BN_FUSED_R];
+#pragma unroll
+  for (int u = 0; u < BN_FUSED_R; ++u) {
+    rr[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (res && threadIdx.x + u * BN_THREADS < n) rr[u] = __ldg(reinterpret_cast<const float4*>(res) + off[u]);
+  }
 #pragma unroll
   for (int u = 0; u < BN_FUSED_R; ++u) {
     const int i = threadIdx.x + u * BN_THREADS;
@@ -750,14 +799,15 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_fwd_fused_kernel(const float
       float4 o;
       o.x = fmaf(v[u].x - p.x, p.y, p.z); o.y = fmaf(v[u].y - p.x, p.y, p.z);
       o.z = fmaf(v[u].z - p.x, p.y, p.z); o.w = fmaf(v[u].w - p.x, p.y, p.z);
-      if (res) {
-        const float4 r4 = __ldg(reinterpret_cast<const float4*>(res) + off[u]);
-        o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
-      }
+      if (res) { o.x += rr[u].x; o.y += rr[u].y; o.z += rr[u].z; o.w += rr[u].w; }
       if (act) { o.x = bn_act(o.x, act); o.y = bn_act(o.y, act); o.z = bn_act(o.z, act); o.w = bn_act(o.w, act); }
       reinterpret_cast<float4*>(y)[off[u]] = o;
     }
   }
+  if (s == 0 && threadIdx.x == 0)
+    fused_channel_book(cs, c, C, me == nullptr, me, running_mean, running_var, rm_old, rv_old, num_batches_tracked, nbt_old,
+                       momentum, save_mean, save_invstd, stats_dense, (double)g.B * (double)g.HW);
+  BN_STAMP(5);
   // the CTA that finishes the grid last advances this rank's epoch for the next exchange
   if (me && threadIdx.x == 0) {
     __threadfence();
@@ -791,30 +841,48 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_fused_kernel(const float
   const int s = blockIdx.x, c = blockIdx.y, C = g.C, L = g.L;
   const int nslab = (g.B - s + g.S - 1) / g.S;
   const int n = nslab * L;
+  BN_STAMP(8);
   const float mu = __ldg(mean + c);
-  // ---- phase 1: masked gradient and x into registers, local sums
+  // ---- phase 1: masked gradient and x into registers, local sums.  All loads (dy, x and the
+  // activation's y: 24 128-bit loads per thread, 124 registers) are issued before the first is used -- masking right behind
+  // each load serialised eight round trips (measured 4.4 us of this kernel's 10)
   float4 vg[BN_FUSED_R], vx[BN_FUSED_R];
   int off[BN_FUSED_R];
   float s1 = 0.f, s2 = 0.f;
+  const float za = act == 3 ? (gamma ? __ldg(gamma + c) : 1.f) * __ldg(invstd + c) : 0.f;
+  const float zb = (act == 3 && beta) ? __ldg(beta + c) : 0.f;
 #pragma unroll
   for (int u = 0; u < BN_FUSED_R; ++u) {
     const int i = threadIdx.x + u * BN_THREADS;
-    vg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-    vx[u] = make_float4(mu, mu, mu, mu);
-    off[u] = 0;
+    off[u] = -1;
     if (i < n) {
       const int k = fdiv(i, g.div_l);
       off[u] = ((s + k * g.S) * C + c) * L + (i - k * L);
-      vg[u] = __ldg(reinterpret_cast<const float4*>(dy) + off[u]);
-      vx[u] = __ldg(reinterpret_cast<const float4*>(x) + off[u]);
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < BN_FUSED_R; h += 8) {
+    float4 vy[8];
+#pragma unroll
+    for (int u = h; u < h + 8; ++u) {
+      vg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      vx[u] = make_float4(mu, mu, mu, mu);
+      vy[u - h] = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (off[u] >= 0) {
+        vg[u] = __ldg(reinterpret_cast<const float4*>(dy) + off[u]);
+        vx[u] = __ldg(reinterpret_cast<const float4*>(x) + off[u]);
+        if (act == 1 || act == 2) vy[u - h] = __ldg(reinterpret_cast<const float4*>(y) + off[u]);
+      }
+    }
+#pragma unroll
+    for (int u = h; u < h + 8; ++u) {
       if (act == 3) {
-        const float za = (gamma ? __ldg(gamma + c) : 1.f) * __ldg(invstd + c), zb = beta ? __ldg(beta + c) : 0.f;
         vg[u].x *= bn_silu_slope(vx[u].x, mu, za, zb); vg[u].y *= bn_silu_slope(vx[u].y, mu, za, zb);
         vg[u].z *= bn_silu_slope(vx[u].z, mu, za, zb); vg[u].w *= bn_silu_slope(vx[u].w, mu, za, zb);
       } else if (act) {
-        const float4 vy = __ldg(reinterpret_cast<const float4*>(y) + off[u]);
-        vg[u].x = bn_act_open(vy.x, act) ? vg[u].x : 0.f; vg[u].y = bn_act_open(vy.y, act) ? vg[u].y : 0.f;
-        vg[u].z = bn_act_open(vy.z, act) ? vg[u].z : 0.f; vg[u].w = bn_act_open(vy.w, act) ? vg[u].w : 0.f;
+        const float4 m4 = vy[u - h];
+        vg[u].x = bn_act_open(m4.x, act) ? vg[u].x : 0.f; vg[u].y = bn_act_open(m4.y, act) ? vg[u].y : 0.f;
+        vg[u].z = bn_act_open(m4.z, act) ? vg[u].z : 0.f; vg[u].w = bn_act_open(m4.w, act) ? vg[u].w : 0.f;
       }
     }
   }
@@ -824,10 +892,13 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_fused_kernel(const float
     s2 = fmaf(vg[u].x, vx[u].x - mu, s2); s2 = fmaf(vg[u].y, vx[u].y - mu, s2);
     s2 = fmaf(vg[u].z, vx[u].z - mu, s2); s2 = fmaf(vg[u].w, vx[u].w - mu, s2);
   }
+  BN_STAMP(9);
   double a = (double)s1, b = (double)s2;
   block_sum2(a, b, sm);
   if (threadIdx.x == 0) ws.partial[c * BN_MAX_SPLIT + s] = make_double2(a, b);
+  BN_STAMP(10);
   const bool barrier_ok = channel_barrier(ws, c, g.S, nullptr, &s_ok);
+  BN_STAMP(11);
   // ---- phase 2: the channel's sums (every CTA of the channel computes the same numbers)
   double pa = 0.0, pb = 0.0;
   if ((int)threadIdx.x < g.S) {
@@ -849,6 +920,7 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_fused_kernel(const float
   float p_y = (float)((double)sg / M), p_z = (float)(is * is * (double)sgx / M);
   const float p_w = (float)((double)ga * is);
   if (!barrier_ok) p_y = __uint_as_float(0x7FC00000u);      // incomplete sums must not pass for a result
+  BN_STAMP(12);
   // ---- phase 3: dx from the registers
 #pragma unroll
   for (int u = 0; u < BN_FUSED_R; ++u) {
@@ -861,6 +933,7 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_fused_kernel(const float
       if (dres) reinterpret_cast<float4*>(dres)[off[u]] = vg[u];
     }
   }
+  BN_STAMP(13);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
@@ -925,6 +998,13 @@ static int elementwise_grid(const BnGeom& g) {
 }  // namespace po2
 
 using namespace po2;
+
+#ifdef PO2_BN_TRACE
+extern "C" int po2_debug_set_bn_trace(void* p) {
+  unsigned long long* q = (unsigned long long*)p;
+  return (int)cudaMemcpyToSymbol(po2::g_bn_trace, &q, sizeof(q));
+}
+#endif
 
 extern "C" {
 

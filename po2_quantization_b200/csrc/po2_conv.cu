@@ -1545,6 +1545,48 @@ int po2_conv2d_fwd_packed_stats(const void* x, const void* packed, const float* 
                      /*pdl=*/false, ep);
 }
 
+// conv2d(x, Q(w)) from the packed operand + the train-mode BatchNorm behind it (+ residual add, + activation) in ONE
+// cooperative launch of the TMA-fed kernel (models/resnet.py:55-71 in train(): out = relu(bn(conv(x)) + shortcut)).
+// conv_out receives the conv result (the norm's backward reads it), y the block output.  Workspace: zeroed once by
+// the caller, then reused (16 bytes of self-resetting barrier counters + the per-CTA partial sums).
+size_t po2_conv2d_bn_workspace(int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups, int compute) {
+  ConvGeom g;
+  if (!fill_geom(g, B, C, H, W, K, R, S, stride, pad, groups)) return 0;
+  if (compute != 2 || !umma_eligible(g) || !plan_umma(g, true)) return 0;
+  TmaPlan tp;
+  if (!tma_enabled() || !plan_tma(g, tp, true, true)) return 0;
+  return 16 + (size_t)tp.m_step * g.ntiles_n * 2 * g.NT * sizeof(double);
+}
+
+int po2_conv2d_bn_fwd_packed(const void* x, const void* packed, const float* scale, void* conv_out, void* y,
+                             const void* residual, const float* gamma, const float* beta, float* running_mean,
+                             float* running_var, long long* num_batches_tracked, float momentum, float eps, int act,
+                             float* save_mean, float* save_invstd, float* stats_dense, int B, int C, int H, int W, int K,
+                             int R, int S, int stride, int pad, int groups, int compute, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  if (!x || !packed || !conv_out || !y || !workspace) return PO2_E_NULL;
+  if (act < 0 || act > 3) return PO2_E_MODE;
+  if ((running_mean == nullptr) != (running_var == nullptr)) return PO2_E_NULL;
+  if (reinterpret_cast<uintptr_t>(workspace) & 15) return PO2_E_ALIGN;
+  ConvGeom g;
+  if (!fill_geom(g, B, C, H, W, K, R, S, stride, pad, groups)) return PO2_E_SHAPE;
+  if (compute != 2 || !umma_eligible(g) || !plan_umma(g, true)) return PO2_E_UNSUPPORTED;
+  TmaPlan tp;
+  if (!tma_enabled() || !plan_tma(g, tp, true, true)) return PO2_E_UNSUPPORTED;
+  if ((int64_t)B * C * H * W >= (1ll << 31) || (int64_t)B * K * g.P * g.Q >= (1ll << 31)) return PO2_E_SIZE;
+  if (workspace_bytes < 16 + (size_t)tp.m_step * g.ntiles_n * 2 * g.NT * sizeof(double)) return PO2_E_WORKSPACE;
+  ConvBnTrain bn{};
+  bn.gamma = gamma; bn.beta = beta; bn.y = (float*)y;
+  bn.running_mean = running_mean; bn.running_var = running_var; bn.num_batches_tracked = num_batches_tracked;
+  bn.momentum = momentum; bn.eps = eps;
+  bn.save_mean = save_mean; bn.save_invstd = save_invstd; bn.stats_dense = stats_dense;
+  bn.tickets = reinterpret_cast<unsigned int*>(workspace);
+  bn.partial = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 16);
+  bn.count = (double)B * (double)g.P * (double)g.Q;
+  const ConvEpilogue ep{nullptr, nullptr, (const float*)residual, act, nullptr};
+  return launch_tma(x, (const uint8_t*)packed, scale, conv_out, g, tp, (cudaStream_t)stream, /*pdl=*/false, ep, &bn);
+}
+
 // QuantizedConv2d.forward in QAT mode as ONE call (models/quantized_conv.py:34-36): quantize the fp32
 // master weight (utils/quantizers.py:21-32 / 41-52) and convolve.  When the shape runs on the
 // tensor-core kernel and needs no channel padding, the quantizer kernel itself emits the packed

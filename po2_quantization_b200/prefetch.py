@@ -23,7 +23,7 @@ from . import _lib, ops
 
 
 class _Slot:
-    __slots__ = ("key", "qw", "scale", "packed", "sse", "packed_d")
+    __slots__ = ("key", "qw", "scale", "packed", "sse", "packed_d", "bn_ws")
 
 
 class _Table:

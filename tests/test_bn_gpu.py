@@ -389,3 +389,64 @@ def test_batch_statistics_from_the_conv_epilogue(shape, monkeypatch):
         err = ((u - v).abs().max() / v.abs().max().clamp_min(1e-12)).item()
         assert err < 2e-4, (name, err)
     assert float(bn.conv_sums(x.device).abs().sum()) == 0.0   # consumed and zeroed for the next forward
+
+
+@pytest.mark.parametrize("case", [
+    dict(B=128, C=16, K=16, HW=32, k=3, res=True, act="relu"),      # ResNet-56 layer classes
+    dict(B=128, C=32, K=32, HW=16, k=3, res=False, act="relu"),
+    dict(B=128, C=64, K=64, HW=8, k=3, res=True, act="relu"),
+    dict(B=16, C=16, K=32, HW=32, k=3, res=False, act=None),        # fewer tiles than SMs, K != C
+    dict(B=32, C=32, K=64, HW=16, k=1, res=False, act="relu6"),     # 1x1
+    dict(B=8, C=16, K=16, HW=16, k=3, res=False, act="silu"),
+], ids=lambda c: "_".join(f"{k}{v}" for k, v in c.items()))
+def test_conv_and_train_mode_norm_in_one_launch(case, monkeypatch):
+    """conv_bn_act in train(): conv + batch statistics + normalise (+ residual add, + activation) as ONE cooperative
+    launch of the TMA-fed kernel (po2_conv2d_bn_fwd_packed) against the separate conv and norm kernels: output,
+    every gradient, the running statistics -- and bit-identical results from one call to the next."""
+    import po2_quantization_b200 as P
+    from po2_quantization_b200 import ops
+    B, C, K, HW, k = case["B"], case["C"], case["K"], case["HW"], case["k"]
+    torch.manual_seed(B + C + K + HW)
+    conv = P.QuantizedConv2d(C, K, k, stride=1, padding=k // 2, bias=False, quantize_fn=P.PowerOfTwoQuantizer, bits=4).cuda()
+    bn = P.FusedSyncBatchNorm(K, act=case["act"] if case["act"] != "relu" else None).cuda().train()
+    relu = case["act"] == "relu"
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(K, device="cuda") + 0.5)
+        bn.bias.copy_(torch.randn(K, device="cuda") * 0.3)
+    x0 = torch.randn(B, C, HW, HW, device="cuda") + 0.2
+    r0 = torch.randn(B, K, HW, HW, device="cuda") if case["res"] else None
+    go = torch.randn(B, K, HW, HW, device="cuda")
+    ops.set_conv_mode("tf32")
+
+    def run(fused):
+        monkeypatch.setenv("PO2_CONV_BN", "1" if fused else "0")
+        bn.running_mean.zero_(); bn.running_var.fill_(1.0); bn.num_batches_tracked.zero_()
+        for m in (conv, bn):
+            m.zero_grad(set_to_none=True)
+        x = x0.clone().requires_grad_(True)
+        r = r0.clone().requires_grad_(True) if r0 is not None else None
+        P.prefetch_weights([conv])
+        before = ops.LAUNCHES
+        y = P.conv_bn_act(conv, bn, x, r, relu)
+        fwd = ops.LAUNCHES - before
+        y.backward(go)
+        torch.cuda.synchronize()
+        return dict(y=y.detach(), gx=x.grad, gr=r.grad if r is not None else None, gw=conv.weight.grad.clone(),
+                    gg=bn.weight.grad.clone(), gb=bn.bias.grad.clone(), rm=bn.running_mean.clone(), rv=bn.running_var.clone(),
+                    nbt=int(bn.num_batches_tracked)), fwd
+
+    try:
+        run(False)                                           # records the input shape for the prefetch
+        want, fwd_sep = run(False)
+        got, fwd_one = run(True)
+        again, _ = run(True)
+    finally:
+        ops.set_conv_mode(ops.DEFAULT_CONV_MODE)
+    assert fwd_one == 1 and fwd_sep >= 2, (fwd_one, fwd_sep)
+    assert got["nbt"] == want["nbt"] == 1
+    for key in ("y", "gx", "gr", "gw", "gg", "gb", "rm", "rv"):
+        if want[key] is None:
+            assert got[key] is None
+            continue
+        assert _rel(got[key], want[key]) < 2e-5, key
+        assert torch.equal(got[key], again[key]), key        # deterministic: fixed-order partial sums
