@@ -269,6 +269,9 @@ int po2_lin_quantize(const void* w, void* y, int K, int C, int RS, int bits, int
  *   dy*(y>0) (act 1), dy*(0<y<6) (act 2) or dy*silu'(z), z = (x-mean)*gamma*invstd + beta (act 3: SiLU behind the
  *   norm, models/mobile_vit.py:16-22; z is recomputed from x, so gamma / beta are needed and y is not);
  *   dgamma = sums[C+c]*invstd, dbeta = sums[c] (local sums, as SyncBatchNorm).
+ *   dy2 (all three backward entries, may be NULL): a second gradient of the same tensor, added on the fly (g is
+ *   formed from dy + dy2) -- the gradient that reaches a block's input over its skip connection
+ *   (models/resnet.py:69 `out += self.shortcut(x)`), instead of an accumulation kernel in front of the norm's backward.
  * po2_bn_bwd_apply: dx = (g - sum_g/M - (x-mean)*invstd^2*sum_gx/M) * gamma*invstd, M = total count
  *   over the R stats entries; `sums` all-reduced over ranks by the caller.  dres (optional): g, the
  *   gradient of the residual branch behind the ReLU. */
@@ -283,9 +286,9 @@ int po2_bn_apply(const void* x, const void* residual, void* y, const float* stat
  * condition as po2_bn_fwd_fused): per-channel sums of the activation-masked gradient, dgamma / dbeta, dx and
  * the masked gradient of the residual branch (dres, may be NULL) -- models/resnet.py:55-71 under autograd.
  * Returns PO2_E_UNSUPPORTED when the pair po2_bn_bwd_reduce + po2_bn_bwd_apply has to be used. */
-int po2_bn_bwd_fused(const void* dy, const void* x, const void* y, const float* save_mean, const float* save_invstd,
-                     const float* gamma, const float* beta, float* dgamma, float* dbeta, void* dx, void* dres, int act,
-                     int B, int C, int HW, void* workspace, size_t workspace_bytes, void* stream);
+int po2_bn_bwd_fused(const void* dy, const void* dy2, const void* x, const void* y, const float* save_mean,
+                     const float* save_invstd, const float* gamma, const float* beta, float* dgamma, float* dbeta, void* dx,
+                     void* dres, int act, int B, int C, int HW, void* workspace, size_t workspace_bytes, void* stream);
 
 /* po2_bn_stats + po2_bn_apply in ONE launch for tensors whose per-channel slice fits the registers of
  * the CTAs working on it (the CIFAR-scale layers): x is read once, the CTAs of a channel meet at a
@@ -297,13 +300,13 @@ int po2_bn_fwd_fused(const void* x, const void* residual, void* y, const float* 
                      float eps, int act, float* save_mean, float* save_invstd, float* stats_dense, int B, int C,
                      int HW, void* workspace, size_t workspace_bytes, void* const* peers, int rank, int world,
                      void* stream);
-int po2_bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* save_mean, const float* save_invstd,
-                      const float* gamma, const float* beta, float* sums, float* dgamma, float* dbeta, int act, int B, int C,
-                      int HW, void* workspace, size_t workspace_bytes, void* const* peers, int rank, int world,
-                      void* stream);
-int po2_bn_bwd_apply(const void* dy, const void* x, const void* y, const float* save_mean, const float* save_invstd,
-                     const float* gamma, const float* beta, const float* sums, const float* stats, int R, void* mailbox,
-                     void* dx, void* dres, int act, int B, int C, int HW, void* stream);
+int po2_bn_bwd_reduce(const void* dy, const void* dy2, const void* x, const void* y, const float* save_mean,
+                      const float* save_invstd, const float* gamma, const float* beta, float* sums, float* dgamma,
+                      float* dbeta, int act, int B, int C, int HW, void* workspace, size_t workspace_bytes,
+                      void* const* peers, int rank, int world, void* stream);
+int po2_bn_bwd_apply(const void* dy, const void* dy2, const void* x, const void* y, const float* save_mean,
+                     const float* save_invstd, const float* gamma, const float* beta, const float* sums, const float* stats,
+                     int R, void* mailbox, void* dx, void* dres, int act, int B, int C, int HW, void* stream);
 
 /* Peer exchange (one NVLink domain, <= 8 ranks): SyncBatchNorm's two collectives done by the kernels
  * themselves.  Every rank allocates one zero-initialised mailbox of po2_bn_mailbox_bytes() in memory

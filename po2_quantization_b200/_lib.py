@@ -70,9 +70,9 @@ SIGNATURES = {
     "po2_bn_apply": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c.c_float, _c.c_float,
                           _i, _i, _vp, _vp, _i, _i, _i, _vp]),
     "po2_bn_fwd_fused": (_i, [_vp] * 8 + [_c.c_float, _c.c_float, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp, _i, _i, _vp]),
-    "po2_bn_bwd_fused": (_i, [_vp] * 11 + [_i] * 4 + [_vp, _sz, _vp]),
-    "po2_bn_bwd_reduce": (_i, [_vp] * 10 + [_i] * 4 + [_vp, _sz, _vp, _i, _i, _vp]),
-    "po2_bn_bwd_apply": (_i, [_vp] * 9 + [_i, _vp, _vp, _vp] + [_i] * 4 + [_vp]),
+    "po2_bn_bwd_fused": (_i, [_vp] * 12 + [_i] * 4 + [_vp, _sz, _vp]),
+    "po2_bn_bwd_reduce": (_i, [_vp] * 11 + [_i] * 4 + [_vp, _sz, _vp, _i, _i, _vp]),
+    "po2_bn_bwd_apply": (_i, [_vp] * 10 + [_i, _vp, _vp, _vp] + [_i] * 4 + [_vp]),
 }
 
 _lock = threading.Lock()

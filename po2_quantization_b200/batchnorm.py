@@ -213,7 +213,7 @@ def bn_apply_sums_out(x, residual, y, sums, stats_dense, weight, bias, running_m
         _ptr(save_mean), _ptr(save_invstd), B, C, HW, ops._stream_ptr(x.device)), "po2_bn_apply_sums")
 
 
-def bn_bwd_fused_out(dy, x, y, save_mean, save_invstd, weight, dgamma, dbeta, dx, dres, relu, bias=None) -> bool:
+def bn_bwd_fused_out(dy, x, y, save_mean, save_invstd, weight, dgamma, dbeta, dx, dres, relu, bias=None, dy2=None) -> bool:
     """sums + apply of the backward in one launch (one rank, tensors that fit the registers of their CTAs);
     False if the shape is not taken"""
     if os.environ.get("PO2_BN_FUSED", "1") != "1" or os.environ.get("PO2_BN_FUSED_BWD", "1") != "1":
@@ -222,7 +222,7 @@ def bn_bwd_fused_out(dy, x, y, save_mean, save_invstd, weight, dgamma, dbeta, dx
     HW = x.numel() // (B * C)
     ws = _bn_workspace(x.device, C)
     rc = _lib.load().po2_bn_bwd_fused(
-        dy.data_ptr(), x.data_ptr(), _ptr(y), save_mean.data_ptr(), save_invstd.data_ptr(), _ptr(weight), _ptr(bias),
+        dy.data_ptr(), _ptr(dy2), x.data_ptr(), _ptr(y), save_mean.data_ptr(), save_invstd.data_ptr(), _ptr(weight), _ptr(bias),
         _ptr(dgamma), _ptr(dbeta), dx.data_ptr(), _ptr(dres), int(relu), B, C, HW, ws.data_ptr(), ws.numel(),
         ops._stream_ptr(x.device))
     if rc == -10:
@@ -233,24 +233,25 @@ def bn_bwd_fused_out(dy, x, y, save_mean, save_invstd, weight, dgamma, dbeta, dx
 
 
 def bn_bwd_reduce_out(dy, x, y, save_mean, save_invstd, sums, dgamma, dbeta, relu, exch=None, weight=None,
-                      bias=None) -> None:
+                      bias=None, dy2=None) -> None:
     B, C = x.shape[0], x.shape[1]
     HW = x.numel() // (B * C)
     ws = _bn_workspace(x.device, C)
     ops.LAUNCHES += 1
     _lib.check(_lib.load().po2_bn_bwd_reduce(
-        dy.data_ptr(), x.data_ptr(), _ptr(y), save_mean.data_ptr(), save_invstd.data_ptr(), _ptr(weight), _ptr(bias),
+        dy.data_ptr(), _ptr(dy2), x.data_ptr(), _ptr(y), save_mean.data_ptr(), save_invstd.data_ptr(), _ptr(weight), _ptr(bias),
         sums.data_ptr(), _ptr(dgamma), _ptr(dbeta), int(relu), B, C, HW, ws.data_ptr(), ws.numel(), *_peer_args(exch),
         ops._stream_ptr(x.device)), "po2_bn_bwd_reduce")
 
 
-def bn_bwd_apply_out(dy, x, y, save_mean, save_invstd, weight, sums, stats, dx, dres, relu, exch=None, bias=None) -> None:
+def bn_bwd_apply_out(dy, x, y, save_mean, save_invstd, weight, sums, stats, dx, dres, relu, exch=None, bias=None,
+                     dy2=None) -> None:
     B, C = x.shape[0], x.shape[1]
     HW = x.numel() // (B * C)
     R = stats.numel() // (2 * C + 1)
     ops.LAUNCHES += 1
     _lib.check(_lib.load().po2_bn_bwd_apply(
-        dy.data_ptr(), x.data_ptr(), _ptr(y), save_mean.data_ptr(), save_invstd.data_ptr(), _ptr(weight), _ptr(bias),
+        dy.data_ptr(), _ptr(dy2), x.data_ptr(), _ptr(y), save_mean.data_ptr(), save_invstd.data_ptr(), _ptr(weight), _ptr(bias),
         _ptr(sums), stats.data_ptr(), R, exch.mailbox if exch is not None else None, dx.data_ptr(), _ptr(dres),
         int(relu), B, C, HW, ops._stream_ptr(x.device)), "po2_bn_bwd_apply")
 
@@ -313,15 +314,28 @@ class _BatchNormTrain(torch.autograd.Function):
     def backward(ctx, dy):
         x, y, weight, save_mean, save_invstd, stats, bias = ctx.saved_tensors
         need_x, need_res, need_w, need_b = ctx.needs_input_grad[:4]
+        # the gradient that came back over a skip connection (_SkipGrad) is added inside the kernels
+        skipped = ctx.__dict__.pop("_po2_skip_grads", None) if hasattr(ctx, "__dict__") else None
+        dy2 = None
+        if skipped:
+            dy2 = skipped[0].contiguous()
+            for extra in skipped[1:]:
+                dy2 = dy2 + extra
+            if dy is None or dy2.shape != dy.shape or dy2.dtype != dy.dtype:
+                dy, dy2 = (dy2 if dy is None else dy + dy2), None
         dx, dres, dgamma, dbeta = bn_backward(dy, x, y, weight, bias, save_mean, save_invstd, stats, ctx.relu,
-                                              ctx.has_res and need_res, ctx.world, ctx.exch, ctx.group)
+                                              ctx.has_res and need_res, ctx.world, ctx.exch, ctx.group, dy2=dy2)
         return (dx if need_x else None, dres, dgamma if need_w else None, dbeta if need_b else None,
                 None, None, None, None, None, None, None, None, None, None)
 
 
-def bn_backward(dy, x, y, weight, bias, save_mean, save_invstd, stats, act, want_res, world=1, exch=None, group=None):
-    """(dx, dres, dgamma, dbeta) of act(bn(x) + residual) in train mode from the tensors the forward saved"""
+def bn_backward(dy, x, y, weight, bias, save_mean, save_invstd, stats, act, want_res, world=1, exch=None, group=None,
+                dy2=None):
+    """(dx, dres, dgamma, dbeta) of act(bn(x) + residual) in train mode from the tensors the forward saved; dy2: a second
+    gradient of the output (a skip connection's), added inside the kernels"""
     dy = dy.contiguous()
+    if dy2 is not None and not act and want_res:
+        dy, dy2 = dy + dy2, None                                     # the residual branch gets dy itself: form it
     C = x.shape[1]
     exch = exch if world > 1 else None
     with torch.cuda.device(x.device):
@@ -333,14 +347,42 @@ def bn_backward(dy, x, y, weight, bias, save_mean, save_invstd, stats, act, want
             dres = torch.empty_like(x) if act else dy                # without the ReLU the branch gets dy itself
         # one rank, small tensor: sums + apply as ONE launch (dy / x / y read once)
         if not (world == 1 and bn_bwd_fused_out(dy, x, y, save_mean, save_invstd, weight, dgamma, dbeta, dx,
-                                                dres if act else None, act, bias)):
+                                                dres if act else None, act, bias, dy2)):
             sums = torch.empty(2 * C, dtype=torch.float32, device=x.device)
-            bn_bwd_reduce_out(dy, x, y, save_mean, save_invstd, sums, dgamma, dbeta, act, exch, weight, bias)
+            bn_bwd_reduce_out(dy, x, y, save_mean, save_invstd, sums, dgamma, dbeta, act, exch, weight, bias, dy2)
             if world > 1 and exch is None:
                 dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
             bn_bwd_apply_out(dy, x, y, save_mean, save_invstd, weight, sums, stats, dx,
-                             dres if act else None, act, exch, bias)
+                             dres if act else None, act, exch, bias, dy2)
     return dx, dres, dgamma, dbeta
+
+
+class _SkipGrad(torch.autograd.Function):
+    """Identity on a tensor that a FusedSyncBatchNorm produced and that is about to be used as another norm's residual
+    branch (models/resnet.py:69 ``out += self.shortcut(x)`` with the identity shortcut).  Its backward does not hand
+    the skip connection's gradient to autograd -- which would add it to the conv branch's gradient with a separate
+    accumulation kernel -- but leaves it at the producing norm's autograd node; that node's backward runs after all
+    its consumers (autograd's dependency count covers this edge although it carries no gradient) and adds the two
+    gradients inside its own kernels (dy + dy2, the same fp32 addition)."""
+
+    @staticmethod
+    def forward(ctx, t, node):
+        ctx.node = node
+        return t.view_as(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        node, ctx.node = ctx.node, None
+        node.__dict__.setdefault("_po2_skip_grads", []).append(g)
+        return None, None
+
+
+def _route_skip_gradient(residual: torch.Tensor) -> torch.Tensor:
+    node = residual.grad_fn
+    if (node is None or type(node).__name__ != "_BatchNormTrainBackward" or not hasattr(node, "__dict__")
+            or os.environ.get("PO2_SKIP_GRAD", "1") != "1"):
+        return residual
+    return _SkipGrad.apply(residual, node)
 
 
 def _kernel_ok(x: torch.Tensor) -> bool:
@@ -397,6 +439,8 @@ class FusedSyncBatchNorm(nn.SyncBatchNorm):
                         n = exch.__dict__["_calls"] = exch.__dict__.get("_calls", 0) + 1
                         if n % 64 == 0:                              # about once per ResNet-56 step
                             exch.check()
+            if residual is not None and torch.is_grad_enabled() and residual.requires_grad:
+                residual = _route_skip_gradient(residual)
             track = self.training and self.track_running_stats
             # SiLU's backward is in the kernels for the plain conv-norm-SiLU case; behind a residual add it stays F.silu
             kact = act if (act != 3 or residual is None) else 0

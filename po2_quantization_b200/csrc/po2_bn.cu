@@ -241,7 +241,10 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const float* __re
                                                                float* __restrict__ dbeta, BnGeom g,
                                                                BnWorkspace ws, BnPeers peers, int act,
                                                                const float* __restrict__ gamma = nullptr,
-                                                               const float* __restrict__ beta = nullptr) {
+                                                               const float* __restrict__ beta = nullptr,
+                                                               const float* __restrict__ dy2 = nullptr) {
+  // dy2 (backward): a second gradient of the same tensor -- the skip connection's -- added on the fly (dy + dy2),
+  // instead of an accumulation kernel in front of this one
   // the consuming kernel (apply / backward apply, launched with programmatic stream serialization) may
   // be scheduled as soon as every CTA of this grid is running; it waits for this grid's completion
   // (griddepcontrol.wait) before it reads anything this grid writes
@@ -275,6 +278,10 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const float* __re
           const size_t off = ((size_t)(s + k * g.S) * C + c) * L + (i - k * L);
           vx[u] = __ldg(reinterpret_cast<const float4*>(x) + off);
           if (MODE != 0) vd[u] = __ldg(reinterpret_cast<const float4*>(dy) + off);
+          if (MODE != 0 && dy2) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(dy2) + off);
+            vd[u].x += t.x; vd[u].y += t.y; vd[u].z += t.z; vd[u].w += t.w;
+          }
           if (MODE == 2 && !silu) vy[u] = __ldg(reinterpret_cast<const float4*>(y) + off);
         }
       }
@@ -306,6 +313,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const float* __re
           if (MODE == 0) { s1 += q; s2 = fmaf(q, q, s2); }
           else {
             float p = __ldg(dy + off);
+            if (dy2) p += __ldg(dy2 + off);
             if (MODE == 2) p = silu ? p * bn_silu_slope(xv, shift, za, zb) : (bn_act_open(__ldg(y + off), act) ? p : 0.f);
             s1 += p; s2 = fmaf(p, q, s2);
           }
@@ -527,7 +535,8 @@ __global__ void __launch_bounds__(BN_THREADS, 4) bn_bwd_apply_kernel(const float
                                                                   BnMailbox* mailbox,
                                                                   float* __restrict__ dx,
                                                                   float* __restrict__ dres, int act, BnGeom g,
-                                                                  const float* __restrict__ beta) {
+                                                                  const float* __restrict__ beta,
+                                                                  const float* __restrict__ dy2) {
   extern __shared__ float4 prm[];
   const int C = g.C;
   float* prb = reinterpret_cast<float*>(prm + C);                 // beta per channel (SiLU: z is recomputed from x)
@@ -562,6 +571,10 @@ __global__ void __launch_bounds__(BN_THREADS, 4) bn_bwd_apply_kernel(const float
         const int i = i0 + u * BN_THREADS;
         if (i < g.total) {
           vd[u] = __ldg(reinterpret_cast<const float4*>(dy) + i);
+          if (dy2) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(dy2) + i);
+            vd[u].x += t.x; vd[u].y += t.y; vd[u].z += t.z; vd[u].w += t.w;
+          }
           vx[u] = __ldg(reinterpret_cast<const float4*>(x) + i);
           if (relu) vy[u] = __ldg(reinterpret_cast<const float4*>(y) + i);
         }
@@ -598,6 +611,7 @@ __global__ void __launch_bounds__(BN_THREADS, 4) bn_bwd_apply_kernel(const float
           const int c = slab - fdiv(slab, g.div_c) * C;
           const float4 p = prm[c];
           float gr = __ldg(dy + i);
+          if (dy2) gr += __ldg(dy2 + i);
           if (relu && !bn_act_open(__ldg(y + i), act)) gr = 0.f;
           if (silu) gr *= bn_silu_slope(__ldg(x + i), p.x, p.w, prb[c]);
           dx[i] = (gr - p.y - (__ldg(x + i) - p.x) * p.z) * p.w;
@@ -862,7 +876,8 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_fused_kernel(const float
                                                                      float* __restrict__ dbeta,
                                                                      float* __restrict__ dx,
                                                                      float* __restrict__ dres, int act, BnGeom g,
-                                                                     BnWorkspace ws, const float* __restrict__ beta) {
+                                                                     BnWorkspace ws, const float* __restrict__ beta,
+                                                                     const float* __restrict__ dy2) {
   __shared__ double sm[BN_THREADS / 32][2];
   __shared__ int s_ok;
   const int s = blockIdx.x, c = blockIdx.y, C = g.C, L = g.L;
@@ -887,16 +902,31 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_fused_kernel(const float
       off[u] = ((s + k * g.S) * C + c) * L + (i - k * L);
     }
   }
+  if (dy2) {
+    // two gradients of this tensor (conv branch + skip connection): summed here, one round trip ahead of the rest
+    float4 t2[BN_FUSED_R];
+#pragma unroll
+    for (int u = 0; u < BN_FUSED_R; ++u) {
+      vg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      t2[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (off[u] >= 0) {
+        vg[u] = __ldg(reinterpret_cast<const float4*>(dy) + off[u]);
+        t2[u] = __ldg(reinterpret_cast<const float4*>(dy2) + off[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < BN_FUSED_R; ++u) { vg[u].x += t2[u].x; vg[u].y += t2[u].y; vg[u].z += t2[u].z; vg[u].w += t2[u].w; }
+  }
 #pragma unroll
   for (int h = 0; h < BN_FUSED_R; h += 8) {
     float4 vy[8];
 #pragma unroll
     for (int u = h; u < h + 8; ++u) {
-      vg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!dy2) vg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       vx[u] = make_float4(mu, mu, mu, mu);
       vy[u - h] = make_float4(1.f, 1.f, 1.f, 1.f);
       if (off[u] >= 0) {
-        vg[u] = __ldg(reinterpret_cast<const float4*>(dy) + off[u]);
+        if (!dy2) vg[u] = __ldg(reinterpret_cast<const float4*>(dy) + off[u]);
         vx[u] = __ldg(reinterpret_cast<const float4*>(x) + off[u]);
         if (act == 1 || act == 2) vy[u - h] = __ldg(reinterpret_cast<const float4*>(y) + off[u]);
       }
@@ -1220,16 +1250,16 @@ int po2_bn_fwd_fused(const void* x, const void* residual, void* y, const float* 
 
 // Backward of the same layer as ONE launch (one rank, tensors that fit the CTAs' registers): sums + apply.
 // PO2_E_UNSUPPORTED: take po2_bn_bwd_reduce + po2_bn_bwd_apply.
-int po2_bn_bwd_fused(const void* dy, const void* x, const void* y, const float* save_mean, const float* save_invstd,
-                     const float* gamma, const float* beta, float* dgamma, float* dbeta, void* dx, void* dres, int act,
-                     int B, int C, int HW, void* workspace, size_t workspace_bytes, void* stream) {
+int po2_bn_bwd_fused(const void* dy, const void* dy2, const void* x, const void* y, const float* save_mean,
+                     const float* save_invstd, const float* gamma, const float* beta, float* dgamma, float* dbeta, void* dx,
+                     void* dres, int act, int B, int C, int HW, void* workspace, size_t workspace_bytes, void* stream) {
   if (!dy || !x || !save_mean || !save_invstd || !dx || !workspace) return PO2_E_NULL;
   if (act < 0 || act > 3 || (act == 3 && dres)) return PO2_E_MODE;      // SiLU: only without a residual branch
   if ((act == 1 || act == 2) && !y) return PO2_E_NULL;
   if (workspace_bytes < po2_bn_workspace_bytes(C)) return PO2_E_WORKSPACE;
   if (!aligned16(workspace)) return PO2_E_ALIGN;
   BnGeom g;
-  const int v = bn_geom(g, B, C, HW, aligned16(dy) && aligned16(x) && aligned16(y) && aligned16(dx) && aligned16(dres));
+  const int v = bn_geom(g, B, C, HW, aligned16(dy) && aligned16(dy2) && aligned16(x) && aligned16(y) && aligned16(dx) && aligned16(dres));
   if (v < 0) return v;
   if (v == 0) return PO2_E_UNSUPPORTED;                                   // 128-bit path only
   const int64_t per_cta = (int64_t)BN_FUSED_R * BN_THREADS;
@@ -1241,9 +1271,9 @@ int po2_bn_bwd_fused(const void* dy, const void* x, const void* y, const float* 
   }
   g.S = (int)need_s;
   BnWorkspace wsv = bn_ws(workspace, C);
-  const float *df = (const float*)dy, *xf = (const float*)x, *yf = (const float*)y;
+  const float *df = (const float*)dy, *xf = (const float*)x, *yf = (const float*)y, *d2f = (const float*)dy2;
   float *dxf = (float*)dx, *drf = (float*)dres;
-  void* args[] = {&df, &xf, &yf, &save_mean, &save_invstd, &gamma, &dgamma, &dbeta, &dxf, &drf, &act, &g, &wsv, &beta};
+  void* args[] = {&df, &xf, &yf, &save_mean, &save_invstd, &gamma, &dgamma, &dbeta, &dxf, &drf, &act, &g, &wsv, &beta, &d2f};
   const cudaError_t e = launch_bn_one((const void*)bn_bwd_fused_kernel, g, C, args, (cudaStream_t)stream);
   if (e == cudaErrorCooperativeLaunchTooLarge) {
     (void)cudaGetLastError();
@@ -1252,17 +1282,17 @@ int po2_bn_bwd_fused(const void* dy, const void* x, const void* y, const float* 
   return (int)e;
 }
 
-int po2_bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* save_mean, const float* save_invstd,
-                      const float* gamma, const float* beta, float* sums, float* dgamma, float* dbeta, int act, int B, int C,
-                      int HW, void* workspace, size_t workspace_bytes, void* const* peers, int rank, int world,
-                      void* stream) {
+int po2_bn_bwd_reduce(const void* dy, const void* dy2, const void* x, const void* y, const float* save_mean,
+                      const float* save_invstd, const float* gamma, const float* beta, float* sums, float* dgamma,
+                      float* dbeta, int act, int B, int C, int HW, void* workspace, size_t workspace_bytes,
+                      void* const* peers, int rank, int world, void* stream) {
   if (!dy || !x || !save_mean || !save_invstd || !sums || !workspace) return PO2_E_NULL;
   if (act < 0 || act > 3) return PO2_E_MODE;
   if ((act == 1 || act == 2) && !y) return PO2_E_NULL;
   if (workspace_bytes < po2_bn_workspace_bytes(C)) return PO2_E_WORKSPACE;
   if (!aligned16(workspace)) return PO2_E_ALIGN;
   BnGeom g;
-  const int v = bn_geom(g, B, C, HW, aligned16(dy) && aligned16(x) && aligned16(y));
+  const int v = bn_geom(g, B, C, HW, aligned16(dy) && aligned16(dy2) && aligned16(x) && aligned16(y));
   if (v < 0) return v;
   BnPeers pr;
   const int pe = make_peers(pr, peers, rank, world);
@@ -1270,26 +1300,26 @@ int po2_bn_bwd_reduce(const void* dy, const void* x, const void* y, const float*
   const BnWorkspace ws = bn_ws(workspace, C);
   const dim3 grid(g.S, C);
   cudaStream_t st = (cudaStream_t)stream;
-  const float *xf = (const float*)x, *df = (const float*)dy, *yf = (const float*)y;
+  const float *xf = (const float*)x, *df = (const float*)dy, *yf = (const float*)y, *d2f = (const float*)dy2;
   if (act != 0) {
-    if (v) bn_reduce_kernel<true, 2><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr, act, gamma, beta);
-    else bn_reduce_kernel<false, 2><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr, act, gamma, beta);
+    if (v) bn_reduce_kernel<true, 2><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr, act, gamma, beta, d2f);
+    else bn_reduce_kernel<false, 2><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr, act, gamma, beta, d2f);
   } else {
-    if (v) bn_reduce_kernel<true, 1><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr, act);
-    else bn_reduce_kernel<false, 1><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr, act);
+    if (v) bn_reduce_kernel<true, 1><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr, act, nullptr, nullptr, d2f);
+    else bn_reduce_kernel<false, 1><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr, act, nullptr, nullptr, d2f);
   }
   return (int)cudaGetLastError();
 }
 
-int po2_bn_bwd_apply(const void* dy, const void* x, const void* y, const float* save_mean, const float* save_invstd,
-                     const float* gamma, const float* beta, const float* sums, const float* stats, int R, void* mailbox,
-                     void* dx, void* dres, int act, int B, int C, int HW, void* stream) {
+int po2_bn_bwd_apply(const void* dy, const void* dy2, const void* x, const void* y, const float* save_mean,
+                     const float* save_invstd, const float* gamma, const float* beta, const float* sums, const float* stats,
+                     int R, void* mailbox, void* dx, void* dres, int act, int B, int C, int HW, void* stream) {
   if (!dy || !x || !save_mean || !save_invstd || (!sums && !mailbox) || !stats || !dx || R < 1) return PO2_E_NULL;
   if (R > BN_MAX_RANKS && mailbox) return PO2_E_SIZE;
   if (act < 0 || act > 3 || (act == 3 && dres)) return PO2_E_MODE;      // SiLU: only without a residual branch
   if ((act == 1 || act == 2) && !y) return PO2_E_NULL;
   BnGeom g;
-  const int v = bn_geom(g, B, C, HW, aligned16(dy) && aligned16(x) && aligned16(y) && aligned16(dx) && aligned16(dres));
+  const int v = bn_geom(g, B, C, HW, aligned16(dy) && aligned16(dy2) && aligned16(x) && aligned16(y) && aligned16(dx) && aligned16(dres));
   if (v < 0) return v;
   const size_t smem = (size_t)C * (sizeof(float4) + sizeof(float));
   cudaStream_t st = (cudaStream_t)stream;
@@ -1309,7 +1339,8 @@ int po2_bn_bwd_apply(const void* dy, const void* x, const void* y, const float* 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return (int)cudaLaunchKernelEx(&cfg, kern, (const float*)dy, (const float*)x, (const float*)y, save_mean, save_invstd,
-                                 gamma, sums, stats, R, (BnMailbox*)mailbox, (float*)dx, (float*)dres, act, g, beta);
+                                 gamma, sums, stats, R, (BnMailbox*)mailbox, (float*)dx, (float*)dres, act, g, beta,
+                                 (const float*)dy2);
 }
 
 }  // extern "C"

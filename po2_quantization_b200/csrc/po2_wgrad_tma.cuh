@@ -457,6 +457,7 @@ static bool plan_wgrad_tma(WgTmaPlan& wp, int B, int C, int H, int W, int K, int
   const size_t fixed = 1024 + 8192 + (3 * K3_MAX_STAGES + 8) * 8 + 64;
   int nst = (int)((WT_SMEM_BUDGET - fixed) / wp.stage_bytes);
   if (nst > K3_MAX_STAGES) nst = K3_MAX_STAGES;
+  { const char* e = getenv("PO2_WT_NST"); if (e && atoi(e) >= 2 && atoi(e) < nst) nst = atoi(e); }   // tuning: shared-memory footprint
   if (nst < 2) return false;
   wp.nst = nst;
   int m_ctas = sms / wp.rsplit;

@@ -60,9 +60,9 @@ def test_argument_errors_of_the_gradient_norm_and_lin_entry_points():
     assert lib.po2_bn_stats(one, 8, 16, 64, one, one, 16, None, 0, 1, None) == -8
     assert lib.po2_bn_apply(one, None, one, one, 1, None, None, None, None, None, None, None, 0.1, 1e-5, 7, 0,
                             None, None, 8, 16, 64, None) == -9                                      # unknown activation
-    assert lib.po2_bn_bwd_reduce(one, one, one, one, one, one, one, one, None, None, 4, 8, 16, 64, one, 1 << 20, None, 0,
+    assert lib.po2_bn_bwd_reduce(one, None, one, one, one, one, one, one, one, None, None, 4, 8, 16, 64, one, 1 << 20, None, 0,
                                  1, None) == -9                                                       # unknown activation
-    assert lib.po2_bn_bwd_apply(one, one, None, one, one, one, one, one, one, 1, None, one, one, 3, 8, 16, 64,
+    assert lib.po2_bn_bwd_apply(one, None, one, None, one, one, one, one, one, one, 1, None, one, one, 3, 8, 16, 64,
                                 None) == -9                                          # SiLU behind a residual add: not here
     assert lib.po2_lin_quantize(one, one, 4096, 4, 9, 4, 10, 0, 0, None) == -10                      # channel too large
     assert lib.po2_lin_quantize(one, one, 16, 4, 9, 1, 10, 0, 0, None) == -2                         # bits

@@ -450,3 +450,48 @@ def test_conv_and_train_mode_norm_in_one_launch(case, monkeypatch):
             continue
         assert _rel(got[key], want[key]) < 2e-5, key
         assert torch.equal(got[key], again[key]), key        # deterministic: fixed-order partial sums
+
+
+def test_skip_connection_gradient_is_added_inside_the_norm_kernels(monkeypatch):
+    """A residual block's input receives two gradients: the conv branch's and the skip connection's.  With the
+    FusedSyncBatchNorm modules of workloads/resnet_cifar.py the second one is left at the producing norm's autograd
+    node (_SkipGrad) and added inside that norm's backward kernels (dy + dy2) instead of by an accumulation kernel:
+    same fp32 addition, so every gradient is bit-identical, with one launch less per identity block.  Both backward
+    forms (one launch, reduce + apply)."""
+    import po2_quantization_b200 as P
+    from po2_quantization_b200 import ops
+    from workloads import resnet_cifar
+    torch.manual_seed(5)
+    model = resnet_cifar(20, 10, P.PowerOfTwoQuantizer, 4).cuda().train()
+    P.enable_weight_prefetch(model)
+    x = torch.randn(32, 3, 32, 32, device="cuda")
+    y = torch.randint(0, 10, (32,), device="cuda")
+    crit = torch.nn.CrossEntropyLoss()
+
+    def grads(skip, fused):
+        monkeypatch.setenv("PO2_SKIP_GRAD", skip)
+        monkeypatch.setenv("PO2_BN_FUSED_BWD", fused)
+        model.zero_grad(set_to_none=True)
+        crit(model(x), y).backward()
+        torch.cuda.synchronize()
+        return [p.grad.clone() for p in model.parameters()]
+
+    grads("0", "1")                                          # warm-up: the first forward records the prefetch shapes
+    for fused in ("1", "0"):
+        want, again, got = grads("0", fused), grads("0", fused), grads("1", fused)
+        stable = [torch.equal(a, b) for a, b in zip(want, again)]       # all but the stem conv's cuDNN weight gradient
+        assert sum(stable) >= len(stable) - 1
+        for ok, a, b in zip(stable, want, got):
+            assert torch.equal(a, b) if ok else torch.allclose(a, b, rtol=1e-4, atol=1e-6)
+    # the accumulation kernels are gone: count torch's add kernels with the profiler
+    from torch.profiler import ProfilerActivity, profile
+
+    def adds(skip):
+        monkeypatch.setenv("PO2_SKIP_GRAD", skip)
+        monkeypatch.setenv("PO2_BN_FUSED_BWD", "1")
+        model.zero_grad(set_to_none=True)
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            crit(model(x), y).backward()
+            torch.cuda.synchronize()
+        return sum(e.count for e in prof.key_averages() if "CUDAFunctor_add" in e.key)
+    assert adds("0") - adds("1") == 7                        # ResNet-20: 9 blocks, 7 of them with an identity shortcut

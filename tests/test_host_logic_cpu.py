@@ -254,8 +254,8 @@ def test_argument_errors_and_planning_queries_of_the_round_2_entry_points():
     assert lib.po2_dilate2(None, one, 4, 8, 8, None) == -3
     assert lib.po2_conv2d_depthwise_dgrad(one, None, one, 2, 8, 4, 4, None) == -3
     assert lib.po2_conv2d_depthwise_wgrad(one, one, one, 2, 8, 4, 4, one, 16, None) == -8
-    assert lib.po2_bn_bwd_fused(one, one, one, one, one, one, one, None, None, one, None, 4, 8, 16, 64, one, 1 << 20, None) == -9
-    assert lib.po2_bn_bwd_fused(one, one, None, one, one, one, one, None, None, one, one, 3, 8, 16, 64, one, 1 << 20, None) == -9
+    assert lib.po2_bn_bwd_fused(one, None, one, one, one, one, one, one, None, None, one, None, 4, 8, 16, 64, one, 1 << 20, None) == -9
+    assert lib.po2_bn_bwd_fused(one, one, one, None, one, one, one, one, None, None, one, one, 3, 8, 16, 64, one, 1 << 20, None) == -9
     assert lib.po2_bn_apply_sums(one, None, one, None, one, None, None, None, None, None, 0.1, 1e-5, 0, None, None, 8, 16, 64, None) == -3
     assert lib.po2_conv2d_fwd_packed_stats(one, one, one, one, *conv, 2, 1, 1, 2, one, None) == -10          # stride 2: not the TMA-fed kernel
     assert lib.po2_conv2d_dgrad_packed(one, None, one, one, *conv, 1, 2, None) == -3
