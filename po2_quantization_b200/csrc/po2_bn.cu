@@ -411,6 +411,7 @@ __global__ void __launch_bounds__(BN_THREADS, 4) bn_apply_kernel(const float* __
   // x / residual were complete before the statistics kernel started; the statistics (and the mailbox
   // epoch) are that kernel's output
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the conv behind may set up under this kernel
   if (sums) {
     // one rank, statistics from the producing conv's epilogue: sums[c] = sum x, sums[C + c] = sum x^2 over the
     // B*HW values of channel c (fp64).  Every CTA derives the same parameters; CTA 0 writes the per-channel
@@ -541,6 +542,7 @@ __global__ void __launch_bounds__(BN_THREADS, 4) bn_bwd_apply_kernel(const float
   const int C = g.C;
   float* prb = reinterpret_cast<float*>(prm + C);                 // beta per channel (SiLU: z is recomputed from x)
   asm volatile("griddepcontrol.wait;" ::: "memory");            // sums / mailbox epoch come from the reduce kernel
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the conv behind may set up under this kernel
   double M = 0.0;
   for (int r = 0; r < R; ++r) M += (double)stats[(size_t)r * (2 * C + 1) + 2 * C];
   const BnGather src = gather_from(nullptr, 0, mailbox);          // R ranks' sums: add them here, in rank order
@@ -757,6 +759,9 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_fwd_fused_kernel(const float
   BnMailbox* me = peers.world > 1 ? peers.box[peers.rank] : nullptr;
   const uint32_t tag = me ? *reinterpret_cast<volatile uint32_t*>(&me->epoch) + 1 : 0;   // read before anyone advances it
   BN_STAMP(0);
+  // a conv launched programmatically behind this kernel may set up (barriers, TMEM, tensor map) under it; it waits for
+  // this grid's completion before it touches y
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const float shift = __ldg(x + (size_t)c * g.HW);
   // thread 0 needs these after the channel barrier: their loads go out now, under phase 1 (behind the barrier
   // they were three serialised round trips of the whole CTA's critical path: measured 2.7 us of 8.9)
@@ -884,6 +889,7 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_fused_kernel(const float
   const int nslab = (g.B - s + g.S - 1) / g.S;
   const int n = nslab * L;
   BN_STAMP(8);
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the data-gradient conv behind may set up under this kernel
   const float mu = __ldg(mean + c);
   // ---- phase 1: masked gradient and x into registers, local sums.  All loads (dy, x and the
   // activation's y: 24 128-bit loads per thread, 124 registers) are issued before the first is used -- masking right behind

@@ -901,9 +901,15 @@ namespace po2 {
 // legal when the kernel directly in front of it in the stream is one of ours that was launched
 // with a full dependency (pack_weights_kernel, fused_kernel): the conv's producers read x without a
 // griddepcontrol.wait, which is safe only if x's producer finished before that kernel started.
+// chain: the operand is already packed and the kernel directly in front in the stream produced x (a norm kernel):
+// the TMA-fed kernel is launched programmatically with the waits of TmaPlan::pdl == 2 (PO2_CONV_PDL_CHAIN=0: off).
+static bool pdl_chain_enabled() {
+  static const bool on = []() { const char* e = getenv("PO2_CONV_PDL_CHAIN"); return !(e && e[0] == '0'); }();
+  return on;
+}
 static int launch_umma(const void* x, const void* w, const float* scale, void* out, ConvGeom& g, int w_format,
                        int bits, int fsr, int transpose, void* pack_buf, cudaStream_t st, bool pdl = true,
-                       const ConvEpilogue& ep = ConvEpilogue{nullptr, nullptr, nullptr, 0, nullptr}) {
+                       const ConvEpilogue& ep = ConvEpilogue{nullptr, nullptr, nullptr, 0, nullptr}, bool chain = false) {
   if (ep.sums && !g.tf32) return PO2_E_UNSUPPORTED;         // only the TMA-fed kernel accumulates statistics
   {
     uint8_t* Bp = reinterpret_cast<uint8_t*>(pack_buf);
@@ -922,7 +928,7 @@ static int launch_umma(const void* x, const void* w, const float* scale, void* o
       if (g.tf32 && tma_enabled() && plan_tma(g, tp, ep.sums != nullptr)) {
         // (the operand may already be packed in K3T's layout: an x that cannot be described by a tensor map --
         // misaligned -- is an error here, not a fallback)
-        return launch_tma(x, Bp, scale, out, g, tp, st, pdl, ep);
+        return launch_tma(x, Bp, scale, out, g, tp, st, (chain && transpose < 0 && pdl_chain_enabled()) ? 2 : (pdl ? 1 : 0), ep);
       }
       if (ep.sums) return PO2_E_UNSUPPORTED;
     }
@@ -1522,7 +1528,7 @@ int po2_conv2d_fwd_packed_ep(const void* x, const void* packed, const float* sca
   if (compute == 1 || !umma_eligible(g) || !plan_umma(g, compute == 2)) return PO2_E_UNSUPPORTED;
   if ((int64_t)B * C * H * W >= (1ll << 31) || (int64_t)B * K * g.P * g.Q >= (1ll << 31)) return PO2_E_SIZE;
   return launch_umma(x, nullptr, scale, out, g, PO2_W_F32_PO2, 4, 1, -1, const_cast<void*>(packed), (cudaStream_t)stream,
-                     /*pdl=*/false, ep);
+                     /*pdl=*/false, ep, /*chain=*/true);
 }
 
 // Training forward from a pre-packed operand that also accumulates the batch statistics of the BatchNorm behind
@@ -1730,7 +1736,7 @@ int po2_conv2d_dgrad_packed(const void* g_out, const void* packed, const float* 
   ConvGeom g;
   if (!dgrad_geom(g, B, C, H, W, K, R, S, pad, compute)) return PO2_E_UNSUPPORTED;
   return launch_umma(g_out, nullptr, scale, gx, g, PO2_W_F32_PO2, 4, 1, -1, const_cast<void*>(packed), (cudaStream_t)stream,
-                     /*pdl=*/false);
+                     /*pdl=*/false, ConvEpilogue{nullptr, nullptr, nullptr, 0, nullptr}, /*chain=*/true);
 }
 
 size_t po2_conv2d_dgrad_workspace(int B, int C, int H, int W, int K, int R, int S, int pad, int compute) {

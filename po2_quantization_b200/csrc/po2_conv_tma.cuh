@@ -58,7 +58,9 @@ struct TmaPlan {
   int NCGS, nchunk;          // 8-channel groups per pipeline stage, stages per tile
   int nst;
   int cps;                   // CTAs per SM the plan was sized for (2 when two CTAs' shared memory and TMEM fit)
-  int pdl;                   // launched with programmatic stream serialization behind the weight-pack kernel
+  int pdl;                   // launched with programmatic stream serialization: 1 = behind the weight-pack kernel (the
+                             // slab copy waits for it, x is older), 2 = behind any kernel, e.g. the norm that produced x
+                             // (the slab copy, the TMA producer and the epilogue all wait)
   int debug;                 // PO2_TMA_DEBUG bit mask (1: no TMA loads, 2: no MMAs, 4: no descriptor prefetch)
   int HW, Himg, Wimg;        // image geometry (ConvGeom's H/W are flattened for 1x1 layers)
   uint32_t stage_bytes, cg_bytes;                 // per stage / per channel group (modes 0-2)
@@ -207,6 +209,9 @@ __global__ void __launch_bounds__(KT_THREADS, STATS ? 1 : 2) conv_tma_kernel(con
     // launch only behind our own pack / quantize kernels), so no griddepcontrol.wait here.
     // (mode 4 issues 3 * APT boxes per stage: they are spread over the lanes of the warp -- a TMA issue costs a
     // thread ~150 cycles -- lane i owns box i; the other modes have one box per stage, issued by lane 0)
+    // pdl == 2 (the layer chain): the kernel in front -- a norm kernel that triggered its dependents early -- is the
+    // producer of x; everything up to here (launch, barriers, TMEM, tensor-map fetch) overlapped its tail
+    if (tp.pdl == 2) asm volatile("griddepcontrol.wait;" ::: "memory");
     {
       uint32_t s = 0, sphase = 0;
       int tr_it = 0;
@@ -825,9 +830,9 @@ static bool tma_takes(const ConvGeom& g) {
 
 // the conv launch behind the packed operand (same contract as the register-fed launch in launch_umma)
 static int launch_tma(const void* x, const uint8_t* Bp, const float* scale, void* out, const ConvGeom& g, const TmaPlan& tp_in,
-                      cudaStream_t st, bool pdl, const ConvEpilogue& ep, const ConvBnTrain* bn = nullptr) {
+                      cudaStream_t st, int pdl, const ConvEpilogue& ep, const ConvBnTrain* bn = nullptr) {
   TmaPlan tp = tp_in;
-  tp.pdl = pdl ? 1 : 0;
+  tp.pdl = pdl;
   CUtensorMap tm;
   if (!encode_x_map(&tm, x, g, tp)) return PO2_E_UNSUPPORTED;
   static PerDeviceOnce attr_once;
