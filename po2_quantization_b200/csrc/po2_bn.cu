@@ -759,10 +759,6 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_fwd_fused_kernel(const float
   BnMailbox* me = peers.world > 1 ? peers.box[peers.rank] : nullptr;
   const uint32_t tag = me ? *reinterpret_cast<volatile uint32_t*>(&me->epoch) + 1 : 0;   // read before anyone advances it
   BN_STAMP(0);
-  // a conv launched programmatically behind this kernel may set up (barriers, TMEM, tensor map) under it; it waits for
-  // this grid's completion before it touches y
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  const float shift = __ldg(x + (size_t)c * g.HW);
   // thread 0 needs these after the channel barrier: their loads go out now, under phase 1 (behind the barrier
   // they were three serialised round trips of the whole CTA's critical path: measured 2.7 us of 8.9)
   float ga = 1.0f, be = 0.0f, rm_old = 0.f, rv_old = 0.f;
@@ -778,6 +774,12 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_fwd_fused_kernel(const float
     if (s == 0 && c == 0 && num_batches_tracked)
       asm volatile("ld.global.cg.s64 %0, [%1];" : "=l"(nbt_old) : "l"(num_batches_tracked));
   }
+  // launched programmatically behind the conv that produces x: everything above ran under its tail.  Then: a conv
+  // launched programmatically behind THIS kernel may set up (barriers, TMEM, tensor map) under it; it waits for this
+  // grid's completion before it touches y
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const float shift = __ldg(x + (size_t)c * g.HW);
   // ---- phase 1: load into registers, shifted sums
   float4 v[BN_FUSED_R];
   int off[BN_FUSED_R];                                   // in 128-bit units (< 2^29, checked on the host)
@@ -889,8 +891,9 @@ __global__ void __launch_bounds__(BN_THREADS, 2) bn_bwd_fused_kernel(const float
   const int nslab = (g.B - s + g.S - 1) / g.S;
   const int n = nslab * L;
   BN_STAMP(8);
+  const float mu = __ldg(mean + c);                         // (the forward's: older than the kernel in front)
+  asm volatile("griddepcontrol.wait;" ::: "memory");        // launched programmatically behind the producer of dy
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the data-gradient conv behind may set up under this kernel
-  const float mu = __ldg(mean + c);
   // ---- phase 1: masked gradient and x into registers, local sums.  All loads (dy, x and the
   // activation's y: 24 128-bit loads per thread, 124 registers) are issued before the first is used -- masking right behind
   // each load serialised eight round trips (measured 4.4 us of this kernel's 10)
@@ -1178,6 +1181,14 @@ int po2_bn_apply_sums(const void* x, const void* residual, void* y, void* sums, 
 // One-launch kernels: the S CTAs of a channel as one thread-block cluster when 2 <= S <= 16 (hardware co-scheduling
 // and barrier; an ordinary launch), else -- or when the cluster launch is refused -- a cooperative launch with the
 // global per-channel barrier.  g (inside args) gets its `cluster` flag here.
+// The one-launch norm kernels as programmatic dependents of the conv in front (they wait before their first tensor
+// load): measured 2.49 vs 2.32 ms per ResNet-56 step -- their CTAs need every register of an SM, scheduled early they
+// only stand in the way of the conv's tail -- so it is off unless PO2_BN_PDL=1.  (The other direction, the conv as a
+// dependent of the norm, is what pays: po2_conv.cu, pdl_chain_enabled.)
+static bool bn_pdl() {
+  static const bool on = []() { const char* e = getenv("PO2_BN_PDL"); return e && e[0] == '1'; }();
+  return on;
+}
 static cudaError_t launch_bn_one(const void* kern, BnGeom& g, int C, void** args, cudaStream_t st) {
   // Measured on the ResNet-56 step: clusters of 4 (the 32-channel layers) take ~1.2 us off each kernel (2.53 -> 2.47 ms
   // per step); clusters of 16 (the 16-channel layers) halve the barrier inside the kernel too, but gang-scheduling 16
@@ -1195,17 +1206,37 @@ static cudaError_t launch_bn_one(const void* kern, BnGeom& g, int C, void** args
       cfg.gridDim = dim3(g.S, C);
       cfg.blockDim = dim3(BN_THREADS);
       cfg.stream = st;
-      cudaLaunchAttribute attr[1];
+      cudaLaunchAttribute attr[2];
       attr[0].id = cudaLaunchAttributeClusterDimension;
       attr[0].val.clusterDim.x = (unsigned)g.S; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // both kernels wait before they read tensors
+      attr[1].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = attr;
-      cfg.numAttrs = 1;
+      cfg.numAttrs = bn_pdl() ? 2 : 1;
       e = cudaLaunchKernelExC(&cfg, kern, args);
       if (e == cudaSuccess) return e;
     }
     (void)cudaGetLastError();                            // cluster shape not schedulable here: the global barrier form
   }
   g.cluster = 0;
+  static bool coop_pdl_ok = true;                        // cooperative + programmatic in one launch: kept while it works
+  if (bn_pdl() && coop_pdl_ok) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(g.S, C);
+    cfg.blockDim = dim3(BN_THREADS);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    const cudaError_t e = cudaLaunchKernelExC(&cfg, kern, args);
+    if (e == cudaSuccess || e == cudaErrorCooperativeLaunchTooLarge) return e;
+    (void)cudaGetLastError();
+    coop_pdl_ok = false;
+  }
   return cudaLaunchCooperativeKernel(kern, dim3(g.S, C), dim3(BN_THREADS), args, 0, st);
 }
 

@@ -150,6 +150,9 @@ __global__ void __launch_bounds__(KT_THREADS, STATS ? 1 : 2) conv_tma_kernel(con
   __syncthreads();
 #endif
   if (tid == 0) K3_TRACE(6, 0);
+  // a norm kernel launched programmatically behind this conv may be scheduled now; it waits for this grid's
+  // completion (griddepcontrol.wait) before it reads the output
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int nt = blockIdx.x % g.ntiles_n;
   const int m_first = blockIdx.x / g.ntiles_n;
   const int nitems = tp.nitems_m, m_step = tp.m_step, nst = tp.nst, nchunk = tp.nchunk;
