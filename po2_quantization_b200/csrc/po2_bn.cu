@@ -245,6 +245,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const float* __re
                                                                const float* __restrict__ dy2 = nullptr) {
   // dy2 (backward): a second gradient of the same tensor -- the skip connection's -- added on the fly (dy + dy2),
   // instead of an accumulation kernel in front of this one
+  // (PO2_BN_REDUCE_PDL=1: this grid is itself a programmatic dependent of the kernel that produced its input)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // the consuming kernel (apply / backward apply, launched with programmatic stream serialization) may
   // be scheduled as soon as every CTA of this grid is running; it waits for this grid's completion
   // (griddepcontrol.wait) before it reads anything this grid writes
@@ -1072,6 +1074,22 @@ static int elementwise_grid(const BnGeom& g) {
   return (int)(ctas < 1 ? 1 : ctas);
 }
 
+// bn_reduce_kernel launches (optionally as a programmatic dependent of the kernel in front: PO2_BN_REDUCE_PDL=1)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_reduce(void (*kern)(KArgs...), dim3 grid, cudaStream_t st, Args... args) {
+  static const bool pdl = []() { const char* e = getenv("PO2_BN_REDUCE_PDL"); return e && e[0] == '1'; }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(BN_THREADS);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 }  // namespace po2
 
 using namespace po2;
@@ -1107,9 +1125,10 @@ int po2_bn_stats(const void* x, int B, int C, int HW, float* stat, void* workspa
   const dim3 grid(g.S, C);
   cudaStream_t st = (cudaStream_t)stream;
   const float* xf = (const float*)x;
-  if (v) bn_reduce_kernel<true, 0><<<grid, BN_THREADS, 0, st>>>(xf, nullptr, nullptr, nullptr, nullptr, stat, nullptr, nullptr, g, ws, pr, 0);
-  else bn_reduce_kernel<false, 0><<<grid, BN_THREADS, 0, st>>>(xf, nullptr, nullptr, nullptr, nullptr, stat, nullptr, nullptr, g, ws, pr, 0);
-  return (int)cudaGetLastError();
+  cudaError_t e_launch;
+  if (v) e_launch = launch_reduce(bn_reduce_kernel<true, 0>, grid, st, xf, nullptr, nullptr, nullptr, nullptr, stat, nullptr, nullptr, g, ws, pr, 0, nullptr, nullptr, nullptr);
+  else e_launch = launch_reduce(bn_reduce_kernel<false, 0>, grid, st, xf, nullptr, nullptr, nullptr, nullptr, stat, nullptr, nullptr, g, ws, pr, 0, nullptr, nullptr, nullptr);
+  return (int)e_launch;
 }
 
 int po2_bn_apply(const void* x, const void* residual, void* y, const float* stats, int R, void* mailbox,
@@ -1338,14 +1357,15 @@ int po2_bn_bwd_reduce(const void* dy, const void* dy2, const void* x, const void
   const dim3 grid(g.S, C);
   cudaStream_t st = (cudaStream_t)stream;
   const float *xf = (const float*)x, *df = (const float*)dy, *yf = (const float*)y, *d2f = (const float*)dy2;
+  cudaError_t e_launch;
   if (act != 0) {
-    if (v) bn_reduce_kernel<true, 2><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr, act, gamma, beta, d2f);
-    else bn_reduce_kernel<false, 2><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr, act, gamma, beta, d2f);
+    if (v) e_launch = launch_reduce(bn_reduce_kernel<true, 2>, grid, st, xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr, act, gamma, beta, d2f);
+    else e_launch = launch_reduce(bn_reduce_kernel<false, 2>, grid, st, xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr, act, gamma, beta, d2f);
   } else {
-    if (v) bn_reduce_kernel<true, 1><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr, act, nullptr, nullptr, d2f);
-    else bn_reduce_kernel<false, 1><<<grid, BN_THREADS, 0, st>>>(xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr, act, nullptr, nullptr, d2f);
+    if (v) e_launch = launch_reduce(bn_reduce_kernel<true, 1>, grid, st, xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr, act, nullptr, nullptr, d2f);
+    else e_launch = launch_reduce(bn_reduce_kernel<false, 1>, grid, st, xf, df, yf, save_mean, save_invstd, sums, dgamma, dbeta, g, ws, pr, act, nullptr, nullptr, d2f);
   }
-  return (int)cudaGetLastError();
+  return (int)e_launch;
 }
 
 int po2_bn_bwd_apply(const void* dy, const void* dy2, const void* x, const void* y, const float* save_mean,

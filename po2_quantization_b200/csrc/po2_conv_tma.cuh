@@ -150,9 +150,6 @@ __global__ void __launch_bounds__(KT_THREADS, STATS ? 1 : 2) conv_tma_kernel(con
   __syncthreads();
 #endif
   if (tid == 0) K3_TRACE(6, 0);
-  // a norm kernel launched programmatically behind this conv may be scheduled now; it waits for this grid's
-  // completion (griddepcontrol.wait) before it reads the output
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int nt = blockIdx.x % g.ntiles_n;
   const int m_first = blockIdx.x / g.ntiles_n;
   const int nitems = tp.nitems_m, m_step = tp.m_step, nst = tp.nst, nchunk = tp.nchunk;
@@ -405,6 +402,10 @@ __global__ void __launch_bounds__(KT_THREADS, STATS ? 1 : 2) conv_tma_kernel(con
         valid = valid && n < g.B && pimg < HW;
         obase = (n * K + kbase) * HW + pimg;
       }
+      // a kernel launched programmatically behind this conv may be scheduled once every CTA is at its last tile (not
+      // earlier: a resident dependent that only waits takes registers and CTA slots from this grid's tail); it waits
+      // for this grid's completion (griddepcontrol.wait) before it reads the output
+      if (m + m_step >= nitems && pass == NPASS - 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
       mbar_wait(tfull + acc, aphase);
       tc_fence_after();
       if (warp == 0 && lane == 0) K3_TRACE(1, 2 * tr_item);
