@@ -15,7 +15,7 @@ lib_path = os.path.join(ROOT, "gpurun_out", "libpo2b200_trace.so")
 os.makedirs(os.path.dirname(lib_path), exist_ok=True)
 WGRAD = len(sys.argv) > 9 and sys.argv[9] == "wgrad"
 COMPUTE = 2 if (len(sys.argv) > 9 and sys.argv[9] == "tf32") or (len(sys.argv) > 10 and sys.argv[10] == "tf32") else 0
-src = [os.path.join(ROOT, "po2_quantization_b200", "csrc", f) for f in ("po2_quant.cu", "po2_conv.cu", "po2_conv_bwd.cu", "po2_bn.cu", "po2_lin.cu")]
+src = [os.path.join(ROOT, "po2_quantization_b200", "csrc", f) for f in ("po2_quant.cu", "po2_conv.cu", "po2_conv_bwd.cu", "po2_bn.cu", "po2_lin.cu", "po2_sgd.cu")]
 subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-shared",
                        "-Xcompiler", "-fPIC", "-DPO2_K3_TRACE", *os.environ.get("PO2_TRACE_DEFS", "").split(), "-I", os.path.join(ROOT, "include"), "-o", lib_path, *src])
 from po2_quantization_b200 import _lib  # noqa: E402
