@@ -1238,23 +1238,18 @@ static cudaError_t launch_bn_one(const void* kern, BnGeom& g, int C, void** args
     (void)cudaGetLastError();                            // cluster shape not schedulable here: the global barrier form
   }
   g.cluster = 0;
-  static bool coop_pdl_ok = true;                        // cooperative + programmatic in one launch: kept while it works
-  if (bn_pdl() && coop_pdl_ok) {
+  if (g.S == 1) {
+    // one CTA per channel: no barrier between CTAs, an ordinary launch (optionally programmatic)
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(g.S, C);
+    cfg.gridDim = dim3(1, C);
     cfg.blockDim = dim3(BN_THREADS);
     cfg.stream = st;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeCooperative;
-    attr[0].val.cooperative = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 2;
-    const cudaError_t e = cudaLaunchKernelExC(&cfg, kern, args);
-    if (e == cudaSuccess || e == cudaErrorCooperativeLaunchTooLarge) return e;
-    (void)cudaGetLastError();
-    coop_pdl_ok = false;
+    cfg.numAttrs = bn_pdl() ? 1 : 0;
+    return cudaLaunchKernelExC(&cfg, kern, args);
   }
   return cudaLaunchCooperativeKernel(kern, dim3(g.S, C), dim3(BN_THREADS), args, 0, st);
 }
