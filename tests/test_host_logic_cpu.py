@@ -269,3 +269,60 @@ def test_argument_errors_and_planning_queries_of_the_round_2_entry_points():
     assert lib.po2_sgd_step(ptrs, ptrs, None, n2, 2, 0.1, 0.9, 1e-4, 0, None) == -3                 # momentum needs buffers
     assert lib.po2_sgd_step(ptrs, odd, ptrs, n2, 2, 0.1, 0.9, 1e-4, 0, None) == -5                  # not a float address
     assert lib.po2_sgd_step(ptrs, ptrs, ptrs, (ctypes.c_longlong * 2)(16, 0), 2, 0.1, 0.9, 1e-4, 0, None) == -4
+
+
+def test_sgd_subclass_delegates_what_the_kernel_does_not_take():
+    """optim.SGD on CPU parameters (and Nesterov / dampening groups anywhere) is torch.optim.SGD's own step: same
+    numbers, same state layout, interchangeable state_dict -- the kernel path is CUDA fp32 only and is covered by
+    tests/test_models_gpu.py."""
+    torch.manual_seed(0)
+    a = [torch.nn.Parameter(torch.randn(5, 3)), torch.nn.Parameter(torch.randn(7))]
+    b = [torch.nn.Parameter(p.detach().clone()) for p in a]
+    oa = P.optim.SGD(a, lr=0.1, momentum=0.9, weight_decay=1e-4)
+    ob = torch.optim.SGD(b, lr=0.1, momentum=0.9, weight_decay=1e-4)
+    assert isinstance(oa, torch.optim.SGD)
+    for step in range(3):
+        for pa, pb in zip(a, b):
+            g = torch.randn(pa.shape)
+            pa.grad, pb.grad = g.clone(), g.clone()
+        assert oa.step(lambda: torch.tensor(1.5)).item() == 1.5          # the closure protocol
+        ob.step()
+    for pa, pb in zip(a, b):
+        assert torch.equal(pa, pb)
+        assert torch.equal(oa.state[pa]["momentum_buffer"], ob.state[pb]["momentum_buffer"])
+    ob.load_state_dict(oa.state_dict())
+    # a parameter without a gradient is skipped, like in torch
+    a[1].grad = None
+    before = a[1].detach().clone()
+    a[0].grad = torch.ones_like(a[0])
+    oa.step()
+    assert torch.equal(a[1], before)
+
+
+def test_round_2_switches_and_planning_queries_on_the_host():
+    import ctypes
+    from po2_quantization_b200 import _lib, batchnorm
+    lib = _lib.load()
+    one = ctypes.c_void_p(4096)
+    # weight gradients on a side stream: a process-wide switch, off unless asked for
+    was = ops.get_wgrad_overlap()
+    try:
+        ops.set_wgrad_overlap(True)
+        assert ops.get_wgrad_overlap() is True
+        ops.join_weight_gradients()                         # nothing pending: a no-op, also without a GPU
+    finally:
+        ops.set_wgrad_overlap(was)
+    # the skip-connection routing only applies to tensors produced by the fused norm's autograd node
+    t = torch.randn(2, 3, requires_grad=True) * 2
+    assert batchnorm._route_skip_gradient(t) is t
+    # conv + train-mode norm in one launch: argument checks before anything touches a device
+    conv = (8, 16, 32, 32, 16, 3, 3)
+    f = ctypes.c_float
+    assert lib.po2_conv2d_bn_fwd_packed(None, one, one, one, one, None, None, None, None, None, None, f(0.1), f(1e-5), 1, one, one,
+                                        one, *conv, 1, 1, 1, 2, one, 1 << 20, None) == -3
+    assert lib.po2_conv2d_bn_fwd_packed(one, one, one, one, one, None, None, None, None, None, None, f(0.1), f(1e-5), 7, one, one,
+                                        one, *conv, 1, 1, 1, 2, one, 1 << 20, None) == -9
+    assert lib.po2_conv2d_bn_fwd_packed(one, one, one, one, one, None, None, None, one, None, None, f(0.1), f(1e-5), 1, one, one,
+                                        one, *conv, 1, 1, 1, 2, one, 1 << 20, None) == -3          # running_mean without running_var
+    assert lib.po2_conv2d_bn_workspace(*conv, 2, 1, 1, 2) == 0                                      # stride 2: not the TMA-fed kernel
+    assert lib.po2_conv2d_bn_workspace(*conv, 1, 1, 1, 0) == 0                                      # bf16 mode: not the TMA-fed kernel
