@@ -320,6 +320,14 @@ int po2_bn_bwd_apply(const void* dy, const void* dy2, const void* x, const void*
  * All ranks must issue the same sequence of exchanges (the rule of any collective). */
 size_t po2_bn_mailbox_bytes(void);
 
+/* ---- weight gradient of the full-precision stem (models/resnet.py:99-102 nn.Conv2d(3, 16, 3, 1, 1); autograd of F.conv2d
+ * w.r.t. the weight -- the stem's input needs no gradient, so this is its whole backward): 3x3, pad 1, stride 1,
+ * C <= 4 input channels, K*C <= 256.  CUDA cores, exact fp32 FMA, one CTA per image + the fixed-order reduce kernel
+ * (deterministic).  Workspace: po2_conv2d_stem_wgrad_workspace(...) bytes (0: shape not taken). */
+size_t po2_conv2d_stem_wgrad_workspace(int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups);
+int po2_conv2d_stem_wgrad(const void* g, const void* x, void* gw, int B, int C, int H, int W, int K, int R, int S, int stride,
+                          int pad, int groups, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- conv + train-mode BatchNorm (+ residual add) (+ activation) in ONE launch --------------------------------
  * models/resnet.py:55-71 in train(): y = act(bn(conv2d(x, Q(w))) + residual) with batch statistics, from the packed
  * operand (po2_conv2d_pack / the multi-tensor quantizer).  The TMA-fed kernel keeps every tile's accumulator in TMEM,

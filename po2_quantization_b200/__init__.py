@@ -14,6 +14,7 @@ from .quantizers import (LinearPowerOfTwoPlusQuantizer, LinearPowerOfTwoQuantize
                          quantizer_dict)
 from .fold import FoldedConvBN, conv_bn_act, fold_conv_bn, fuse_batchnorm  # noqa: F401
 from . import optim  # noqa: F401
+from .stem import StemConv2d, accelerate_stem  # noqa: F401
 from .checkpoint import load_packed_checkpoint, pack_state_dict, save_packed_checkpoint, unpack_state_dict  # noqa: F401
 
 __version__ = "0.1.0"

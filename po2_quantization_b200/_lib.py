@@ -53,6 +53,8 @@ SIGNATURES = {
     "po2_dilate2": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "po2_conv2d_bn_workspace": (_sz, [_i] * 11),
     "po2_conv2d_bn_fwd_packed": (_i, [_vp] * 11 + [_c.c_float, _c.c_float, _i, _vp, _vp, _vp] + [_i] * 11 + [_vp, _sz, _vp]),
+    "po2_conv2d_stem_wgrad_workspace": (_sz, [_i] * 10),
+    "po2_conv2d_stem_wgrad": (_i, [_vp, _vp, _vp] + [_i] * 10 + [_vp, _sz, _vp]),
     "po2_sgd_step": (_i, [_vp, _vp, _vp, _vp, _i, _c.c_float, _c.c_float, _c.c_float, _i, _vp]),
     "po2_sgd_max_tensors_per_launch": (_i, []),
     "po2_conv2d_depthwise_dgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -163,6 +163,9 @@ __device__ __forceinline__ float conv_epilogue(float v, const ConvEpilogue& ep, 
   return conv_act(v, ep.act);
 }
 
+// csrc/po2_conv.cu: gw[(k*C + c)*ntaps + tap] = sum over parts of partial[part][tap][k][c], in part order (launched
+// programmatically behind the kernel that wrote the partials)
+int launch_wgrad_reduce(const float* partial, float* gw, int nparts, int K, int C, int ntaps, cudaStream_t st);
 // csrc/po2_conv_bwd.cu: fp32 cluster split-K GEMM for 1x1 convs on feature maps of <= 16 pixels
 bool pw_small_takes(int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups);
 int launch_pw_small(const float* x, const float* w, float* out, int B, int C, int HW, int K, const ConvEpilogue& ep,

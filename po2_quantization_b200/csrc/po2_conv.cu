@@ -1294,6 +1294,20 @@ __global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __r
   }
 }
 
+int launch_wgrad_reduce(const float* partial, float* gw, int nparts, int K, int C, int ntaps, cudaStream_t st) {
+  const int n = ntaps * C * K;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((n + 31) / 32));
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, conv_wgrad_reduce_kernel, partial, gw, nparts, K, C, ntaps);
+}
+
 static bool plan_wgrad(ConvGeom& g, WgGeom& wg) {
   // g: forward geometry already through plan_umma(g, false) (flat padded space, tap offsets, producer fast path)
   if (g.K > 128 || g.Cpad > 256) return false;

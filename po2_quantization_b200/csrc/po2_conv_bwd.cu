@@ -124,6 +124,98 @@ __global__ void __launch_bounds__(DWG_THREADS) dw_wgrad_kernel(const float* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Weight gradient of a plain 3x3 pad-1 stride-1 conv with very few input channels -- the full-precision stem of the
+// reference's models (models/resnet.py:99-102: nn.Conv2d(3, 16, 3, 1, 1)); the input needs no gradient, so this is
+// the layer's whole backward.  cuDNN's wgrad takes 40 us on the 128 x 3 x 32 x 32 batch (the last cuDNN kernel of the
+// ResNet-56 step besides the stem's forward).  CUDA cores, exact fp32 FMA:
+//   gw[k][c][r][s] = sum_{n,h,w} g[n][k][h][w] * x[n][c][h + r - 1][w + s - 1]
+// One CTA per image (grid-stride): g[n] (K rows, padded by one float against bank conflicts) and the zero-haloed
+// x[n] are staged in shared memory; thread (row group, k, c) walks its rows with a sliding 3x3 window -- one g load
+// and three x loads per nine FMAs --, the row groups are added through shared memory in a fixed order, and the CTA's
+// partial [tap][k][c] goes to conv_wgrad_reduce_kernel (fixed order over CTAs: deterministic).
+// ------------------------------------------------------------------------------------------------
+constexpr int SW_THREADS = 256;
+__global__ void __launch_bounds__(SW_THREADS) stem_wgrad_kernel(const float* __restrict__ g, const float* __restrict__ x,
+                                                                float* __restrict__ partial, int B, int C, int H, int W,
+                                                                int K) {
+  extern __shared__ float sw_smem[];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the reduce kernel waits for this grid's completion
+  const int HW = H * W, GS = HW + 1, XW = W + 2, XS = (H + 2) * XW;
+  float* sg = sw_smem;                          // [K][HW + 1]
+  float* sx = sg + K * GS;                      // [C][H + 2][W + 2]
+  float* red = sx + C * XS;                     // [RG][K * C][9]
+  const int KC = K * C, RG = SW_THREADS / KC;   // row groups
+  const int tid = threadIdx.x, pair = tid % KC, rg = tid / KC;
+  const bool active = rg < RG;
+  const int k = pair / C, c = pair - k * C;
+  float tot[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) tot[i] = 0.f;
+  for (int i = tid; i < C * XS; i += SW_THREADS) sx[i] = 0.f;       // the halo stays zero for every image
+  for (int n = blockIdx.x; n < B; n += gridDim.x) {
+    __syncthreads();
+    const float* pg = g + (size_t)n * K * HW;
+    const float* px = x + (size_t)n * C * HW;
+    for (int i = tid; i < K * HW; i += SW_THREADS) {
+      const int kk = i / HW;
+      sg[kk * GS + (i - kk * HW)] = __ldg(pg + i);
+    }
+    for (int i = tid; i < C * HW; i += SW_THREADS) {
+      const int cc = i / HW, p = i - cc * HW, h = p / W, w = p - h * W;
+      sx[cc * XS + (h + 1) * XW + (w + 1)] = __ldg(px + i);
+    }
+    __syncthreads();
+    float acc[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) acc[i] = 0.f;
+    if (active) {
+      const float* gk = sg + k * GS;
+      const float* xc = sx + c * XS;
+      for (int h = rg; h < H; h += RG) {
+        const float* x0 = xc + h * XW;          // rows h-1, h, h+1 of the image = rows h, h+1, h+2 of the padded plane
+        float a0 = x0[0], a1 = x0[1], b0 = x0[XW], b1 = x0[XW + 1], c0 = x0[2 * XW], c1 = x0[2 * XW + 1];
+        for (int w = 0; w < W; ++w) {
+          const float gv = gk[h * W + w];
+          const float a2 = x0[w + 2], b2 = x0[XW + w + 2], c2 = x0[2 * XW + w + 2];
+          acc[0] = fmaf(gv, a0, acc[0]); acc[1] = fmaf(gv, a1, acc[1]); acc[2] = fmaf(gv, a2, acc[2]);
+          acc[3] = fmaf(gv, b0, acc[3]); acc[4] = fmaf(gv, b1, acc[4]); acc[5] = fmaf(gv, b2, acc[5]);
+          acc[6] = fmaf(gv, c0, acc[6]); acc[7] = fmaf(gv, c1, acc[7]); acc[8] = fmaf(gv, c2, acc[8]);
+          a0 = a1; a1 = a2; b0 = b1; b1 = b2; c0 = c1; c1 = c2;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 9; ++i) red[(rg * KC + pair) * 9 + i] = acc[i];
+    }
+    __syncthreads();
+    if (tid < KC) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        float v = 0.f;
+        for (int q = 0; q < RG; ++q) v += red[(q * KC + tid) * 9 + i];
+        tot[i] += v;
+      }
+    }
+  }
+  if (tid < KC) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) partial[((size_t)blockIdx.x * 9 + i) * KC + k * C + c] = tot[i];   // [cta][tap][k][c]
+  }
+}
+static size_t stem_wgrad_smem(int C, int H, int W, int K) {
+  const int KC = K * C, RG = SW_THREADS / (KC > 0 ? KC : 1);
+  return ((size_t)K * (H * W + 1) + (size_t)C * (H + 2) * (W + 2) + (size_t)RG * KC * 9) * sizeof(float);
+}
+static bool stem_wgrad_takes(int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups) {
+  if (R != 3 || S != 3 || stride != 1 || pad != 1 || groups != 1 || B < 1) return false;
+  if (C < 1 || C > 4 || K < 1 || K * C > SW_THREADS || H < 1 || W < 1) return false;
+  return stem_wgrad_smem(C, H, W, K) <= 200 * 1024 && (int64_t)B * K * H * W < (1ll << 31);
+}
+static int stem_wgrad_ctas(int B) {
+  const int sms = device_sm_count();
+  return B < sms ? B : sms;
+}
+
 constexpr int DWG_MAX_C = 4096;
 constexpr int DWG_MAX_SPLIT = 32;
 
@@ -132,6 +224,29 @@ constexpr int DWG_MAX_SPLIT = 32;
 using namespace po2;
 
 extern "C" {
+
+size_t po2_conv2d_stem_wgrad_workspace(int B, int C, int H, int W, int K, int R, int S, int stride, int pad, int groups) {
+  if (!stem_wgrad_takes(B, C, H, W, K, R, S, stride, pad, groups)) return 0;
+  return (size_t)stem_wgrad_ctas(B) * 9 * K * C * sizeof(float);
+}
+
+int po2_conv2d_stem_wgrad(const void* g, const void* x, void* gw, int B, int C, int H, int W, int K, int R, int S, int stride,
+                          int pad, int groups, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!g || !x || !gw || !workspace) return PO2_E_NULL;
+  if (!stem_wgrad_takes(B, C, H, W, K, R, S, stride, pad, groups)) return PO2_E_UNSUPPORTED;
+  const int ctas = stem_wgrad_ctas(B);
+  if (workspace_bytes < (size_t)ctas * 9 * K * C * sizeof(float)) return PO2_E_WORKSPACE;
+  const size_t smem = stem_wgrad_smem(C, H, W, K);
+  static PerDeviceOnce once;
+  if (cudaError_t e0 = once.run([]() -> cudaError_t {
+        return cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      })) return (int)e0;
+  cudaStream_t st = (cudaStream_t)stream;
+  stem_wgrad_kernel<<<ctas, SW_THREADS, smem, st>>>((const float*)g, (const float*)x, (float*)workspace, B, C, H, W, K);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  return launch_wgrad_reduce((const float*)workspace, (float*)gw, ctas, K, C, 9, st);
+}
 
 int po2_dilate2(const void* g, void* g_up, int planes, int P, int Q, void* stream) {
   if (!g || !g_up) return PO2_E_NULL;

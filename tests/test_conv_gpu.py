@@ -710,3 +710,38 @@ def test_conv_epilogue_affine_residual_activation(case, act):
     if packed is not None:
         out2 = torch.ops.po2.conv2d_packed_ep(x, packed, scale, K, k, k, stride, pad, groups, 2, a, b, res, act)
         assert torch.equal(out, out2), name
+
+
+@pytest.mark.parametrize("shape", [(128, 3, 32, 32, 16), (5, 3, 32, 32, 16), (300, 1, 28, 28, 8), (4, 4, 17, 23, 32), (2, 3, 40, 40, 24)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_stem_conv_weight_gradient_kernel(shape):
+    """StemConv2d (the full-precision 3 -> 16 stem, models/resnet.py:99-102): forward is F.conv2d, the weight gradient
+    runs on po2_conv2d_stem_wgrad -- against fp64 autograd, deterministic, state_dict and initialisation untouched;
+    accelerate_stem re-classes a plain nn.Conv2d in place."""
+    import po2_quantization_b200 as P
+    from po2_quantization_b200 import ops
+    B, C, H, W, K = shape
+    torch.manual_seed(sum(shape))
+    ref = torch.nn.Conv2d(C, K, 3, 1, 1, bias=False).cuda()
+    m = torch.nn.Conv2d(C, K, 3, 1, 1, bias=False).cuda()
+    m.load_state_dict(ref.state_dict())
+    assert P.accelerate_stem(m) == 1 and isinstance(m, P.StemConv2d) and list(m.state_dict()) == ["weight"]
+    x = torch.randn(B, C, H, W, device="cuda")
+    go = torch.randn(B, K, H, W, device="cuda")
+    before = ops.LAUNCHES
+    y = m(x)
+    y.backward(go)
+    assert ops.LAUNCHES - before == 2                      # stem_wgrad_kernel + conv_wgrad_reduce_kernel
+    first = m.weight.grad.clone()
+    m.weight.grad = None
+    m(x).backward(go)
+    assert torch.equal(first, m.weight.grad)               # fixed-order partial sums
+    w64 = ref.weight.detach().double().requires_grad_(True)
+    torch.nn.functional.conv2d(x.double(), w64, None, 1, 1).backward(go.double())
+    err = ((m.weight.grad.double() - w64.grad).abs().max() / w64.grad.abs().max()).item()
+    assert err < 2e-5, err
+    # an input that needs its own gradient goes to the library path with both gradients
+    x2 = x.clone().requires_grad_(True)
+    m.weight.grad = None
+    m(x2).backward(go)
+    assert x2.grad is not None and torch.allclose(m.weight.grad, first, rtol=2e-2, atol=2e-2 * first.abs().max().item())

@@ -326,3 +326,15 @@ def test_round_2_switches_and_planning_queries_on_the_host():
                                         one, *conv, 1, 1, 1, 2, one, 1 << 20, None) == -3          # running_mean without running_var
     assert lib.po2_conv2d_bn_workspace(*conv, 2, 1, 1, 2) == 0                                      # stride 2: not the TMA-fed kernel
     assert lib.po2_conv2d_bn_workspace(*conv, 1, 1, 1, 0) == 0                                      # bf16 mode: not the TMA-fed kernel
+    # the stem's weight-gradient kernel: which shapes it takes is a host-side question
+    assert lib.po2_conv2d_stem_wgrad_workspace(128, 3, 64, 64, 24, 3, 3, 1, 1, 1) == 0               # g[n] does not fit shared memory
+    assert lib.po2_conv2d_stem_wgrad_workspace(128, 16, 32, 32, 16, 3, 3, 1, 1, 1) == 0              # not a small-C layer
+    assert lib.po2_conv2d_stem_wgrad_workspace(128, 3, 32, 32, 16, 3, 3, 2, 1, 1) == 0               # stride 2
+    assert lib.po2_conv2d_stem_wgrad(one, one, one, 128, 3, 32, 32, 16, 3, 3, 1, 1, 1, None, 0, None) == -3
+    assert lib.po2_conv2d_stem_wgrad(one, one, one, 128, 3, 32, 32, 16, 5, 5, 1, 2, 1, one, 1 << 20, None) == -10
+    m = torch.nn.Sequential(torch.nn.Conv2d(3, 16, 3, 1, 1, bias=False), torch.nn.Conv2d(16, 16, 3, 1, 1, bias=False),
+                            torch.nn.Conv2d(3, 8, 3, 2, 1, bias=False), torch.nn.Conv2d(3, 8, 3, 1, 1, bias=True))
+    keys = list(m.state_dict())
+    assert P.accelerate_stem(m) == 1 and isinstance(m[0], P.StemConv2d) and type(m[1]) is torch.nn.Conv2d
+    assert list(m.state_dict()) == keys
+    assert m[0](torch.randn(2, 3, 8, 8)).shape == (2, 16, 8, 8)                                     # CPU: nn.Conv2d's own forward

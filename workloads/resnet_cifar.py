@@ -51,9 +51,12 @@ class _Block(nn.Module):
 
 
 class ResNetCifar(nn.Module):
-    def __init__(self, conv_cls, norm_cls, n: int, num_classes: int, quantize_fn: Optional[Callable], bits: int):
+    def __init__(self, conv_cls, norm_cls, n: int, num_classes: int, quantize_fn: Optional[Callable], bits: int,
+                 stem_cls=nn.Conv2d):
         super().__init__()
-        self.conv1 = nn.Conv2d(3, 16, kernel_size=3, stride=1, padding=1, bias=False)   # never quantized
+        # never quantized (models/resnet.py:99-102); with this repo's classes StemConv2d = nn.Conv2d with the weight
+        # gradient on the small-C kernel
+        self.conv1 = stem_cls(3, 16, kernel_size=3, stride=1, padding=1, bias=False)
         self.bn1 = norm_cls(16)
         c_in = 16
         for si, (c_out, stride) in enumerate(((16, 1), (32, 2), (64, 2)), start=1):
@@ -88,6 +91,8 @@ def resnet_cifar(depth: int, num_classes: int = 10, quantize_fn=None, bits: int 
             from po2_quantization_b200 import FusedSyncBatchNorm as norm_cls
         else:
             norm_cls = nn.SyncBatchNorm
+    stem_cls = nn.Conv2d
     if conv_cls is None:
         from po2_quantization_b200 import QuantizedConv2d as conv_cls
-    return ResNetCifar(conv_cls, norm_cls, (depth - 2) // 6, num_classes, quantize_fn, bits)
+        from po2_quantization_b200 import StemConv2d as stem_cls
+    return ResNetCifar(conv_cls, norm_cls, (depth - 2) // 6, num_classes, quantize_fn, bits, stem_cls)
