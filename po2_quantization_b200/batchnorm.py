@@ -372,8 +372,7 @@ class _SkipGrad(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        node, ctx.node = ctx.node, None
-        node.__dict__.setdefault("_po2_skip_grads", []).append(g)
+        ctx.node.__dict__.setdefault("_po2_skip_grads", []).append(g)      # (kept on ctx: backward may run again)
         return None, None
 
 

@@ -483,6 +483,16 @@ def test_skip_connection_gradient_is_added_inside_the_norm_kernels(monkeypatch):
         assert sum(stable) >= len(stable) - 1
         for ok, a, b in zip(stable, want, got):
             assert torch.equal(a, b) if ok else torch.allclose(a, b, rtol=1e-4, atol=1e-6)
+    # a graph that is walked twice (retain_graph): the skip gradient is routed again, gradients accumulate to 2x
+    monkeypatch.setenv("PO2_SKIP_GRAD", "1")
+    model.zero_grad(set_to_none=True)
+    loss = crit(model(x), y)
+    loss.backward(retain_graph=True)
+    once = [p.grad.clone() for p in model.parameters()]
+    loss.backward()
+    torch.cuda.synchronize()
+    for a, p in zip(once, model.parameters()):
+        assert torch.allclose(p.grad, 2 * a, rtol=1e-4, atol=1e-6)
     # the accumulation kernels are gone: count torch's add kernels with the profiler
     from torch.profiler import ProfilerActivity, profile
 
