@@ -186,6 +186,7 @@ def _try_conv_bn_train(conv, bn, x, residual, act):
         return None
     if x.numel() // x.shape[1] <= 1:
         return None
+    prefetch.wait_for_quantizer(x.device)
     return _ConvBNTrain.apply(x, conv.weight, residual, bn.weight, bn.bias, slot, (conv.stride[0], conv.padding[0], conv.groups,
                                                                                   ops.COMPUTE["tf32"]), bn, act)
 

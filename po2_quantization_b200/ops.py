@@ -455,13 +455,18 @@ def join_weight_gradients() -> None:
     _side_pending.clear()
 
 
+def side_stream(dev) -> "torch.cuda.Stream":
+    side = _side_streams.get(dev.index)
+    if side is None:
+        side = _side_streams[dev.index] = torch.cuda.Stream(dev)     # lowest priority: the main branch goes first
+    return side
+
+
 def _wgrad_on_side_stream(g, x, gw, pad, compute, ready=None) -> bool:
     """ready: event on the backward stream after which g exists (default: everything queued so far)"""
     global _side_task
     dev = x.device
-    side = _side_streams.get(dev.index)
-    if side is None:
-        side = _side_streams[dev.index] = torch.cuda.Stream(dev)     # lowest priority: the main branch goes first
+    side = side_stream(dev)
     main = torch.cuda.current_stream(dev)
     if ready is not None:
         side.wait_event(ready)

@@ -53,6 +53,11 @@ class SGD(torch.optim.SGD):
                     ops.LAUNCHES += (n + per - 1) // per
                     _lib.check(lib.po2_sgd_step(pp, gg, bb, nn_, n, float(group["lr"]), mom, float(group["weight_decay"]),
                                                 int(first), ops._stream_ptr(dev)), "po2_sgd_step")
+                # the kernel wrote through raw pointers: tell autograd (and everything keyed on Tensor._version, like
+                # the weight prefetch that re-quantizes only changed weights) that these tensors changed in place
+                torch.autograd.graph.increment_version(ps)
+                if mom != 0.0:
+                    torch.autograd.graph.increment_version([self.state[p]["momentum_buffer"] for p in ps])
         if rest:
             # hand what the kernel does not take to the stock implementation: hide the gradients that are done
             keep = set(id(p) for p in rest)

@@ -156,6 +156,7 @@ class QuantizedConv2d(nn.Conv2d):
             if not slot or slot.key != prefetch._layer_key(self, input.shape, mode):
                 self.__dict__["_po2_xshape"] = tuple(input.shape)
                 return None
+            prefetch.wait_for_quantizer(input.device)
             return ops.conv2d_packed_ep(input, slot.packed, slot.scale, K, R, S, self.stride[0], self.padding[0], self.groups,
                                         compute, ep_a, ep_b, residual, int(act))
         tag = getattr(self, "_po2_ptq", None)
@@ -190,6 +191,8 @@ class QuantizedConv2d(nn.Conv2d):
                 slot = self.__dict__.get("_po2_prefetch")
                 if (slot and slot.sse is not None and slot.key is not None and slot.key[0] == w._version
                         and slot.key[3] == int(self.bits) and slot.key[4] == bool(plus)):
+                    from . import prefetch
+                    prefetch.wait_for_quantizer(w.device)
                     return slot.sse.to(torch.float32), w.numel()
                 sse = ops.quantize_full(w.detach(), int(self.bits), 1, bool(plus))[4]
                 return sse.to(torch.float32), w.numel()

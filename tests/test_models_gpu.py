@@ -517,6 +517,8 @@ def test_multi_tensor_sgd_is_torch_sgd_bit_for_bit(momentum, wd):
             assert (sa is None) == (sb is None)
             if sa is not None:
                 assert torch.equal(sa, sb)
+    # in-place semantics: the version counters moved like torch's (the weight prefetch keys on them)
+    assert all(pa._version == pb._version for pa, pb in zip(a[:-1], b[:-1])) and a[0]._version >= 4
     # the state dicts are interchangeable
     ob.load_state_dict(oa.state_dict())
     oa.load_state_dict(ob.state_dict())
@@ -531,3 +533,59 @@ def test_multi_tensor_sgd_is_torch_sgd_bit_for_bit(momentum, wd):
         oc.step()
         od.step()
     assert torch.equal(c[0], d[0])
+
+
+def test_weights_are_requantized_after_the_multi_tensor_sgd_step():
+    """The prefetch quantizes a layer again only when its weight's version changed: optim.SGD must bump it (it writes
+    through raw pointers).  After a step the prefetched quantized weight has to be Q(new weight), in eager mode and
+    inside a captured step."""
+    from workloads import resnet_cifar
+    torch.manual_seed(4)
+    dev = torch.device("cuda:0")
+    model = resnet_cifar(20, 10, P.PowerOfTwoQuantizer, 4).to(dev).train()
+    P.enable_weight_prefetch(model)
+    opt = P.optim.SGD(model.parameters(), lr=0.5, momentum=0.9, weight_decay=1e-4)
+    x = torch.randn(32, 3, 32, 32, device=dev)
+    y = torch.randint(0, 10, (32,), device=dev)
+    crit = nn.CrossEntropyLoss()
+    conv = [m for m in model.modules() if isinstance(m, P.QuantizedConv2d)][3]
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        crit(model(x), y).backward()
+        opt.step()
+
+    def check():
+        model(x)                                             # the forward pre-hook prefetches
+        torch.cuda.synchronize()
+        want = P.PowerOfTwoQuantizer.forward(None, conv.weight.detach(), bits=4)
+        assert torch.equal(conv.__dict__["_po2_prefetch"].qw, want)
+
+    for _ in range(3):
+        step()
+        check()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            step()
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            step()
+        before = conv.weight.detach().clone()
+        for _ in range(2):
+            g.replay()
+        s.synchronize()
+        assert not torch.equal(before, conv.weight)          # the captured optimizer step moves the weights ...
+        g.replay()
+        s.synchronize()
+    torch.cuda.current_stream().wait_stream(s)
+    # ... and the captured forward quantized the weights it started from: compare with the last replay's input weights
+    w_before_last = conv.weight.detach().clone()
+    with torch.cuda.stream(s):
+        g.replay()
+        s.synchronize()
+    torch.cuda.synchronize()
+    want = P.PowerOfTwoQuantizer.forward(None, w_before_last, bits=4)
+    assert torch.equal(conv.__dict__["_po2_prefetch"].qw, want)
