@@ -12,7 +12,7 @@ from .quantized_conv import QuantizedConv2d  # noqa: F401
 from .quantizers import (LinearPowerOfTwoPlusQuantizer, LinearPowerOfTwoQuantizer,  # noqa: F401
                          PowerOfTwoPlusQuantizer, PowerOfTwoQuantizer, model_quantization_error, quantize_model,
                          quantizer_dict)
-from .fold import FoldedConvBN, conv_bn_act, fold_conv_bn, fuse_batchnorm  # noqa: F401
+from .fold import FoldedConvBN, conv_bn_act, fold_conv_bn, fuse_batchnorm, invalidate_caches  # noqa: F401
 from . import optim  # noqa: F401
 from .stem import StemConv2d, accelerate_stem  # noqa: F401
 from .checkpoint import load_packed_checkpoint, pack_state_dict, save_packed_checkpoint, unpack_state_dict  # noqa: F401

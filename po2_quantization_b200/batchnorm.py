@@ -448,6 +448,10 @@ class FusedSyncBatchNorm(nn.SyncBatchNorm):
                 self.running_var if track else None, self.num_batches_tracked if track else None,
                 self.momentum if self.momentum is not None else 0.0, self.eps, kact, group, world, exch,
                 sums if world == 1 else None)
+            if track:
+                # the kernels wrote the running statistics through raw pointers: bump their version counters, as
+                # torch's in-place update would (fold._affine caches the eval-mode scale / shift on them)
+                torch.autograd.graph.increment_version([self.running_mean, self.running_var, self.num_batches_tracked])
             return F.silu(out) if kact != act else out
         if fast and not use_batch_stats and not (torch.is_grad_enabled() and (
                 input.requires_grad or (residual is not None and residual.requires_grad) or

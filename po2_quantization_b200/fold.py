@@ -125,6 +125,8 @@ class _ConvBNTrain(torch.autograd.Function):
                 _p(bn.num_batches_tracked if track else None), float(bn.momentum if bn.momentum is not None else 0.0),
                 float(bn.eps), int(act), save_mean.data_ptr(), save_invstd.data_ptr(), stats.data_ptr(), B, C, H, W_, K, R, S,
                 stride, pad, groups, compute, ws.data_ptr(), ws.numel(), ops._stream_ptr(dev)), "po2_conv2d_bn_fwd_packed")
+        if track:
+            torch.autograd.graph.increment_version([bn.running_mean, bn.running_var, bn.num_batches_tracked])
         ctx.save_for_backward(x, slot.qw, slot.scale, conv_out, y if act in (1, 2) else None, gamma, save_mean, save_invstd,
                               stats, beta if act == 3 else None)
         ctx.cfg = (stride, pad, groups, compute, int(act), residual is not None)
@@ -216,6 +218,23 @@ def fold_conv_bn(model: nn.Module) -> int:
                 seq._modules[k0] = FoldedConvBN(m0, m1)
                 seq._modules[k1] = nn.Identity()
                 n += 1
+    return n
+
+
+def invalidate_caches(model: nn.Module) -> int:
+    """Drop everything this library caches per module keyed on ``Tensor._version``: prefetched / packed weight operands
+    (``QuantizedConv2d``) and the folded scale / shift of eval-mode norms.  Needed after REPLAYING a captured training
+    step: a CUDA-graph replay runs the optimizer's and the norms' kernels without executing any Python, so version
+    counters do not move (true of ``torch.optim`` in-place updates as well) and an eager forward afterwards would meet
+    caches that look current but hold the operands of an earlier step.  Returns the number of modules touched."""
+    n = 0
+    for m in model.modules():
+        d = m.__dict__
+        hit = False
+        for k in ("_po2_prefetch", "_po2_pack_cache", "_po2_affine"):
+            if d.pop(k, None) is not None:
+                hit = True
+        n += int(hit)
     return n
 
 

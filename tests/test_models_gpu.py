@@ -589,3 +589,61 @@ def test_weights_are_requantized_after_the_multi_tensor_sgd_step():
     torch.cuda.synchronize()
     want = P.PowerOfTwoQuantizer.forward(None, w_before_last, bits=4)
     assert torch.equal(conv.__dict__["_po2_prefetch"].qw, want)
+
+
+def test_eval_after_more_training_sees_the_new_running_statistics_and_weights():
+    """Caches keyed on Tensor._version (folded eval-mode norms, prefetched operands) must not survive updates that our
+    kernels make through raw pointers: train -> eval (folded) -> train -> eval again has to match the unfolded
+    evaluation each time; after graph replays (no Python runs, no version moves) invalidate_caches() does it."""
+    from workloads import resnet_cifar
+    torch.manual_seed(6)
+    dev = torch.device("cuda:0")
+    model = resnet_cifar(20, 10, P.PowerOfTwoQuantizer, 4).to(dev)
+    P.enable_weight_prefetch(model)
+    opt = P.optim.SGD(model.parameters(), lr=0.2, momentum=0.9)
+    x = torch.randn(32, 3, 32, 32, device=dev)
+    y = torch.randint(0, 10, (32,), device=dev)
+    crit = nn.CrossEntropyLoss()
+
+    def step():
+        model.train()
+        opt.zero_grad(set_to_none=True)
+        crit(model(x), y).backward()
+        opt.step()
+
+    def evals():
+        model.eval()
+        with torch.no_grad():
+            folded = model(x)
+            os.environ["PO2_FOLD_BN"] = "0"
+            try:
+                plain = model(x)
+            finally:
+                os.environ.pop("PO2_FOLD_BN", None)
+        return folded, plain
+
+    for _ in range(3):
+        step()
+        step()
+        folded, plain = evals()
+        assert ((folded - plain).abs().max() / plain.abs().max()).item() < 1e-3
+    # a captured step replayed: versions do not move, so the caches must be dropped by hand
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            step()
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            step()
+        for _ in range(4):
+            g.replay()
+        s.synchronize()
+    torch.cuda.current_stream().wait_stream(s)
+    assert P.invalidate_caches(model) > 0
+    folded, plain = evals()
+    assert ((folded - plain).abs().max() / plain.abs().max()).item() < 1e-3
+    # and the quantized weights the evaluation used are those of the current master weights
+    conv = [m for m in model.modules() if isinstance(m, P.QuantizedConv2d)][2]
+    assert torch.equal(conv.__dict__["_po2_prefetch"].qw, P.PowerOfTwoQuantizer.forward(None, conv.weight.detach(), bits=4))
